@@ -1,0 +1,91 @@
+"""In-tree build of the CUDA engine: nvcc -> incerto_b200/lib/libincerto_b200.so.
+
+Every translation unit is compiled for sm_100a only
+(`-gencode arch=compute_100a,code=sm_100a -lineinfo`); nvcc cross-compiles
+without a GPU.  Objects are cached by source mtime so rebuilds are incremental.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "libincerto_b200.so")
+
+SOURCES = [
+    "engine.cu",
+    "sampling.cu",
+    "module_forest.cu",
+    "comm.cu",
+    "kernels_generic.cu",
+    "kernels_coin.cu",
+    "kernels_forest.cu",
+    "kernels_grid.cu",
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; the engine has no non-CUDA build")
+
+
+def _deps_mtime() -> float:
+    m = 0.0
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".cuh", ".hpp", ".h")):
+                m = max(m, os.path.getmtime(os.path.join(root, f)))
+    return m
+
+
+def build(verbose: bool = False, force: bool = False, extra_flags: list[str] | None = None) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_m = _deps_mtime()
+    flags = NVCC_FLAGS + (extra_flags or [])
+    jobs = []
+    objs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
+            jobs.append([nvcc, *flags, "-c", s, "-o", o])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if verbose and (r.stdout or r.stderr):
+            print(r.stdout + r.stderr, flush=True)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(run, jobs))
+    if jobs or not os.path.exists(LIB):
+        # libcudart is linked statically (nvcc default); NCCL is dlopen-ed at attach time
+        run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
+    print(path)

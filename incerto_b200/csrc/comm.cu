@@ -1,0 +1,210 @@
+// NCCL plumbing (one process per GPU).  The reference has no communication
+// backend at all; this exists only for (a) the 1-column halo
+// exchange of a row-partitioned forest-fire grid and (b) all-reduce of
+// cross-replica / cross-slab aggregate statistics.
+//
+// NCCL is bound lazily with dlopen so that the library loads (and single-GPU
+// simulations run) on hosts without it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "modules.hpp"
+
+namespace incerto
+{
+
+struct NcclApi
+{
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int32_t nccl_load()
+{
+    if (g_nccl.handle) return INCERTO_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names)
+    {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h)
+    {
+        set_error("cannot load NCCL: %s", dlerror());
+        return INCERTO_ERR_COMM;
+    }
+#define INC_SYM(field, name)                                                \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name)); \
+    if (!g_nccl.field)                                                      \
+    {                                                                       \
+        set_error("NCCL symbol %s missing", name);                          \
+        return INCERTO_ERR_COMM;                                            \
+    }
+    INC_SYM(GetUniqueId, "ncclGetUniqueId")
+    INC_SYM(CommInitRank, "ncclCommInitRank")
+    INC_SYM(CommDestroy, "ncclCommDestroy")
+    INC_SYM(AllReduce, "ncclAllReduce")
+    INC_SYM(Send, "ncclSend")
+    INC_SYM(Recv, "ncclRecv")
+    INC_SYM(GroupStart, "ncclGroupStart")
+    INC_SYM(GroupEnd, "ncclGroupEnd")
+    INC_SYM(GetErrorString, "ncclGetErrorString")
+#undef INC_SYM
+    g_nccl.handle = h;
+    return INCERTO_OK;
+}
+
+#define INC_NCCL(call)                                                                   \
+    do                                                                                   \
+    {                                                                                    \
+        ncclResult_t r__ = (call);                                                       \
+        if (r__ != ncclSuccess)                                                          \
+        {                                                                                \
+            set_error("NCCL error %d (%s) in %s", static_cast<int>(r__), g_nccl.GetErrorString(r__), #call); \
+            return INCERTO_ERR_COMM;                                                     \
+        }                                                                                \
+    } while (0)
+
+struct Comm
+{
+    ncclComm_t comm = nullptr;
+    uint32_t rank = 0, world = 1;
+};
+
+int32_t comm_unique_id(uint8_t out[128])
+{
+    INC_TRY(nccl_load());
+    ncclUniqueId id;
+    INC_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out, &id, 128);
+    return INCERTO_OK;
+}
+
+int32_t comm_attach(Sim& s, const uint8_t idb[128], uint32_t rank, uint32_t world)
+{
+    INC_TRY(nccl_load());
+    if (s.comm) comm_free(s);
+    INC_CUDA(cudaSetDevice(s.device));
+    ncclUniqueId id;
+    std::memcpy(&id, idb, 128);
+    Comm* c = new Comm;
+    c->rank = rank;
+    c->world = world;
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, static_cast<int>(world), id, static_cast<int>(rank));
+    if (r != ncclSuccess)
+    {
+        set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        delete c;
+        return INCERTO_ERR_COMM;
+    }
+    s.comm = c;
+    return INCERTO_OK;
+}
+
+void comm_free(Sim& s)
+{
+    if (!s.comm) return;
+    if (s.comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm->comm);
+    delete s.comm;
+    s.comm = nullptr;
+}
+
+int32_t comm_allreduce(Sim& s, void* d_buf, uint32_t n, int is_f64, uint32_t op)
+{
+    if (!s.comm)
+    {
+        set_error("no communicator attached");
+        return INCERTO_ERR_COMM;
+    }
+    const ncclRedOp_t ops[3] = {ncclSum, ncclMin, ncclMax};
+    if (op > 2) return INCERTO_ERR_INVALID_ARGUMENT;
+    INC_NCCL(g_nccl.AllReduce(d_buf, d_buf, n, is_f64 ? ncclFloat64 : ncclUint64, ops[op], s.comm->comm, s.stream));
+    return INCERTO_OK;
+}
+
+int32_t comm_halo(Sim& s, const void* const* d_send_lo, void* const* d_recv_lo, const void* const* d_send_hi,
+                  void* const* d_recv_hi, const size_t* bytes, uint32_t n_msgs)
+{
+    if (!s.comm)
+    {
+        set_error("no communicator attached");
+        return INCERTO_ERR_COMM;
+    }
+    Comm& c = *s.comm;
+    INC_NCCL(g_nccl.GroupStart());
+    for (uint32_t m = 0; m < n_msgs; ++m)
+    {
+        if (c.rank > 0)
+        {
+            INC_NCCL(g_nccl.Send(d_send_lo[m], bytes[m], ncclUint8, static_cast<int>(c.rank) - 1, c.comm, s.stream));
+            INC_NCCL(g_nccl.Recv(d_recv_lo[m], bytes[m], ncclUint8, static_cast<int>(c.rank) - 1, c.comm, s.stream));
+        }
+        if (c.rank + 1 < c.world)
+        {
+            INC_NCCL(g_nccl.Send(d_send_hi[m], bytes[m], ncclUint8, static_cast<int>(c.rank) + 1, c.comm, s.stream));
+            INC_NCCL(g_nccl.Recv(d_recv_hi[m], bytes[m], ncclUint8, static_cast<int>(c.rank) + 1, c.comm, s.stream));
+        }
+    }
+    INC_NCCL(g_nccl.GroupEnd());
+    return INCERTO_OK;
+}
+
+} // namespace incerto
+
+using namespace incerto;
+
+extern "C"
+{
+
+int32_t incerto_comm_unique_id(uint8_t out[128])
+{
+    if (!out) return INCERTO_ERR_INVALID_ARGUMENT;
+    return comm_unique_id(out);
+}
+
+int32_t incerto_sim_attach_comm(incerto_sim* s, const uint8_t unique_id[128], uint32_t rank, uint32_t world)
+{
+    Sim* S = reinterpret_cast<Sim*>(s);
+    if (!S || !unique_id || world == 0 || rank >= world) return INCERTO_ERR_INVALID_ARGUMENT;
+    return comm_attach(*S, unique_id, rank, world);
+}
+
+static int32_t allreduce_host(Sim& S, void* values, uint32_t n, int is_f64, uint32_t op)
+{
+    if (!values || !n) return INCERTO_ERR_INVALID_ARGUMENT;
+    INC_CUDA(cudaSetDevice(S.device));
+    INC_TRY(ensure_scratch(S, static_cast<size_t>(n) * 8));
+    INC_CUDA(cudaMemcpyAsync(S.d_scratch, values, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, S.stream));
+    INC_TRY(comm_allreduce(S, S.d_scratch, n, is_f64, op));
+    INC_CUDA(cudaMemcpyAsync(values, S.d_scratch, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, S.stream));
+    INC_CUDA(cudaStreamSynchronize(S.stream));
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_allreduce_u64(incerto_sim* s, uint64_t* values, uint32_t n, uint32_t op)
+{
+    Sim* S = reinterpret_cast<Sim*>(s);
+    if (!S) return INCERTO_ERR_INVALID_ARGUMENT;
+    return allreduce_host(*S, values, n, 0, op);
+}
+
+int32_t incerto_sim_allreduce_f64(incerto_sim* s, double* values, uint32_t n, uint32_t op)
+{
+    Sim* S = reinterpret_cast<Sim*>(s);
+    if (!S) return INCERTO_ERR_INVALID_ARGUMENT;
+    return allreduce_host(*S, values, n, 1, op);
+}
+
+} // extern "C"

@@ -1,0 +1,83 @@
+// Device helpers shared by the kernels: vector loads, warp/block reductions,
+// the "last block combines" pattern used for every aggregate.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace incerto
+{
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(void* p, const uint4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+
+// Block-wide sum of up to N values per thread; result valid in thread 0.
+// smem must hold N * 32 elements of T.
+template <typename T, int N>
+__device__ __forceinline__ void block_sum(T (&v)[N], T* smem)
+{
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0)
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) smem[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+        {
+            T x = lane < nwarps ? smem[i * 32 + lane] : T(0);
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
+// Returns true in every thread of exactly one block: the last one to arrive.
+// The caller must have written its partials and will read all partials after.
+__device__ __forceinline__ bool last_block_arrives(uint32_t* ticket, uint32_t total_blocks)
+{
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+    {
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_last = (t == total_blocks - 1) ? 1u : 0u;
+        if (s_last) *ticket = 0u; // leave the ticket ready for the next launch
+    }
+    __syncthreads();
+    const bool last = s_last != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+} // namespace incerto

@@ -1,0 +1,980 @@
+// Engine core: handles, builder, spawners, the per-step program and run loop.
+//
+// Reference surface restated here (host side of the boundary):
+//   SimulationBuilder::new/add_systems/add_entity_spawner/build   src/simulation_builder.rs:42-70,154-158,295-305
+//   Simulation::run                                                src/simulation.rs:25-31
+//   StepNumberPlugin                                               src/plugins/step_number.rs:6-23
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+
+#include "modules.hpp"
+
+namespace incerto
+{
+
+// ------------------------------------------------------------------- errors
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    set_error("CUDA error %d (%s) in %s at %s:%d", static_cast<int>(e), cudaGetErrorString(e), what, file, line);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? INCERTO_ERR_NO_DEVICE : INCERTO_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------- Sim
+Sim::Sim() : mods(new Modules) {}
+
+Sim::~Sim()
+{
+    if (stream == nullptr && d_scratch == nullptr && tables.empty()) return;
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    forest_free(*this);
+    comm_free(*this);
+    for (auto& t : tables)
+    {
+        for (auto& c : t.cols)
+        {
+            cudaFree(c.d);
+            cudaFree(c.d_alt);
+        }
+        cudaFree(t.d_flags);
+        cudaFree(t.d_flags_alt);
+        cudaFree(t.d_uid);
+    }
+    for (auto& se : series)
+    {
+        cudaFree(se.d_values);
+        cudaFree(se.d_counts);
+    }
+    for (auto& g : grids)
+    {
+        cudaFree(g.d_cell_start);
+        cudaFree(g.d_cursor);
+        cudaFree(g.d_sorted_rows);
+    }
+    cudaFree(d_scratch);
+    cudaFree(d_ticket);
+    cudaFree(d_error);
+    cudaFree(d_flush);
+    cudaFree(mods->d_step);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    for (auto& p : ev_pool)
+    {
+        cudaEventDestroy(p.first);
+        cudaEventDestroy(p.second);
+    }
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int32_t ensure_scratch(Sim& s, size_t bytes)
+{
+    if (bytes <= s.scratch_bytes) return INCERTO_OK;
+    if (s.d_scratch)
+    {
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+        INC_CUDA(cudaFree(s.d_scratch));
+        s.d_scratch = nullptr;
+    }
+    bytes = (bytes + 0xfffff) & ~static_cast<size_t>(0xfffff);
+    INC_CUDA(cudaMalloc(&s.d_scratch, bytes));
+    s.scratch_bytes = bytes;
+    return INCERTO_OK;
+}
+
+int32_t ensure_pinned(Sim& s, size_t bytes)
+{
+    if (bytes <= s.pinned_bytes) return INCERTO_OK;
+    if (s.h_pinned)
+    {
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+        INC_CUDA(cudaFreeHost(s.h_pinned));
+        s.h_pinned = nullptr;
+    }
+    bytes = (bytes + 0xffff) & ~static_cast<size_t>(0xffff);
+    INC_CUDA(cudaMallocHost(&s.h_pinned, bytes));
+    s.pinned_bytes = bytes;
+    return INCERTO_OK;
+}
+
+KernelStat& kstat(Sim& s, const char* name)
+{
+    for (auto& k : s.kstats)
+        if (k.name == name || std::strcmp(k.name, name) == 0) return k;
+    KernelStat k;
+    k.name = name;
+    s.kstats.push_back(k);
+    return s.kstats.back();
+}
+
+struct PendingTimer
+{
+    cudaEvent_t a, b;
+    size_t stat;
+};
+static thread_local std::vector<PendingTimer> g_pending; // resolved at synchronize
+
+KTimer::KTimer(Sim& s_, const char* name, double bytes) : s(s_), st(kstat(s_, name))
+{
+    st.launches += 1;
+    st.algorithmic_bytes += bytes;
+    s.launches += 1;
+    if (s.profiling)
+    {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s.stream);
+    }
+}
+KTimer::~KTimer()
+{
+    if (a)
+    {
+        cudaEventRecord(b, s.stream);
+        PendingTimer p;
+        p.a = a;
+        p.b = b;
+        p.stat = static_cast<size_t>(&st - s.kstats.data());
+        g_pending.push_back(p);
+    }
+}
+
+static void resolve_timers(Sim& s)
+{
+    for (auto& p : g_pending)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess && p.stat < s.kstats.size())
+            s.kstats[p.stat].device_ms += ms;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_pending.clear();
+}
+
+int table_for_components(Sim& s, const std::vector<int>& comps)
+{
+    for (size_t ti = 0; ti < s.tables.size(); ++ti)
+    {
+        bool ok = true;
+        for (int c : comps)
+        {
+            if (c < 0 || c >= static_cast<int>(s.comps.size())) return -1;
+            if (s.comps[c].dtype == INCERTO_MARKER) continue;
+            if (!s.tables[ti].has(c)) ok = false;
+        }
+        if (ok) return static_cast<int>(ti);
+    }
+    return -1;
+}
+
+int32_t validate_filter(const Sim& s, const FilterSpec& f)
+{
+    for (int c : f.with)
+    {
+        if (c < 0 || c >= static_cast<int>(s.comps.size()))
+        {
+            set_error("filter names an unregistered component handle %d", c);
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        }
+        if (!s.comps[c].exists) return INCERTO_ERR_COMPONENT_DOES_NOT_EXIST;
+    }
+    for (int c : f.without)
+    {
+        if (c < 0 || c >= static_cast<int>(s.comps.size()))
+        {
+            set_error("filter names an unregistered component handle %d", c);
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        }
+        if (!s.comps[c].exists) return INCERTO_ERR_COMPONENT_DOES_NOT_EXIST;
+    }
+    return INCERTO_OK;
+}
+
+RowFilter row_filter(const Sim& s, const Table& t, const FilterSpec& f)
+{
+    RowFilter r;
+    r.need_set = kAliveBit;
+    for (int c : f.with)
+    {
+        const ComponentInfo& ci = s.comps[c];
+        if (ci.dtype == INCERTO_MARKER)
+            r.need_set |= static_cast<uint8_t>(1u << ci.marker_bit);
+        else if (!t.has(c))
+            r.impossible = true;
+    }
+    for (int c : f.without)
+    {
+        const ComponentInfo& ci = s.comps[c];
+        if (ci.dtype == INCERTO_MARKER)
+            r.need_clear |= static_cast<uint8_t>(1u << ci.marker_bit);
+        else if (t.has(c))
+            r.impossible = true;
+    }
+    r.trivial = (r.need_set == kAliveBit) && r.need_clear == 0 && t.all_alive;
+    return r;
+}
+
+// ------------------------------------------------------------------ spawning
+static std::vector<int> signature_of(const Sim& s, const HostSpawn& sp)
+{
+    std::vector<int> sig;
+    for (auto& c : sp.cols)
+        if (s.comps[c.comp].dtype != INCERTO_MARKER) sig.push_back(c.comp);
+    std::sort(sig.begin(), sig.end());
+    return sig;
+}
+
+static int find_or_add_table(Sim& s, const std::vector<int>& sig)
+{
+    for (size_t i = 0; i < s.tables.size(); ++i)
+        if (s.tables[i].signature == sig) return static_cast<int>(i);
+    Table t;
+    t.signature = sig;
+    for (int c : sig)
+    {
+        Column col;
+        col.comp = c;
+        col.row_bytes = s.comps[c].row_bytes();
+        t.cols.push_back(col);
+    }
+    s.tables.push_back(std::move(t));
+    return static_cast<int>(s.tables.size()) - 1;
+}
+
+// Device spawners that create generic tables (coin tossers ...) are expanded here.
+static int32_t device_spawn_signature(Sim& s, const HostSpawn& sp, std::vector<int>& sig, uint64_t& n)
+{
+    switch (sp.kind)
+    {
+    case INCERTO_SPAWN_COIN_TOSSERS:
+    {
+        if (sp.params.size() != sizeof(incerto_spawn_coin_tossers_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_spawn_coin_tossers_params p;
+        std::memcpy(&p, sp.params.data(), sizeof(p));
+        sig = {p.num_heads, p.num_tosses};
+        std::sort(sig.begin(), sig.end());
+        n = p.num_entities;
+        return INCERTO_OK;
+    }
+    case INCERTO_SPAWN_FOREST_GRID:
+    {
+        if (sp.params.size() != sizeof(incerto_spawn_forest_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_spawn_forest_params p;
+        std::memcpy(&p, sp.params.data(), sizeof(p));
+        sig = {p.position, p.cell};
+        std::sort(sig.begin(), sig.end());
+        n = static_cast<uint64_t>(p.width) * p.height + p.initial_fire_count;
+        return INCERTO_OK;
+    }
+    default:
+        set_error("device spawner kind %u is not implemented", sp.kind);
+        return INCERTO_ERR_UNSUPPORTED;
+    }
+}
+
+static int32_t run_spawners(Sim& s, bool first_time)
+{
+    // pass 1: rows per table
+    std::vector<uint64_t> rows(s.tables.size(), 0);
+    std::vector<int> spawn_table(s.spawns.size(), -1);
+    for (size_t i = 0; i < s.spawns.size(); ++i)
+    {
+        const HostSpawn& sp = s.spawns[i];
+        std::vector<int> sig;
+        uint64_t n = sp.n;
+        if (sp.device_kind)
+            INC_TRY(device_spawn_signature(s, sp, sig, n));
+        else
+            sig = signature_of(s, sp);
+        for (int c : sig)
+        {
+            if (c < 0 || c >= static_cast<int>(s.comps.size()))
+            {
+                set_error("spawner names an unregistered component handle %d", c);
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            s.comps[c].exists = true;
+        }
+        for (auto& c : sp.cols) s.comps[c.comp].exists = true;
+        const int ti = find_or_add_table(s, sig);
+        if (static_cast<size_t>(ti) >= rows.size()) rows.resize(ti + 1, 0);
+        rows[ti] += n;
+        spawn_table[i] = ti;
+    }
+    // allocate
+    for (size_t ti = 0; ti < s.tables.size(); ++ti)
+    {
+        Table& t = s.tables[ti];
+        const bool dense_device =
+            std::any_of(s.spawns.begin(), s.spawns.end(), [&](const HostSpawn& sp) {
+                return sp.device_kind && sp.kind == INCERTO_SPAWN_FOREST_GRID;
+            }) &&
+            s.mods->forest.table == static_cast<int>(ti);
+        if (first_time)
+        {
+            t.n = rows[ti];
+            t.n_spawned = rows[ti];
+            if (rows[ti] >= (1ull << 32))
+            {
+                set_error("a table holds at most 2^32-1 entities per replica (uid is 32 bit)");
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+        }
+        else if (t.n_spawned != rows[ti])
+        {
+            set_error("reset: spawner row count changed");
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        }
+        (void)dense_device;
+    }
+    // pass 2: fill
+    std::vector<uint64_t> cursor(s.tables.size(), 0);
+    for (size_t i = 0; i < s.spawns.size(); ++i)
+    {
+        const HostSpawn& sp = s.spawns[i];
+        const int ti = spawn_table[i];
+        Table& t = s.tables[ti];
+        if (sp.device_kind && sp.kind == INCERTO_SPAWN_FOREST_GRID)
+        {
+            if (cursor[ti] != 0)
+            {
+                set_error("the forest grid spawner must be the first spawner of its archetype");
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            s.mods->forest.table = ti;
+            INC_TRY(forest_spawn_device(s, sp));
+            std::vector<int> sig;
+            uint64_t n = 0;
+            INC_TRY(device_spawn_signature(s, sp, sig, n));
+            cursor[ti] += n;
+            continue;
+        }
+        // generic columns
+        if (first_time || t.d_flags == nullptr)
+        {
+            if (t.d_flags == nullptr && t.n)
+            {
+                INC_CUDA(cudaMalloc(&t.d_flags, t.n));
+                for (auto& c : t.cols)
+                    if (c.d == nullptr) INC_CUDA(cudaMalloc(&c.d, t.n * c.row_bytes));
+            }
+        }
+        uint64_t n = sp.n;
+        const uint64_t off = cursor[ti];
+        if (sp.device_kind)
+        {
+            std::vector<int> sig;
+            INC_TRY(device_spawn_signature(s, sp, sig, n));
+            // coin tossers: CoinTosser::default() (coin_toss.rs:60-62) -> zeros
+            for (auto& c : t.cols) INC_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(c.d) + off * c.row_bytes, 0, n * c.row_bytes, s.stream));
+            INC_CUDA(cudaMemsetAsync(t.d_flags + off, kAliveBit, n, s.stream));
+            cursor[ti] += n;
+            continue;
+        }
+        // flags: alive + markers
+        std::vector<uint8_t> flags(n, kAliveBit);
+        for (auto& c : sp.cols)
+        {
+            const ComponentInfo& ci = s.comps[c.comp];
+            if (ci.dtype != INCERTO_MARKER) continue;
+            const uint8_t bit = static_cast<uint8_t>(1u << ci.marker_bit);
+            if (!c.has_data)
+                for (auto& f : flags) f |= bit;
+            else
+                for (uint64_t r = 0; r < n; ++r)
+                    if (c.data[r]) flags[r] |= bit;
+        }
+        INC_CUDA(cudaMemcpyAsync(t.d_flags + off, flags.data(), n, cudaMemcpyHostToDevice, s.stream));
+        for (auto& c : sp.cols)
+        {
+            const ComponentInfo& ci = s.comps[c.comp];
+            if (ci.dtype == INCERTO_MARKER) continue;
+            Column* col = t.col(c.comp);
+            const size_t es = dtype_size(ci.dtype);
+            if (ci.lanes == 3)
+            {
+                // 3 lanes are padded to a stride of 4 on the device
+                std::vector<uint8_t> padded(n * 4 * es, 0);
+                for (uint64_t r = 0; r < n; ++r) std::memcpy(&padded[r * 4 * es], &c.data[r * 3 * es], 3 * es);
+                INC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(col->d) + off * col->row_bytes, padded.data(),
+                                         padded.size(), cudaMemcpyHostToDevice, s.stream));
+                INC_CUDA(cudaStreamSynchronize(s.stream));
+            }
+            else
+            {
+                INC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(col->d) + off * col->row_bytes, c.data.data(),
+                                         n * col->row_bytes, cudaMemcpyHostToDevice, s.stream));
+            }
+        }
+        INC_CUDA(cudaStreamSynchronize(s.stream)); // `flags` is a stack-owned staging buffer
+        cursor[ti] += n;
+    }
+    for (auto& t : s.tables)
+    {
+        t.all_alive = true;
+        t.n = t.n_spawned;
+        if (t.d_uid)
+        {
+            INC_CUDA(cudaFree(t.d_uid));
+            t.d_uid = nullptr;
+        }
+    }
+    return INCERTO_OK;
+}
+
+// ------------------------------------------------------------ step program
+static int32_t bind_generic_systems(Sim& s)
+{
+    auto& prog = s.mods->program;
+    std::vector<SystemInst> sorted = s.systems;
+    std::stable_sort(sorted.begin(), sorted.end(),
+                     [](const SystemInst& a, const SystemInst& b) { return a.kind < b.kind; });
+    bool forest_added = false;
+    for (const SystemInst& sys : sorted)
+    {
+        switch (sys.kind)
+        {
+        case INCERTO_SYS_ADD_CONST:
+        {
+            if (sys.params.size() != sizeof(incerto_add_const_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+            incerto_add_const_params p;
+            std::memcpy(&p, sys.params.data(), sizeof(p));
+            if (p.target < 0 || p.target >= static_cast<int>(s.comps.size()) || p.n_with > 4)
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            s.comps[p.target].exists = true;
+            FilterSpec f;
+            for (uint32_t i = 0; i < p.n_with; ++i)
+            {
+                if (p.with[i] < 0 || p.with[i] >= static_cast<int>(s.comps.size())) return INCERTO_ERR_INVALID_ARGUMENT;
+                f.with.push_back(p.with[i]);
+                s.comps[p.with[i]].exists = true;
+            }
+            StepOp op;
+            op.name = "add_const";
+            op.fn = [p, f](Sim& sim, uint64_t, uint32_t nsteps) -> int32_t {
+                for (auto& t : sim.tables)
+                {
+                    Column* c = t.col(p.target);
+                    if (!c || !t.n) continue;
+                    RowFilter rf = row_filter(sim, t, f);
+                    if (rf.impossible) continue;
+                    const ComponentInfo& ci = sim.comps[p.target];
+                    KTimer kt(sim, "add_const", 2.0 * t.n * dtype_size(ci.dtype));
+                    launch_add_const(c->d, ci.dtype, ci.stride(), rf.trivial ? nullptr : t.d_flags, rf.need_set, t.n,
+                                     p.amount * static_cast<int64_t>(nsteps), sim.stream);
+                }
+                return INCERTO_OK;
+            };
+            op.multi_step_ok = true;
+            prog.push_back(op);
+            break;
+        }
+        case INCERTO_SYS_ADD_COLUMN:
+        {
+            if (sys.params.size() != sizeof(incerto_add_column_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+            incerto_add_column_params p;
+            std::memcpy(&p, sys.params.data(), sizeof(p));
+            if (p.target < 0 || p.source < 0 || p.target >= static_cast<int>(s.comps.size()) ||
+                p.source >= static_cast<int>(s.comps.size()))
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            s.comps[p.target].exists = true;
+            s.comps[p.source].exists = true;
+            StepOp op;
+            op.name = "add_column";
+            op.fn = [p](Sim& sim, uint64_t, uint32_t) -> int32_t {
+                for (auto& t : sim.tables)
+                {
+                    Column* d = t.col(p.target);
+                    Column* sc = t.col(p.source);
+                    if (!d || !sc || !t.n) continue;
+                    KTimer kt(sim, "add_column", 3.0 * t.n * dtype_size(sim.comps[p.target].dtype));
+                    launch_add_column(d->d, sim.comps[p.target].dtype, sc->d, sim.comps[p.source].dtype,
+                                      t.all_alive ? nullptr : t.d_flags, t.n, sim.stream);
+                }
+                return INCERTO_OK;
+            };
+            prog.push_back(op);
+            break;
+        }
+        case INCERTO_SYS_COIN_TOSS:
+        {
+            if (sys.params.size() != sizeof(incerto_coin_toss_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+            incerto_coin_toss_params p;
+            std::memcpy(&p, sys.params.data(), sizeof(p));
+            if (p.num_heads < 0 || p.num_tosses < 0 || p.num_heads >= static_cast<int>(s.comps.size()) ||
+                p.num_tosses >= static_cast<int>(s.comps.size()))
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            const int dt = s.comps[p.num_heads].dtype;
+            if ((dt != INCERTO_U32 && dt != INCERTO_U64) || s.comps[p.num_tosses].dtype != dt ||
+                s.comps[p.num_heads].lanes != 1 || s.comps[p.num_tosses].lanes != 1)
+            {
+                set_error("coin_toss: num_heads/num_tosses must both be U32 or both U64 scalar columns");
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            s.comps[p.num_heads].exists = true;
+            s.comps[p.num_tosses].exists = true;
+            s.mods->coin.active = true;
+            s.mods->coin.comp_heads = p.num_heads;
+            s.mods->coin.comp_tosses = p.num_tosses;
+            s.mods->coin.odds = p.odds_heads;
+            StepOp op;
+            op.name = "coin_toss";
+            op.multi_step_ok = true;
+            op.fn = [p, dt](Sim& sim, uint64_t first_step, uint32_t nsteps) -> int32_t {
+                const PhiloxKey key = make_key(sim.seed, sim.replica, TAG_COIN_TOSS);
+                const uint64_t thr = bernoulli_threshold(p.odds_heads);
+                for (auto& t : sim.tables)
+                {
+                    Column* h = t.col(p.num_heads);
+                    Column* c = t.col(p.num_tosses);
+                    if (!h || !c || !t.n) continue;
+                    const uint8_t* flags = t.all_alive ? nullptr : t.d_flags;
+                    // 16 B per entity-update; a multi-step launch still moves 16 B per entity
+                    KTimer kt(sim, nsteps == 1 ? "coin_toss_step" : "coin_toss_multistep",
+                              (dt == INCERTO_U32 ? 16.0 : 32.0) * t.n);
+                    if (dt == INCERTO_U32)
+                        launch_coin_toss(static_cast<uint32_t*>(h->d), static_cast<uint32_t*>(c->d), t.d_uid, flags,
+                                         t.n, key, thr, static_cast<uint32_t>(first_step), nsteps, sim.stream);
+                    else
+                        launch_coin_toss_u64(static_cast<uint64_t*>(h->d), static_cast<uint64_t*>(c->d), t.d_uid,
+                                             flags, t.n, key, thr, static_cast<uint32_t>(first_step), nsteps,
+                                             sim.stream);
+                }
+                return INCERTO_OK;
+            };
+            prog.push_back(op);
+            break;
+        }
+        case INCERTO_SYS_FOREST_SPREAD:
+        case INCERTO_SYS_FOREST_BURN_PROGRESSION:
+        case INCERTO_SYS_FOREST_REGROWTH:
+        {
+            if (!forest_added)
+            {
+                INC_TRY(forest_bind(s));
+                StepOp op;
+                op.name = "forest_step";
+                op.bumps_device_step = true;
+                op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return forest_step(sim, first_step, nsteps); };
+                prog.push_back(op);
+                forest_added = true;
+            }
+            break;
+        }
+        default:
+            set_error("system kind %u is not implemented in this build", sys.kind);
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+    }
+    return INCERTO_OK;
+}
+
+// implemented in sampling.cu
+int32_t series_prepare(Sim& s, uint64_t first_step, uint64_t nsteps);
+int32_t series_sample_step(Sim& s, uint64_t step);
+void series_after_run(Sim& s);
+void series_clear(Sim& s);
+int32_t grids_allocate(Sim& s);
+int32_t grids_rebuild_for_step(Sim& s, uint64_t step);
+
+static int32_t do_run(Sim& s, uint64_t num_steps)
+{
+    INC_CUDA(cudaSetDevice(s.device));
+    if (s.run_pending) INC_TRY(incerto_sim_synchronize(reinterpret_cast<incerto_sim*>(&s)));
+    s.last_launches = s.launches;
+    INC_TRY(series_prepare(s, s.step, num_steps));
+    INC_CUDA(cudaEventRecord(s.ev_begin, s.stream));
+    auto& prog = s.mods->program;
+    bool all_multi = !prog.empty();
+    bool device_bump = false;
+    for (auto& op : prog)
+    {
+        all_multi = all_multi && op.multi_step_ok;
+        device_bump = device_bump || op.bumps_device_step;
+    }
+    uint64_t remaining = num_steps;
+    while (remaining)
+    {
+        uint64_t k = 1;
+        if (all_multi)
+        {
+            k = std::min<uint64_t>(remaining, 1u << 20);
+            for (auto& se : s.series)
+            {
+                const uint64_t next = ((s.step + se.interval - 1) / se.interval) * se.interval; // next sampling step
+                k = std::min<uint64_t>(k, next - s.step + 1);
+            }
+        }
+        INC_TRY(grids_rebuild_for_step(s, s.step));
+        for (auto& op : prog) INC_TRY(op.fn(s, s.step, static_cast<uint32_t>(k)));
+        s.step += k - 1;
+        INC_TRY(series_sample_step(s, s.step)); // PostUpdate (time_series.rs:100,175-178)
+        s.step += 1;                            // Last (step_number.rs:16)
+        if (!device_bump)
+        {
+            // keep the device mirror in lock step
+            const uint32_t v = static_cast<uint32_t>(s.step);
+            INC_CUDA(cudaMemcpyAsync(s.mods->d_step, &v, sizeof(v), cudaMemcpyHostToDevice, s.stream));
+        }
+        remaining -= k;
+    }
+    INC_CUDA(cudaEventRecord(s.ev_end, s.stream));
+    s.run_pending = true;
+    series_after_run(s);
+    return INCERTO_OK;
+}
+
+} // namespace incerto
+
+using namespace incerto;
+
+// =========================================================================
+//                                  C ABI
+// =========================================================================
+extern "C"
+{
+
+const char* incerto_last_error_message(void) { return g_error; }
+uint32_t incerto_abi_version(void) { return INCERTO_B200_ABI_VERSION; }
+
+int32_t incerto_builder_new(incerto_builder** out)
+{
+    if (!out) return INCERTO_ERR_INVALID_ARGUMENT;
+    Builder* b = new Builder;
+    b->sim.reset(new Sim);
+    *out = reinterpret_cast<incerto_builder*>(b);
+    return INCERTO_OK;
+}
+
+void incerto_builder_free(incerto_builder* b) { delete reinterpret_cast<Builder*>(b); }
+
+#define INC_BUILDER(b)                                    \
+    Builder* B = reinterpret_cast<Builder*>(b);           \
+    if (!B || !B->sim)                                    \
+    {                                                     \
+        set_error("null or consumed builder handle");     \
+        return INCERTO_ERR_INVALID_ARGUMENT;              \
+    }                                                     \
+    Sim& S = *B->sim;
+
+int32_t incerto_builder_set_seed(incerto_builder* b, uint64_t seed, uint32_t replica)
+{
+    INC_BUILDER(b);
+    S.seed = seed;
+    S.replica = replica;
+    return INCERTO_OK;
+}
+
+int32_t incerto_builder_set_device(incerto_builder* b, int32_t ordinal)
+{
+    INC_BUILDER(b);
+    S.device = ordinal;
+    B->device_set = true;
+    return INCERTO_OK;
+}
+
+int32_t incerto_builder_set_row_partition(incerto_builder* b, uint32_t rank, uint32_t world)
+{
+    INC_BUILDER(b);
+    if (world == 0 || rank >= world) return INCERTO_ERR_INVALID_ARGUMENT;
+    S.part_rank = rank;
+    S.part_world = world;
+    return INCERTO_OK;
+}
+
+int32_t incerto_builder_register_component(incerto_builder* b, const char* name, incerto_dtype dtype, uint32_t lanes,
+                                           incerto_component* out)
+{
+    INC_BUILDER(b);
+    if (!out || dtype < INCERTO_MARKER || dtype > INCERTO_F64 || lanes < 1 || lanes > 3 ||
+        (dtype == INCERTO_MARKER && lanes != 1))
+    {
+        set_error("register_component: bad dtype/lanes");
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    ComponentInfo ci;
+    ci.name = name ? name : "";
+    ci.dtype = dtype;
+    ci.lanes = lanes;
+    if (dtype == INCERTO_MARKER)
+    {
+        int used = 0;
+        for (auto& c : S.comps)
+            if (c.dtype == INCERTO_MARKER) ++used;
+        if (used >= kMaxMarkers)
+        {
+            set_error("at most %d marker components per simulation", kMaxMarkers);
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+        ci.marker_bit = used + 1;
+    }
+    S.comps.push_back(ci);
+    *out = static_cast<incerto_component>(S.comps.size() - 1);
+    return INCERTO_OK;
+}
+
+int32_t incerto_builder_add_entity_spawner(incerto_builder* b, uint64_t n, const incerto_column_data* columns,
+                                           uint32_t n_columns)
+{
+    INC_BUILDER(b);
+    if (n_columns && !columns) return INCERTO_ERR_INVALID_ARGUMENT;
+    HostSpawn sp;
+    sp.n = n;
+    for (uint32_t i = 0; i < n_columns; ++i)
+    {
+        const int c = columns[i].component;
+        if (c < 0 || c >= static_cast<int>(S.comps.size()))
+        {
+            set_error("spawner names an unregistered component handle %d", c);
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        }
+        for (auto& prev : sp.cols)
+            if (prev.comp == c)
+            {
+                set_error("component listed twice in one bundle");
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+        const ComponentInfo& ci = S.comps[c];
+        HostSpawn::Col col;
+        col.comp = c;
+        col.has_data = columns[i].data != nullptr;
+        if (ci.dtype == INCERTO_MARKER)
+        {
+            if (col.has_data) col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + n);
+        }
+        else
+        {
+            if (!col.has_data && n)
+            {
+                set_error("data component '%s' spawned without values", ci.name.c_str());
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            const size_t bytes = n * dtype_size(ci.dtype) * ci.lanes;
+            if (n) col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + bytes);
+        }
+        sp.cols.push_back(std::move(col));
+    }
+    S.spawns.push_back(std::move(sp));
+    return INCERTO_OK;
+}
+
+int32_t incerto_builder_add_device_spawner(incerto_builder* b, uint32_t kind, const void* params, uint32_t params_size)
+{
+    INC_BUILDER(b);
+    if (!params || !params_size) return INCERTO_ERR_INVALID_ARGUMENT;
+    HostSpawn sp;
+    sp.device_kind = true;
+    sp.kind = kind;
+    sp.params.assign(static_cast<const uint8_t*>(params), static_cast<const uint8_t*>(params) + params_size);
+    S.spawns.push_back(std::move(sp));
+    return INCERTO_OK;
+}
+
+int32_t incerto_builder_add_systems(incerto_builder* b, const incerto_system_desc* systems, uint32_t n)
+{
+    INC_BUILDER(b);
+    if (n && !systems) return INCERTO_ERR_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        SystemInst si;
+        si.kind = systems[i].kind;
+        if (systems[i].params && systems[i].params_size)
+            si.params.assign(static_cast<const uint8_t*>(systems[i].params),
+                             static_cast<const uint8_t*>(systems[i].params) + systems[i].params_size);
+        si.order = static_cast<uint32_t>(S.systems.size());
+        S.systems.push_back(std::move(si));
+    }
+    return INCERTO_OK;
+}
+
+int32_t incerto_builder_build(incerto_builder* b, incerto_sim** out)
+{
+    Builder* B = reinterpret_cast<Builder*>(b);
+    if (!B || !B->sim || !out)
+    {
+        set_error("null or consumed builder handle");
+        delete B;
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    std::unique_ptr<Builder> owner(B); // consumed, also on failure (simulation_builder.rs:295 takes self)
+    Sim& S = *B->sim;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+    {
+        set_error("no CUDA device available (%s); this engine has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return INCERTO_ERR_NO_DEVICE;
+    }
+    if (S.device < 0 || S.device >= ndev)
+    {
+        set_error("device ordinal %d out of range (%d devices)", S.device, ndev);
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    INC_CUDA(cudaSetDevice(S.device));
+    INC_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    INC_CUDA(cudaEventCreate(&S.ev_begin));
+    INC_CUDA(cudaEventCreate(&S.ev_end));
+    INC_CUDA(cudaMalloc(&S.d_ticket, 64));
+    INC_CUDA(cudaMemsetAsync(S.d_ticket, 0, 64, S.stream));
+    INC_CUDA(cudaMalloc(&S.d_error, 64));
+    INC_CUDA(cudaMemsetAsync(S.d_error, 0, 64, S.stream));
+    INC_CUDA(cudaMalloc(&S.mods->d_step, 64));
+    const uint32_t one = 1;
+    INC_CUDA(cudaMemcpyAsync(S.mods->d_step, &one, sizeof(one), cudaMemcpyHostToDevice, S.stream));
+    INC_TRY(ensure_scratch(S, 1u << 20));
+    INC_TRY(ensure_pinned(S, 1u << 16));
+    S.step = 1; // SimulationBuilder::new runs one empty update (simulation_builder.rs:50)
+
+    // components named by grids and series "exist" like the query state of a bevy system
+    for (auto& g : S.grids)
+    {
+        S.comps[g.position].exists = true;
+        S.comps[g.component].exists = true;
+    }
+    INC_TRY(run_spawners(S, true));
+    INC_TRY(bind_generic_systems(S));
+    INC_TRY(grids_allocate(S));
+    INC_CUDA(cudaStreamSynchronize(S.stream));
+    *out = reinterpret_cast<incerto_sim*>(B->sim.release());
+    return INCERTO_OK;
+}
+
+#define INC_SIM(s)                                \
+    Sim* SP = reinterpret_cast<Sim*>(s);          \
+    if (!SP)                                      \
+    {                                             \
+        set_error("null simulation handle");      \
+        return INCERTO_ERR_INVALID_ARGUMENT;      \
+    }                                             \
+    Sim& S = *SP;
+
+int32_t incerto_sim_run(incerto_sim* s, uint64_t num_steps)
+{
+    INC_SIM(s);
+    INC_TRY(do_run(S, num_steps));
+    return incerto_sim_synchronize(s);
+}
+
+int32_t incerto_sim_run_async(incerto_sim* s, uint64_t num_steps)
+{
+    INC_SIM(s);
+    return do_run(S, num_steps);
+}
+
+int32_t incerto_sim_synchronize(incerto_sim* s)
+{
+    INC_SIM(s);
+    INC_CUDA(cudaSetDevice(S.device));
+    INC_CUDA(cudaStreamSynchronize(S.stream));
+    if (S.run_pending)
+    {
+        float ms = 0.f;
+        INC_CUDA(cudaEventElapsedTime(&ms, S.ev_begin, S.ev_end));
+        S.last_ms = ms;
+        S.last_launches = S.launches - S.last_launches;
+        S.run_pending = false;
+    }
+    resolve_timers(S);
+    uint32_t err[2] = {0, 0};
+    INC_CUDA(cudaMemcpy(err, S.d_error, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err[0])
+    {
+        INC_CUDA(cudaMemset(S.d_error, 0, 64));
+        set_error("device raised error flag %u (detail %u)", err[0], err[1]);
+        return static_cast<int32_t>(err[0]);
+    }
+    return INCERTO_OK;
+}
+
+void incerto_sim_destroy(incerto_sim* s) { delete reinterpret_cast<Sim*>(s); }
+
+int32_t incerto_sim_reset(incerto_sim* s, uint32_t replica)
+{
+    INC_SIM(s);
+    INC_CUDA(cudaSetDevice(S.device));
+    INC_CUDA(cudaStreamSynchronize(S.stream));
+    S.replica = replica;
+    S.step = 1;
+    const uint32_t one = 1;
+    INC_CUDA(cudaMemcpyAsync(S.mods->d_step, &one, sizeof(one), cudaMemcpyHostToDevice, S.stream));
+    series_clear(S);
+    INC_TRY(run_spawners(S, false));
+    if (S.mods->forest.active) INC_TRY(forest_reset_after_spawn(S));
+    for (auto& g : S.grids) g.built_step = ~0ull;
+    INC_CUDA(cudaStreamSynchronize(S.stream));
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_step_number(incerto_sim* s, uint64_t* out)
+{
+    INC_SIM(s);
+    if (!out) return INCERTO_ERR_INVALID_ARGUMENT;
+    *out = S.step;
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_last_run_stats(incerto_sim* s, double* device_ms, uint64_t* kernel_launches)
+{
+    INC_SIM(s);
+    if (S.run_pending) INC_TRY(incerto_sim_synchronize(s));
+    if (device_ms) *device_ms = S.last_ms;
+    if (kernel_launches) *kernel_launches = S.last_launches;
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_set_profiling(incerto_sim* s, uint32_t enabled)
+{
+    INC_SIM(s);
+    S.profiling = enabled != 0;
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_kernel_stats(incerto_sim* s, incerto_kernel_stat* out, uint32_t capacity, uint32_t* n_out)
+{
+    INC_SIM(s);
+    if (S.run_pending) INC_TRY(incerto_sim_synchronize(s));
+    uint32_t n = 0;
+    for (auto& k : S.kstats)
+    {
+        if (out && n < capacity)
+        {
+            out[n].name = k.name;
+            out[n].launches = k.launches;
+            out[n].device_ms = k.device_ms;
+            out[n].algorithmic_bytes = k.algorithmic_bytes;
+        }
+        ++n;
+    }
+    if (n_out) *n_out = n;
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_flush_l2(incerto_sim* s)
+{
+    INC_SIM(s);
+    INC_CUDA(cudaSetDevice(S.device));
+    if (!S.d_flush)
+    {
+        S.flush_bytes = 512ull << 20; // 4x the 126 MB L2
+        INC_CUDA(cudaMalloc(&S.d_flush, S.flush_bytes));
+    }
+    static uint32_t v = 0;
+    launch_flush(S.d_flush, S.flush_bytes, ++v, S.stream);
+    INC_CUDA(cudaGetLastError());
+    return INCERTO_OK;
+}
+
+} // extern "C"

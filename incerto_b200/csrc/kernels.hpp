@@ -1,0 +1,119 @@
+// Launch wrappers of the sm_100a kernels (definitions in kernels_*.cu).
+// Everything here takes raw device pointers and a stream; no engine types.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "philox.cuh"
+
+namespace incerto
+{
+
+constexpr int kNumSMs = 148;
+
+// ------------------------------------------------------------------ generic
+struct ReduceRecord
+{
+    uint64_t count;
+    uint64_t sum_bits; // i64 / u64 (wrapping) or f64 bits
+    uint64_t min_bits; // value widened to 64 bit (i64 / u64 / f64 bits)
+    uint64_t max_bits;
+    uint32_t nan_seen;
+    uint32_t pad;
+};
+
+// count / sum / min / max of lane `lane` of a strided column under a row filter.
+// out: one ReduceRecord in device memory. scratch: >= max_blocks * sizeof(ReduceRecord).
+void launch_reduce_column(const void* col, int dtype, uint32_t stride, uint32_t lane, const uint8_t* flags,
+                          uint8_t need_set, uint8_t need_clear, uint64_t n, ReduceRecord* out, void* scratch,
+                          uint32_t* ticket, cudaStream_t st);
+// rows matching the filter; out u64.
+void launch_count_rows(const uint8_t* flags, uint8_t need_set, uint8_t need_clear, uint64_t n, uint64_t* out,
+                       void* scratch, uint32_t* ticket, cudaStream_t st);
+
+// k-th smallest (0-based) of the filtered column, by 8-bit MSD radix select on
+// order-preserving keys. state: 4 + 256 u64 of device scratch. The value (widened
+// to 64 bit like ReduceRecord::min_bits) lands in state[0], an index-out-of-range
+// flag in state[3].  k comes from `arg` (mode 0) or is derived on the device from
+// d_rec->count: mode 1 = Median (count/2), mode 2 = Percentile<arg>.
+void launch_radix_select(const void* col, int dtype, uint32_t stride, uint32_t lane, const uint8_t* flags,
+                         uint8_t need_set, uint8_t need_clear, uint64_t n, const ReduceRecord* d_rec, uint32_t mode,
+                         uint64_t arg, uint64_t* state, cudaStream_t st);
+constexpr size_t kSelectStateWords = 4 + 256;
+
+void launch_add_const(void* col, int dtype, uint32_t stride, const uint8_t* flags, uint8_t need_set, uint64_t n,
+                      int64_t amount, cudaStream_t st);
+void launch_add_column(void* dst, int dst_dtype, const void* src, int src_dtype, const uint8_t* flags, uint64_t n,
+                       cudaStream_t st);
+// rows whose identifier equals id_bits: out[0] = matches, out[1] = first matching row.
+void launch_find_id(const void* col, int dtype, uint32_t stride, const uint8_t* flags, uint64_t n,
+                    uint64_t id_bits, uint64_t* out, cudaStream_t st);
+void launch_iota_u32(uint32_t* p, uint64_t n, cudaStream_t st);
+void launch_flush(uint8_t* p, size_t bytes, uint32_t value, cudaStream_t st);
+// step counter kept on the device so that captured step programs need no new arguments
+void launch_step_increment(uint32_t* d_step, cudaStream_t st);
+
+// stream compaction of a table by its alive bit (ballot + prefix sum)
+// d_block_counts: >= ceil(n/1024)+1 u32; returns nothing; new_n is read back from d_block_counts[nblocks].
+void launch_compact_offsets(const uint8_t* flags, uint64_t n, uint32_t* d_block_counts, cudaStream_t st);
+void launch_compact_scan(uint32_t* d_block_counts, uint32_t nblocks, cudaStream_t st);
+void launch_compact_scatter(const void* src, void* dst, uint32_t row_bytes, const uint8_t* flags, uint64_t n,
+                            const uint32_t* d_block_offsets, cudaStream_t st);
+
+// ---------------------------------------------------------------- coin toss
+// examples/coin_toss.rs:67-81. heads/tosses are u32 columns; `steps` >= 1 steps
+// are applied back to back in registers (entities are independent).
+void launch_coin_toss(uint32_t* heads, uint32_t* tosses, const uint32_t* uid, const uint8_t* flags, uint64_t n,
+                      PhiloxKey key, uint64_t threshold, uint32_t first_step, uint32_t steps, cudaStream_t st);
+void launch_coin_toss_u64(uint64_t* heads, uint64_t* tosses, const uint32_t* uid, const uint8_t* flags, uint64_t n,
+                          PhiloxKey key, uint64_t threshold, uint32_t first_step, uint32_t steps, cudaStream_t st);
+// examples/coin_toss.rs:33-49: out[0] = f64 sum of heads/tosses, out[1] = count (as u64 bits)
+void launch_coin_odds(const void* heads, const void* tosses, int dtype, const uint8_t* flags, uint8_t need_set,
+                      uint8_t need_clear, uint64_t n, double* out, void* scratch, uint32_t* ticket,
+                      cudaStream_t st);
+
+// -------------------------------------------------------------- forest fire
+struct ForestArgs
+{
+    const uint8_t* cur; // W*H cells, x-major (uid = x*H + y), rows [x_begin-?]: see kernels_forest.cu
+    uint8_t* next;
+    int32_t W, H;           // global grid
+    int32_t x_begin, x_end; // slab owned by this process
+    const uint8_t* halo_lo; // H cells of column x_begin-1 (nullptr: out of bounds)
+    const uint8_t* halo_hi; // H cells of column x_end
+    // overlay entities (the extra igniters of forest_fire.rs:260-278)
+    uint32_t n_overlay;
+    const int16_t* ov_pos;   // n_overlay * 2 (x, y)
+    const uint8_t* ov_cur;
+    uint8_t* ov_next;
+    uint32_t ov_uid_base;    // uid of overlay entity 0 (= W*H)
+    // enabled systems and parameters
+    uint32_t do_spread, do_progress, do_regrow;
+    uint64_t thr_spread;
+    uint64_t thr_regrow;        // floor(p * 2^32)
+    uint64_t thr_regrow_l2;     // floor(256 * p * 2^32), used when regrow_two_level
+    uint32_t regrow_two_level;  // p * 256 <= 1
+    uint32_t burn_duration;
+    uint32_t bump_step;         // this launch ends the step: StepNumber += 1 on the device
+    PhiloxKey key_spread, key_regrow;
+    const uint32_t* d_step;
+    // fused FireStats (forest_fire.rs:104-134): per-step record + series ring
+    uint64_t* stats_partials; // gridDim * 4
+    uint32_t* ticket;
+    uint64_t* stats_out;      // 5 u64: healthy, burning, burned, empty, total (state after this step)
+    uint8_t* series_values;   // nullptr or ring of incerto_fire_stats
+    uint64_t* series_counts;
+    uint64_t series_interval, series_capacity;
+};
+void launch_forest_step(const ForestArgs& a, cudaStream_t st);
+void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
+                           cudaStream_t st);
+int forest_step_grid_blocks(int32_t slab_w, int32_t H);
+void launch_forest_spawn(uint8_t* cells, int32_t W, int32_t H, int32_t x_begin, int32_t x_end, PhiloxKey key,
+                         uint64_t thr_density, cudaStream_t st);
+// FireStats of the owned columns of a pitched slab (standalone sample_aggregate)
+void launch_forest_stats(const uint8_t* slab, int32_t H, int32_t slab_w, uint64_t* out5, void* scratch,
+                         uint32_t* ticket, cudaStream_t st);
+
+} // namespace incerto

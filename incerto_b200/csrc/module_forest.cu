@@ -1,0 +1,499 @@
+// Forest-fire module: dense pitched slab + overlay entities + row partition.
+// Host side of kernels_forest.cu; see that file for the layout and draw contract.
+//
+// Reference: examples/forest_fire.rs (spawn :234-279, systems :282-365, stats :104-134).
+#include <algorithm>
+
+#include "modules.hpp"
+
+namespace incerto
+{
+
+static constexpr size_t kLead = 256; // bytes before column 0 / after the last column (reads of y-1 / y+1 bytes)
+
+static void forest_partition(const Sim& s, ForestModule& fm)
+{
+    fm.x_begin = static_cast<int32_t>(static_cast<int64_t>(fm.W) * s.part_rank / s.part_world);
+    fm.x_end = static_cast<int32_t>(static_cast<int64_t>(fm.W) * (s.part_rank + 1) / s.part_world);
+}
+
+static int owner_rank_of_column(const Sim& s, const ForestModule& fm, int32_t x)
+{
+    for (uint32_t r = 0; r < s.part_world; ++r)
+    {
+        const int32_t b = static_cast<int32_t>(static_cast<int64_t>(fm.W) * r / s.part_world);
+        const int32_t e = static_cast<int32_t>(static_cast<int64_t>(fm.W) * (r + 1) / s.part_world);
+        if (x >= b && x < e) return static_cast<int>(r);
+    }
+    return -1;
+}
+
+static int32_t forest_alloc(Sim& s, ForestModule& fm)
+{
+    fm.pitch = (static_cast<uint32_t>(fm.H) + 15u) & ~15u;
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    const size_t bytes = static_cast<size_t>(slab_w + 2) * fm.pitch;
+    if (fm.d_alloc[0] && bytes == fm.slab_bytes) return INCERTO_OK;
+    forest_free(s);
+    fm.slab_bytes = bytes;
+    for (int i = 0; i < 2; ++i)
+    {
+        INC_CUDA(cudaMalloc(&fm.d_alloc[i], bytes + 2 * kLead));
+        fm.d_slab[i] = fm.d_alloc[i] + kLead;
+    }
+    const int blocks = forest_step_grid_blocks(static_cast<int32_t>(slab_w), fm.H);
+    INC_CUDA(cudaMalloc(&fm.d_partials, static_cast<size_t>(blocks) * 4 * sizeof(uint64_t)));
+    INC_CUDA(cudaMalloc(&fm.d_stats, 8 * sizeof(uint64_t)));
+    const size_t nov = std::max<uint32_t>(fm.n_overlay, 1);
+    INC_CUDA(cudaMalloc(&fm.d_ov_pos, nov * 2 * sizeof(int16_t)));
+    for (int i = 0; i < 2; ++i) INC_CUDA(cudaMalloc(&fm.d_ov[i], nov));
+    INC_CUDA(cudaMalloc(&fm.d_ov_lo, nov));
+    INC_CUDA(cudaMalloc(&fm.d_ov_hi, nov));
+    INC_CUDA(cudaMalloc(&fm.d_ov_owner, nov));
+    return INCERTO_OK;
+}
+
+void forest_free(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    for (int i = 0; i < 2; ++i)
+    {
+        cudaFree(fm.d_alloc[i]);
+        fm.d_alloc[i] = fm.d_slab[i] = nullptr;
+        cudaFree(fm.d_ov[i]);
+        fm.d_ov[i] = nullptr;
+    }
+    cudaFree(fm.d_partials);
+    cudaFree(fm.d_stats);
+    cudaFree(fm.d_ov_pos);
+    cudaFree(fm.d_ov_lo);
+    cudaFree(fm.d_ov_hi);
+    cudaFree(fm.d_ov_owner);
+    fm.d_partials = nullptr;
+    fm.d_stats = nullptr;
+    fm.d_ov_pos = nullptr;
+    fm.d_ov_lo = fm.d_ov_hi = fm.d_ov_owner = nullptr;
+    fm.slab_bytes = 0;
+}
+
+// upload overlay positions / initial states / owners
+static int32_t forest_upload_overlays(Sim& s, ForestModule& fm, const std::vector<uint8_t>& states)
+{
+    fm.h_ov_owner.assign(fm.n_overlay, 0);
+    for (uint32_t k = 0; k < fm.n_overlay; ++k)
+    {
+        const int o = owner_rank_of_column(s, fm, fm.h_ov_pos[2 * k]);
+        uint8_t code = 3;
+        if (o == static_cast<int>(s.part_rank))
+            code = 0;
+        else if (o + 1 == static_cast<int>(s.part_rank))
+            code = 1;
+        else if (o == static_cast<int>(s.part_rank) + 1)
+            code = 2;
+        fm.h_ov_owner[k] = code;
+    }
+    if (fm.n_overlay)
+    {
+        INC_CUDA(cudaMemcpyAsync(fm.d_ov_pos, fm.h_ov_pos.data(), fm.n_overlay * 2 * sizeof(int16_t),
+                                 cudaMemcpyHostToDevice, s.stream));
+        INC_CUDA(cudaMemcpyAsync(fm.d_ov_owner, fm.h_ov_owner.data(), fm.n_overlay, cudaMemcpyHostToDevice, s.stream));
+        for (uint8_t* p : {fm.d_ov[0], fm.d_ov[1], fm.d_ov_lo, fm.d_ov_hi})
+            INC_CUDA(cudaMemcpyAsync(p, states.data(), fm.n_overlay, cudaMemcpyHostToDevice, s.stream));
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+    }
+    return INCERTO_OK;
+}
+
+// INCERTO_SPAWN_FOREST_GRID: examples/forest_fire.rs:234-279 restated with the
+// Philox contract: cell uid = x*H + y is Healthy iff word (uid&3) of
+// philox(FOREST_SPAWN, (uid>>2,0,0,0)) < floor(density*2^32); igniter k sits at
+// index mulhi32(word 0 of philox(FOREST_IGNITE, (k,0,0,0)), W*H) of the x-major
+// position list (:261-263) and gets uid W*H + k.
+int32_t forest_spawn_device(Sim& s, const HostSpawn& sp)
+{
+    ForestModule& fm = s.mods->forest;
+    incerto_spawn_forest_params p;
+    std::memcpy(&p, sp.params.data(), sizeof(p));
+    if (p.width <= 0 || p.height <= 0 || p.width > 32767 || p.height > 32767 || p.burn_duration < 1 ||
+        p.burn_duration > 63 || p.initial_fire_count > 256 ||
+        static_cast<uint64_t>(p.width) * p.height + p.initial_fire_count >= (1ull << 32))
+    {
+        set_error("forest spawner: bad grid size / burn duration / fire count");
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    fm.comp_pos = p.position;
+    fm.comp_cell = p.cell;
+    fm.W = p.width;
+    fm.H = p.height;
+    fm.n_overlay = p.initial_fire_count;
+    forest_partition(s, fm);
+    INC_TRY(forest_alloc(s, fm));
+    for (int i = 0; i < 2; ++i) INC_CUDA(cudaMemsetAsync(fm.d_alloc[i], 0, fm.slab_bytes + 2 * kLead, s.stream));
+    const PhiloxKey key = make_key(s.seed, s.replica, TAG_FOREST_SPAWN);
+    // own columns plus the in-grid halo columns (a pure function of uid, so no exchange is needed)
+    const int32_t lo = std::max(fm.x_begin - 1, 0), hi = std::min(fm.x_end + 1, fm.W);
+    launch_forest_spawn(fm.d_slab[0] + static_cast<size_t>(lo - (fm.x_begin - 1)) * fm.pitch - fm.pitch, fm.W, fm.H,
+                        lo, hi, key, bernoulli_threshold(p.initial_forest_density), s.stream);
+    INC_CUDA(cudaGetLastError());
+    fm.cur = 0;
+    fm.h_ov_pos.resize(2 * static_cast<size_t>(fm.n_overlay));
+    const PhiloxKey kign = make_key(s.seed, s.replica, TAG_FOREST_IGNITE);
+    const uint32_t cells = static_cast<uint32_t>(fm.W) * static_cast<uint32_t>(fm.H);
+    for (uint32_t k = 0; k < fm.n_overlay; ++k)
+    {
+        const uint4 r = philox4x32_10(k, 0u, 0u, 0u, kign);
+        const uint32_t idx = uniform_below(r.x, cells);
+        fm.h_ov_pos[2 * k] = static_cast<int16_t>(idx / fm.H);
+        fm.h_ov_pos[2 * k + 1] = static_cast<int16_t>(idx % fm.H);
+    }
+    std::vector<uint8_t> st(std::max<uint32_t>(fm.n_overlay, 1), static_cast<uint8_t>(p.burn_duration));
+    INC_TRY(forest_upload_overlays(s, fm, st));
+    fm.stats_valid = false;
+    Table& t = s.tables[fm.table];
+    t.dense_w = fm.W;
+    t.dense_h = fm.H;
+    t.x_begin = fm.x_begin;
+    t.x_end = fm.x_end;
+    t.all_alive = true;
+    return INCERTO_OK;
+}
+
+// Host-spawned forest: find the dense x-major prefix among the spawned rows and
+// move the cell column into the pitched slab.
+static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
+{
+    Table& t = s.tables[fm.table];
+    const ComponentInfo& pc = s.comps[fm.comp_pos];
+    const ComponentInfo& cc = s.comps[fm.comp_cell];
+    if (pc.lanes != 2 || (pc.dtype != INCERTO_I16 && pc.dtype != INCERTO_U16 && pc.dtype != INCERTO_I32) ||
+        cc.dtype != INCERTO_U8 || cc.lanes != 1)
+    {
+        set_error("forest: position must be a 2-lane I16/I32 component and cell a U8 component");
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    // W, H come from the spatial grid bounds (forest_fire.rs:151-157)
+    const GridInst* grid = nullptr;
+    for (auto& g : s.grids)
+        if (g.position == fm.comp_pos && g.dim == 2) grid = &g;
+    if (!grid || !grid->bounded || grid->bmin[0] != 0 || grid->bmin[1] != 0)
+    {
+        set_error("forest systems need add_spatial_grid(position, cell) with bounds (0,0)..(W-1,H-1)");
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    fm.W = grid->bmax[0] + 1;
+    fm.H = grid->bmax[1] + 1;
+    const uint64_t cells = static_cast<uint64_t>(fm.W) * fm.H;
+    // concatenate the host spawns of this archetype
+    std::vector<int32_t> px, py;
+    std::vector<uint8_t> st;
+    for (auto& sp : s.spawns)
+    {
+        if (sp.device_kind) continue;
+        const HostSpawn::Col* pcol = nullptr;
+        const HostSpawn::Col* ccol = nullptr;
+        size_t ndata = 0;
+        for (auto& c : sp.cols)
+        {
+            if (c.comp == fm.comp_pos) pcol = &c;
+            if (c.comp == fm.comp_cell) ccol = &c;
+            if (s.comps[c.comp].dtype != INCERTO_MARKER) ++ndata;
+        }
+        if (!pcol || !ccol || ndata != 2) continue;
+        for (uint64_t r = 0; r < sp.n; ++r)
+        {
+            if (pc.dtype == INCERTO_I32)
+            {
+                const int32_t* p = reinterpret_cast<const int32_t*>(pcol->data.data());
+                px.push_back(p[2 * r]);
+                py.push_back(p[2 * r + 1]);
+            }
+            else
+            {
+                const int16_t* p = reinterpret_cast<const int16_t*>(pcol->data.data());
+                px.push_back(p[2 * r]);
+                py.push_back(p[2 * r + 1]);
+            }
+            st.push_back(ccol->data[r]);
+        }
+    }
+    if (px.size() != t.n_spawned || px.size() < cells)
+    {
+        set_error("forest: the spawned cells do not cover the %dx%d grid", fm.W, fm.H);
+        return INCERTO_ERR_UNSUPPORTED;
+    }
+    for (uint64_t i = 0; i < cells; ++i)
+        if (px[i] != static_cast<int32_t>(i / fm.H) || py[i] != static_cast<int32_t>(i % fm.H))
+        {
+            set_error("forest: cells must be spawned in x-major order (for x {for y}) as forest_fire.rs:239-257 does");
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+    for (uint64_t i = 0; i < px.size(); ++i)
+    {
+        if (px[i] < 0 || px[i] >= fm.W || py[i] < 0 || py[i] >= fm.H)
+        {
+            set_error("entity at position (%d, %d) outside spatial grid bounds", px[i], py[i]); // spatial_grid.rs:276-279
+            return INCERTO_ERR_OUT_OF_BOUNDS;
+        }
+        const uint8_t v = st[i];
+        const bool ok = v == INCERTO_CELL_BURNED || v == INCERTO_CELL_HEALTHY || v == INCERTO_CELL_EMPTY || (v >= 1 && v <= 63);
+        if (!ok)
+        {
+            set_error("forest: invalid cell state code 0x%02x", v);
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        }
+    }
+    fm.n_overlay = static_cast<uint32_t>(px.size() - cells);
+    if (fm.n_overlay > 256)
+    {
+        set_error("forest: at most 256 overlay entities on top of the dense grid");
+        return INCERTO_ERR_UNSUPPORTED;
+    }
+    forest_partition(s, fm);
+    INC_TRY(forest_alloc(s, fm));
+    for (int i = 0; i < 2; ++i) INC_CUDA(cudaMemsetAsync(fm.d_alloc[i], 0, fm.slab_bytes + 2 * kLead, s.stream));
+    const int32_t lo = std::max(fm.x_begin - 1, 0), hi = std::min(fm.x_end + 1, fm.W);
+    INC_CUDA(cudaMemcpy2DAsync(fm.d_slab[0] + static_cast<size_t>(lo - (fm.x_begin - 1)) * fm.pitch, fm.pitch,
+                               st.data() + static_cast<size_t>(lo) * fm.H, fm.H, fm.H, hi - lo, cudaMemcpyHostToDevice,
+                               s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    fm.cur = 0;
+    fm.h_ov_pos.resize(2 * static_cast<size_t>(fm.n_overlay));
+    std::vector<uint8_t> ovst(std::max<uint32_t>(fm.n_overlay, 1), 0);
+    for (uint32_t k = 0; k < fm.n_overlay; ++k)
+    {
+        fm.h_ov_pos[2 * k] = static_cast<int16_t>(px[cells + k]);
+        fm.h_ov_pos[2 * k + 1] = static_cast<int16_t>(py[cells + k]);
+        ovst[k] = st[cells + k];
+    }
+    INC_TRY(forest_upload_overlays(s, fm, ovst));
+    // the generic columns are no longer needed
+    for (auto& c : t.cols)
+    {
+        cudaFree(c.d);
+        c.d = nullptr;
+    }
+    cudaFree(t.d_flags);
+    t.d_flags = nullptr;
+    t.dense_w = fm.W;
+    t.dense_h = fm.H;
+    t.x_begin = fm.x_begin;
+    t.x_end = fm.x_end;
+    fm.stats_valid = false;
+    return INCERTO_OK;
+}
+
+int32_t forest_bind(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    bool first = true;
+    for (auto& sys : s.systems)
+    {
+        if (sys.kind < INCERTO_SYS_FOREST_SPREAD || sys.kind > INCERTO_SYS_FOREST_REGROWTH) continue;
+        if (sys.params.size() != sizeof(incerto_forest_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_forest_params p;
+        std::memcpy(&p, sys.params.data(), sizeof(p));
+        if (p.position < 0 || p.cell < 0 || p.position >= static_cast<int>(s.comps.size()) ||
+            p.cell >= static_cast<int>(s.comps.size()))
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        if (first)
+        {
+            if (fm.comp_pos >= 0 && (fm.comp_pos != p.position || fm.comp_cell != p.cell))
+            {
+                set_error("forest systems and the forest spawner name different components");
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            fm.comp_pos = p.position;
+            fm.comp_cell = p.cell;
+            first = false;
+        }
+        else if (p.position != fm.comp_pos || p.cell != fm.comp_cell)
+        {
+            set_error("forest systems must agree on their components");
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        }
+        if (sys.kind == INCERTO_SYS_FOREST_SPREAD)
+        {
+            fm.do_spread = true;
+            fm.p_spread = p.probability;
+            if (p.burn_duration < 1 || p.burn_duration > 63)
+            {
+                set_error("forest: burn_duration must be in 1..=63");
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            fm.burn_duration = p.burn_duration;
+        }
+        else if (sys.kind == INCERTO_SYS_FOREST_BURN_PROGRESSION)
+            fm.do_progress = true;
+        else
+        {
+            fm.do_regrow = true;
+            fm.p_regrow = p.probability;
+        }
+    }
+    s.comps[fm.comp_pos].exists = true;
+    s.comps[fm.comp_cell].exists = true;
+    if (fm.table < 0)
+    {
+        fm.table = table_for_components(s, {fm.comp_pos, fm.comp_cell});
+        if (fm.table < 0)
+        {
+            set_error("forest systems: no entities carry (position, cell)");
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+        INC_TRY(forest_adopt_host_table(s, fm));
+    }
+    fm.active = true;
+    return INCERTO_OK;
+}
+
+int32_t forest_reset_after_spawn(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    Table& t = s.tables[fm.table];
+    bool device_spawned = false;
+    for (auto& sp : s.spawns)
+        if (sp.device_kind && sp.kind == INCERTO_SPAWN_FOREST_GRID) device_spawned = true;
+    if (!device_spawned) INC_TRY(forest_adopt_host_table(s, fm));
+    (void)t;
+    return INCERTO_OK;
+}
+
+int32_t forest_halo_exchange(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    if (s.part_world <= 1) return INCERTO_OK;
+    if (!s.comm)
+    {
+        set_error("row-partitioned forest needs incerto_sim_attach_comm before run");
+        return INCERTO_ERR_COMM;
+    }
+    // `cur` already points at the buffer the step just produced
+    uint8_t* slab = fm.d_slab[fm.cur];
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    const void* send_lo[2] = {slab + static_cast<size_t>(1) * fm.pitch, fm.d_ov[fm.cur]};
+    void* recv_lo[2] = {slab, fm.d_ov_lo};
+    const void* send_hi[2] = {slab + static_cast<size_t>(slab_w) * fm.pitch, fm.d_ov[fm.cur]};
+    void* recv_hi[2] = {slab + static_cast<size_t>(slab_w + 1) * fm.pitch, fm.d_ov_hi};
+    const size_t bytes[2] = {fm.pitch, std::max<uint32_t>(fm.n_overlay, 1)};
+    return comm_halo(s, send_lo, recv_lo, send_hi, recv_hi, bytes, fm.n_overlay ? 2 : 1);
+}
+
+int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps)
+{
+    ForestModule& fm = s.mods->forest;
+    (void)first_step;
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    for (uint32_t i = 0; i < nsteps; ++i)
+    {
+        ForestArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.cur = fm.d_slab[fm.cur];
+        a.next = fm.d_slab[1 - fm.cur];
+        a.W = fm.W;
+        a.H = fm.H;
+        a.x_begin = fm.x_begin;
+        a.x_end = fm.x_end;
+        a.n_overlay = fm.n_overlay;
+        a.ov_pos = fm.d_ov_pos;
+        a.ov_cur = fm.d_ov[fm.cur];
+        a.ov_next = fm.d_ov[1 - fm.cur];
+        a.ov_uid_base = static_cast<uint32_t>(fm.W) * static_cast<uint32_t>(fm.H);
+        a.do_spread = fm.do_spread;
+        a.do_progress = fm.do_progress;
+        a.do_regrow = fm.do_regrow;
+        a.thr_spread = bernoulli_threshold(fm.p_spread);
+        a.thr_regrow = bernoulli_threshold(fm.p_regrow);
+        a.regrow_two_level = (fm.p_regrow * 256.0 <= 1.0) ? 1u : 0u;
+        a.thr_regrow_l2 = bernoulli_threshold(fm.p_regrow * 256.0);
+        a.burn_duration = fm.burn_duration;
+        a.bump_step = 1;
+        a.key_spread = make_key(s.seed, s.replica, TAG_FOREST_SPREAD);
+        a.key_regrow = make_key(s.seed, s.replica, TAG_FOREST_REGROW);
+        a.d_step = s.mods->d_step;
+        a.stats_partials = fm.d_partials;
+        a.ticket = s.d_ticket;
+        a.stats_out = fm.d_stats;
+        if (fm.series >= 0)
+        {
+            SeriesInst& se = s.series[fm.series];
+            a.series_values = se.d_values;
+            a.series_counts = se.d_counts;
+            a.series_interval = se.interval;
+            a.series_capacity = se.capacity;
+        }
+        {
+            // 2 B per cell-update (1 B read + 1 B written)
+            KTimer kt(s, "forest_step", 2.0 * slab_w * fm.H);
+            launch_forest_step_ex(a, fm.d_ov_lo, fm.d_ov_hi, fm.d_ov_owner, s.stream);
+        }
+        INC_CUDA(cudaGetLastError());
+        fm.cur = 1 - fm.cur;
+        fm.stats_valid = true;
+        INC_TRY(forest_halo_exchange(s));
+    }
+    return INCERTO_OK;
+}
+
+int32_t forest_read_cells(Sim& s, uint8_t* out_rows)
+{
+    ForestModule& fm = s.mods->forest;
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    INC_CUDA(cudaMemcpy2DAsync(out_rows, fm.H, fm.d_slab[fm.cur] + fm.pitch, fm.pitch, fm.H, slab_w,
+                               cudaMemcpyDeviceToHost, s.stream));
+    if (fm.n_overlay)
+        INC_CUDA(cudaMemcpyAsync(out_rows + static_cast<size_t>(slab_w) * fm.H, fm.d_ov[fm.cur], fm.n_overlay,
+                                 cudaMemcpyDeviceToHost, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    return INCERTO_OK;
+}
+
+int32_t forest_stats_now(Sim& s, uint64_t out5[5])
+{
+    ForestModule& fm = s.mods->forest;
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    if (fm.stats_valid)
+    {
+        INC_CUDA(cudaMemcpyAsync(out5, fm.d_stats, 5 * 8, cudaMemcpyDeviceToHost, s.stream));
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+    }
+    else
+    {
+        INC_TRY(ensure_scratch(s, 4 * 8 * kNumSMs * 8 + 64));
+        uint64_t* d_out = reinterpret_cast<uint64_t*>(s.d_scratch + 4 * 8 * kNumSMs * 8);
+        {
+            KTimer kt(s, "forest_stats", 1.0 * slab_w * fm.H);
+            launch_forest_stats(fm.d_slab[fm.cur], fm.H, static_cast<int32_t>(slab_w), d_out, s.d_scratch, s.d_ticket,
+                                s.stream);
+        }
+        INC_CUDA(cudaMemcpyAsync(out5, d_out, 5 * 8, cudaMemcpyDeviceToHost, s.stream));
+        std::vector<uint8_t> ov(std::max<uint32_t>(fm.n_overlay, 1));
+        if (fm.n_overlay)
+            INC_CUDA(cudaMemcpyAsync(ov.data(), fm.d_ov[fm.cur], fm.n_overlay, cudaMemcpyDeviceToHost, s.stream));
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+        for (uint32_t k = 0; k < fm.n_overlay; ++k)
+        {
+            if (fm.h_ov_owner[k] != 0) continue;
+            const uint8_t v = ov[k];
+            if (v & 0x40)
+                ++out5[0];
+            else if (v & 0x80)
+                ++out5[3];
+            else if (v & 0x3f)
+                ++out5[1];
+            else
+                ++out5[2];
+            ++out5[4];
+        }
+    }
+    if (s.part_world > 1 && s.comm)
+    {
+        INC_TRY(ensure_scratch(s, 64));
+        INC_CUDA(cudaMemcpyAsync(s.d_scratch, out5, 40, cudaMemcpyHostToDevice, s.stream));
+        INC_TRY(comm_allreduce(s, s.d_scratch, 5, 0, 0));
+        INC_CUDA(cudaMemcpyAsync(out5, s.d_scratch, 40, cudaMemcpyDeviceToHost, s.stream));
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+    }
+    return INCERTO_OK;
+}
+
+} // namespace incerto

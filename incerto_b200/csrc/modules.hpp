@@ -1,0 +1,82 @@
+// Workload modules: device state whose layout is specialised beyond the
+// generic SoA table.
+#pragma once
+#include "engine.hpp"
+#include "kernels.hpp"
+
+namespace incerto
+{
+
+struct StepOp
+{
+    const char* name = "";
+    // advance `nsteps` steps starting at StepNumber == first_step
+    std::function<int32_t(Sim&, uint64_t first_step, uint32_t nsteps)> fn;
+    bool multi_step_ok = false; // entity-local: may apply several steps per launch
+    bool bumps_device_step = false;
+};
+
+struct ForestModule
+{
+    bool active = false;
+    int table = -1;
+    int comp_pos = -1, comp_cell = -1;
+    int32_t W = 0, H = 0, x_begin = 0, x_end = 0;
+    uint32_t pitch = 0;
+    size_t slab_bytes = 0;          // (slab_w + 2) * pitch
+    uint8_t* d_alloc[2] = {nullptr, nullptr}; // with 256 B lead/tail padding
+    uint8_t* d_slab[2] = {nullptr, nullptr};  // column 0 of each buffer
+    int cur = 0;
+    uint32_t n_overlay = 0;
+    std::vector<int16_t> h_ov_pos;
+    std::vector<uint8_t> h_ov_owner;
+    int16_t* d_ov_pos = nullptr;
+    uint8_t* d_ov[2] = {nullptr, nullptr};
+    uint8_t* d_ov_lo = nullptr; // overlay states received from the neighbours (row partition)
+    uint8_t* d_ov_hi = nullptr;
+    uint8_t* d_ov_owner = nullptr;
+    bool do_spread = false, do_progress = false, do_regrow = false;
+    double p_spread = 0, p_regrow = 0;
+    uint32_t burn_duration = 3;
+    uint64_t* d_partials = nullptr;
+    uint64_t* d_stats = nullptr; // 5 u64 of the last step
+    int series = -1;             // index of the fused FireStats series, -1 if none
+    bool stats_valid = false;
+};
+
+struct CoinModule
+{
+    bool active = false;
+    int table = -1;
+    int comp_heads = -1, comp_tosses = -1;
+    double odds = 0.5;
+};
+
+struct Sim::Modules
+{
+    ForestModule forest;
+    CoinModule coin;
+    std::vector<StepOp> program;
+    uint32_t* d_step = nullptr; // device mirror of StepNumber
+};
+
+// module_forest.cu
+int32_t forest_spawn_device(Sim& s, const HostSpawn& sp);
+int32_t forest_bind(Sim& s);
+int32_t forest_reset_after_spawn(Sim& s);
+int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps);
+int32_t forest_read_cells(Sim& s, uint8_t* out_rows); // W*H + overlays, uid order (this rank's slab only in partition mode)
+int32_t forest_stats_now(Sim& s, uint64_t out5[5]);
+void forest_free(Sim& s);
+int32_t forest_halo_exchange(Sim& s);
+
+// comm.cpp
+int32_t comm_unique_id(uint8_t out[128]);
+int32_t comm_attach(Sim& s, const uint8_t id[128], uint32_t rank, uint32_t world);
+void comm_free(Sim& s);
+int32_t comm_allreduce(Sim& s, void* d_buf, uint32_t n, int is_f64, uint32_t op);
+// send `bytes_lo` from d_send_lo to rank-1 and `bytes_hi` from d_send_hi to rank+1, receive likewise
+int32_t comm_halo(Sim& s, const void* const* d_send_lo, void* const* d_recv_lo, const void* const* d_send_hi,
+                  void* const* d_recv_hi, const size_t* bytes, uint32_t n_msgs);
+
+} // namespace incerto

@@ -1,0 +1,246 @@
+// ORACLE — test infrastructure, not product code (see philox.hpp).
+// extern "C" surface for the ctypes-driven tests and bench.py's CPU baseline.
+#include <cstring>
+#include <thread>
+
+#include "coin_toss.hpp"
+#include "forest_fire.hpp"
+#include "library.hpp"
+#include "philox.hpp"
+
+using namespace oracle;
+
+extern "C"
+{
+
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    const U4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    std::memcpy(out, r.w, 16);
+}
+uint64_t oracle_threshold(double p) { return threshold(p); }
+uint32_t oracle_below(uint32_t u, uint32_t n) { return below(u, n); }
+
+// ---------------------------------------------------------------- coin toss
+// heads/tosses: n u64 each, updated in place; returns the aggregate (coin_toss.rs:33-49)
+double oracle_coin_toss_run(uint64_t seed, uint32_t replica, uint64_t n, double odds, uint64_t first_step,
+                            uint64_t steps, uint64_t* heads, uint64_t* tosses)
+{
+    CoinTossSim sim(seed, replica, n, odds);
+    sim.step = first_step;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        sim.tossers[i].num_heads = heads[i];
+        sim.tossers[i].num_tosses = tosses[i];
+    }
+    sim.run(steps);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        heads[i] = sim.tossers[i].num_heads;
+        tosses[i] = sim.tossers[i].num_tosses;
+    }
+    return sim.sample_aggregate();
+}
+
+// ------------------------------------------------------------- forest fire
+struct ForestHandle
+{
+    ForestSim sim;
+    ForestHandle(const ForestParams& p, uint64_t seed, uint32_t replica) : sim(p, seed, replica) {}
+};
+
+void* oracle_forest_new(uint64_t seed, uint32_t replica, int32_t width, int32_t height, double density,
+                        double p_spread, uint32_t burn_duration, double p_regrow, uint32_t fire_count,
+                        uint32_t systems_mask /* 1 spread, 2 progression, 4 regrowth */)
+{
+    ForestParams p;
+    p.width = width;
+    p.height = height;
+    p.initial_forest_density = density;
+    p.fire_spread_probability = p_spread;
+    p.burn_duration = burn_duration;
+    p.regrowth_probability = p_regrow;
+    p.initial_fire_count = fire_count;
+    p.spread = systems_mask & 1;
+    p.progression = systems_mask & 2;
+    p.regrowth = systems_mask & 4;
+    return new ForestHandle(p, seed, replica);
+}
+void oracle_forest_free(void* h) { delete static_cast<ForestHandle*>(h); }
+void oracle_forest_spawn(void* h) { static_cast<ForestHandle*>(h)->sim.spawn_forest_grid(); }
+// explicit entities: n positions (x,y int32 pairs) and n state codes (device encoding)
+void oracle_forest_spawn_explicit(void* h, uint64_t n, const int32_t* xy, const uint8_t* states)
+{
+    std::vector<Pos> pos(n);
+    std::vector<uint8_t> st(states, states + n);
+    for (uint64_t i = 0; i < n; ++i) pos[i] = Pos{xy[2 * i], xy[2 * i + 1], 0};
+    static_cast<ForestHandle*>(h)->sim.spawn_explicit(pos, st);
+}
+void oracle_forest_run(void* h, uint64_t steps) { static_cast<ForestHandle*>(h)->sim.run(steps); }
+uint64_t oracle_forest_num_entities(void* h) { return static_cast<ForestHandle*>(h)->sim.cell.size(); }
+void oracle_forest_cells(void* h, uint8_t* states_out, int32_t* xy_out)
+{
+    ForestSim& s = static_cast<ForestHandle*>(h)->sim;
+    for (size_t i = 0; i < s.cell.size(); ++i)
+    {
+        if (states_out) states_out[i] = encode_cell(s.cell[i]);
+        if (xy_out)
+        {
+            xy_out[2 * i] = s.position[i].x;
+            xy_out[2 * i + 1] = s.position[i].y;
+        }
+    }
+}
+void oracle_forest_stats(void* h, uint64_t out5[5])
+{
+    const FireStats f = static_cast<ForestHandle*>(h)->sim.sample_aggregate();
+    out5[0] = f.healthy_count;
+    out5[1] = f.burning_count;
+    out5[2] = f.burned_count;
+    out5[3] = f.empty_count;
+    out5[4] = f.total_cells;
+}
+uint64_t oracle_forest_series_len(void* h) { return static_cast<ForestHandle*>(h)->sim.series.size(); }
+void oracle_forest_series(void* h, uint64_t* out /* len * 5 */)
+{
+    ForestSim& s = static_cast<ForestHandle*>(h)->sim;
+    for (size_t i = 0; i < s.series.size(); ++i)
+    {
+        out[5 * i + 0] = s.series[i].healthy_count;
+        out[5 * i + 1] = s.series[i].burning_count;
+        out[5 * i + 2] = s.series[i].burned_count;
+        out[5 * i + 3] = s.series[i].empty_count;
+        out[5 * i + 4] = s.series[i].total_cells;
+    }
+}
+
+// CPU baseline helper: `threads` independent replicas of the same forest run side by side
+// (Bevy itself runs these three conflicting systems serially on one core; independent
+// replicas are the only multi-core axis).  Returns cell-updates performed.
+uint64_t oracle_forest_bench(uint64_t seed, int32_t width, int32_t height, uint64_t steps, uint32_t threads)
+{
+    std::vector<std::thread> pool;
+    std::vector<uint64_t> done(threads, 0);
+    for (uint32_t t = 0; t < threads; ++t)
+        pool.emplace_back([&, t]() {
+            ForestParams p;
+            p.width = width;
+            p.height = height;
+            ForestSim sim(p, seed, t);
+            sim.spawn_forest_grid();
+            sim.run(steps);
+            done[t] = static_cast<uint64_t>(sim.cell.size()) * steps;
+        });
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < threads; ++t)
+    {
+        pool[t].join();
+        total += done[t];
+    }
+    return total;
+}
+
+// ------------------------------------------------------- library: aggregators
+#define ORACLE_AGG(T, NAME)                                                                          \
+    int oracle_aggregate_##NAME(const T* v, uint64_t n, uint32_t kind, uint32_t P, T* out)           \
+    {                                                                                                \
+        try                                                                                          \
+        {                                                                                            \
+            std::vector<T> x(v, v + n);                                                              \
+            switch (kind)                                                                            \
+            {                                                                                        \
+            case 3: *out = agg_minimum<T>(x); break;                                                 \
+            case 4: *out = agg_maximum<T>(x); break;                                                 \
+            case 5: *out = agg_mean<T>(x); break;                                                    \
+            case 6: *out = agg_median<T>(x); break;                                                  \
+            case 7: *out = agg_percentile<T>(x, P); break;                                           \
+            default: return -1;                                                                      \
+            }                                                                                        \
+            return 0;                                                                                \
+        }                                                                                            \
+        catch (const std::out_of_range&)                                                             \
+        {                                                                                            \
+            return 36;                                                                               \
+        }                                                                                            \
+        catch (const std::exception&)                                                                \
+        {                                                                                            \
+            return 35;                                                                               \
+        }                                                                                            \
+    }
+ORACLE_AGG(uint8_t, u8)
+ORACLE_AGG(uint16_t, u16)
+ORACLE_AGG(uint32_t, u32)
+ORACLE_AGG(uint64_t, u64)
+ORACLE_AGG(int8_t, i8)
+ORACLE_AGG(int16_t, i16)
+ORACLE_AGG(int32_t, i32)
+ORACLE_AGG(int64_t, i64)
+ORACLE_AGG(float, f32)
+ORACLE_AGG(double, f64)
+
+// ------------------------------------------------------- library: spatial grid
+void* oracle_grid_new(int dim, int has_bounds, const int32_t* bounds)
+{
+    SpatialGrid* g = new SpatialGrid;
+    g->dim = dim;
+    g->bounds.some = has_bounds != 0;
+    if (has_bounds)
+    {
+        g->bounds.min = Pos{bounds[0], bounds[1], dim == 3 ? bounds[2] : 0};
+        g->bounds.max = Pos{bounds[dim], bounds[dim + 1], dim == 3 ? bounds[dim + 2] : 0};
+    }
+    return g;
+}
+void oracle_grid_free(void* g) { delete static_cast<SpatialGrid*>(g); }
+int oracle_grid_insert(void* g, uint32_t e, const int32_t* p)
+{
+    SpatialGrid* G = static_cast<SpatialGrid*>(g);
+    try
+    {
+        G->insert_or_update(e, Pos{p[0], p[1], G->dim == 3 ? p[2] : 0});
+    }
+    catch (const std::out_of_range&)
+    {
+        return 34;
+    }
+    return 0;
+}
+void oracle_grid_remove(void* g, uint32_t e) { static_cast<SpatialGrid*>(g)->remove(e); }
+uint64_t oracle_grid_query(void* g, int mode /*0 at, 1 neighbors, 2 orthogonal*/, const int32_t* p, uint32_t* out,
+                           uint64_t cap)
+{
+    SpatialGrid* G = static_cast<SpatialGrid*>(g);
+    const Pos q{p[0], p[1], G->dim == 3 ? p[2] : 0};
+    uint64_t n = 0;
+    auto f = [&](Entity e) {
+        if (n < cap) out[n] = e;
+        ++n;
+    };
+    if (mode == 0)
+        G->entities_at(q, f);
+    else if (mode == 1)
+        G->neighbors_of(q, f);
+    else
+        G->orthogonal_neighbors_of(q, f);
+    return n;
+}
+uint64_t oracle_grid_num_entities(void* g) { return static_cast<SpatialGrid*>(g)->num_entities(); }
+int oracle_grid_in_bounds(void* g, const int32_t* p)
+{
+    SpatialGrid* G = static_cast<SpatialGrid*>(g);
+    return G->in_bounds(Pos{p[0], p[1], G->dim == 3 ? p[2] : 0}) ? 1 : 0;
+}
+uint64_t oracle_neighbor_offsets(int dim, int orthogonal, int32_t* out /* up to 26*3 */)
+{
+    const Pos o{0, 0, 0};
+    const std::vector<Pos> v = orthogonal ? neighbors_orthogonal(o, dim) : neighbors(o, dim);
+    for (size_t i = 0; i < v.size(); ++i)
+    {
+        out[3 * i] = v[i].x;
+        out[3 * i + 1] = v[i].y;
+        out[3 * i + 2] = v[i].z;
+    }
+    return v.size();
+}
+
+} // extern "C"

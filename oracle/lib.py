@@ -1,0 +1,83 @@
+"""ORACLE — test infrastructure, not product code.  ctypes loader of oracle/_build/liboracle.so."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    return LIB
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    lib = C.CDLL(LIB)
+    vp = C.c_void_p
+    u64p, u32p, i32p, u8p = (C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8))
+    lib.oracle_philox4x32_10.argtypes = [u32p, u32p, u32p]
+    lib.oracle_philox4x32_10.restype = None
+    lib.oracle_threshold.argtypes = [C.c_double]
+    lib.oracle_threshold.restype = C.c_uint64
+    lib.oracle_below.argtypes = [C.c_uint32, C.c_uint32]
+    lib.oracle_below.restype = C.c_uint32
+    lib.oracle_coin_toss_run.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, u64p, u64p]
+    lib.oracle_coin_toss_run.restype = C.c_double
+    lib.oracle_forest_new.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_uint32,
+                                      C.c_double, C.c_uint32, C.c_uint32]
+    lib.oracle_forest_new.restype = vp
+    lib.oracle_forest_free.argtypes = [vp]
+    lib.oracle_forest_free.restype = None
+    lib.oracle_forest_spawn.argtypes = [vp]
+    lib.oracle_forest_spawn.restype = None
+    lib.oracle_forest_spawn_explicit.argtypes = [vp, C.c_uint64, i32p, u8p]
+    lib.oracle_forest_spawn_explicit.restype = None
+    lib.oracle_forest_run.argtypes = [vp, C.c_uint64]
+    lib.oracle_forest_run.restype = None
+    lib.oracle_forest_num_entities.argtypes = [vp]
+    lib.oracle_forest_num_entities.restype = C.c_uint64
+    lib.oracle_forest_cells.argtypes = [vp, u8p, i32p]
+    lib.oracle_forest_cells.restype = None
+    lib.oracle_forest_stats.argtypes = [vp, u64p]
+    lib.oracle_forest_stats.restype = None
+    lib.oracle_forest_series_len.argtypes = [vp]
+    lib.oracle_forest_series_len.restype = C.c_uint64
+    lib.oracle_forest_series.argtypes = [vp, u64p]
+    lib.oracle_forest_series.restype = None
+    lib.oracle_forest_bench.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
+    lib.oracle_forest_bench.restype = C.c_uint64
+    for name, ct in (("u8", C.c_uint8), ("u16", C.c_uint16), ("u32", C.c_uint32), ("u64", C.c_uint64),
+                     ("i8", C.c_int8), ("i16", C.c_int16), ("i32", C.c_int32), ("i64", C.c_int64),
+                     ("f32", C.c_float), ("f64", C.c_double)):
+        fn = getattr(lib, f"oracle_aggregate_{name}")
+        fn.argtypes = [C.POINTER(ct), C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(ct)]
+        fn.restype = C.c_int
+    lib.oracle_grid_new.argtypes = [C.c_int, C.c_int, i32p]
+    lib.oracle_grid_new.restype = vp
+    lib.oracle_grid_free.argtypes = [vp]
+    lib.oracle_grid_free.restype = None
+    lib.oracle_grid_insert.argtypes = [vp, C.c_uint32, i32p]
+    lib.oracle_grid_insert.restype = C.c_int
+    lib.oracle_grid_remove.argtypes = [vp, C.c_uint32]
+    lib.oracle_grid_remove.restype = None
+    lib.oracle_grid_query.argtypes = [vp, C.c_int, i32p, u32p, C.c_uint64]
+    lib.oracle_grid_query.restype = C.c_uint64
+    lib.oracle_grid_num_entities.argtypes = [vp]
+    lib.oracle_grid_num_entities.restype = C.c_uint64
+    lib.oracle_grid_in_bounds.argtypes = [vp, i32p]
+    lib.oracle_grid_in_bounds.restype = C.c_int
+    lib.oracle_neighbor_offsets.argtypes = [C.c_int, C.c_int, i32p]
+    lib.oracle_neighbor_offsets.restype = C.c_uint64
+    _lib = lib
+    return lib

@@ -1,0 +1,162 @@
+"""forest_fire (examples/forest_fire.rs) on the GPU vs the CPU oracle: bit-exact cell states and FireStats."""
+import numpy as np
+import pytest
+
+import incerto_b200 as ib
+from incerto_b200 import _ffi as F
+from conftest import SEED
+from oracle.forest import ForestOracle
+
+pytestmark = pytest.mark.gpu
+
+HEALTHY, EMPTY, BURNED = 0x40, 0x80, 0x00
+
+
+def build_device_forest(W, H, replica=0, density=0.7, p_spread=0.6, burn=3, p_regrow=0.001, fires=3, systems=7,
+                        series=1, seed=SEED):
+    """forest_fire.rs:147-170 with the built-in device spawner."""
+    b = ib.SimulationBuilder(seed=seed, replica=replica)
+    pos = b.component("GridPosition2D", F.I16, lanes=2)
+    cell = b.component("ForestCell.state", F.U8)
+    b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
+    b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_FOREST_GRID, F.SpawnForestParams(pos.handle, cell.handle, W, H, density,
+                                                                                   burn, fires)))
+    if systems & 1:
+        b.add_systems(ib.FireSpread(pos, cell, p_spread, burn))
+    if systems & 2:
+        b.add_systems(ib.BurnProgression(pos, cell))
+    if systems & 4:
+        b.add_systems(ib.Regrowth(pos, cell, p_regrow))
+    if series:
+        b.record_aggregate_time_series(ib.FireStatsOf(cell), series)
+    return b.build(), pos, cell
+
+
+def stats_tuple(fs):
+    return (fs.healthy_count, fs.burning_count, fs.burned_count, fs.empty_count, fs.total_cells)
+
+
+@pytest.mark.parametrize("W,H", [(50, 50), (64, 64), (37, 53), (5, 3), (1, 1), (130, 48), (48, 130), (33, 16), (4, 100)])
+def test_parity_device_spawn(W, H):
+    """Reference config (50x50, :33-44) and ragged shapes: every cell identical to the oracle after each phase."""
+    steps = 60
+    sim, pos, cell = build_device_forest(W, H)
+    o = ForestOracle(SEED, 0, W, H).spawn()
+    st0, xy0 = o.cells()
+    assert np.array_equal(sim.read_component(cell), st0)          # spawn parity (:239-278)
+    assert np.array_equal(sim.read_component(pos), xy0.astype(np.int16))
+    assert stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell))) == tuple(int(x) for x in o.stats())
+    for chunk in (1, 1, 7, steps - 9):
+        sim.run(chunk)
+        o.run(chunk)
+        assert np.array_equal(sim.read_component(cell), o.cells()[0])
+        assert stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell))) == tuple(int(x) for x in o.stats())
+    ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
+    assert ts.time() == list(range(1, steps + 1))
+    got = np.array([stats_tuple(v) for v in ts.values()], dtype=np.uint64)
+    assert np.array_equal(got, o.series())
+    assert int(got[0, 4]) == W * H + 3                             # total_cells counts the 3 extra igniters (:260-278)
+
+
+@pytest.mark.parametrize("replica", [1, 2, 5])
+def test_parity_fire_actually_spreads(replica):
+    """A denser forest so that the front crosses chunk, column-quad and CTA-tile borders."""
+    W, H, steps = 96, 160, 120
+    sim, pos, cell = build_device_forest(W, H, replica=replica, density=0.9, p_regrow=0.003, fires=5)
+    o = ForestOracle(SEED, replica, W, H, density=0.9, p_regrow=0.003, fires=5).spawn()
+    sim.run(steps)
+    o.run(steps)
+    st = sim.read_component(cell)
+    assert np.array_equal(st, o.cells()[0])
+    s = o.stats()
+    assert s[2] > 0.3 * W * H                                      # the fire really burned a large area
+    assert np.array_equal(np.array([stats_tuple(v) for v in sim.get_aggregate_time_series(ib.FireStatsOf(cell)).values()],
+                                   dtype=np.uint64), o.series())
+
+
+@pytest.mark.parametrize("systems", [1, 2, 3, 4, 5, 6])
+def test_parity_system_subsets(systems):
+    """Any subset of the three systems may be added (simulation_builder.rs:66-70)."""
+    W, H = 40, 48
+    sim, pos, cell = build_device_forest(W, H, density=0.85, p_regrow=0.02, systems=systems, series=0)
+    o = ForestOracle(SEED, 0, W, H, density=0.85, p_regrow=0.02, systems=systems).spawn()
+    sim.run(25)
+    o.run(25)
+    assert np.array_equal(sim.read_component(cell), o.cells()[0])
+
+
+def test_regrowth_one_level_draw():
+    """p_regrow above 1/256 uses the single 32-bit draw of the contract."""
+    W, H = 32, 48
+    sim, pos, cell = build_device_forest(W, H, density=0.5, p_regrow=0.05)
+    o = ForestOracle(SEED, 0, W, H, density=0.5, p_regrow=0.05).spawn()
+    sim.run(40)
+    o.run(40)
+    assert np.array_equal(sim.read_component(cell), o.cells()[0])
+
+
+def test_parity_host_spawn_with_overlays():
+    """Host-side spawner exactly as forest_fire.rs:234-279 does it: cells x-major, then extra burning entities on top,
+    including two on the same cell, one on the border, one Healthy and one Empty overlay."""
+    W, H = 24, 40
+    rng = np.random.default_rng(9)
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H), indexing="ij")
+    xy = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int32)
+    st = np.where(rng.random(W * H) < 0.85, HEALTHY, EMPTY).astype(np.uint8)
+    ov_xy = np.array([[3, 3], [3, 3], [0, 0], [W - 1, H - 1], [10, 20], [11, 20], [12, 7]], np.int32)
+    ov_st = np.array([3, 2, 3, 3, HEALTHY, EMPTY, BURNED], np.uint8)
+    all_xy, all_st = np.concatenate([xy, ov_xy]), np.concatenate([st, ov_st])
+
+    b = ib.SimulationBuilder(seed=SEED)
+    pos = b.component("GridPosition2D", F.I16, lanes=2)
+    cell = b.component("ForestCell.state", F.U8)
+    b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
+    b.add_entity_spawner(lambda s: s.spawn_batch(len(all_st), {pos: all_xy.astype(np.int16), cell: all_st}))
+    b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.004))
+    b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
+    sim = b.build()
+    o = ForestOracle(SEED, 0, W, H, p_regrow=0.004, fires=0).spawn_explicit(all_xy, all_st)
+    for _ in range(50):
+        sim.run(1)
+        o.run(1)
+        got = sim.read_component(cell)
+        assert np.array_equal(got, o.cells()[0])
+    assert np.array_equal(np.array([stats_tuple(v) for v in sim.get_aggregate_time_series(ib.FireStatsOf(cell)).values()],
+                                   dtype=np.uint64), o.series())
+    g = b.last_grid
+    assert sim.grid_entities_at(g, (3, 3)) == [3 * H + 3, W * H, W * H + 1]
+    assert sim.grid_neighbors_of(g, (0, 0), orthogonal=True) == sorted([1, H])
+
+
+def test_reset_and_replicas():
+    sim, pos, cell = build_device_forest(64, 64, replica=4)
+    sim.run(30)
+    a = sim.read_component(cell).copy()
+    sim.reset(4)
+    sim.run(30)
+    assert np.array_equal(a, sim.read_component(cell))
+    sim.reset(7)
+    sim.run(30)
+    o = ForestOracle(SEED, 7, 64, 64).spawn().run(30)
+    assert np.array_equal(sim.read_component(cell), o.cells()[0])
+    assert sim.get_aggregate_time_series(ib.FireStatsOf(cell)).len() == 30
+
+
+def test_full_size_properties():
+    """BASELINE config 1 (4096 x 4096): size-independent invariants + a window checked against the oracle."""
+    W = H = 4096
+    sim, pos, cell = build_device_forest(W, H, series=1)
+    fs0 = stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell)))
+    assert fs0[4] == W * H + 3 and abs(fs0[0] / (W * H) - 0.7) < 1e-3
+    sim.run(40)
+    ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
+    vals = np.array([stats_tuple(v) for v in ts.values()], dtype=np.int64)
+    assert (vals[:, :4].sum(1) == W * H + 3).all()                 # every entity is in exactly one state
+    assert (np.diff(vals[:, 2]) >= 0).all()                        # Burned never reverts (no system leaves Burned)
+    assert vals[-1, 1] > 0                                         # still burning
+    # regrowth rate: Empty -> Healthy with p = 0.001 per step
+    regrown = fs0[3] - vals[-1, 3]
+    assert abs(regrown / (fs0[3] * 40 * 0.001) - 1.0) < 0.05
+    st = sim.read_component(cell)
+    assert stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell))) == tuple(vals[-1])
+    assert int((st == HEALTHY).sum()) == vals[-1, 0] and int((st == EMPTY).sum()) == vals[-1, 3]

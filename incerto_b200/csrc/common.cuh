@@ -66,10 +66,11 @@ __device__ __forceinline__ void block_sum(T (&v)[N], T* smem)
 __device__ __forceinline__ bool last_block_arrives(uint32_t* ticket, uint32_t total_blocks)
 {
     __shared__ uint32_t s_last;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0)
     {
+        // the barrier orders the block's writes before this thread; its fence is cumulative over them
+        __threadfence();
         const uint32_t t = atomicAdd(ticket, 1u);
         s_last = (t == total_blocks - 1) ? 1u : 0u;
         if (s_last) *ticket = 0u; // leave the ticket ready for the next launch

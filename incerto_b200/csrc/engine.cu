@@ -567,6 +567,8 @@ static int32_t bind_generic_systems(Sim& s)
                 StepOp op;
                 op.name = "forest_step";
                 op.bumps_device_step = true;
+                op.whole_run_ok = true;
+                op.prepare = [](Sim& sim, uint64_t nsteps) { return forest_prepare(sim, nsteps); };
                 op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return forest_step(sim, first_step, nsteps); };
                 prog.push_back(op);
                 forest_added = true;
@@ -595,6 +597,8 @@ static int32_t do_run(Sim& s, uint64_t num_steps)
     if (s.run_pending) INC_TRY(incerto_sim_synchronize(reinterpret_cast<incerto_sim*>(&s)));
     s.last_launches = s.launches;
     INC_TRY(series_prepare(s, s.step, num_steps));
+    for (auto& op : s.mods->program)
+        if (op.prepare) INC_TRY(op.prepare(s, num_steps));
     INC_CUDA(cudaEventRecord(s.ev_begin, s.stream));
     auto& prog = s.mods->program;
     bool all_multi = !prog.empty();
@@ -605,6 +609,24 @@ static int32_t do_run(Sim& s, uint64_t num_steps)
         device_bump = device_bump || op.bumps_device_step;
     }
     uint64_t remaining = num_steps;
+    // one op that owns the whole step (and samples its own fused series): hand it the run in one go,
+    // so that it can replay a captured graph of steps
+    bool whole = prog.size() == 1 && prog[0].whole_run_ok && remaining > 0;
+    for (size_t i = 0; i < s.series.size() && whole; ++i) whole = static_cast<int>(i) == s.mods->forest.series;
+    for (auto& g : s.grids) whole = whole && (g.d_cell_start == nullptr);
+    if (whole)
+    {
+        uint64_t left = remaining;
+        while (left)
+        {
+            const uint32_t k = static_cast<uint32_t>(std::min<uint64_t>(left, 1u << 20));
+            INC_TRY(prog[0].fn(s, s.step, k));
+            s.step += k;
+            left -= k;
+        }
+        for (auto& se : s.series) se.n_slots = std::max<uint64_t>(se.n_slots, std::min<uint64_t>((s.step - 1) / se.interval, se.capacity));
+        remaining = 0;
+    }
     while (remaining)
     {
         uint64_t k = 1;
@@ -843,6 +865,20 @@ int32_t incerto_builder_build(incerto_builder* b, incerto_sim** out)
     {
         S.comps[g.position].exists = true;
         S.comps[g.component].exists = true;
+    }
+    for (auto& se : S.series)
+    {
+        // the sampling systems hold Query<&C, F> / Query<(&C, &Id)>: their components get registered
+        if (se.per_entity)
+        {
+            S.comps[se.component].exists = true;
+            S.comps[se.identifier].exists = true;
+            continue;
+        }
+        S.comps[se.agg.component].exists = true;
+        if (se.agg.component2 >= 0) S.comps[se.agg.component2].exists = true;
+        for (int c : se.agg.filter.with) S.comps[c].exists = true;
+        for (int c : se.agg.filter.without) S.comps[c].exists = true;
     }
     INC_TRY(run_spawners(S, true));
     INC_TRY(bind_generic_systems(S));

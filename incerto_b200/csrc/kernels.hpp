@@ -84,10 +84,12 @@ struct ForestArgs
     const uint8_t* halo_hi; // H cells of column x_end
     // overlay entities (the extra igniters of forest_fire.rs:260-278)
     uint32_t n_overlay;
-    const int16_t* ov_pos;   // n_overlay * 2 (x, y)
+    const int16_t* ov_pos;   // n_overlay * 2 (x, y), device
+    const uint32_t* near_bits;  // device bitmap, one bit per CTA tile with an overlay entity within one cell
     const uint8_t* ov_cur;
     uint8_t* ov_next;
     uint32_t ov_uid_base;    // uid of overlay entity 0 (= W*H)
+    uint32_t ov_owned;       // overlay entities whose position lies in this slab
     // enabled systems and parameters
     uint32_t do_spread, do_progress, do_regrow;
     uint64_t thr_spread;
@@ -99,7 +101,8 @@ struct ForestArgs
     PhiloxKey key_spread, key_regrow;
     const uint32_t* d_step;
     // fused FireStats (forest_fire.rs:104-134): per-step record + series ring
-    uint64_t* stats_partials; // gridDim * 4
+    uint64_t* stats_run;      // running totals (healthy, burning, empty) of this slab + owned overlays
+    uint32_t* error;          // device error flag
     uint32_t* ticket;
     uint64_t* stats_out;      // 5 u64: healthy, burning, burned, empty, total (state after this step)
     uint8_t* series_values;   // nullptr or ring of incerto_fire_stats
@@ -110,6 +113,9 @@ void launch_forest_step(const ForestArgs& a, cudaStream_t st);
 void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
                            cudaStream_t st);
 int forest_step_grid_blocks(int32_t slab_w, int32_t H);
+uint32_t forest_pitch(int32_t H);            // bytes per column: H rounded up to whole CTA tiles
+uint32_t forest_alloc_cols(int32_t slab_w);  // columns allocated: slab_w rounded up to whole CTA tiles + 2 halos
+void forest_tile_shape(uint32_t* cols, uint32_t* rows);
 void launch_forest_spawn(uint8_t* cells, int32_t W, int32_t H, int32_t x_begin, int32_t x_end, PhiloxKey key,
                          uint64_t thr_density, cudaStream_t st);
 // FireStats of the owned columns of a pitched slab (standalone sample_aggregate)

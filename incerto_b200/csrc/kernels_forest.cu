@@ -39,6 +39,10 @@ namespace
 constexpr int kTX = 32;  // chunks (16 cells) along y per CTA
 constexpr int kTY = 8;   // column quads per CTA
 constexpr int kColsPerThread = 4;
+#ifndef INCERTO_FOREST_MIN_BLOCKS
+#define INCERTO_FOREST_MIN_BLOCKS 4
+#endif
+constexpr int kMinBlocks = INCERTO_FOREST_MIN_BLOCKS;
 
 __device__ __forceinline__ uint32_t burn_bits(uint32_t w)
 {
@@ -51,360 +55,428 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t v)
     return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
 }
 
+constexpr int kMaxNear = 64;       // overlay entities within one cell of a CTA tile
+
 struct ForestConst
 {
     ForestArgs a;
     uint32_t pitch, chunks_per_col, slab_w;
     uint32_t regrow_two_level;
     uint64_t thr_regrow_l2;
-    const uint8_t* ov_lo;  // overlay states received from the lower / upper neighbour rank
+    const uint8_t* ov_lo;    // overlay states received from the lower / upper neighbour rank
     const uint8_t* ov_hi;
     const uint8_t* ov_owner; // 0 = this rank, 1 = lower neighbour, 2 = upper neighbour, 3 = elsewhere
+    const uint32_t* near_bits; // one bit per CTA tile: an overlay entity lies within one cell of the tile
+    uint32_t* error;
+    PhiloxRoundKeys rk_spread, rk_regrow; // key schedules of the two streams, as constant operands
 };
 
-__device__ __forceinline__ uint8_t ignited_value(const ForestArgs& a)
+__device__ __forceinline__ uint32_t ignited_value(const ForestArgs& a)
 {
     // Burning{burn_duration} (forest_fire.rs:324-326) then, when progression is
     // enabled, one progression step in the same update (:340-349)
-    if (!a.do_progress) return static_cast<uint8_t>(a.burn_duration);
-    return a.burn_duration > 1 ? static_cast<uint8_t>(a.burn_duration - 1) : 0;
+    if (!a.do_progress) return a.burn_duration;
+    return a.burn_duration > 1 ? a.burn_duration - 1 : 0;
 }
 
 __device__ __forceinline__ bool regrow_draw(const ForestConst& c, uint32_t uid, uint32_t step)
 {
     if (c.regrow_two_level)
     {
-        const uint4 l1 = philox4x32_10(uid >> 4, 0u, step, 0u, c.a.key_regrow);
+        const uint4 l1 = philox4x32_10(uid >> 4, 0u, step, 0u, c.rk_regrow);
         const uint32_t w = word_of(l1, (uid >> 2) & 3u);
         if ((w >> (8 * (uid & 3u))) & 0xffu) return false;
     }
-    const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.a.key_regrow);
+    const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.rk_regrow);
     return bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2);
 }
 
-// The vectorised body: each thread owns 4 adjacent columns x 16 cells.
-template <bool ALIGNED>
-__global__ void __launch_bounds__(kTX* kTY) forest_step_kernel(const ForestConst c)
+// FireStats category of a state code as a delta vector (healthy, burning, empty); burned is implicit
+struct Delta
+{
+    int32_t h = 0, b = 0, e = 0;
+    __device__ __forceinline__ void add(uint32_t s, int32_t sign)
+    {
+        h += (s & 0x40u) ? sign : 0;
+        e += (s & 0x80u) ? sign : 0;
+        b += (s & 0x3fu) ? sign : 0;
+    }
+};
+
+// Overlay entities near this CTA's tile, staged in shared memory.  Overlay entities are the igniters the
+// reference spawns on top of existing cells (forest_fire.rs:260-278) — or any other entity sharing a
+// cell of the dense grid.  The vector path ignores them; the thread that owns a cell an overlay can
+// influence re-evaluates that cell with `marked`, a scalar restatement of fire_spread_system for one
+// position (:296-316).
+struct NearOverlays
+{
+    int16_t x[kMaxNear], y[kMaxNear];
+    uint16_t k[kMaxNear];
+    uint8_t old[kMaxNear], owner[kMaxNear];
+    uint32_t n;
+};
+
+__device__ __forceinline__ bool overlay_marked(const ForestConst& c, const NearOverlays& nr, uint32_t step, int px, int py)
 {
     const ForestArgs& a = c.a;
-    const uint32_t step = *a.d_step;
+    if (!a.do_spread) return false;
+    const uint8_t* pc = a.cur + static_cast<size_t>(px - a.x_begin + 1) * c.pitch + py;
+    // old states of the base cell and of its four orthogonal neighbours (halo columns hold the neighbour rank's cells)
+    const uint32_t s_c = pc[0];
+    const uint32_t s_n = py > 0 ? pc[-1] : 0u;
+    const uint32_t s_w = px > 0 ? pc[-static_cast<ptrdiff_t>(c.pitch)] : 0u;
+    const uint32_t s_e = px + 1 < a.W ? pc[c.pitch] : 0u;
+    const uint32_t s_s = py + 1 < a.H ? pc[1] : 0u;
+    const uint32_t base_dirs = ((s_n & 0x3f) ? 1u : 0u) | ((s_w & 0x3f) ? 2u : 0u) | ((s_e & 0x3f) ? 4u : 0u) | ((s_s & 0x3f) ? 8u : 0u);
+    const uint32_t n = nr.n < kMaxNear ? nr.n : kMaxNear;
+    // healthy entities at p: the base cell (e == -1) and overlays
+    for (int e = -1; e < static_cast<int>(n); ++e)
+    {
+        uint32_t uid_t;
+        if (e < 0)
+        {
+            if (s_c != 0x40u) continue;
+            uid_t = static_cast<uint32_t>(px) * a.H + py;
+        }
+        else
+        {
+            if (nr.x[e] != px || nr.y[e] != py || nr.old[e] != 0x40) continue;
+            uid_t = a.ov_uid_base + nr.k[e];
+        }
+        if (base_dirs)
+        {
+            const uint4 r = philox4x32_10(uid_t, 0u, step, 0u, c.rk_spread);
+            if (((base_dirs & 1u) && bernoulli(r.x, a.thr_spread)) || ((base_dirs & 2u) && bernoulli(r.y, a.thr_spread)) ||
+                ((base_dirs & 4u) && bernoulli(r.z, a.thr_spread)) || ((base_dirs & 8u) && bernoulli(r.w, a.thr_spread)))
+                return true;
+        }
+        for (uint32_t o = 0; o < n; ++o)
+        {
+            if (!(nr.old[o] & 0x3f)) continue;
+            const int dx = nr.x[o] - px, dy = nr.y[o] - py;
+            if (dx * dx + dy * dy != 1) continue; // burning overlay on an orthogonally adjacent position
+            const uint4 rp = philox4x32_10(uid_t, a.ov_uid_base + nr.k[o], step, 1u, c.rk_spread);
+            if (bernoulli(rp.x, a.thr_spread)) return true;
+        }
+    }
+    return false;
+}
+
+// The vectorised body: each thread owns 4 adjacent columns x 16 cells.
+//  * streaming path, fully unrolled and register resident: 128-bit loads of the chunk and its W/E
+//    neighbours, a warp-uniform "is there any fire around" vote that skips progression/spread work for the
+//    (vast majority of) warps far from the front, the level-1 regrowth draw (one Philox call per 16 cells),
+//    the 128-bit store;
+//  * rare events — healthy cells next to fire, empty cells that passed level 1 — are packed into one
+//    event word per column and handled afterwards by a single rolled loop that patches single bytes of
+//    the freshly written buffer;
+//  * FireStats are kept incrementally: only state transitions are counted (one warp-aggregated atomic
+//    when a warp saw any), the last block to arrive publishes the running totals.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const __grid_constant__ ForestConst c)
+{
+    const ForestArgs& a = c.a;
+    // The slab is padded to whole CTA tiles (pitch a multiple of 512 B, columns a multiple of 32 plus the
+    // two halo columns; pad bytes are BURNED = inert), so no load or store below needs a bounds predicate.
     const uint32_t cy = blockIdx.x * kTX + threadIdx.x;
     const uint32_t lx0 = 1 + (blockIdx.y * kTY + threadIdx.y) * kColsPerThread;
-    const bool chunk_ok = cy < c.chunks_per_col;
     const uint32_t lane = threadIdx.x; // blockDim.x == 32: one warp per threadIdx.y
+    const uint32_t tid = threadIdx.y * kTX + threadIdx.x;
+    const uint32_t y0 = cy * 16;
+    const uint32_t H = static_cast<uint32_t>(a.H);
+    constexpr bool chunk_ok = true;
 
-    uint32_t n_healthy = 0, n_burning = 0, n_empty = 0;
+    __shared__ uint32_t s_done; // warps of this block that finished (see the end of the kernel)
+    __shared__ int32_t s_delta[3];
+    if (tid < 3) s_delta[tid] = 0;
+    if (tid == 0) s_done = 0;
 
-    // columns lx0-1 .. lx0+4
+    // ---- loads first: columns lx0-1 .. lx0+4
+    const uint8_t* p0 = a.cur + static_cast<size_t>(lx0 - 1) * c.pitch + y0;
     uint4 v[kColsPerThread + 2];
 #pragma unroll
-    for (int j = 0; j < kColsPerThread + 2; ++j)
+    for (int j = 0; j < kColsPerThread + 2; ++j) v[j] = *reinterpret_cast<const uint4*>(p0 + static_cast<size_t>(j) * c.pitch);
+    // the word just outside the warp's y span, per column: lane 0 needs the cell y0-1 (top byte of the word
+    // before its chunk), lane 31 the cell y0+16 (bottom byte of the word after it)
+    uint32_t edge = 0; // bit j-1: that cell of my column j is burning
+    if ((lane == 0 && cy > 0) || (lane == 31 && cy + 1 < c.chunks_per_col))
     {
-        const uint32_t lx = lx0 - 1 + j;
-        if (chunk_ok && lx <= c.slab_w + 1)
-            v[j] = *reinterpret_cast<const uint4*>(a.cur + static_cast<size_t>(lx) * c.pitch + static_cast<size_t>(cy) * 16);
-        else
-            v[j] = make_uint4(0, 0, 0, 0);
+        const ptrdiff_t d = lane == 0 ? -4 : 16;
+        const uint32_t m = lane == 0 ? 0x3f000000u : 0x0000003fu;
+#pragma unroll
+        for (int j = 1; j <= kColsPerThread; ++j)
+            edge |= ((*reinterpret_cast<const uint32_t*>(p0 + static_cast<size_t>(j) * c.pitch + d) & m) ? 1u : 0u) << (j - 1);
     }
+    const uint32_t step = *a.d_step;
 
-    const uint8_t ign = ignited_value(a);
-
-#pragma unroll
-    for (int j = 1; j <= kColsPerThread; ++j)
-    {
-        const uint32_t lx = lx0 - 1 + j;
-        const bool col_ok = chunk_ok && lx <= c.slab_w; // uniform across the warp except chunk_ok
-        uint32_t cw[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-        uint32_t B[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) B[k] = burn_bits(cw[k]);
-
-        // burning flags of the y-1 / y+1 cells living in the adjacent chunks
-        uint32_t prev = __shfl_up_sync(kFullMask, B[3] >> 24, 1);
-        uint32_t next = __shfl_down_sync(kFullMask, B[0] & 1u, 1);
-        if (lane == 0)
-        {
-            prev = 0;
-            if (col_ok && cy > 0)
-            {
-                const uint8_t s = a.cur[static_cast<size_t>(lx) * c.pitch + static_cast<size_t>(cy) * 16 - 1];
-                prev = (s & 0x3f) ? 1u : 0u;
-            }
-        }
-        if (lane == 31)
-        {
-            next = 0;
-            if (col_ok && cy + 1 < c.chunks_per_col)
-            {
-                const uint8_t s = a.cur[static_cast<size_t>(lx) * c.pitch + static_cast<size_t>(cy) * 16 + 16];
-                next = (s & 0x3f) ? 1u : 0u;
-            }
-        }
-        if (!col_ok) continue;
-
-        const uint32_t gx = static_cast<uint32_t>(a.x_begin) + lx - 1;
-        const uint32_t uid0 = gx * static_cast<uint32_t>(a.H) + cy * 16;
-
-        uint32_t nw[4];
-        // ---- progression of cells already burning (:340-349)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) nw[k] = a.do_progress ? cw[k] - B[k] : cw[k];
-
-        // ---- spread (:282-329)
-        if (a.do_spread)
-        {
-            const uint32_t ww[4] = {v[j - 1].x, v[j - 1].y, v[j - 1].z, v[j - 1].w};
-            const uint32_t ew[4] = {v[j + 1].x, v[j + 1].y, v[j + 1].z, v[j + 1].w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                const uint32_t bn = __funnelshift_l(k == 0 ? (prev << 24) : B[k - 1], B[k], 8);
-                const uint32_t bs = __funnelshift_r(B[k], k == 3 ? next : B[k + 1], 8);
-                const uint32_t src = bn | (burn_bits(ww[k]) << 1) | (burn_bits(ew[k]) << 2) | (bs << 3);
-                const uint32_t healthy = (cw[k] >> 6) & 0x01010101u;
-                uint32_t cand = src & (healthy * 0x0fu);
-                while (cand)
-                {
-                    const int bit = __ffs(cand) - 1;
-                    const int byte = bit >> 3;
-                    const uint32_t dirs = (cand >> (8 * byte)) & 0x0fu;
-                    cand &= ~(0xffu << (8 * byte));
-                    const uint32_t uid = uid0 + 4 * k + byte;
-                    const uint4 r = philox4x32_10(uid, 0u, step, 0u, a.key_spread);
-                    const bool hit = ((dirs & 1u) && bernoulli(r.x, a.thr_spread)) ||
-                                     ((dirs & 2u) && bernoulli(r.y, a.thr_spread)) ||
-                                     ((dirs & 4u) && bernoulli(r.z, a.thr_spread)) ||
-                                     ((dirs & 8u) && bernoulli(r.w, a.thr_spread));
-                    if (hit) nw[k] = (nw[k] & ~(0xffu << (8 * byte))) | (static_cast<uint32_t>(ign) << (8 * byte));
-                }
-            }
-        }
-
-        // ---- regrowth (:354-365): only EMPTY cells draw
-        if (a.do_regrow)
-        {
-            uint32_t E[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) E[k] = cw[k] & 0x80808080u;
-            if (E[0] | E[1] | E[2] | E[3])
-            {
-                if (ALIGNED && c.regrow_two_level)
-                {
-                    // uid0 % 16 == 0: one level-1 call covers the 16 cells of this chunk
-                    const uint4 l1 = philox4x32_10(uid0 >> 4, 0u, step, 0u, a.key_regrow);
-                    const uint32_t lw[4] = {l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                    {
-                        uint32_t pass = zero_bytes(lw[k]) & E[k];
-                        if (pass)
-                        {
-                            const uint4 l2 = philox4x32_10((uid0 >> 2) + k, 0u, step, 1u, a.key_regrow);
-                            const uint32_t l2w[4] = {l2.x, l2.y, l2.z, l2.w};
-#pragma unroll
-                            for (int byte = 0; byte < 4; ++byte)
-                                if ((pass >> (8 * byte + 7)) & 1u)
-                                    if (bernoulli(l2w[byte], c.thr_regrow_l2)) nw[k] ^= 0xc0u << (8 * byte);
-                        }
-                    }
-                }
-                else
-                {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                    {
-                        uint32_t e = E[k];
-                        while (e)
-                        {
-                            const int byte = (__ffs(e) - 1) >> 3;
-                            e &= ~(0xffu << (8 * byte));
-                            if (regrow_draw(c, uid0 + 4 * k + byte, step)) nw[k] ^= 0xc0u << (8 * byte);
-                        }
-                    }
-                }
-            }
-        }
-
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-            n_healthy += __popc(nw[k] & 0x40404040u);
-            n_empty += __popc(nw[k] & 0x80808080u);
-            n_burning += __popc(burn_bits(nw[k]));
-        }
-        *reinterpret_cast<uint4*>(a.next + static_cast<size_t>(lx) * c.pitch + static_cast<size_t>(cy) * 16) =
-            make_uint4(nw[0], nw[1], nw[2], nw[3]);
-    }
-
-    // ---- fused FireStats: block partials, combined by the last block
-    uint32_t sv[3] = {n_healthy, n_burning, n_empty};
-    __shared__ uint32_t s_red[3 * 32];
-    {
-        const int warp = threadIdx.y;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) sv[i] = warp_sum(sv[i]);
-        if (lane == 0)
-        {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) s_red[i * 32 + warp] = sv[i];
-        }
-    }
-    __syncthreads();
-    const uint32_t bid = blockIdx.y * gridDim.x + blockIdx.x;
-    const uint32_t nblocks = gridDim.x * gridDim.y;
-    if (threadIdx.y == 0 && lane < 3)
-    {
-        uint32_t t = 0;
-        for (int w = 0; w < kTY; ++w) t += s_red[lane * 32 + w];
-        a.stats_partials[static_cast<size_t>(bid) * 4 + lane] = t;
-    }
-    if (!last_block_arrives(a.ticket, nblocks)) return;
-
-    // ================= last block: combine + overlay entities =================
-    const uint32_t tid = threadIdx.y * kTX + threadIdx.x;
-    uint64_t tot[3] = {0, 0, 0};
-    for (uint32_t b = tid; b < nblocks; b += kTX * kTY)
-    {
-        tot[0] += a.stats_partials[static_cast<size_t>(b) * 4 + 0];
-        tot[1] += a.stats_partials[static_cast<size_t>(b) * 4 + 1];
-        tot[2] += a.stats_partials[static_cast<size_t>(b) * 4 + 2];
-    }
-    __shared__ uint64_t s_tot[3 * 32];
-    block_sum<uint64_t, 3>(tot, s_tot);
-    if (tid != 0) return;
-
-    int64_t healthy = static_cast<int64_t>(tot[0]), burning = static_cast<int64_t>(tot[1]),
-            empty = static_cast<int64_t>(tot[2]);
-    const int64_t owned = static_cast<int64_t>(c.slab_w) * a.H;
-    int64_t burned = owned - healthy - burning - empty;
-
-    // ---- overlay entities (the igniters spawned on top of existing cells,
-    // forest_fire.rs:260-278): a scalar restatement of the three systems for the
-    // positions they can influence.
+    // ---- overlays that can touch this CTA's tile (usually none): one bit per tile, prepared by the host.
+    // The staging into shared memory (two barriers) only happens in the CTAs that have one nearby.
+    __shared__ NearOverlays nr;
     const uint32_t nov = a.n_overlay;
-    auto ov_old = [&](uint32_t k) -> uint8_t {
-        const uint8_t o = c.ov_owner ? c.ov_owner[k] : 0;
-        if (o == 0) return a.ov_cur[k];
-        if (o == 1) return c.ov_lo ? c.ov_lo[k] : 0;
-        if (o == 2) return c.ov_hi ? c.ov_hi[k] : 0;
-        return 0;
-    };
-    auto in_grid = [&](int x, int y) { return x >= 0 && x < a.W && y >= 0 && y < a.H; };
-    auto visible = [&](int x) { return x >= a.x_begin - 1 && x <= a.x_end; }; // own columns + halos
-    auto base_ptr = [&](const uint8_t* buf, int x, int y) -> const uint8_t* {
-        return buf + static_cast<size_t>(x - a.x_begin + 1) * c.pitch + y;
-    };
-    const int DX[4] = {0, -1, 1, 0}, DY[4] = {-1, 0, 0, 1};
-    auto category_adjust = [&](uint8_t s, int64_t delta) {
-        if (s & 0x40)
-            healthy += delta;
-        else if (s & 0x80)
-            empty += delta;
-        else if (s & 0x3f)
-            burning += delta;
-        else
-            burned += delta;
-    };
-    // is position (px,py) marked by fire_spread this step?  (:296-316)
-    auto marked = [&](int px, int py) -> bool {
-        if (!a.do_spread) return false;
-        // healthy entities at p: base cell and overlays
-        for (int e = -1; e < static_cast<int>(nov); ++e)
+    uint32_t n_near = 0;
+    bool any_near = false;
+    if (nov)
+    {
+        const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+        any_near = (c.near_bits[tile >> 5] >> (tile & 31)) & 1u;
+    }
+    __syncthreads(); // s_done is initialised; all warps are still in step here, so this barrier is cheap
+    if (any_near) // CTA-uniform
+    {
+        const int tx0 = a.x_begin + static_cast<int>(blockIdx.y * kTY * kColsPerThread);
+        const int ty0 = static_cast<int>(blockIdx.x * kTX * 16);
+        if (tid == 0) nr.n = 0;
+        __syncthreads();
+        for (uint32_t k = tid; k < nov; k += kTX * kTY)
         {
-            uint32_t uid_t;
-            if (e < 0)
+            const int ox = a.ov_pos[2 * k], oy = a.ov_pos[2 * k + 1];
+            if (ox >= tx0 - 1 && ox <= tx0 + kTY * kColsPerThread && oy >= ty0 - 1 && oy <= ty0 + kTX * 16)
             {
-                if (*base_ptr(a.cur, px, py) != 0x40) continue;
-                uid_t = static_cast<uint32_t>(px) * a.H + py;
+                const uint32_t i = atomicAdd(&nr.n, 1u);
+                if (i < kMaxNear)
+                {
+                    const uint8_t o = c.ov_owner ? c.ov_owner[k] : 0;
+                    nr.x[i] = static_cast<int16_t>(ox);
+                    nr.y[i] = static_cast<int16_t>(oy);
+                    nr.k[i] = static_cast<uint16_t>(k);
+                    nr.owner[i] = o;
+                    nr.old[i] = o == 0 ? a.ov_cur[k] : (o == 1 ? (c.ov_lo ? c.ov_lo[k] : 0) : (o == 2 ? (c.ov_hi ? c.ov_hi[k] : 0) : 0));
+                }
+                else if (c.error)
+                    atomicCAS(c.error, 0u, 37u); // INCERTO_ERR_UNSUPPORTED: too many overlay entities around one tile
+            }
+        }
+        __syncthreads();
+        n_near = nr.n < kMaxNear ? nr.n : kMaxNear;
+    }
+
+    // ---- is there any fire in what this warp loaded?
+    uint32_t ob = edge;
+#pragma unroll
+    for (int j = 0; j < kColsPerThread + 2; ++j) ob |= (v[j].x | v[j].y | v[j].z | v[j].w) & 0x3f3f3f3fu;
+    const bool fire = __any_sync(kFullMask, ob != 0);
+
+    const uint32_t ign = ignited_value(a);
+    Delta dl;
+    uint32_t ev[kColsPerThread] = {0, 0, 0, 0}; // per column: bit 8b+k = spread candidate, bit 8b+4+k = regrowth
+                                                // draw owed, for cell 4k+b of the chunk
+    uint8_t* q0 = a.next + (p0 - a.cur);
+    if (!fire) // warp-uniform, and by far the common case: no progression, no spread — the chunk is copied
+    {
+#pragma unroll
+        for (int j = 1; j <= kColsPerThread; ++j)
+            if (lx0 - 1 + j <= c.slab_w) *reinterpret_cast<uint4*>(q0 + static_cast<size_t>(j) * c.pitch) = v[j];
+    }
+    else
+    {
+#pragma unroll
+        for (int j = 1; j <= kColsPerThread; ++j)
+        {
+            const uint32_t cw[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            uint32_t B[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) B[k] = burn_bits(cw[k]);
+            uint32_t prev = __shfl_up_sync(kFullMask, B[3] >> 24, 1);
+            uint32_t next = __shfl_down_sync(kFullMask, B[0] & 1u, 1);
+            if (lane == 0) prev = (edge >> (j - 1)) & 1u;
+            if (lane == 31) next = (edge >> (j - 1)) & 1u;
+            if (lx0 - 1 + j > c.slab_w) continue; // warp-uniform; only in the last, partial column quad
+            uint32_t nw[4] = {cw[0], cw[1], cw[2], cw[3]};
+            // ---- progression of cells already burning (:340-349); Burning{1} -> Burned leaves the burning count
+            if (a.do_progress)
+            {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    nw[k] = cw[k] - B[k];
+                    dl.b -= __popc(zero_bytes((cw[k] & 0x3f3f3f3fu) ^ 0x01010101u));
+                }
+            }
+            // ---- spread (:282-329): healthy cells with a burning orthogonal neighbour take draws below
+            if (a.do_spread)
+            {
+                const uint32_t ww[4] = {v[j - 1].x, v[j - 1].y, v[j - 1].z, v[j - 1].w};
+                const uint32_t ew[4] = {v[j + 1].x, v[j + 1].y, v[j + 1].z, v[j + 1].w};
+                uint32_t evj = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const uint32_t bn = __funnelshift_l(k == 0 ? (prev << 24) : B[k - 1], B[k], 8);
+                    const uint32_t bs = __funnelshift_r(B[k], k == 3 ? next : B[k + 1], 8);
+                    const uint32_t src = bn | burn_bits(ww[k]) | burn_bits(ew[k]) | bs;
+                    evj |= (src & (cw[k] >> 6) & 0x01010101u) << k;
+                }
+                ev[j - 1] = evj;
+            }
+            *reinterpret_cast<uint4*>(q0 + static_cast<size_t>(j) * c.pitch) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+        }
+    }
+
+    // ---- regrowth (:354-365): only EMPTY cells draw.  The four level-1 Philox calls of the thread's columns
+    // sit in one basic block so that their dependent multiply chains interleave.
+    if (a.do_regrow)
+    {
+#pragma unroll
+        for (int j = 1; j <= kColsPerThread; ++j)
+        {
+            const uint32_t e0 = v[j].x & 0x80808080u, e1 = v[j].y & 0x80808080u, e2 = v[j].z & 0x80808080u,
+                           e3 = v[j].w & 0x80808080u;
+            uint32_t evj;
+            if (ALIGNED && c.regrow_two_level)
+            {
+                // uid0 % 16 == 0: one level-1 call covers the 16 cells of this chunk; ~1/256 of the empty
+                // cells pass it and take the level-2 draw in the rare-event loop
+                const uint32_t uid0 = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + y0;
+                const uint4 l1 = philox4x32_10(uid0 >> 4, 0u, step, 0u, c.rk_regrow);
+                evj = ((zero_bytes(l1.x) & e0) >> 3) | ((zero_bytes(l1.y) & e1) >> 2) | ((zero_bytes(l1.z) & e2) >> 1) |
+                      (zero_bytes(l1.w) & e3);
+            }
+            else
+                evj = (e0 >> 3) | (e1 >> 2) | (e2 >> 1) | e3;
+            if (lx0 - 1 + j <= c.slab_w) ev[j - 1] |= evj;
+        }
+    }
+
+    // ================= rare events: patch single cells of the buffer just written =================
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half)
+    {
+        uint64_t evs = half ? (static_cast<uint64_t>(ev[2]) | (static_cast<uint64_t>(ev[3]) << 32))
+                            : (static_cast<uint64_t>(ev[0]) | (static_cast<uint64_t>(ev[1]) << 32));
+        while (evs)
+        {
+            const int bit = __ffsll(static_cast<long long>(evs)) - 1;
+            evs &= evs - 1;
+            const uint32_t lx = lx0 + 2 * half + (bit >> 5);
+            const uint32_t y = y0 + 4 * (bit & 3) + ((bit >> 3) & 3);
+            const size_t off = static_cast<size_t>(lx) * c.pitch + y;
+            const uint32_t uid = (static_cast<uint32_t>(a.x_begin) + lx - 1) * H + y;
+            if (!(bit & 4))
+            {
+                // (a) spread draws of a healthy cell at the fire front: word d of one call, d = N, W, E, S
+                const uint8_t* pc = a.cur + off;
+                uint32_t dirs = 0;
+                if (y > 0 && (pc[-1] & 0x3f)) dirs |= 1u;
+                if (pc[-static_cast<ptrdiff_t>(c.pitch)] & 0x3f) dirs |= 2u;
+                if (pc[c.pitch] & 0x3f) dirs |= 4u;
+                if (y + 1 < H && (pc[1] & 0x3f)) dirs |= 8u;
+                const uint4 r = philox4x32_10(uid, 0u, step, 0u, c.rk_spread);
+                const bool hit = ((dirs & 1u) && bernoulli(r.x, a.thr_spread)) || ((dirs & 2u) && bernoulli(r.y, a.thr_spread)) ||
+                                 ((dirs & 4u) && bernoulli(r.z, a.thr_spread)) || ((dirs & 8u) && bernoulli(r.w, a.thr_spread));
+                if (hit)
+                {
+                    a.next[off] = static_cast<uint8_t>(ign);
+                    dl.h -= 1;
+                    dl.b += ign ? 1 : 0;
+                }
             }
             else
             {
-                if (a.ov_pos[2 * e] != px || a.ov_pos[2 * e + 1] != py || ov_old(e) != 0x40) continue;
-                uid_t = a.ov_uid_base + e;
-            }
-            uint4 r = make_uint4(0, 0, 0, 0);
-            bool have_r = false;
-            for (int d = 0; d < 4; ++d)
-            {
-                const int qx = px + DX[d], qy = py + DY[d];
-                if (!in_grid(qx, qy)) continue;
-                if (visible(qx) && ((*base_ptr(a.cur, qx, qy)) & 0x3f) && !((*base_ptr(a.cur, qx, qy)) & 0xc0))
+                // (b) regrowth draw still owed
+                bool grow;
+                if (ALIGNED && c.regrow_two_level)
                 {
-                    if (!have_r)
-                    {
-                        r = philox4x32_10(uid_t, 0u, step, 0u, a.key_spread);
-                        have_r = true;
-                    }
-                    if (bernoulli(word_of(r, d), a.thr_spread)) return true;
+                    const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.rk_regrow);
+                    grow = bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2);
                 }
-                for (uint32_t o = 0; o < nov; ++o)
+                else
+                    grow = regrow_draw(c, uid, step);
+                if (grow)
                 {
-                    if (a.ov_pos[2 * o] != qx || a.ov_pos[2 * o + 1] != qy) continue;
-                    const uint8_t so = ov_old(o);
-                    if (!(so & 0x3f) || (so & 0xc0)) continue;
-                    const uint4 rp = philox4x32_10(uid_t, a.ov_uid_base + o, step, 1u, a.key_spread);
-                    if (bernoulli(rp.x, a.thr_spread)) return true;
+                    a.next[off] = 0x40;
+                    dl.e -= 1;
+                    dl.h += 1;
                 }
             }
         }
-        return false;
-    };
-
-    if (nov)
+    }
+    // (c) cells an overlay entity can influence, and the overlay entities living in this thread's tile
+    if (n_near && chunk_ok)
     {
-        // overlays first take their own progression / regrowth; marking overrides below
-        for (uint32_t k = 0; k < nov; ++k)
+        const int gx0 = a.x_begin + static_cast<int>(lx0) - 1; // my columns: gx0 .. gx0+3
+        for (uint32_t i = 0; i < n_near; ++i)
         {
-            uint8_t s = ov_old(k);
-            if (a.do_progress && (s & 0x3f) && !(s & 0xc0)) s = static_cast<uint8_t>(s - 1);
-            if (a.do_regrow && s == 0x80 && regrow_draw(c, a.ov_uid_base + k, step)) s = 0x40;
-            a.ov_next[k] = s;
-        }
-        // affected positions: every overlay position and its 4 orthogonal neighbours
-        for (uint32_t k = 0; k < nov; ++k)
-        {
-            for (int d = -1; d < 4; ++d)
+            const int ox = nr.x[i], oy = nr.y[i];
+            if (ox < gx0 - 1 || ox > gx0 + kColsPerThread || oy < static_cast<int>(y0) - 1 || oy > static_cast<int>(y0) + 16)
+                continue;
+            const bool src_burning = (nr.old[i] & 0x3f) != 0;
+            for (int d = 0; d < 5; ++d)
             {
-                const int px = a.ov_pos[2 * k] + (d < 0 ? 0 : DX[d]);
-                const int py = a.ov_pos[2 * k + 1] + (d < 0 ? 0 : DY[d]);
-                if (!in_grid(px, py) || px < a.x_begin || px >= a.x_end) continue;
-                // dedupe against positions already handled
-                bool seen = false;
-                for (uint32_t k2 = 0; k2 <= k && !seen; ++k2)
-                    for (int d2 = -1; d2 < 4 && !seen; ++d2)
-                    {
-                        if (k2 == k && d2 >= d) break;
-                        const int qx = a.ov_pos[2 * k2] + (d2 < 0 ? 0 : DX[d2]);
-                        const int qy = a.ov_pos[2 * k2 + 1] + (d2 < 0 ? 0 : DY[d2]);
-                        seen = (qx == px && qy == py);
-                    }
-                if (seen) continue;
-                if (!marked(px, py)) continue;
-                // every entity at a marked position becomes Burning{duration} (:320-328)
-                uint8_t* nb = const_cast<uint8_t*>(base_ptr(a.next, px, py));
-                category_adjust(*nb, -1);
-                *nb = ign;
-                category_adjust(ign, +1);
-                for (uint32_t o = 0; o < nov; ++o)
-                    if (a.ov_pos[2 * o] == px && a.ov_pos[2 * o + 1] == py) a.ov_next[o] = ign;
+                // the overlay's own cell, then N, W, E, S of it; a neighbour is only affected while the overlay burns
+                if (d > 0 && !src_burning) break;
+                const int px = ox + (d == 2 ? -1 : (d == 3 ? 1 : 0));
+                const int py = oy + (d == 1 ? -1 : (d == 4 ? 1 : 0));
+                if (px < gx0 || px >= gx0 + kColsPerThread || px >= a.x_end || py < static_cast<int>(y0) ||
+                    py >= static_cast<int>(y0) + 16 || py >= a.H)
+                    continue;
+                // several overlays may make a thread visit the same cell twice: the patch is idempotent
+                const bool m = overlay_marked(c, nr, step, px, py);
+                if (m)
+                {
+                    // every entity at a marked position becomes Burning{duration} (:320-328)
+                    uint8_t* nb = a.next + static_cast<size_t>(px - a.x_begin + 1) * c.pitch + py;
+                    dl.add(*nb, -1);
+                    *nb = static_cast<uint8_t>(ign);
+                    dl.add(ign, +1);
+                }
+                if (d == 0 && nr.owner[i] == 0)
+                {
+                    // the overlay entity itself: progression / regrowth, overridden by ignition
+                    const uint32_t s0 = nr.old[i];
+                    uint32_t s1 = s0;
+                    if (a.do_progress && (s1 & 0x3f)) s1 -= 1;
+                    if (a.do_regrow && s1 == 0x80 && regrow_draw(c, a.ov_uid_base + nr.k[i], step)) s1 = 0x40;
+                    if (m) s1 = ign;
+                    a.ov_next[nr.k[i]] = static_cast<uint8_t>(s1);
+                    dl.add(s0, -1);
+                    dl.add(s1, +1);
+                }
             }
-        }
-        // overlay entities this rank owns are counted here
-        for (uint32_t k = 0; k < nov; ++k)
-        {
-            const uint8_t o = c.ov_owner ? c.ov_owner[k] : 0;
-            if (o == 0) category_adjust(a.ov_next[k], +1);
         }
     }
 
-    uint64_t total = static_cast<uint64_t>(owned);
-    for (uint32_t k = 0; k < nov; ++k)
-        if ((c.ov_owner ? c.ov_owner[k] : 0) == 0) ++total;
+    // ---- incremental FireStats: warps that saw a transition add their deltas to the block's counters
+    if (__any_sync(kFullMask, (dl.h | dl.b | dl.e) != 0))
+    {
+        const int32_t h = warp_sum(dl.h), b = warp_sum(dl.b), e = warp_sum(dl.e);
+        if (lane == 0)
+        {
+            if (h) atomicAdd(&s_delta[0], h);
+            if (b) atomicAdd(&s_delta[1], b);
+            if (e) atomicAdd(&s_delta[2], e);
+        }
+    }
+    // Completion without a trailing block barrier (warps finish at very different times because of the
+    // rare-event loops): every warp arrives on a shared counter; the last warp of the block pushes the
+    // block's deltas to the running totals and takes the grid ticket; the last block publishes.
+    if (lane != 0) return;
+    __threadfence_block();
+    if (atomicAdd(&s_done, 1u) != kTY - 1) return;
+    {
+        unsigned long long* run = reinterpret_cast<unsigned long long*>(a.stats_run);
+        const int32_t h = atomicAdd(&s_delta[0], 0), b = atomicAdd(&s_delta[1], 0), e = atomicAdd(&s_delta[2], 0);
+        if (h) atomicAdd(run + 0, static_cast<unsigned long long>(static_cast<long long>(h)));
+        if (b) atomicAdd(run + 1, static_cast<unsigned long long>(static_cast<long long>(b)));
+        if (e) atomicAdd(run + 2, static_cast<unsigned long long>(static_cast<long long>(e)));
+        if (h | b | e) __threadfence(); // the totals are updated before this block is counted
+    }
+    const uint32_t nblocks = gridDim.x * gridDim.y;
+    const uint32_t t = atomicAdd(a.ticket, 1u);
+    if (t != nblocks - 1) return;
+    *a.ticket = 0u; // ready for the next launch
+    __threadfence();
 
-    a.stats_out[0] = static_cast<uint64_t>(healthy);
-    a.stats_out[1] = static_cast<uint64_t>(burning);
-    a.stats_out[2] = static_cast<uint64_t>(burned);
-    a.stats_out[3] = static_cast<uint64_t>(empty);
+    // ================= last block: publish the step's FireStats =================
+    unsigned long long* run = reinterpret_cast<unsigned long long*>(a.stats_run);
+    const uint64_t healthy = atomicAdd(run + 0, 0ull);
+    const uint64_t burning = atomicAdd(run + 1, 0ull);
+    const uint64_t empty = atomicAdd(run + 2, 0ull);
+    const uint64_t total = static_cast<uint64_t>(c.slab_w) * a.H + a.ov_owned;
+    const uint64_t burned = total - healthy - burning - empty;
+    a.stats_out[0] = healthy;
+    a.stats_out[1] = burning;
+    a.stats_out[2] = burned;
+    a.stats_out[3] = empty;
     a.stats_out[4] = total;
     if (a.series_values && a.series_interval && (step % a.series_interval) == 0)
     {
@@ -413,10 +485,10 @@ __global__ void __launch_bounds__(kTX* kTY) forest_step_kernel(const ForestConst
         if (slot < a.series_capacity)
         {
             uint64_t* rec = reinterpret_cast<uint64_t*>(a.series_values) + slot * 5;
-            rec[0] = static_cast<uint64_t>(healthy);
-            rec[1] = static_cast<uint64_t>(burning);
-            rec[2] = static_cast<uint64_t>(burned);
-            rec[3] = static_cast<uint64_t>(empty);
+            rec[0] = healthy;
+            rec[1] = burning;
+            rec[2] = burned;
+            rec[3] = empty;
             rec[4] = total;
             a.series_counts[slot] = total;
         }
@@ -491,16 +563,20 @@ void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint
     ForestConst c;
     c.a = a;
     c.slab_w = static_cast<uint32_t>(a.x_end - a.x_begin);
-    c.pitch = (static_cast<uint32_t>(a.H) + 15u) & ~15u;
+    c.pitch = forest_pitch(a.H);
     c.chunks_per_col = c.pitch / 16;
     c.regrow_two_level = a.regrow_two_level;
     c.thr_regrow_l2 = a.regrow_two_level ? a.thr_regrow_l2 : a.thr_regrow;
     c.ov_lo = ov_lo;
     c.ov_hi = ov_hi;
     c.ov_owner = ov_owner;
+    c.near_bits = a.near_bits;
+    c.error = a.error;
+    c.rk_spread = make_round_keys(a.key_spread);
+    c.rk_regrow = make_round_keys(a.key_regrow);
     dim3 block(kTX, kTY);
     dim3 grid((c.chunks_per_col + kTX - 1) / kTX, (c.slab_w + kTY * kColsPerThread - 1) / (kTY * kColsPerThread));
-    if ((a.H % 16) == 0)
+    if ((a.H % 16) == 0) // uid of a chunk's first cell is a multiple of 16: one level-1 call per chunk
         forest_step_kernel<true><<<grid, block, 0, st>>>(c);
     else
         forest_step_kernel<false><<<grid, block, 0, st>>>(c);
@@ -508,9 +584,20 @@ void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint
 
 void launch_forest_step(const ForestArgs& a, cudaStream_t st) { launch_forest_step_ex(a, nullptr, nullptr, nullptr, st); }
 
+uint32_t forest_pitch(int32_t H) { return (static_cast<uint32_t>(H) + kTX * 16 - 1) / (kTX * 16) * (kTX * 16); }
+uint32_t forest_alloc_cols(int32_t slab_w)
+{
+    return (static_cast<uint32_t>(slab_w) + kTY * kColsPerThread - 1) / (kTY * kColsPerThread) * (kTY * kColsPerThread) + 2;
+}
+void forest_tile_shape(uint32_t* cols, uint32_t* rows)
+{
+    *cols = kTY * kColsPerThread;
+    *rows = kTX * 16;
+}
+
 int forest_step_grid_blocks(int32_t slab_w, int32_t H)
 {
-    const uint32_t chunks = ((static_cast<uint32_t>(H) + 15u) & ~15u) / 16;
+    const uint32_t chunks = forest_pitch(H) / 16;
     return static_cast<int>(((chunks + kTX - 1) / kTX) *
                             ((static_cast<uint32_t>(slab_w) + kTY * kColsPerThread - 1) / (kTY * kColsPerThread)));
 }
@@ -519,7 +606,7 @@ void launch_forest_spawn(uint8_t* cells, int32_t W, int32_t H, int32_t x_begin, 
                          uint64_t thr_density, cudaStream_t st)
 {
     (void)W;
-    const uint32_t pitch = (static_cast<uint32_t>(H) + 15u) & ~15u;
+    const uint32_t pitch = forest_pitch(H);
     forest_spawn_kernel<<<kNumSMs * 8, 256, 0, st>>>(cells, H, pitch, x_begin, static_cast<uint32_t>(x_end - x_begin),
                                                      key, thr_density);
 }
@@ -531,7 +618,7 @@ void launch_forest_stats(const uint8_t* slab, int32_t H, int32_t slab_w, uint64_
     uint64_t b = (n + 256 * 16 - 1) / (256 * 16);
     if (b < 1) b = 1;
     if (b > static_cast<uint64_t>(kNumSMs) * 8) b = kNumSMs * 8;
-    const uint32_t pitch = (static_cast<uint32_t>(H) + 15u) & ~15u;
+    const uint32_t pitch = forest_pitch(H);
     forest_stats_kernel<<<static_cast<int>(b), 256, 0, st>>>(slab, static_cast<uint32_t>(H), pitch,
                                                              static_cast<uint32_t>(slab_w), out5,
                                                              static_cast<uint64_t*>(scratch), ticket);

@@ -30,9 +30,14 @@ static int owner_rank_of_column(const Sim& s, const ForestModule& fm, int32_t x)
 
 static int32_t forest_alloc(Sim& s, ForestModule& fm)
 {
-    fm.pitch = (static_cast<uint32_t>(fm.H) + 15u) & ~15u;
+    fm.pitch = forest_pitch(fm.H);
     const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
-    const size_t bytes = static_cast<size_t>(slab_w + 2) * fm.pitch;
+    const size_t bytes = static_cast<size_t>(forest_alloc_cols(static_cast<int32_t>(slab_w))) * fm.pitch;
+    if (bytes >= (1ull << 32))
+    {
+        set_error("forest slab larger than 4 GiB per GPU is not supported");
+        return INCERTO_ERR_UNSUPPORTED;
+    }
     if (fm.d_alloc[0] && bytes == fm.slab_bytes) return INCERTO_OK;
     forest_free(s);
     fm.slab_bytes = bytes;
@@ -41,8 +46,8 @@ static int32_t forest_alloc(Sim& s, ForestModule& fm)
         INC_CUDA(cudaMalloc(&fm.d_alloc[i], bytes + 2 * kLead));
         fm.d_slab[i] = fm.d_alloc[i] + kLead;
     }
-    const int blocks = forest_step_grid_blocks(static_cast<int32_t>(slab_w), fm.H);
-    INC_CUDA(cudaMalloc(&fm.d_partials, static_cast<size_t>(blocks) * 4 * sizeof(uint64_t)));
+    INC_CUDA(cudaMalloc(&fm.d_stats_run, 8 * sizeof(uint64_t)));
+    INC_CUDA(cudaMemsetAsync(fm.d_stats_run, 0, 8 * sizeof(uint64_t), s.stream));
     INC_CUDA(cudaMalloc(&fm.d_stats, 8 * sizeof(uint64_t)));
     const size_t nov = std::max<uint32_t>(fm.n_overlay, 1);
     INC_CUDA(cudaMalloc(&fm.d_ov_pos, nov * 2 * sizeof(int16_t)));
@@ -50,12 +55,21 @@ static int32_t forest_alloc(Sim& s, ForestModule& fm)
     INC_CUDA(cudaMalloc(&fm.d_ov_lo, nov));
     INC_CUDA(cudaMalloc(&fm.d_ov_hi, nov));
     INC_CUDA(cudaMalloc(&fm.d_ov_owner, nov));
+    {
+        uint32_t tc, tr;
+        forest_tile_shape(&tc, &tr);
+        const size_t tiles = static_cast<size_t>(fm.pitch / tr) * ((forest_alloc_cols(static_cast<int32_t>(slab_w)) - 2) / tc);
+        INC_CUDA(cudaMalloc(&fm.d_near_bits, (tiles / 32 + 1) * sizeof(uint32_t)));
+    }
     return INCERTO_OK;
 }
+
+void forest_graph_free(ForestModule& fm);
 
 void forest_free(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
+    forest_graph_free(fm);
     for (int i = 0; i < 2; ++i)
     {
         cudaFree(fm.d_alloc[i]);
@@ -63,13 +77,15 @@ void forest_free(Sim& s)
         cudaFree(fm.d_ov[i]);
         fm.d_ov[i] = nullptr;
     }
-    cudaFree(fm.d_partials);
+    cudaFree(fm.d_stats_run);
     cudaFree(fm.d_stats);
     cudaFree(fm.d_ov_pos);
     cudaFree(fm.d_ov_lo);
     cudaFree(fm.d_ov_hi);
     cudaFree(fm.d_ov_owner);
-    fm.d_partials = nullptr;
+    cudaFree(fm.d_near_bits);
+    fm.d_near_bits = nullptr;
+    fm.d_stats_run = nullptr;
     fm.d_stats = nullptr;
     fm.d_ov_pos = nullptr;
     fm.d_ov_lo = fm.d_ov_hi = fm.d_ov_owner = nullptr;
@@ -92,6 +108,26 @@ static int32_t forest_upload_overlays(Sim& s, ForestModule& fm, const std::vecto
             code = 2;
         fm.h_ov_owner[k] = code;
     }
+    {
+        // CTA tiles with an overlay entity within one cell (the kernel stages those overlays in shared memory)
+        uint32_t tc, tr;
+        forest_tile_shape(&tc, &tr);
+        const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+        const uint32_t tiles_along_y = fm.pitch / tr;
+        const size_t tiles = static_cast<size_t>(tiles_along_y) * ((forest_alloc_cols(static_cast<int32_t>(slab_w)) - 2) / tc);
+        std::vector<uint32_t> bits(tiles / 32 + 1, 0u);
+        for (uint32_t k = 0; k < fm.n_overlay; ++k)
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy)
+                {
+                    const int x = fm.h_ov_pos[2 * k] + dx, y = fm.h_ov_pos[2 * k + 1] + dy;
+                    if (x < fm.x_begin || x >= fm.x_end || y < 0 || y >= fm.H) continue;
+                    const size_t tile = static_cast<size_t>((x - fm.x_begin) / tc) * tiles_along_y + static_cast<uint32_t>(y) / tr;
+                    bits[tile >> 5] |= 1u << (tile & 31);
+                }
+        INC_CUDA(cudaMemcpyAsync(fm.d_near_bits, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+    }
     if (fm.n_overlay)
     {
         INC_CUDA(cudaMemcpyAsync(fm.d_ov_pos, fm.h_ov_pos.data(), fm.n_overlay * 2 * sizeof(int16_t),
@@ -101,6 +137,42 @@ static int32_t forest_upload_overlays(Sim& s, ForestModule& fm, const std::vecto
             INC_CUDA(cudaMemcpyAsync(p, states.data(), fm.n_overlay, cudaMemcpyHostToDevice, s.stream));
         INC_CUDA(cudaStreamSynchronize(s.stream));
     }
+    return INCERTO_OK;
+}
+
+// FireStats of the freshly spawned slab (+ the overlay entities this rank owns): the step kernel
+// keeps them current by counting transitions only.
+static int32_t forest_init_stats(Sim& s, ForestModule& fm, const std::vector<uint8_t>& ov_states)
+{
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    INC_TRY(ensure_scratch(s, 4 * 8 * kNumSMs * 8 + 64));
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(s.d_scratch + 4 * 8 * kNumSMs * 8);
+    {
+        KTimer kt(s, "forest_stats", 1.0 * slab_w * fm.H);
+        launch_forest_stats(fm.d_slab[fm.cur], fm.H, static_cast<int32_t>(slab_w), d_out, s.d_scratch, s.d_ticket, s.stream);
+    }
+    uint64_t st[5];
+    INC_CUDA(cudaMemcpyAsync(st, d_out, sizeof(st), cudaMemcpyDeviceToHost, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    for (uint32_t k = 0; k < fm.n_overlay; ++k)
+    {
+        if (fm.h_ov_owner[k] != 0) continue;
+        const uint8_t v = ov_states[k];
+        if (v & 0x40)
+            ++st[0];
+        else if (v & 0x80)
+            ++st[3];
+        else if (v & 0x3f)
+            ++st[1];
+        else
+            ++st[2];
+        ++st[4];
+    }
+    const uint64_t run[3] = {st[0], st[1], st[3]};
+    INC_CUDA(cudaMemcpyAsync(fm.d_stats_run, run, sizeof(run), cudaMemcpyHostToDevice, s.stream));
+    INC_CUDA(cudaMemcpyAsync(fm.d_stats, st, sizeof(st), cudaMemcpyHostToDevice, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    fm.stats_valid = true;
     return INCERTO_OK;
 }
 
@@ -148,7 +220,7 @@ int32_t forest_spawn_device(Sim& s, const HostSpawn& sp)
     }
     std::vector<uint8_t> st(std::max<uint32_t>(fm.n_overlay, 1), static_cast<uint8_t>(p.burn_duration));
     INC_TRY(forest_upload_overlays(s, fm, st));
-    fm.stats_valid = false;
+    INC_TRY(forest_init_stats(s, fm, st));
     Table& t = s.tables[fm.table];
     t.dense_w = fm.W;
     t.dense_h = fm.H;
@@ -278,7 +350,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     t.dense_h = fm.H;
     t.x_begin = fm.x_begin;
     t.x_end = fm.x_end;
-    fm.stats_valid = false;
+    INC_TRY(forest_init_stats(s, fm, ovst));
     return INCERTO_OK;
 }
 
@@ -349,6 +421,7 @@ int32_t forest_bind(Sim& s)
 int32_t forest_reset_after_spawn(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
+    forest_graph_free(fm); // the replica key is baked into the captured kernel parameters
     Table& t = s.tables[fm.table];
     bool device_spawned = false;
     for (auto& sp : s.spawns)
@@ -378,59 +451,138 @@ int32_t forest_halo_exchange(Sim& s)
     return comm_halo(s, send_lo, recv_lo, send_hi, recv_hi, bytes, fm.n_overlay ? 2 : 1);
 }
 
+static int32_t forest_launch_one(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    ForestArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.cur = fm.d_slab[fm.cur];
+    a.next = fm.d_slab[1 - fm.cur];
+    a.W = fm.W;
+    a.H = fm.H;
+    a.x_begin = fm.x_begin;
+    a.x_end = fm.x_end;
+    a.n_overlay = fm.n_overlay;
+    a.ov_pos = fm.d_ov_pos;
+    a.near_bits = fm.d_near_bits;
+    a.ov_cur = fm.d_ov[fm.cur];
+    a.ov_next = fm.d_ov[1 - fm.cur];
+    a.ov_uid_base = static_cast<uint32_t>(fm.W) * static_cast<uint32_t>(fm.H);
+    a.ov_owned = static_cast<uint32_t>(std::count(fm.h_ov_owner.begin(), fm.h_ov_owner.end(), uint8_t(0)));
+    a.do_spread = fm.do_spread;
+    a.do_progress = fm.do_progress;
+    a.do_regrow = fm.do_regrow;
+    a.thr_spread = bernoulli_threshold(fm.p_spread);
+    a.thr_regrow = bernoulli_threshold(fm.p_regrow);
+    a.regrow_two_level = (fm.p_regrow * 256.0 <= 1.0) ? 1u : 0u;
+    a.thr_regrow_l2 = bernoulli_threshold(fm.p_regrow * 256.0);
+    a.burn_duration = fm.burn_duration;
+    a.bump_step = 1;
+    a.key_spread = make_key(s.seed, s.replica, TAG_FOREST_SPREAD);
+    a.key_regrow = make_key(s.seed, s.replica, TAG_FOREST_REGROW);
+    a.d_step = s.mods->d_step;
+    a.stats_run = fm.d_stats_run;
+    a.error = s.d_error;
+    a.ticket = s.d_ticket;
+    a.stats_out = fm.d_stats;
+    if (fm.series >= 0)
+    {
+        SeriesInst& se = s.series[fm.series];
+        a.series_values = se.d_values;
+        a.series_counts = se.d_counts;
+        a.series_interval = se.interval;
+        a.series_capacity = se.capacity;
+    }
+    {
+        // 2 B per cell-update (1 B read + 1 B written)
+        KTimer kt(s, "forest_step", 2.0 * slab_w * fm.H);
+        launch_forest_step_ex(a, fm.d_ov_lo, fm.d_ov_hi, fm.d_ov_owner, s.stream);
+    }
+    INC_CUDA(cudaGetLastError());
+    fm.cur = 1 - fm.cur;
+    return INCERTO_OK;
+}
+
+void forest_graph_free(ForestModule& fm)
+{
+    if (fm.graph_exec) cudaGraphExecDestroy(fm.graph_exec);
+    fm.graph_exec = nullptr;
+    fm.graph_steps = 0;
+}
+
+// Launch-bound inner loop -> CUDA graph: the step kernel reads StepNumber from device memory and bumps
+// it itself, so a captured run of steps replays without new arguments.
+static constexpr uint32_t kGraphSteps = 16;
+
+static int32_t forest_graph_ensure(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    const void* sv = fm.series >= 0 ? s.series[fm.series].d_values : nullptr;
+    const uint64_t sc = fm.series >= 0 ? s.series[fm.series].capacity : 0;
+    if (fm.graph_exec && fm.graph_cur == fm.cur && fm.graph_series_values == sv && fm.graph_series_capacity == sc)
+        return INCERTO_OK;
+    forest_graph_free(fm);
+    cudaGraph_t graph = nullptr;
+    const int cur0 = fm.cur;
+    INC_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+    int32_t st = INCERTO_OK;
+    for (uint32_t i = 0; i < kGraphSteps && st == INCERTO_OK; ++i) st = forest_launch_one(s);
+    cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+    fm.cur = cur0; // nothing ran yet
+    if (st != INCERTO_OK)
+    {
+        if (graph) cudaGraphDestroy(graph);
+        return st;
+    }
+    INC_CUDA(e);
+    e = cudaGraphInstantiate(&fm.graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    INC_CUDA(e);
+    fm.graph_steps = kGraphSteps;
+    fm.graph_cur = cur0;
+    fm.graph_series_values = sv;
+    fm.graph_series_capacity = sc;
+    // the launches counted during capture did not run
+    s.launches -= kGraphSteps;
+    kstat(s, "forest_step").launches -= kGraphSteps;
+    kstat(s, "forest_step").algorithmic_bytes -= 2.0 * (fm.x_end - fm.x_begin) * fm.H * kGraphSteps;
+    return INCERTO_OK;
+}
+
+static bool forest_use_graph(const Sim& s, uint64_t nsteps) { return s.part_world == 1 && !s.profiling && nsteps >= 2 * kGraphSteps; }
+
+int32_t forest_prepare(Sim& s, uint64_t nsteps)
+{
+    if (forest_use_graph(s, nsteps)) INC_TRY(forest_graph_ensure(s));
+    return INCERTO_OK;
+}
+
 int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps)
 {
     ForestModule& fm = s.mods->forest;
     (void)first_step;
-    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
-    for (uint32_t i = 0; i < nsteps; ++i)
+    uint32_t done = 0;
+    if (forest_use_graph(s, nsteps))
     {
-        ForestArgs a;
-        std::memset(&a, 0, sizeof(a));
-        a.cur = fm.d_slab[fm.cur];
-        a.next = fm.d_slab[1 - fm.cur];
-        a.W = fm.W;
-        a.H = fm.H;
-        a.x_begin = fm.x_begin;
-        a.x_end = fm.x_end;
-        a.n_overlay = fm.n_overlay;
-        a.ov_pos = fm.d_ov_pos;
-        a.ov_cur = fm.d_ov[fm.cur];
-        a.ov_next = fm.d_ov[1 - fm.cur];
-        a.ov_uid_base = static_cast<uint32_t>(fm.W) * static_cast<uint32_t>(fm.H);
-        a.do_spread = fm.do_spread;
-        a.do_progress = fm.do_progress;
-        a.do_regrow = fm.do_regrow;
-        a.thr_spread = bernoulli_threshold(fm.p_spread);
-        a.thr_regrow = bernoulli_threshold(fm.p_regrow);
-        a.regrow_two_level = (fm.p_regrow * 256.0 <= 1.0) ? 1u : 0u;
-        a.thr_regrow_l2 = bernoulli_threshold(fm.p_regrow * 256.0);
-        a.burn_duration = fm.burn_duration;
-        a.bump_step = 1;
-        a.key_spread = make_key(s.seed, s.replica, TAG_FOREST_SPREAD);
-        a.key_regrow = make_key(s.seed, s.replica, TAG_FOREST_REGROW);
-        a.d_step = s.mods->d_step;
-        a.stats_partials = fm.d_partials;
-        a.ticket = s.d_ticket;
-        a.stats_out = fm.d_stats;
-        if (fm.series >= 0)
+        INC_TRY(forest_graph_ensure(s));
+        const double bytes = 2.0 * (fm.x_end - fm.x_begin) * fm.H;
+        while (nsteps - done >= kGraphSteps)
         {
-            SeriesInst& se = s.series[fm.series];
-            a.series_values = se.d_values;
-            a.series_counts = se.d_counts;
-            a.series_interval = se.interval;
-            a.series_capacity = se.capacity;
+            INC_CUDA(cudaGraphLaunch(fm.graph_exec, s.stream));
+            done += kGraphSteps;
+            s.launches += kGraphSteps;
+            KernelStat& ks = kstat(s, "forest_step");
+            ks.launches += kGraphSteps;
+            ks.algorithmic_bytes += bytes * kGraphSteps;
         }
-        {
-            // 2 B per cell-update (1 B read + 1 B written)
-            KTimer kt(s, "forest_step", 2.0 * slab_w * fm.H);
-            launch_forest_step_ex(a, fm.d_ov_lo, fm.d_ov_hi, fm.d_ov_owner, s.stream);
-        }
-        INC_CUDA(cudaGetLastError());
-        fm.cur = 1 - fm.cur;
-        fm.stats_valid = true;
+    }
+    for (; done < nsteps; ++done)
+    {
+        INC_TRY(forest_launch_one(s));
         INC_TRY(forest_halo_exchange(s));
     }
+    fm.stats_valid = true;
     return INCERTO_OK;
 }
 
@@ -450,41 +602,8 @@ int32_t forest_read_cells(Sim& s, uint8_t* out_rows)
 int32_t forest_stats_now(Sim& s, uint64_t out5[5])
 {
     ForestModule& fm = s.mods->forest;
-    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
-    if (fm.stats_valid)
-    {
-        INC_CUDA(cudaMemcpyAsync(out5, fm.d_stats, 5 * 8, cudaMemcpyDeviceToHost, s.stream));
-        INC_CUDA(cudaStreamSynchronize(s.stream));
-    }
-    else
-    {
-        INC_TRY(ensure_scratch(s, 4 * 8 * kNumSMs * 8 + 64));
-        uint64_t* d_out = reinterpret_cast<uint64_t*>(s.d_scratch + 4 * 8 * kNumSMs * 8);
-        {
-            KTimer kt(s, "forest_stats", 1.0 * slab_w * fm.H);
-            launch_forest_stats(fm.d_slab[fm.cur], fm.H, static_cast<int32_t>(slab_w), d_out, s.d_scratch, s.d_ticket,
-                                s.stream);
-        }
-        INC_CUDA(cudaMemcpyAsync(out5, d_out, 5 * 8, cudaMemcpyDeviceToHost, s.stream));
-        std::vector<uint8_t> ov(std::max<uint32_t>(fm.n_overlay, 1));
-        if (fm.n_overlay)
-            INC_CUDA(cudaMemcpyAsync(ov.data(), fm.d_ov[fm.cur], fm.n_overlay, cudaMemcpyDeviceToHost, s.stream));
-        INC_CUDA(cudaStreamSynchronize(s.stream));
-        for (uint32_t k = 0; k < fm.n_overlay; ++k)
-        {
-            if (fm.h_ov_owner[k] != 0) continue;
-            const uint8_t v = ov[k];
-            if (v & 0x40)
-                ++out5[0];
-            else if (v & 0x80)
-                ++out5[3];
-            else if (v & 0x3f)
-                ++out5[1];
-            else
-                ++out5[2];
-            ++out5[4];
-        }
-    }
+    INC_CUDA(cudaMemcpyAsync(out5, fm.d_stats, 5 * 8, cudaMemcpyDeviceToHost, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
     if (s.part_world > 1 && s.comm)
     {
         INC_TRY(ensure_scratch(s, 64));

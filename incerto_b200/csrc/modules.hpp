@@ -13,6 +13,9 @@ struct StepOp
     // advance `nsteps` steps starting at StepNumber == first_step
     std::function<int32_t(Sim&, uint64_t first_step, uint32_t nsteps)> fn;
     bool multi_step_ok = false; // entity-local: may apply several steps per launch
+    bool whole_run_ok = false;  // fn may be handed every step of a run at once (it samples its own fused series)
+    // host-side preparation (graph capture ...) done before the run's timing events are recorded
+    std::function<int32_t(Sim&, uint64_t nsteps)> prepare;
     bool bumps_device_step = false;
 };
 
@@ -35,13 +38,20 @@ struct ForestModule
     uint8_t* d_ov_lo = nullptr; // overlay states received from the neighbours (row partition)
     uint8_t* d_ov_hi = nullptr;
     uint8_t* d_ov_owner = nullptr;
+    uint32_t* d_near_bits = nullptr; // one bit per CTA tile with an overlay entity within one cell
     bool do_spread = false, do_progress = false, do_regrow = false;
     double p_spread = 0, p_regrow = 0;
     uint32_t burn_duration = 3;
-    uint64_t* d_partials = nullptr;
+    uint64_t* d_stats_run = nullptr; // running (healthy, burning, empty) totals kept by the step kernel
     uint64_t* d_stats = nullptr; // 5 u64 of the last step
     int series = -1;             // index of the fused FireStats series, -1 if none
     bool stats_valid = false;
+    // captured step program: `graph_steps` consecutive steps (even, so the ping-pong buffers line up)
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_steps = 0;
+    int graph_cur = 0;
+    const void* graph_series_values = nullptr;
+    uint64_t graph_series_capacity = 0;
 };
 
 struct CoinModule
@@ -65,6 +75,7 @@ int32_t forest_spawn_device(Sim& s, const HostSpawn& sp);
 int32_t forest_bind(Sim& s);
 int32_t forest_reset_after_spawn(Sim& s);
 int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps);
+int32_t forest_prepare(Sim& s, uint64_t nsteps);
 int32_t forest_read_cells(Sim& s, uint8_t* out_rows); // W*H + overlays, uid order (this rank's slab only in partition mode)
 int32_t forest_stats_now(Sim& s, uint64_t out5[5]);
 void forest_free(Sim& s);

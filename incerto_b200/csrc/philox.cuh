@@ -73,6 +73,42 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1
     return make_uint4(c0, c1, c2, c3);
 }
 
+// The ten round keys of a stream, precomputed on the host.  Kernels keep them in their parameter
+// block (constant bank), which turns the key schedule into constant operands of the xor instructions.
+struct PhiloxRoundKeys
+{
+    uint32_t k[20];
+};
+__host__ __device__ __forceinline__ PhiloxRoundKeys make_round_keys(PhiloxKey key)
+{
+    PhiloxRoundKeys r;
+    uint32_t k0 = key.k0, k1 = key.k1;
+    for (int i = 0; i < 10; ++i)
+    {
+        r.k[2 * i] = k0;
+        r.k[2 * i + 1] = k1;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return r;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxRoundKeys& rk)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+    {
+        const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
+        const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk.k[2 * r];
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk.k[2 * r + 1];
+        c1 = static_cast<uint32_t>(p1);
+        c3 = static_cast<uint32_t>(p0);
+        c0 = n0;
+        c2 = n2;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // bernoulli(p): u < floor(p * 2^32), threshold precomputed on the host as u64
 // (p >= 1 -> 2^32 -> always true; p <= 0 -> 0 -> never).
 __host__ __device__ __forceinline__ bool bernoulli(uint32_t u, uint64_t threshold)

@@ -22,6 +22,8 @@ SOURCES = [
     "engine.cu",
     "sampling.cu",
     "module_forest.cu",
+    "module_pandemic.cu",
+    "kernels_pandemic.cu",
     "comm.cu",
     "kernels_generic.cu",
     "kernels_coin.cu",
@@ -53,7 +55,13 @@ def _deps_mtime() -> float:
     return m
 
 
-def build(verbose: bool = False, force: bool = False, extra_flags: list[str] | None = None) -> str:
+def build(verbose: bool = False, force: bool = False, extra_flags: list[str] | None = None,
+          variant: str | None = None) -> str:
+    """`variant` builds a tuning variant into lib/libincerto_b200.<variant>.so (selected with INCERTO_B200_LIB)."""
+    global OBJDIR, LIB
+    if variant:
+        OBJDIR = os.path.join(HERE, "build", variant)
+        LIB = os.path.join(LIBDIR, f"libincerto_b200.{variant}.so")
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()

@@ -39,6 +39,7 @@ Sim::~Sim()
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     forest_free(*this);
+    pandemic_free(*this);
     comm_free(*this);
     for (auto& t : tables)
     {
@@ -278,6 +279,19 @@ static int32_t device_spawn_signature(Sim& s, const HostSpawn& sp, std::vector<i
         n = static_cast<uint64_t>(p.width) * p.height + p.initial_fire_count;
         return INCERTO_OK;
     }
+    case INCERTO_SPAWN_PANDEMIC_PEOPLE:
+    {
+        if (sp.params.size() != sizeof(incerto_spawn_pandemic_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_spawn_pandemic_params p;
+        std::memcpy(&p, sp.params.data(), sizeof(p));
+        auto bad = [&](int c) { return c < 0 || c >= static_cast<int>(s.comps.size()); };
+        if (bad(p.person) || bad(p.position) || bad(p.infected)) return INCERTO_ERR_INVALID_ARGUMENT;
+        s.comps[p.person].exists = true;
+        s.comps[p.infected].exists = true;
+        sig = {p.position};
+        n = p.initial_population;
+        return INCERTO_OK;
+    }
     default:
         set_error("device spawner kind %u is not implemented", sp.kind);
         return INCERTO_ERR_UNSUPPORTED;
@@ -377,6 +391,12 @@ static int32_t run_spawners(Sim& s, bool first_time)
         {
             std::vector<int> sig;
             INC_TRY(device_spawn_signature(s, sp, sig, n));
+            if (sp.kind == INCERTO_SPAWN_PANDEMIC_PEOPLE)
+            {
+                INC_TRY(pandemic_spawn_device(s, sp, t, off));
+                cursor[ti] += n;
+                continue;
+            }
             // coin tossers: CoinTosser::default() (coin_toss.rs:60-62) -> zeros
             for (auto& c : t.cols) INC_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(c.d) + off * c.row_bytes, 0, n * c.row_bytes, s.stream));
             INC_CUDA(cudaMemsetAsync(t.d_flags + off, kAliveBit, n, s.stream));
@@ -572,6 +592,21 @@ static int32_t bind_generic_systems(Sim& s)
                 op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return forest_step(sim, first_step, nsteps); };
                 prog.push_back(op);
                 forest_added = true;
+            }
+            break;
+        }
+        case INCERTO_SYS_PANDEMIC_MOVE:
+        case INCERTO_SYS_PANDEMIC_INFECT:
+        case INCERTO_SYS_PANDEMIC_DIE:
+        case INCERTO_SYS_PANDEMIC_RECOVER:
+        {
+            if (!s.mods->pandemic.active)
+            {
+                INC_TRY(pandemic_bind(s));
+                StepOp op;
+                op.name = "pandemic_step";
+                op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return pandemic_step(sim, first_step, nsteps); };
+                prog.push_back(op);
             }
             break;
         }
@@ -949,6 +984,7 @@ int32_t incerto_sim_reset(incerto_sim* s, uint32_t replica)
     series_clear(S);
     INC_TRY(run_spawners(S, false));
     if (S.mods->forest.active) INC_TRY(forest_reset_after_spawn(S));
+    if (S.mods->pandemic.active) INC_TRY(pandemic_reset(S));
     for (auto& g : S.grids) g.built_step = ~0ull;
     INC_CUDA(cudaStreamSynchronize(S.stream));
     return INCERTO_OK;

@@ -37,10 +37,13 @@ namespace
 {
 
 constexpr int kTX = 32;  // chunks (16 cells) along y per CTA
-constexpr int kTY = 8;   // column quads per CTA
+#ifndef INCERTO_FOREST_TY
+#define INCERTO_FOREST_TY 4
+#endif
+constexpr int kTY = INCERTO_FOREST_TY;   // column quads (warps) per CTA
 constexpr int kColsPerThread = 4;
 #ifndef INCERTO_FOREST_MIN_BLOCKS
-#define INCERTO_FOREST_MIN_BLOCKS 4
+#define INCERTO_FOREST_MIN_BLOCKS 10
 #endif
 constexpr int kMinBlocks = INCERTO_FOREST_MIN_BLOCKS;
 

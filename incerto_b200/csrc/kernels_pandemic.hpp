@@ -1,0 +1,35 @@
+// pandemic kernels (examples/pandemic.rs). See kernels_pandemic.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.hpp"
+
+namespace incerto
+{
+
+struct PandemicArgs
+{
+    uint32_t* pos;        // x | y << 16 per row
+    uint8_t* flags;       // bit 0 alive, marker bits
+    const uint32_t* uid;  // nullptr: uid == row
+    uint64_t n;
+    uint32_t grid_size;
+    uint32_t step;
+    uint32_t bit_person, bit_infected;
+    uint32_t do_move, do_infect, do_die, do_recover;
+    uint32_t fate_two_level;
+    uint64_t thr_infect, thr_die, thr_recover, thr_start_infected;
+    PhiloxRoundKeys rk_spawn, rk_move, rk_fate, rk_infect;
+    // scratch: per-cell lists of infected people
+    uint32_t* cell_bits;     // 1 bit per cell: some infected person stands here this step
+    uint32_t* cell_head;     // (step & 0xff) << 24 | row of the list head
+    uint32_t* next_infected; // per row: next infected row in the same cell, 0xffffff = end
+};
+
+void launch_pandemic_spawn(const PandemicArgs& a, cudaStream_t st);
+void launch_pandemic_move(const PandemicArgs& a, cudaStream_t st);
+void launch_pandemic_interact(const PandemicArgs& a, cudaStream_t st);
+
+} // namespace incerto

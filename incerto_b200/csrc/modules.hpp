@@ -54,6 +54,19 @@ struct ForestModule
     uint64_t graph_series_capacity = 0;
 };
 
+struct PandemicModule
+{
+    bool active = false;
+    int table = -1;
+    int comp_person = -1, comp_position = -1, comp_infected = -1;
+    uint32_t grid_size = 0;
+    bool do_move = false, do_infect = false, do_die = false, do_recover = false;
+    double p_infect = 0, p_die = 0, p_recover = 0;
+    uint32_t* d_cell_bits = nullptr;
+    uint32_t* d_cell_head = nullptr;
+    uint32_t* d_next = nullptr;
+};
+
 struct CoinModule
 {
     bool active = false;
@@ -66,6 +79,7 @@ struct Sim::Modules
 {
     ForestModule forest;
     CoinModule coin;
+    PandemicModule pandemic;
     std::vector<StepOp> program;
     uint32_t* d_step = nullptr; // device mirror of StepNumber
 };
@@ -80,6 +94,13 @@ int32_t forest_read_cells(Sim& s, uint8_t* out_rows); // W*H + overlays, uid ord
 int32_t forest_stats_now(Sim& s, uint64_t out5[5]);
 void forest_free(Sim& s);
 int32_t forest_halo_exchange(Sim& s);
+
+// module_pandemic.cu
+int32_t pandemic_bind(Sim& s);
+int32_t pandemic_step(Sim& s, uint64_t first_step, uint32_t nsteps);
+int32_t pandemic_spawn_device(Sim& s, const HostSpawn& sp, Table& t, uint64_t row_offset);
+void pandemic_free(Sim& s);
+int32_t pandemic_reset(Sim& s);
 
 // comm.cpp
 int32_t comm_unique_id(uint8_t out[128]);

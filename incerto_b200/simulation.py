@@ -194,6 +194,23 @@ def Regrowth(position, cell, probability: float) -> System:
     return System(F.SYS_FOREST_REGROWTH, F.ForestParams(position.handle, cell.handle, probability, 0))
 
 
+# examples/pandemic.rs:115-223
+def PeopleMove(person, position, infected, grid_size: int) -> System:
+    return System(F.SYS_PANDEMIC_MOVE, F.PandemicParams(person.handle, position.handle, infected.handle, grid_size, 0.0))
+
+
+def PeopleInfectOthers(person, position, infected, grid_size: int, chance: float) -> System:
+    return System(F.SYS_PANDEMIC_INFECT, F.PandemicParams(person.handle, position.handle, infected.handle, grid_size, chance))
+
+
+def PeopleInfectedMayDie(person, position, infected, grid_size: int, chance: float) -> System:
+    return System(F.SYS_PANDEMIC_DIE, F.PandemicParams(person.handle, position.handle, infected.handle, grid_size, chance))
+
+
+def PeopleInfectedMayRecover(person, position, infected, grid_size: int, chance: float) -> System:
+    return System(F.SYS_PANDEMIC_RECOVER, F.PandemicParams(person.handle, position.handle, infected.handle, grid_size, chance))
+
+
 @dataclass
 class DeviceSpawner:
     kind: int
@@ -508,20 +525,20 @@ class Simulation:
         _check(self._lib.incerto_sim_num_entities(self._h, component.handle, C.byref(out)))
         return out.value
 
-    def read_component(self, component: Component, with_uids: bool = False):
-        n = self.num_entities(component) if component.dtype == F.MARKER else None
-        if n is None:
-            out_n = C.c_uint64()
-            fs, keep = _filter_struct([With(component)])
-            _check(self._lib.incerto_sim_count(self._h, C.byref(fs), C.byref(out_n)))
-            n = out_n.value
+    def read_component(self, component: Component, with_uids: bool = False, rows_of: Component | None = None):
+        """Column contents of the live rows in row order (markers: 0/1 per live row of the tables holding `rows_of`)."""
         if component.dtype == F.MARKER:
-            raise ValueError("read_component: use count() for markers")
-        out = np.zeros((n, component.lanes), dtype=component.np_dtype)
+            if rows_of is None:
+                raise ValueError("read_component of a marker needs rows_of=<a data component of the same archetype>")
+            n = self.num_entities(rows_of)
+            out = np.zeros((n, 1), dtype=np.uint8)
+        else:
+            n = self.num_entities(component)
+            out = np.zeros((n, component.lanes), dtype=component.np_dtype)
         uids = np.zeros(n, dtype=np.uint64)
         _check(self._lib.incerto_sim_read_component(self._h, component.handle, out.ctypes.data_as(C.c_void_p),
                                                     out.nbytes, uids.ctypes.data_as(C.POINTER(C.c_uint64))))
-        out = out[:, 0] if component.lanes == 1 else out
+        out = out[:, 0] if out.shape[1] == 1 else out
         return (out, uids) if with_uids else out
 
     def last_run_stats(self) -> tuple[float, int]:

@@ -6,6 +6,7 @@
 #include "coin_toss.hpp"
 #include "forest_fire.hpp"
 #include "library.hpp"
+#include "pandemic.hpp"
 #include "philox.hpp"
 
 using namespace oracle;
@@ -139,6 +140,47 @@ uint64_t oracle_forest_bench(uint64_t seed, int32_t width, int32_t height, uint6
     }
     return total;
 }
+
+// ---------------------------------------------------------------- pandemic
+void* oracle_pandemic_new(uint64_t seed, uint32_t replica, uint64_t population, uint32_t grid_size, double p_start,
+                          double p_infect, double p_recover, double p_die, uint32_t systems_mask /* 1 move 2 infect 4 die 8 recover */,
+                          uint32_t nested_loop)
+{
+    PandemicParams p;
+    p.initial_population = population;
+    p.grid_size = grid_size;
+    p.chance_start_infected = p_start;
+    p.chance_infect_other = p_infect;
+    p.chance_recover = p_recover;
+    p.chance_die = p_die;
+    p.move = systems_mask & 1;
+    p.infect = systems_mask & 2;
+    p.die = systems_mask & 4;
+    p.recover = systems_mask & 8;
+    p.nested_loop = nested_loop != 0;
+    return new PandemicSim(p, seed, replica);
+}
+void oracle_pandemic_free(void* h) { delete static_cast<PandemicSim*>(h); }
+void oracle_pandemic_spawn(void* h) { static_cast<PandemicSim*>(h)->spawn_people(); }
+void oracle_pandemic_spawn_explicit(void* h, uint64_t n, const uint16_t* xy, const uint8_t* infected)
+{
+    static_cast<PandemicSim*>(h)->spawn_explicit(n, xy, infected);
+}
+void oracle_pandemic_run(void* h, uint64_t steps) { static_cast<PandemicSim*>(h)->run(steps); }
+uint64_t oracle_pandemic_num_slots(void* h) { return static_cast<PandemicSim*>(h)->x.size(); }
+// per spawn slot: position, alive, infected
+void oracle_pandemic_state(void* h, uint16_t* xy, uint8_t* alive, uint8_t* infected)
+{
+    PandemicSim& s = *static_cast<PandemicSim*>(h);
+    for (size_t i = 0; i < s.x.size(); ++i)
+    {
+        xy[2 * i] = static_cast<uint16_t>(s.x[i]);
+        xy[2 * i + 1] = static_cast<uint16_t>(s.y[i]);
+        alive[i] = s.alive[i];
+        infected[i] = s.infected[i];
+    }
+}
+void oracle_pandemic_counts(void* h, uint64_t out3[3]) { static_cast<PandemicSim*>(h)->counts(out3); }
 
 // ------------------------------------------------------- library: aggregators
 #define ORACLE_AGG(T, NAME)                                                                          \

@@ -57,6 +57,24 @@ def load() -> C.CDLL:
     lib.oracle_forest_series.restype = None
     lib.oracle_forest_bench.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
     lib.oracle_forest_bench.restype = C.c_uint64
+    u16p = C.POINTER(C.c_uint16)
+    lib.oracle_pandemic_new.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.c_uint32, C.c_uint32]
+    lib.oracle_pandemic_new.restype = vp
+    lib.oracle_pandemic_free.argtypes = [vp]
+    lib.oracle_pandemic_free.restype = None
+    lib.oracle_pandemic_spawn.argtypes = [vp]
+    lib.oracle_pandemic_spawn.restype = None
+    lib.oracle_pandemic_spawn_explicit.argtypes = [vp, C.c_uint64, u16p, u8p]
+    lib.oracle_pandemic_spawn_explicit.restype = None
+    lib.oracle_pandemic_run.argtypes = [vp, C.c_uint64]
+    lib.oracle_pandemic_run.restype = None
+    lib.oracle_pandemic_num_slots.argtypes = [vp]
+    lib.oracle_pandemic_num_slots.restype = C.c_uint64
+    lib.oracle_pandemic_state.argtypes = [vp, u16p, u8p, u8p]
+    lib.oracle_pandemic_state.restype = None
+    lib.oracle_pandemic_counts.argtypes = [vp, u64p]
+    lib.oracle_pandemic_counts.restype = None
     for name, ct in (("u8", C.c_uint8), ("u16", C.c_uint16), ("u32", C.c_uint32), ("u64", C.c_uint64),
                      ("i8", C.c_int8), ("i16", C.c_int16), ("i32", C.c_int32), ("i64", C.c_int64),
                      ("f32", C.c_float), ("f64", C.c_double)):

@@ -8,6 +8,6 @@ from . import _ffi
 from .simulation import *  # noqa: F401,F403
 from .simulation import (Aggregate, BuilderError, Component, DeviceSpawner, EngineError, SamplingError,  # noqa: F401
                          Simulation, SimulationBuilder, SimulationError, Spawner, System, TimeSeries, With, Without,
-                         comm_unique_id)
+                         comm_unique_id, partition_range)
 
 __version__ = "0.1.0"

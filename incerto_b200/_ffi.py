@@ -143,7 +143,8 @@ SYMBOLS = [
     "incerto_sim_grid_position_of", "incerto_sim_grid_in_bounds", "incerto_sim_step_number",
     "incerto_sim_num_entities", "incerto_sim_read_component", "incerto_sim_last_run_stats",
     "incerto_sim_set_profiling", "incerto_sim_kernel_stats", "incerto_sim_flush_l2", "incerto_comm_unique_id",
-    "incerto_sim_attach_comm", "incerto_sim_allreduce_u64", "incerto_sim_allreduce_f64",
+    "incerto_sim_attach_comm", "incerto_sim_allreduce_u64", "incerto_sim_allreduce_f64", "incerto_sim_halo_export",
+    "incerto_sim_halo_import", "incerto_partition_range",
 ]
 
 _lib = None
@@ -212,6 +213,9 @@ def load() -> C.CDLL:
     lib.incerto_sim_attach_comm.argtypes = [vp, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32]
     lib.incerto_sim_allreduce_u64.argtypes = [vp, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32]
     lib.incerto_sim_allreduce_f64.argtypes = [vp, C.POINTER(C.c_double), C.c_uint32, C.c_uint32]
+    lib.incerto_sim_halo_export.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.incerto_sim_halo_import.argtypes = [vp, C.c_uint32, vp, C.c_size_t]
+    lib.incerto_partition_range.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     _lib = lib
     return lib
 

@@ -353,6 +353,17 @@ static int32_t run_spawners(Sim& s, bool first_time)
         }
         (void)dense_device;
     }
+    // tables the forest module adopts from the host spawn data never need their generic columns on the device
+    int forest_pos = -1, forest_cell = -1;
+    for (auto& sys : s.systems)
+        if (sys.kind >= INCERTO_SYS_FOREST_SPREAD && sys.kind <= INCERTO_SYS_FOREST_REGROWTH &&
+            sys.params.size() == sizeof(incerto_forest_params))
+        {
+            incerto_forest_params fp;
+            std::memcpy(&fp, sys.params.data(), sizeof(fp));
+            forest_pos = fp.position;
+            forest_cell = fp.cell;
+        }
     // pass 2: fill
     std::vector<uint64_t> cursor(s.tables.size(), 0);
     for (size_t i = 0; i < s.spawns.size(); ++i)
@@ -373,6 +384,11 @@ static int32_t run_spawners(Sim& s, bool first_time)
             uint64_t n = 0;
             INC_TRY(device_spawn_signature(s, sp, sig, n));
             cursor[ti] += n;
+            continue;
+        }
+        if (!sp.device_kind && forest_pos >= 0 && t.signature.size() == 2 && t.has(forest_pos) && t.has(forest_cell))
+        {
+            cursor[ti] += sp.n; // adopted by forest_bind / forest_reset_after_spawn straight from the host buffers
             continue;
         }
         // generic columns

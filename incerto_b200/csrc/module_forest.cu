@@ -13,16 +13,15 @@ static constexpr size_t kLead = 256; // bytes before column 0 / after the last c
 
 static void forest_partition(const Sim& s, ForestModule& fm)
 {
-    fm.x_begin = static_cast<int32_t>(static_cast<int64_t>(fm.W) * s.part_rank / s.part_world);
-    fm.x_end = static_cast<int32_t>(static_cast<int64_t>(fm.W) * (s.part_rank + 1) / s.part_world);
+    incerto_partition_range(fm.W, s.part_rank, s.part_world, &fm.x_begin, &fm.x_end);
 }
 
 static int owner_rank_of_column(const Sim& s, const ForestModule& fm, int32_t x)
 {
     for (uint32_t r = 0; r < s.part_world; ++r)
     {
-        const int32_t b = static_cast<int32_t>(static_cast<int64_t>(fm.W) * r / s.part_world);
-        const int32_t e = static_cast<int32_t>(static_cast<int64_t>(fm.W) * (r + 1) / s.part_world);
+        int32_t b, e;
+        incerto_partition_range(fm.W, r, s.part_world, &b, &e);
         if (x >= b && x < e) return static_cast<int>(r);
     }
     return -1;
@@ -255,9 +254,16 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     fm.W = grid->bmax[0] + 1;
     fm.H = grid->bmax[1] + 1;
     const uint64_t cells = static_cast<uint64_t>(fm.W) * fm.H;
-    // concatenate the host spawns of this archetype
-    std::vector<int32_t> px, py;
-    std::vector<uint8_t> st;
+    // Walk the host spawns of this archetype in spawn order without copying them: rows [0, cells) must be the
+    // dense x-major grid (forest_fire.rs:239-257), the rest are overlay entities.
+    struct Piece
+    {
+        const uint8_t* pos;
+        const uint8_t* st;
+        uint64_t n;
+    };
+    std::vector<Piece> pieces;
+    uint64_t total = 0;
     for (auto& sp : s.spawns)
     {
         if (sp.device_kind) continue;
@@ -271,50 +277,82 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
             if (s.comps[c.comp].dtype != INCERTO_MARKER) ++ndata;
         }
         if (!pcol || !ccol || ndata != 2) continue;
-        for (uint64_t r = 0; r < sp.n; ++r)
-        {
-            if (pc.dtype == INCERTO_I32)
-            {
-                const int32_t* p = reinterpret_cast<const int32_t*>(pcol->data.data());
-                px.push_back(p[2 * r]);
-                py.push_back(p[2 * r + 1]);
-            }
-            else
-            {
-                const int16_t* p = reinterpret_cast<const int16_t*>(pcol->data.data());
-                px.push_back(p[2 * r]);
-                py.push_back(p[2 * r + 1]);
-            }
-            st.push_back(ccol->data[r]);
-        }
+        pieces.push_back(Piece{pcol->data.data(), ccol->data.data(), sp.n});
+        total += sp.n;
     }
-    if (px.size() != t.n_spawned || px.size() < cells)
+    if (total != t.n_spawned || total < cells)
     {
         set_error("forest: the spawned cells do not cover the %dx%d grid", fm.W, fm.H);
         return INCERTO_ERR_UNSUPPORTED;
     }
-    for (uint64_t i = 0; i < cells; ++i)
-        if (px[i] != static_cast<int32_t>(i / fm.H) || py[i] != static_cast<int32_t>(i % fm.H))
+    const bool wide = pc.dtype == INCERTO_I32;
+    auto pos_at = [&](const Piece& pz, uint64_t r, int32_t& x, int32_t& y) {
+        if (wide)
         {
-            set_error("forest: cells must be spawned in x-major order (for x {for y}) as forest_fire.rs:239-257 does");
-            return INCERTO_ERR_UNSUPPORTED;
+            const int32_t* q = reinterpret_cast<const int32_t*>(pz.pos);
+            x = q[2 * r];
+            y = q[2 * r + 1];
         }
-    for (uint64_t i = 0; i < px.size(); ++i)
+        else
+        {
+            const int16_t* q = reinterpret_cast<const int16_t*>(pz.pos);
+            x = q[2 * r];
+            y = q[2 * r + 1];
+        }
+    };
+    std::vector<uint8_t> st(total);
+    std::vector<int32_t> ov_x, ov_y;
     {
-        if (px[i] < 0 || px[i] >= fm.W || py[i] < 0 || py[i] >= fm.H)
+        uint64_t g = 0; // global row
+        int32_t ex = 0, ey = 0; // expected position of the next dense row
+        for (auto& pz : pieces)
         {
-            set_error("entity at position (%d, %d) outside spatial grid bounds", px[i], py[i]); // spatial_grid.rs:276-279
-            return INCERTO_ERR_OUT_OF_BOUNDS;
+            std::memcpy(st.data() + g, pz.st, pz.n);
+            for (uint64_t r = 0; r < pz.n; ++r, ++g)
+            {
+                int32_t x, y;
+                pos_at(pz, r, x, y);
+                if (g < cells)
+                {
+                    if (x != ex || y != ey)
+                    {
+                        set_error("forest: cells must be spawned in x-major order (for x {for y}) as forest_fire.rs:239-257 does");
+                        return INCERTO_ERR_UNSUPPORTED;
+                    }
+                    if (++ey == fm.H)
+                    {
+                        ey = 0;
+                        ++ex;
+                    }
+                }
+                else
+                {
+                    if (x < 0 || x >= fm.W || y < 0 || y >= fm.H)
+                    {
+                        set_error("entity at position (%d, %d) outside spatial grid bounds", x, y); // spatial_grid.rs:276-279
+                        return INCERTO_ERR_OUT_OF_BOUNDS;
+                    }
+                    ov_x.push_back(x);
+                    ov_y.push_back(y);
+                }
+            }
         }
-        const uint8_t v = st[i];
-        const bool ok = v == INCERTO_CELL_BURNED || v == INCERTO_CELL_HEALTHY || v == INCERTO_CELL_EMPTY || (v >= 1 && v <= 63);
+    }
+    {
+        // state codes: BURNED 0, BURNING 1..63, HEALTHY 0x40, EMPTY 0x80
+        bool ok = true;
+        for (uint64_t i = 0; i < total && ok; ++i)
+        {
+            const uint8_t v = st[i];
+            ok = v <= 63 || v == INCERTO_CELL_HEALTHY || v == INCERTO_CELL_EMPTY;
+        }
         if (!ok)
         {
-            set_error("forest: invalid cell state code 0x%02x", v);
+            set_error("forest: invalid cell state code");
             return INCERTO_ERR_INVALID_ARGUMENT;
         }
     }
-    fm.n_overlay = static_cast<uint32_t>(px.size() - cells);
+    fm.n_overlay = static_cast<uint32_t>(total - cells);
     if (fm.n_overlay > 256)
     {
         set_error("forest: at most 256 overlay entities on top of the dense grid");
@@ -333,8 +371,8 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     std::vector<uint8_t> ovst(std::max<uint32_t>(fm.n_overlay, 1), 0);
     for (uint32_t k = 0; k < fm.n_overlay; ++k)
     {
-        fm.h_ov_pos[2 * k] = static_cast<int16_t>(px[cells + k]);
-        fm.h_ov_pos[2 * k + 1] = static_cast<int16_t>(py[cells + k]);
+        fm.h_ov_pos[2 * k] = static_cast<int16_t>(ov_x[k]);
+        fm.h_ov_pos[2 * k + 1] = static_cast<int16_t>(ov_y[k]);
         ovst[k] = st[cells + k];
     }
     INC_TRY(forest_upload_overlays(s, fm, ovst));
@@ -435,11 +473,7 @@ int32_t forest_halo_exchange(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
     if (s.part_world <= 1) return INCERTO_OK;
-    if (!s.comm)
-    {
-        set_error("row-partitioned forest needs incerto_sim_attach_comm before run");
-        return INCERTO_ERR_COMM;
-    }
+    if (!s.comm) return INCERTO_OK; // manual halo transport: the host moves the columns (incerto_sim_halo_*)
     // `cur` already points at the buffer the step just produced
     uint8_t* slab = fm.d_slab[fm.cur];
     const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
@@ -616,3 +650,55 @@ int32_t forest_stats_now(Sim& s, uint64_t out5[5])
 }
 
 } // namespace incerto
+
+using namespace incerto;
+
+extern "C"
+{
+
+int32_t incerto_partition_range(int32_t width, uint32_t rank, uint32_t world, int32_t* begin, int32_t* end)
+{
+    if (width < 0 || world == 0 || rank >= world || !begin || !end) return INCERTO_ERR_INVALID_ARGUMENT;
+    *begin = static_cast<int32_t>(static_cast<int64_t>(width) * rank / world);
+    *end = static_cast<int32_t>(static_cast<int64_t>(width) * (rank + 1) / world);
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_halo_export(incerto_sim* sp, uint32_t side, void* out, size_t capacity, size_t* n_out)
+{
+    Sim* S = reinterpret_cast<Sim*>(sp);
+    if (!S || side > 1 || !out) return INCERTO_ERR_INVALID_ARGUMENT;
+    ForestModule& fm = S->mods->forest;
+    if (!fm.active) return INCERTO_ERR_UNSUPPORTED;
+    INC_CUDA(cudaSetDevice(S->device));
+    const size_t n = static_cast<size_t>(fm.H) + fm.n_overlay;
+    if (n_out) *n_out = n;
+    if (capacity < n) return INCERTO_ERR_INVALID_ARGUMENT;
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    const uint8_t* col = fm.d_slab[fm.cur] + static_cast<size_t>(side == 0 ? 1 : slab_w) * fm.pitch;
+    INC_CUDA(cudaMemcpyAsync(out, col, fm.H, cudaMemcpyDeviceToHost, S->stream));
+    if (fm.n_overlay)
+        INC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(out) + fm.H, fm.d_ov[fm.cur], fm.n_overlay, cudaMemcpyDeviceToHost, S->stream));
+    INC_CUDA(cudaStreamSynchronize(S->stream));
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_halo_import(incerto_sim* sp, uint32_t side, const void* in, size_t n)
+{
+    Sim* S = reinterpret_cast<Sim*>(sp);
+    if (!S || side > 1 || !in) return INCERTO_ERR_INVALID_ARGUMENT;
+    ForestModule& fm = S->mods->forest;
+    if (!fm.active) return INCERTO_ERR_UNSUPPORTED;
+    INC_CUDA(cudaSetDevice(S->device));
+    if (n != static_cast<size_t>(fm.H) + fm.n_overlay) return INCERTO_ERR_INVALID_ARGUMENT;
+    const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    uint8_t* col = fm.d_slab[fm.cur] + static_cast<size_t>(side == 0 ? 0 : slab_w + 1) * fm.pitch;
+    INC_CUDA(cudaMemcpyAsync(col, in, fm.H, cudaMemcpyHostToDevice, S->stream));
+    if (fm.n_overlay)
+        INC_CUDA(cudaMemcpyAsync(side == 0 ? fm.d_ov_lo : fm.d_ov_hi, static_cast<const uint8_t*>(in) + fm.H, fm.n_overlay,
+                                 cudaMemcpyHostToDevice, S->stream));
+    INC_CUDA(cudaStreamSynchronize(S->stream));
+    return INCERTO_OK;
+}
+
+} // extern "C"

@@ -360,7 +360,7 @@ class SimulationBuilder:
                     if chunks is None:
                         arr[i].data = None
                     else:
-                        a = np.ascontiguousarray(np.concatenate(chunks, axis=0))
+                        a = np.ascontiguousarray(chunks[0] if len(chunks) == 1 else np.concatenate(chunks, axis=0))
                         keep.append(a)
                         arr[i].data = a.ctypes.data_as(C.c_void_p)
                 _check(self._lib.incerto_builder_add_entity_spawner(self._h, n, arr, len(cols)))
@@ -559,6 +559,16 @@ class Simulation:
     def flush_l2(self) -> None:
         _check(self._lib.incerto_sim_flush_l2(self._h))
 
+    def halo_export(self, side: int) -> np.ndarray:
+        n = C.c_size_t()
+        buf = np.zeros(1 << 16, dtype=np.uint8)
+        _check(self._lib.incerto_sim_halo_export(self._h, side, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def halo_import(self, side: int, data: np.ndarray) -> None:
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        _check(self._lib.incerto_sim_halo_import(self._h, side, d.ctypes.data_as(C.c_void_p), d.nbytes))
+
     def attach_comm(self, unique_id: bytes, rank: int, world: int) -> None:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _check(self._lib.incerto_sim_attach_comm(self._h, buf, rank, world))
@@ -572,6 +582,12 @@ class Simulation:
         v = np.ascontiguousarray(values, dtype=np.float64)
         _check(self._lib.incerto_sim_allreduce_f64(self._h, v.ctypes.data_as(C.POINTER(C.c_double)), v.size, op))
         return v
+
+
+def partition_range(width: int, rank: int, world: int) -> tuple[int, int]:
+    b, e = C.c_int32(), C.c_int32()
+    _check(F.load().incerto_partition_range(width, rank, world, C.byref(b), C.byref(e)))
+    return b.value, e.value
 
 
 def comm_unique_id() -> bytes:

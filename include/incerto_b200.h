@@ -502,6 +502,15 @@ int32_t incerto_sim_flush_l2(incerto_sim* s);
  * forest-fire halo exchange and for cross-replica aggregate reductions. */
 int32_t incerto_comm_unique_id(uint8_t out[128]);
 int32_t incerto_sim_attach_comm(incerto_sim* s, const uint8_t unique_id[128], uint32_t rank, uint32_t world);
+/* Manual halo transport for the row-partitioned forest (any host transport instead of NCCL; also how
+ * the partition is tested on a single GPU).  When no communicator is attached, `run` leaves the halo
+ * columns alone and the host moves them between steps: export the boundary of side 0 (lowest owned
+ * column) / 1 (highest) — H cell bytes followed by the overlay-entity states — and import it into the
+ * neighbour's halo of the opposite side. */
+int32_t incerto_sim_halo_export(incerto_sim* s, uint32_t side, void* out, size_t capacity, size_t* n_out);
+int32_t incerto_sim_halo_import(incerto_sim* s, uint32_t side, const void* in, size_t n);
+/* Columns [begin, end) of a W-column grid owned by `rank` of `world` (pure host arithmetic). */
+int32_t incerto_partition_range(int32_t width, uint32_t rank, uint32_t world, int32_t* begin, int32_t* end);
 /* All-reduce `n` u64 (sum) / f64 (sum, min, max) values in place across the
  * attached communicator: cross-replica aggregate statistics. op: 0 sum, 1 min, 2 max. */
 int32_t incerto_sim_allreduce_u64(incerto_sim* s, uint64_t* values, uint32_t n, uint32_t op);

@@ -58,6 +58,9 @@ extern "C" {
     pub fn incerto_sim_flush_l2(s: *mut incerto_sim) -> i32;
     pub fn incerto_comm_unique_id(out: *mut u8) -> i32;
     pub fn incerto_sim_attach_comm(s: *mut incerto_sim, unique_id: *const u8, rank: u32, world: u32) -> i32;
+    pub fn incerto_sim_halo_export(s: *mut incerto_sim, side: u32, out: *mut c_void, capacity: usize, n_out: *mut usize) -> i32;
+    pub fn incerto_sim_halo_import(s: *mut incerto_sim, side: u32, input: *const c_void, n: usize) -> i32;
+    pub fn incerto_partition_range(width: i32, rank: u32, world: u32, begin: *mut i32, end: *mut i32) -> i32;
     pub fn incerto_sim_allreduce_u64(s: *mut incerto_sim, values: *mut u64, n: u32, op: u32) -> i32;
     pub fn incerto_sim_allreduce_f64(s: *mut incerto_sim, values: *mut f64, n: u32, op: u32) -> i32;
 }

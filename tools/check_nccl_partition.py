@@ -1,0 +1,42 @@
+"""Run under torchrun: row-partitioned forest over NCCL (real halo exchange) vs the CPU oracle."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import incerto_b200 as ib
+from incerto_b200 import _ffi as F
+from incerto_b200 import dist as D
+from oracle.forest import ForestOracle
+
+SEED = 0x1CE27002025
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+W, H, steps = 64 * world, 96, 80
+b = ib.SimulationBuilder(seed=SEED, device=local)
+pos = b.component("GridPosition2D", F.I16, lanes=2)
+cell = b.component("ForestCell.state", F.U8)
+b.set_row_partition(rank, world)
+b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
+b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_FOREST_GRID, F.SpawnForestParams(pos.handle, cell.handle, W, H, 0.85, 3, 6)))
+b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.004))
+b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
+sim = b.build()
+sim.attach_comm(D.share_unique_id(dist, ib.comm_unique_id, rank), rank, world)
+sim.run(steps)
+o = ForestOracle(SEED, 0, W, H, density=0.85, p_regrow=0.004, fires=6).spawn().run(steps)
+want = o.cells()[0]
+xb, xe = ib.partition_range(W, rank, world)
+got = sim.read_component(cell)[:(xe - xb) * H]
+ok = np.array_equal(got, want[xb * H:xe * H])
+fs = sim.sample_aggregate(ib.FireStatsOf(cell))          # all-reduced over the communicator
+stats_ok = (fs.healthy_count, fs.burning_count, fs.burned_count, fs.empty_count, fs.total_cells) == tuple(int(v) for v in o.stats())
+ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
+series_ok = np.array_equal(np.array([(v.healthy_count, v.burning_count, v.burned_count, v.empty_count, v.total_cells) for v in ts.values()], dtype=np.uint64), o.series())
+print(f"rank {rank}/{world}: slab parity {ok}, all-reduced stats {stats_ok}, series {series_ok}, burned {int(o.stats()[2])}", flush=True)
+flag = torch.tensor([int(ok and stats_ok and series_ok)], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)

@@ -24,6 +24,8 @@ SOURCES = [
     "module_forest.cu",
     "module_pandemic.cu",
     "kernels_pandemic.cu",
+    "module_air.cu",
+    "kernels_air.cu",
     "comm.cu",
     "kernels_generic.cu",
     "kernels_coin.cu",

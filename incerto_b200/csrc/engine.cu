@@ -40,6 +40,7 @@ Sim::~Sim()
     if (stream) cudaStreamSynchronize(stream);
     forest_free(*this);
     pandemic_free(*this);
+    air_free(*this);
     comm_free(*this);
     for (auto& t : tables)
     {
@@ -62,6 +63,8 @@ Sim::~Sim()
         cudaFree(g.d_cell_start);
         cudaFree(g.d_cursor);
         cudaFree(g.d_sorted_rows);
+        cudaFree(g.d_snap_pos);
+        cudaFree(g.d_snap_flags);
     }
     cudaFree(d_scratch);
     cudaFree(d_ticket);
@@ -292,6 +295,18 @@ static int32_t device_spawn_signature(Sim& s, const HostSpawn& sp, std::vector<i
         n = p.initial_population;
         return INCERTO_OK;
     }
+    case INCERTO_SPAWN_AIRCRAFT:
+    {
+        if (sp.params.size() != sizeof(incerto_spawn_aircraft_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_spawn_aircraft_params p;
+        std::memcpy(&p, sp.params.data(), sizeof(p));
+        auto bad = [&](int c) { return c < 0 || c >= static_cast<int>(s.comps.size()); };
+        if (bad(p.position) || bad(p.target_altitude)) return INCERTO_ERR_INVALID_ARGUMENT;
+        sig = {p.position, p.target_altitude};
+        std::sort(sig.begin(), sig.end());
+        n = p.num_aircraft;
+        return INCERTO_OK;
+    }
     default:
         set_error("device spawner kind %u is not implemented", sp.kind);
         return INCERTO_ERR_UNSUPPORTED;
@@ -410,6 +425,12 @@ static int32_t run_spawners(Sim& s, bool first_time)
             if (sp.kind == INCERTO_SPAWN_PANDEMIC_PEOPLE)
             {
                 INC_TRY(pandemic_spawn_device(s, sp, t, off));
+                cursor[ti] += n;
+                continue;
+            }
+            if (sp.kind == INCERTO_SPAWN_AIRCRAFT)
+            {
+                INC_TRY(air_spawn_device(s, sp, t, off));
                 cursor[ti] += n;
                 continue;
             }
@@ -626,6 +647,19 @@ static int32_t bind_generic_systems(Sim& s)
             }
             break;
         }
+        case INCERTO_SYS_AIR_CHECK_CONFLICTS:
+        case INCERTO_SYS_AIR_MOVE:
+        {
+            if (!s.mods->air.active)
+            {
+                INC_TRY(air_bind(s));
+                StepOp op;
+                op.name = "air_step";
+                op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return air_step(sim, first_step, nsteps); };
+                prog.push_back(op);
+            }
+            break;
+        }
         default:
             set_error("system kind %u is not implemented in this build", sys.kind);
             return INCERTO_ERR_UNSUPPORTED;
@@ -640,7 +674,7 @@ int32_t series_sample_step(Sim& s, uint64_t step);
 void series_after_run(Sim& s);
 void series_clear(Sim& s);
 int32_t grids_allocate(Sim& s);
-int32_t grids_rebuild_for_step(Sim& s, uint64_t step);
+int32_t grids_rebuild_for_step(Sim& s, uint64_t step, bool last_of_run);
 
 static int32_t do_run(Sim& s, uint64_t num_steps)
 {
@@ -690,7 +724,7 @@ static int32_t do_run(Sim& s, uint64_t num_steps)
                 k = std::min<uint64_t>(k, next - s.step + 1);
             }
         }
-        INC_TRY(grids_rebuild_for_step(s, s.step));
+        INC_TRY(grids_rebuild_for_step(s, s.step, remaining == k));
         for (auto& op : prog) INC_TRY(op.fn(s, s.step, static_cast<uint32_t>(k)));
         s.step += k - 1;
         INC_TRY(series_sample_step(s, s.step)); // PostUpdate (time_series.rs:100,175-178)
@@ -1001,7 +1035,12 @@ int32_t incerto_sim_reset(incerto_sim* s, uint32_t replica)
     INC_TRY(run_spawners(S, false));
     if (S.mods->forest.active) INC_TRY(forest_reset_after_spawn(S));
     if (S.mods->pandemic.active) INC_TRY(pandemic_reset(S));
-    for (auto& g : S.grids) g.built_step = ~0ull;
+    if (S.mods->air.active) INC_TRY(air_reset(S));
+    for (auto& g : S.grids)
+    {
+        g.built_step = ~0ull;
+        g.snap_valid = g.snap_built = false;
+    }
     INC_CUDA(cudaStreamSynchronize(S.stream));
     return INCERTO_OK;
 }

@@ -188,7 +188,13 @@ struct GridInst
     uint64_t cap_rows = 0;
     uint64_t built_step = ~0ull;
     uint64_t n_indexed = 0;
-    bool needed_by_kernels = false; // rebuilt every step only when a system consumes it
+    // lazy: the dense table is not rebuilt every step (huge / sparse grids whose consumers keep their own
+    // index); the positions seen by the last PreUpdate are snapshotted and the table is built when queried
+    bool lazy = false;
+    void* d_snap_pos = nullptr;
+    uint8_t* d_snap_flags = nullptr;
+    uint64_t snap_n = 0;
+    bool snap_valid = false, snap_built = false;
 };
 
 struct KernelStat

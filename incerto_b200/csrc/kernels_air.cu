@@ -1,0 +1,224 @@
+// air_traffic_3d: examples/air_traffic_3d.rs
+//   spawn_aircraft  :61-90
+//   move_aircraft   :93-121
+//   check_conflicts :124-162  (SpatialGrid3D::neighbors_of, src/plugins/spatial_grid.rs:331-350)
+// Pinned order: check_conflicts -> move_aircraft.  The grid the reference queries is the
+// PreUpdate snapshot (positions at the start of the step), and with this order the positions the
+// distance test reads are the same ones, so `length_squared <= 1` over the 26 neighbour cells (centre
+// excluded) selects exactly the aircraft in the 6 face-neighbour cells.
+//
+// Device layout: GridPosition3D = int16 x, y, z + one pad lane (8 B), target_altitude int16 (2 B).
+// Algorithmic bytes per aircraft-update: 18 (position 8 r + 8 w, target 2 r).
+//
+// The airspace is sparse (reference density 15 / 4000 cells), so the reference's HashMap<pos, HashSet>
+// becomes a device hash table of per-cell occupancy counts rebuilt every step (no dense cell table):
+// open addressing, 64-bit slots tag:8 | key:32 | count:24.  The tag changes every step, which makes last
+// step's entries read as empty: the table is only cleared when the tag wraps (every 255 steps).
+//
+// Draw contract:
+//   spawn  aircraft uid: a = philox(key[ASPW], (uid,0,0,0)), b = philox(key[ASPW], (uid,0,0,1));
+//          x = mulhi(a.x,SIZE), y = mulhi(a.y,SIZE), z = mulhi(a.z,HEIGHT), type = mulhi(a.w,3), target = mulhi(b.x,HEIGHT)
+//   move   r = philox(key[AMOV], (uid,0,step,0)); horizontal = r.x < thr(0.7); dx = mulhi(r.y,3)-1; dy = mulhi(r.z,3)-1
+#include "../../include/incerto_b200.h"
+#include "common.cuh"
+#include "kernels_air.hpp"
+
+namespace incerto
+{
+namespace
+{
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int lane16(uint32_t w, int hi) { return static_cast<int16_t>(hi ? (w >> 16) : (w & 0xffffu)); }
+
+__device__ __forceinline__ uint32_t slot_of(const AirArgs& a, uint32_t key)
+{
+    return (key * 0x9E3779B1u) >> a.slot_shift;
+}
+
+__device__ __forceinline__ void index_insert(const AirArgs& a, uint32_t key)
+{
+    uint32_t h = slot_of(a, key);
+    const unsigned long long fresh = (static_cast<unsigned long long>(a.tag) << 56) | (static_cast<unsigned long long>(key) << 24) | 1ull;
+    for (uint32_t guard = 0; guard <= a.slot_mask; )
+    {
+        const unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&a.slots[h]);
+        if (static_cast<uint32_t>(old >> 56) != a.tag)
+        {
+            if (atomicCAS(&a.slots[h], old, fresh) == old) return;
+            continue; // somebody claimed the slot first: look at it again
+        }
+        if (static_cast<uint32_t>(old >> 24) == key)
+        {
+            atomicAdd(&a.slots[h], 1ull);
+            return;
+        }
+        h = (h + 1) & a.slot_mask;
+        ++guard;
+    }
+}
+
+__device__ __forceinline__ uint32_t index_count(const AirArgs& a, uint32_t key)
+{
+    uint32_t h = slot_of(a, key);
+    for (uint32_t guard = 0; guard <= a.slot_mask; ++guard)
+    {
+        const unsigned long long s = a.slots[h];
+        if (static_cast<uint32_t>(s >> 56) != a.tag) return 0;
+        if (static_cast<uint32_t>(s >> 24) == key) return static_cast<uint32_t>(s) & 0x00ffffffu;
+        h = (h + 1) & a.slot_mask;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(kThreads) air_spawn_kernel(AirArgs a, int16_t* target_out, uint8_t* flags_out)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride)
+    {
+        const uint4 r = philox4x32_10(static_cast<uint32_t>(i), 0u, 0u, 0u, a.rk_spawn);
+        const uint4 q = philox4x32_10(static_cast<uint32_t>(i), 0u, 0u, 1u, a.rk_spawn);
+        const uint32_t x = uniform_below(r.x, a.size), y = uniform_below(r.y, a.size), z = uniform_below(r.z, a.height);
+        a.pos[i] = make_uint2(x | (y << 16), z);
+        target_out[i] = static_cast<int16_t>(uniform_below(q.x, a.height));
+        flags_out[i] = 1u;
+    }
+}
+
+// PreUpdate: spatial_grid_update_system (spatial_grid.rs:434-443) as a full rebuild of the occupancy index
+__global__ void __launch_bounds__(kThreads) air_index_kernel(AirArgs a)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (first == 0)
+    {
+        a.acc[0] = 0;
+        a.acc[1] = 0;
+    }
+    for (uint64_t i = first; i < a.n; i += gstride)
+    {
+        if (a.flags && !(a.flags[i] & 1u)) continue;
+        const uint2 p = a.pos[i];
+        const int x = lane16(p.x, 0) - a.bmin[0], y = lane16(p.x, 1) - a.bmin[1], z = lane16(p.y, 0) - a.bmin[2];
+        if (x < 0 || x >= a.ext[0] || y < 0 || y >= a.ext[1] || z < 0 || z >= a.ext[2])
+        {
+            // "entity at position {position:?} outside spatial grid bounds" (spatial_grid.rs:276-279)
+            if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u)
+                a.error[1] = static_cast<uint32_t>(i);
+            continue;
+        }
+        index_insert(a, (static_cast<uint32_t>(x) * a.ext[1] + static_cast<uint32_t>(y)) * a.ext[2] + static_cast<uint32_t>(z));
+    }
+}
+
+// check_conflicts + move_aircraft; one thread = 2 consecutive rows (one 128-bit position load/store)
+__global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
+{
+    const uint64_t npairs = (a.n + 1) >> 1;
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    uint32_t conflicts = 0, indexed = 0;
+    for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < npairs; q += gstride)
+    {
+        const uint64_t row0 = q * 2;
+        const bool full = row0 + 2 <= a.n;
+        uint2 p[2];
+        uint32_t t2;
+        if (full)
+        {
+            const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
+            p[0] = make_uint2(v.x, v.y);
+            p[1] = make_uint2(v.z, v.w);
+            t2 = *reinterpret_cast<const uint32_t*>(a.target + row0);
+        }
+        else
+        {
+            p[0] = a.pos[row0];
+            p[1] = p[0];
+            t2 = static_cast<uint16_t>(a.target[row0]);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            if (k == 1 && !full) break;
+            const uint64_t row = row0 + k;
+            if (a.flags && !(a.flags[row] & 1u)) continue;
+            int x = lane16(p[k].x, 0), y = lane16(p[k].x, 1), z = lane16(p[k].y, 0);
+            if (a.do_check)
+            {
+                // neighbors_of filters the neighbour cells by the grid bounds (:337-340); aircraft outside
+                // the bounds were already reported by the index kernel
+                const int gx = x - a.bmin[0], gy = y - a.bmin[1], gz = z - a.bmin[2];
+                if (gx >= 0 && gx < a.ext[0] && gy >= 0 && gy < a.ext[1] && gz >= 0 && gz < a.ext[2])
+                {
+                    const uint32_t key = (static_cast<uint32_t>(gx) * a.ext[1] + static_cast<uint32_t>(gy)) * a.ext[2] + static_cast<uint32_t>(gz);
+                    const uint32_t sx = static_cast<uint32_t>(a.ext[1]) * a.ext[2], sy = a.ext[2];
+                    if (gx > 0) conflicts += index_count(a, key - sx);
+                    if (gx < a.ext[0] - 1) conflicts += index_count(a, key + sx);
+                    if (gy > 0) conflicts += index_count(a, key - sy);
+                    if (gy < a.ext[1] - 1) conflicts += index_count(a, key + sy);
+                    if (gz > 0) conflicts += index_count(a, key - 1);
+                    if (gz < a.ext[2] - 1) conflicts += index_count(a, key + 1);
+                    indexed += 1;
+                }
+            }
+            if (a.do_move)
+            {
+                const int target = lane16(t2, k);
+                // :98-105 one altitude level towards the target
+                z += (z < target) ? 1 : ((z > target) ? -1 : 0);
+                const uint32_t uid = a.uid ? a.uid[row] : static_cast<uint32_t>(row);
+                const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_move);
+                if (bernoulli(r.x, a.thr_move)) // :108
+                {
+                    const int dx = static_cast<int>(uniform_below(r.y, 3u)) - 1, dy = static_cast<int>(uniform_below(r.z, 3u)) - 1;
+                    x = min(max(x + dx, 0), a.size - 1); // :113-114 clamp(0, AIRSPACE_SIZE - 1)
+                    y = min(max(y + dy, 0), a.size - 1);
+                }
+                p[k] = make_uint2((static_cast<uint32_t>(x) & 0xffffu) | (static_cast<uint32_t>(y) << 16),
+                                  (static_cast<uint32_t>(z) & 0xffffu) | (p[k].y & 0xffff0000u));
+            }
+        }
+        if (a.do_move)
+        {
+            if (full)
+                *reinterpret_cast<uint4*>(a.pos + row0) = make_uint4(p[0].x, p[0].y, p[1].x, p[1].y);
+            else
+                a.pos[row0] = p[0];
+        }
+    }
+    if (a.do_check)
+    {
+        uint32_t v[2] = {conflicts, indexed};
+        __shared__ uint32_t smem[64];
+        block_sum<uint32_t, 2>(v, smem);
+        if (threadIdx.x == 0)
+        {
+            if (v[0]) atomicAdd(reinterpret_cast<unsigned long long*>(&a.acc[0]), static_cast<unsigned long long>(v[0]));
+            if (v[1]) atomicAdd(reinterpret_cast<unsigned long long*>(&a.acc[1]), static_cast<unsigned long long>(v[1]));
+        }
+    }
+}
+
+inline int blocks_for(uint64_t items)
+{
+    uint64_t b = (items + kThreads - 1) / kThreads;
+    const uint64_t cap = static_cast<uint64_t>(kNumSMs) * 8 * 2;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+} // namespace
+
+void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out, cudaStream_t st)
+{
+    air_spawn_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a, target_out, flags_out);
+}
+void launch_air_index(const AirArgs& a, cudaStream_t st) { air_index_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
+void launch_air_step(const AirArgs& a, cudaStream_t st)
+{
+    air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);
+}
+
+} // namespace incerto

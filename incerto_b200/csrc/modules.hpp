@@ -67,6 +67,20 @@ struct PandemicModule
     uint32_t* d_next = nullptr;
 };
 
+struct AirModule
+{
+    bool active = false;
+    int table = -1;
+    int comp_pos = -1, comp_target = -1;
+    int32_t size = 0, height = 0;
+    bool do_check = false, do_move = false;
+    double p_move = 0.7;
+    int grid = -1;                        // SpatialGrid3D<Aircraft> the conflict check reads
+    unsigned long long* d_slots = nullptr; // per-step occupancy hash (kernels_air.cu)
+    uint32_t n_slots = 0, slot_bits = 0;
+    uint64_t* d_acc = nullptr;            // [0] conflicts of the last step (pairs counted twice), [1] aircraft indexed
+};
+
 struct CoinModule
 {
     bool active = false;
@@ -80,6 +94,7 @@ struct Sim::Modules
     ForestModule forest;
     CoinModule coin;
     PandemicModule pandemic;
+    AirModule air;
     std::vector<StepOp> program;
     uint32_t* d_step = nullptr; // device mirror of StepNumber
 };
@@ -101,6 +116,13 @@ int32_t pandemic_step(Sim& s, uint64_t first_step, uint32_t nsteps);
 int32_t pandemic_spawn_device(Sim& s, const HostSpawn& sp, Table& t, uint64_t row_offset);
 void pandemic_free(Sim& s);
 int32_t pandemic_reset(Sim& s);
+
+// module_air.cu
+int32_t air_bind(Sim& s);
+int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps);
+int32_t air_spawn_device(Sim& s, const HostSpawn& sp, Table& t, uint64_t row_offset);
+void air_free(Sim& s);
+int32_t air_reset(Sim& s);
 
 // comm.cpp
 int32_t comm_unique_id(uint8_t out[128]);

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 
 #include "kernels_grid.hpp"
 #include "modules.hpp"
@@ -154,6 +155,17 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
         g.rec.count = t.n;
         INC_CUDA(cudaMemcpyAsync(d_raw, &g, sizeof(g), cudaMemcpyHostToDevice, s.stream));
         INC_CUDA(cudaStreamSynchronize(s.stream));
+        return INCERTO_OK;
+    }
+    if (a.kind == INCERTO_AGG_AIR_CONFLICTS)
+    {
+        AirModule& am = s.mods->air;
+        if (!am.active || am.table != ti || !am.d_acc)
+        {
+            set_error("AIR_CONFLICTS needs the check_conflicts system on this component's table");
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+        INC_CUDA(cudaMemcpyAsync(d_raw, am.d_acc, 16, cudaMemcpyDeviceToDevice, s.stream));
         return INCERTO_OK;
     }
     if (a.kind == INCERTO_AGG_COIN_ODDS)
@@ -419,6 +431,21 @@ static int32_t aggregate_finalize(const Sim& s, const AggSpec& a, const uint8_t*
         store_as<double>(out, sum / static_cast<double>(cnt)); // coin_toss.rs:48
         return INCERTO_OK;
     }
+    if (a.kind == INCERTO_AGG_AIR_CONFLICTS)
+    {
+        uint64_t twice = 0, indexed = 0;
+        for (size_t i = 0; i < n_raws; ++i)
+        {
+            uint64_t v[2];
+            std::memcpy(v, raws + i * 16, 16);
+            twice += v[0];
+            indexed += v[1];
+        }
+        if (count_out) *count_out = indexed;
+        if (!indexed) return INCERTO_ERR_AGGREGATE_NO_ENTITIES;
+        store_as<uint64_t>(out, twice / 2); // "Divide by 2 since each conflict is counted twice", air_traffic_3d.rs:160
+        return INCERTO_OK;
+    }
     if (a.kind == INCERTO_AGG_FIRE_STATS)
     {
         incerto_fire_stats fs;
@@ -520,7 +547,7 @@ int32_t series_sample_step(Sim& s, uint64_t step)
         const size_t rs = raw_size(se.agg.kind);
         INC_TRY(aggregate_launch(s, se.agg, tabs[0], se.d_values + slot * rs));
         // count: first u64 of GenericRaw; second u64 of coin odds
-        const size_t count_off = is_generic_kind(se.agg.kind) ? 0 : (se.agg.kind == INCERTO_AGG_COIN_ODDS ? 8 : 32);
+        const size_t count_off = is_generic_kind(se.agg.kind) ? 0 : ((se.agg.kind == INCERTO_AGG_COIN_ODDS || se.agg.kind == INCERTO_AGG_AIR_CONFLICTS) ? 8 : 32);
         INC_CUDA(cudaMemcpyAsync(se.d_counts + slot, se.d_values + slot * rs + count_off, 8, cudaMemcpyDeviceToDevice,
                                  s.stream));
         se.n_slots = std::max(se.n_slots, slot + 1);
@@ -595,6 +622,15 @@ static int32_t series_materialize(Sim& s, SeriesInst& se)
 }
 
 // -------------------------------------------------------------------- grids
+static int32_t grid_alloc_dense(GridInst& g)
+{
+    if (g.d_cell_start) return INCERTO_OK;
+    INC_CUDA(cudaMalloc(&g.d_cell_start, (g.n_cells + 1) * 4));
+    INC_CUDA(cudaMalloc(&g.d_cursor, g.n_cells * 4));
+    INC_CUDA(cudaMalloc(&g.d_sorted_rows, std::max<uint64_t>(g.cap_rows, 1) * 4));
+    return INCERTO_OK;
+}
+
 int32_t grids_allocate(Sim& s)
 {
     for (auto& g : s.grids)
@@ -621,10 +657,11 @@ int32_t grids_allocate(Sim& s)
             return INCERTO_ERR_UNSUPPORTED;
         }
         g.n_cells = cells;
-        INC_CUDA(cudaMalloc(&g.d_cell_start, (cells + 1) * 4));
-        INC_CUDA(cudaMalloc(&g.d_cursor, cells * 4));
         g.cap_rows = s.tables[g.table].n;
-        INC_CUDA(cudaMalloc(&g.d_sorted_rows, std::max<uint64_t>(g.cap_rows, 1) * 4));
+        if (const char* e = std::getenv("INCERTO_B200_GRID_LAZY_CELLS"))
+            if (cells >= std::strtoull(e, nullptr, 10)) g.lazy = true;
+        if (cells > (1ull << 27)) g.lazy = true; // >= 1.5 GB of cell tables: build on demand only
+        if (!g.lazy) INC_TRY(grid_alloc_dense(g));
     }
     return INCERTO_OK;
 }
@@ -641,14 +678,32 @@ static GridDesc grid_desc(const GridInst& g)
     return d;
 }
 
-static int32_t grid_rebuild(Sim& s, GridInst& g, uint64_t step)
+static int32_t grid_rebuild(Sim& s, GridInst& g, uint64_t step, bool last_of_run)
 {
-    if (g.table < 0 || !g.d_cell_start) return INCERTO_OK;
+    if (g.table < 0 || g.n_cells == 0) return INCERTO_OK;
     Table& t = s.tables[g.table];
     FilterSpec f;
     f.with.push_back(g.component);
     RowFilter rf = row_filter(s, t, f);
     Column* pc = t.col(g.position);
+    if (g.lazy)
+    {
+        // only what a host query after this run can observe is kept: the positions at the last PreUpdate
+        if (!last_of_run) return INCERTO_OK;
+        if (!g.d_snap_pos)
+        {
+            INC_CUDA(cudaMalloc(&g.d_snap_pos, std::max<uint64_t>(g.cap_rows, 1) * pc->row_bytes));
+            INC_CUDA(cudaMalloc(&g.d_snap_flags, std::max<uint64_t>(g.cap_rows, 1)));
+        }
+        KTimer kt(s, "grid_snapshot", 2.0 * t.n * (pc->row_bytes + 1));
+        INC_CUDA(cudaMemcpyAsync(g.d_snap_pos, pc->d, t.n * pc->row_bytes, cudaMemcpyDeviceToDevice, s.stream));
+        INC_CUDA(cudaMemcpyAsync(g.d_snap_flags, t.d_flags, t.n, cudaMemcpyDeviceToDevice, s.stream));
+        g.snap_n = t.n;
+        g.snap_valid = true;
+        g.snap_built = false;
+        g.built_step = step;
+        return INCERTO_OK;
+    }
     INC_TRY(ensure_scratch(s, scan_scratch_bytes(g.n_cells) + 256));
     KTimer kt(s, "grid_build", 16.0 * t.n + 12.0 * g.n_cells);
     launch_grid_build(grid_desc(g), static_cast<const int16_t*>(pc->d), s.comps[g.position].stride(),
@@ -659,11 +714,30 @@ static int32_t grid_rebuild(Sim& s, GridInst& g, uint64_t step)
     return INCERTO_OK;
 }
 
-int32_t grids_rebuild_for_step(Sim& s, uint64_t step)
+// host query on a lazy grid: build the dense table from the snapshot of the last PreUpdate
+static int32_t grid_ensure_built(Sim& s, GridInst& g)
+{
+    if (!g.lazy || !g.snap_valid || g.snap_built) return INCERTO_OK;
+    INC_TRY(grid_alloc_dense(g));
+    FilterSpec f;
+    f.with.push_back(g.component);
+    RowFilter rf = row_filter(s, s.tables[g.table], f);
+    INC_TRY(ensure_scratch(s, scan_scratch_bytes(g.n_cells) + 256));
+    KTimer kt(s, "grid_build", 16.0 * g.snap_n + 12.0 * g.n_cells);
+    launch_grid_build(grid_desc(g), static_cast<const int16_t*>(g.d_snap_pos), s.comps[g.position].stride(),
+                      g.d_snap_flags, rf.need_set, g.snap_n, g.d_cell_start, g.d_cursor, g.d_sorted_rows,
+                      reinterpret_cast<uint32_t*>(s.d_scratch), s.d_error, s.stream);
+    INC_CUDA(cudaGetLastError());
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    g.snap_built = true;
+    return INCERTO_OK;
+}
+
+int32_t grids_rebuild_for_step(Sim& s, uint64_t step, bool last_of_run)
 {
     // PreUpdate maintenance (spatial_grid.rs:418-425): the index seen during
     // step k holds the positions as of the end of step k-1.
-    for (auto& g : s.grids) INC_TRY(grid_rebuild(s, g, step));
+    for (auto& g : s.grids) INC_TRY(grid_rebuild(s, g, step, last_of_run));
     return INCERTO_OK;
 }
 
@@ -1176,6 +1250,7 @@ static int32_t grid_cell_uids(Sim& S, GridInst& g, const int32_t* pos, std::vect
                 out.push_back(static_cast<uint64_t>(fm.W) * fm.H + q);
         return INCERTO_OK;
     }
+    INC_TRY(grid_ensure_built(S, g));
     if (g.table < 0 || !g.d_cell_start || g.built_step == ~0ull) return INCERTO_OK;
     GridDesc d = grid_desc(g);
     const uint64_t key = grid_cell_key(d, pos[0], pos[1], g.dim == 3 ? pos[2] : 0);
@@ -1287,6 +1362,7 @@ int32_t incerto_sim_grid_num_entities(incerto_sim* s, incerto_grid g, uint64_t* 
         *out = S.step > 1 ? S.tables[G->table].n : 0;
         return INCERTO_OK;
     }
+    INC_TRY(grid_ensure_built(S, *G));
     if (G->table < 0 || !G->d_cell_start || G->built_step == ~0ull) return INCERTO_OK;
     uint32_t total = 0;
     INC_CUDA(cudaMemcpy(&total, G->d_cell_start + G->n_cells, 4, cudaMemcpyDeviceToHost));

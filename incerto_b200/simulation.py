@@ -155,6 +155,7 @@ def Percentile(c, p: int): return Aggregate(c, F.AGG_PERCENTILE, percentile=p)  
 def CoinOdds(heads, tosses): return Aggregate(heads, F.AGG_COIN_ODDS, component2=tosses)   # coin_toss.rs:33-49
 def FireStatsOf(cell): return Aggregate(cell, F.AGG_FIRE_STATS)                          # forest_fire.rs:104-134
 def PandemicStatsOf(c, initial_population): return Aggregate(c, F.AGG_PANDEMIC_STATS, param=initial_population)
+def AirConflicts(c): return Aggregate(c, F.AGG_AIR_CONFLICTS)   # `conflicts / 2` of the last step, air_traffic_3d.rs:130-161
 
 
 # ------------------------------------------------------------------ systems
@@ -209,6 +210,17 @@ def PeopleInfectedMayDie(person, position, infected, grid_size: int, chance: flo
 
 def PeopleInfectedMayRecover(person, position, infected, grid_size: int, chance: float) -> System:
     return System(F.SYS_PANDEMIC_RECOVER, F.PandemicParams(person.handle, position.handle, infected.handle, grid_size, chance))
+
+
+# examples/air_traffic_3d.rs:93-162
+def CheckConflicts(position, target_altitude, airspace_size: int, airspace_height: int) -> System:
+    return System(F.SYS_AIR_CHECK_CONFLICTS, F.AirParams(position.handle, target_altitude.handle, airspace_size,
+                                                         airspace_height, 0.0))
+
+
+def MoveAircraft(position, target_altitude, airspace_size: int, airspace_height: int, chance_horizontal_move: float = 0.7) -> System:
+    return System(F.SYS_AIR_MOVE, F.AirParams(position.handle, target_altitude.handle, airspace_size, airspace_height,
+                                              chance_horizontal_move))
 
 
 @dataclass

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <thread>
 
+#include "air_traffic.hpp"
 #include "coin_toss.hpp"
 #include "forest_fire.hpp"
 #include "library.hpp"
@@ -181,6 +182,57 @@ void oracle_pandemic_state(void* h, uint16_t* xy, uint8_t* alive, uint8_t* infec
     }
 }
 void oracle_pandemic_counts(void* h, uint64_t out3[3]) { static_cast<PandemicSim*>(h)->counts(out3); }
+
+
+// ------------------------------------------------------------ air_traffic_3d
+void* oracle_air_new(uint64_t seed, uint32_t replica, uint64_t n, int32_t size, int32_t height, double p_move,
+                     uint32_t systems_mask /* 1 check_conflicts, 2 move */)
+{
+    AirParams p;
+    p.num_aircraft = n;
+    p.airspace_size = size;
+    p.airspace_height = height;
+    p.chance_horizontal_move = p_move;
+    p.check = systems_mask & 1;
+    p.move = systems_mask & 2;
+    return new AirSim(p, seed, replica);
+}
+void oracle_air_free(void* h) { delete static_cast<AirSim*>(h); }
+void oracle_air_spawn(void* h) { static_cast<AirSim*>(h)->spawn_aircraft(); }
+void oracle_air_spawn_explicit(void* h, uint64_t n, const int32_t* xyz, const int32_t* target)
+{
+    static_cast<AirSim*>(h)->spawn_explicit(n, xyz, target);
+}
+int oracle_air_run(void* h, uint64_t steps)
+{
+    try
+    {
+        static_cast<AirSim*>(h)->run(steps);
+    }
+    catch (const std::out_of_range&)
+    {
+        return 34;
+    }
+    return 0;
+}
+uint64_t oracle_air_num(void* h) { return static_cast<AirSim*>(h)->position.size(); }
+void oracle_air_state(void* h, int32_t* xyz, int32_t* target)
+{
+    AirSim& s = *static_cast<AirSim*>(h);
+    for (size_t i = 0; i < s.position.size(); ++i)
+    {
+        xyz[3 * i] = s.position[i].x;
+        xyz[3 * i + 1] = s.position[i].y;
+        xyz[3 * i + 2] = s.position[i].z;
+        target[i] = s.target_altitude[i];
+    }
+}
+uint64_t oracle_air_series(void* h, uint64_t* out, uint64_t cap)
+{
+    AirSim& s = *static_cast<AirSim*>(h);
+    for (size_t i = 0; i < s.series.size() && i < cap; ++i) out[i] = s.series[i];
+    return s.series.size();
+}
 
 // ------------------------------------------------------- library: aggregators
 #define ORACLE_AGG(T, NAME)                                                                          \

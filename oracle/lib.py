@@ -75,6 +75,22 @@ def load() -> C.CDLL:
     lib.oracle_pandemic_state.restype = None
     lib.oracle_pandemic_counts.argtypes = [vp, u64p]
     lib.oracle_pandemic_counts.restype = None
+    lib.oracle_air_new.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, C.c_int32, C.c_double, C.c_uint32]
+    lib.oracle_air_new.restype = vp
+    lib.oracle_air_free.argtypes = [vp]
+    lib.oracle_air_free.restype = None
+    lib.oracle_air_spawn.argtypes = [vp]
+    lib.oracle_air_spawn.restype = None
+    lib.oracle_air_spawn_explicit.argtypes = [vp, C.c_uint64, i32p, i32p]
+    lib.oracle_air_spawn_explicit.restype = None
+    lib.oracle_air_run.argtypes = [vp, C.c_uint64]
+    lib.oracle_air_run.restype = C.c_int
+    lib.oracle_air_num.argtypes = [vp]
+    lib.oracle_air_num.restype = C.c_uint64
+    lib.oracle_air_state.argtypes = [vp, i32p, i32p]
+    lib.oracle_air_state.restype = None
+    lib.oracle_air_series.argtypes = [vp, u64p, C.c_uint64]
+    lib.oracle_air_series.restype = C.c_uint64
     for name, ct in (("u8", C.c_uint8), ("u16", C.c_uint16), ("u32", C.c_uint32), ("u64", C.c_uint64),
                      ("i8", C.c_int8), ("i16", C.c_int16), ("i32", C.c_int32), ("i64", C.c_int64),
                      ("f32", C.c_float), ("f64", C.c_double)):

@@ -24,6 +24,8 @@ SOURCES = [
     "module_forest.cu",
     "module_pandemic.cu",
     "kernels_pandemic.cu",
+    "module_traders.cu",
+    "kernels_traders.cu",
     "module_air.cu",
     "kernels_air.cu",
     "comm.cu",

@@ -109,6 +109,25 @@ class SpawnAircraftParams(C.Structure):
                 ("airspace_size", C.c_int32), ("airspace_height", C.c_int32)]
 
 
+class TradersParams(C.Structure):
+    _fields_ = [("trader_id", component_t), ("cash", component_t), ("portfolio", component_t),
+                ("net_worth", component_t), ("stock_id", component_t), ("stock_price", component_t),
+                ("stock_delisted", component_t), ("chance_buy", C.c_double), ("chance_sell", C.c_double),
+                ("buy_shares_min", C.c_uint32), ("buy_shares_max", C.c_uint32), ("price_change_mean", C.c_double),
+                ("price_change_std_dev", C.c_double)]
+
+
+class SpawnTradersParams(C.Structure):
+    _fields_ = [("trader_id", component_t), ("cash", component_t), ("portfolio", component_t),
+                ("net_worth", component_t), ("num_traders", C.c_uint64), ("initial_cash", C.c_double),
+                ("num_stocks", C.c_uint32)]
+
+
+class SpawnStocksParams(C.Structure):
+    _fields_ = [("stock_id", component_t), ("stock_price", component_t), ("stock_delisted", component_t),
+                ("num_stocks", C.c_uint32), ("initial_price", C.c_double)]
+
+
 class FireStats(C.Structure):
     _fields_ = [("healthy_count", C.c_uint64), ("burning_count", C.c_uint64), ("burned_count", C.c_uint64),
                 ("empty_count", C.c_uint64), ("total_cells", C.c_uint64)]
@@ -141,7 +160,7 @@ SYMBOLS = [
     "incerto_sim_get_aggregate_time_series", "incerto_sim_get_time_series", "incerto_sim_grid_entities_at",
     "incerto_sim_grid_neighbors_of", "incerto_sim_grid_is_empty", "incerto_sim_grid_num_entities",
     "incerto_sim_grid_position_of", "incerto_sim_grid_in_bounds", "incerto_sim_step_number",
-    "incerto_sim_num_entities", "incerto_sim_read_component", "incerto_sim_last_run_stats",
+    "incerto_sim_num_entities", "incerto_sim_read_component", "incerto_sim_read_marker", "incerto_sim_last_run_stats",
     "incerto_sim_set_profiling", "incerto_sim_kernel_stats", "incerto_sim_flush_l2", "incerto_comm_unique_id",
     "incerto_sim_attach_comm", "incerto_sim_allreduce_u64", "incerto_sim_allreduce_f64", "incerto_sim_halo_export",
     "incerto_sim_halo_import", "incerto_partition_range",
@@ -205,6 +224,7 @@ def load() -> C.CDLL:
     lib.incerto_sim_step_number.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.incerto_sim_num_entities.argtypes = [vp, component_t, C.POINTER(C.c_uint64)]
     lib.incerto_sim_read_component.argtypes = [vp, component_t, vp, C.c_size_t, C.POINTER(C.c_uint64)]
+    lib.incerto_sim_read_marker.argtypes = [vp, component_t, component_t, vp, C.c_size_t]
     lib.incerto_sim_last_run_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.incerto_sim_set_profiling.argtypes = [vp, C.c_uint32]
     lib.incerto_sim_kernel_stats.argtypes = [vp, C.POINTER(KernelStat), C.c_uint32, C.POINTER(C.c_uint32)]

@@ -295,6 +295,30 @@ static int32_t device_spawn_signature(Sim& s, const HostSpawn& sp, std::vector<i
         n = p.initial_population;
         return INCERTO_OK;
     }
+    case INCERTO_SPAWN_TRADERS:
+    {
+        if (sp.params.size() != sizeof(incerto_spawn_traders_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_spawn_traders_params p;
+        std::memcpy(&p, sp.params.data(), sizeof(p));
+        auto bad = [&](int c) { return c < 0 || c >= static_cast<int>(s.comps.size()); };
+        if (bad(p.trader_id) || bad(p.cash) || bad(p.portfolio) || bad(p.net_worth)) return INCERTO_ERR_INVALID_ARGUMENT;
+        sig = {p.trader_id, p.cash, p.portfolio, p.net_worth};
+        std::sort(sig.begin(), sig.end());
+        n = p.num_traders;
+        return INCERTO_OK;
+    }
+    case INCERTO_SPAWN_STOCKS:
+    {
+        if (sp.params.size() != sizeof(incerto_spawn_stocks_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_spawn_stocks_params p;
+        std::memcpy(&p, sp.params.data(), sizeof(p));
+        auto bad = [&](int c) { return c < 0 || c >= static_cast<int>(s.comps.size()); };
+        if (bad(p.stock_id) || bad(p.stock_price) || bad(p.stock_delisted)) return INCERTO_ERR_INVALID_ARGUMENT;
+        sig = {p.stock_id, p.stock_price};
+        std::sort(sig.begin(), sig.end());
+        n = p.num_stocks;
+        return INCERTO_OK;
+    }
     case INCERTO_SPAWN_AIRCRAFT:
     {
         if (sp.params.size() != sizeof(incerto_spawn_aircraft_params)) return INCERTO_ERR_INVALID_ARGUMENT;
@@ -342,6 +366,7 @@ static int32_t run_spawners(Sim& s, bool first_time)
         rows[ti] += n;
         spawn_table[i] = ti;
     }
+    INC_TRY(traders_layout(s, rows)); // the managed portfolio's width depends on the number of stocks
     // allocate
     for (size_t ti = 0; ti < s.tables.size(); ++ti)
     {
@@ -416,6 +441,10 @@ static int32_t run_spawners(Sim& s, bool first_time)
                     if (c.d == nullptr) INC_CUDA(cudaMalloc(&c.d, t.n * c.row_bytes));
             }
         }
+        // engine-managed columns start empty (Trader.portfolio: HashMap::new(), traders.rs:123)
+        for (auto& c : t.cols)
+            if (s.comps[c.comp].managed_bytes && cursor[ti] == 0 && c.d)
+                INC_CUDA(cudaMemsetAsync(c.d, 0, t.n_spawned * c.row_bytes, s.stream));
         uint64_t n = sp.n;
         const uint64_t off = cursor[ti];
         if (sp.device_kind)
@@ -425,6 +454,12 @@ static int32_t run_spawners(Sim& s, bool first_time)
             if (sp.kind == INCERTO_SPAWN_PANDEMIC_PEOPLE)
             {
                 INC_TRY(pandemic_spawn_device(s, sp, t, off));
+                cursor[ti] += n;
+                continue;
+            }
+            if (sp.kind == INCERTO_SPAWN_TRADERS || sp.kind == INCERTO_SPAWN_STOCKS)
+            {
+                INC_TRY(traders_spawn_device(s, sp, t, off));
                 cursor[ti] += n;
                 continue;
             }
@@ -460,6 +495,13 @@ static int32_t run_spawners(Sim& s, bool first_time)
             if (ci.dtype == INCERTO_MARKER) continue;
             Column* col = t.col(c.comp);
             const size_t es = dtype_size(ci.dtype);
+            if (ci.managed_bytes) continue; // zeroed above; host values are not accepted for managed layouts
+            if (!c.has_data)
+            {
+                // no values: Default::default()
+                INC_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(col->d) + off * col->row_bytes, 0, n * col->row_bytes, s.stream));
+                continue;
+            }
             if (ci.lanes == 3)
             {
                 // 3 lanes are padded to a stride of 4 on the device
@@ -643,6 +685,21 @@ static int32_t bind_generic_systems(Sim& s)
                 StepOp op;
                 op.name = "pandemic_step";
                 op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return pandemic_step(sim, first_step, nsteps); };
+                prog.push_back(op);
+            }
+            break;
+        }
+        case INCERTO_SYS_TRADERS_BUY:
+        case INCERTO_SYS_TRADERS_SELL:
+        case INCERTO_SYS_TRADERS_NET_WORTH:
+        case INCERTO_SYS_STOCKS_PRICE_CHANGE:
+        {
+            if (!s.mods->traders.active)
+            {
+                INC_TRY(traders_bind(s));
+                StepOp op;
+                op.name = "traders_step";
+                op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return traders_step(sim, first_step, nsteps); };
                 prog.push_back(op);
             }
             break;
@@ -863,13 +920,8 @@ int32_t incerto_builder_add_entity_spawner(incerto_builder* b, uint64_t n, const
         }
         else
         {
-            if (!col.has_data && n)
-            {
-                set_error("data component '%s' spawned without values", ci.name.c_str());
-                return INCERTO_ERR_INVALID_ARGUMENT;
-            }
             const size_t bytes = n * dtype_size(ci.dtype) * ci.lanes;
-            if (n) col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + bytes);
+            if (n && col.has_data) col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + bytes);
         }
         sp.cols.push_back(std::move(col));
     }

@@ -1,0 +1,218 @@
+// traders: examples/traders.rs
+//   traders_may_buy_shares      :165-197
+//   traders_may_sell_shares     :199-236
+//   traders_calculate_net_worth :239-263
+//   stocks_price_change         :140-163
+// Pinned order: buy -> sell -> net worth (one fused pass per trader, stocks visited in
+// StockId order) -> price change (second kernel), StockDelisted inserted at the end of the step.
+//
+// Device layout: cash f64, net worth f64, portfolio = 4 bits per stock (#shares, 0 = not owned; the
+// reference's HashMap<StockId, usize>) stored word-major (word w of every trader contiguous) so that a
+// warp reads 128 contiguous bytes per word.  The stock table (price f64 + delisted) of the replica is
+// staged in shared memory.  Algorithmic bytes per trader-update at 100 stocks: 124 (portfolio 52 r +
+// up to 52 w - only changed words are written -, cash 8 + 8, net worth 8 w).  The kernel is bound by
+// the integer pipe (Philox), not by HBM: see DESIGN.md §5.
+//
+// Draw contract: two-level Bernoulli with byte granularity, T1 = min(256, ceil(256 p)):
+//   buy   (trader t, stock s): L1 = byte (s & 15) of philox(key[TBUY], (t, s >> 4, step, 0)) < T1;
+//         L2 = philox(key[TBUY], (t, s, step, 1)): decides = L2.x < floor(256 p / T1 * 2^32),
+//         num_shares = min + mulhi(L2.y, max - min + 1)                              (:178, :182)
+//   sell  same with key[TSEL]; drawn for owned stocks only                          (:218)
+//   price stock s: z = det_normal(philox(key[TPRC], (s, 0, step, 0))) (detmath.cuh); change = mean + sd * z (:148-155)
+#include "common.cuh"
+#include "detmath.cuh"
+#include "kernels_traders.hpp"
+
+namespace incerto
+{
+namespace
+{
+
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ uint32_t byte_of(const uint4& v, uint32_t b)
+{
+    const uint32_t w = word_of(v, b >> 2);
+    return (w >> (8 * (b & 3))) & 0xffu;
+}
+
+// 0xff in every byte of w that is < t (t <= 256)
+__device__ __forceinline__ uint32_t bytes_below(uint32_t w, uint32_t t)
+{
+    if (t >= 256u) return 0xffffffffu;
+    return __vcmpltu4(w, t * 0x01010101u);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
+{
+    __shared__ double s_price[kTradersMaxStocks];
+    __shared__ uint32_t s_listed[kTradersMaxStocks / 32]; // bit s: stock s exists and is not delisted
+    for (uint32_t i = threadIdx.x; i < kTradersMaxStocks / 32; i += blockDim.x) s_listed[i] = 0;
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < a.num_stocks; s += blockDim.x)
+    {
+        s_price[s] = a.price[s];
+        const uint32_t fl = a.stock_flags[s];
+        if ((fl & 1u) && !(fl & a.bit_delisted)) atomicOr(&s_listed[s >> 5], 1u << (s & 31));
+    }
+    __syncthreads();
+    const uint32_t nw_used = (a.num_stocks + 7) >> 3;
+    const uint32_t nblk = (a.num_stocks + 15) >> 4;
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t row = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < a.n; row += gstride)
+    {
+        if (a.trader_flags && !(a.trader_flags[row] & 1u)) continue;
+        const uint32_t uid = a.trader_uid ? a.trader_uid[row] : static_cast<uint32_t>(row);
+        uint32_t pw[NW], pw0[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+        {
+            pw[w] = (static_cast<uint32_t>(w) < nw_used) ? a.portfolio[static_cast<uint64_t>(w) * a.n_cap + row] : 0u;
+            pw0[w] = pw[w];
+        }
+        double cash = a.cash[row];
+
+        if (a.do_buy)
+        {
+#pragma unroll
+            for (int b = 0; b < (NW + 1) / 2; ++b)
+            {
+                if (static_cast<uint32_t>(b) >= nblk) break;
+                const uint4 l1 = philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_buy);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    // candidates: level-1 byte below T1, listed, not owned yet
+                    uint32_t m = bytes_below(word_of(l1, j), a.buy_t1) & 0x01010101u;
+                    if (!m) continue;
+                    const uint32_t s0 = 16u * b + 4u * j;
+                    const uint32_t listed4 = (s_listed[s0 >> 5] >> (s0 & 31)) & 0xfu;
+                    const uint32_t nib4 = (pw[2 * b + (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        if (!((m >> (8 * k)) & 1u) || !((listed4 >> k) & 1u) || ((nib4 >> (4 * k)) & 0xfu)) continue;
+                        const uint32_t s = s0 + k;
+                        const uint4 l2 = philox4x32_10(uid, s, a.step, 1u, a.rk_buy);
+                        if (!bernoulli(l2.x, a.buy_thr2)) continue;
+                        const uint32_t num_shares = a.shares_min + uniform_below(l2.y, a.shares_range);
+                        const double amount = dm_mul(static_cast<double>(num_shares), s_price[s]);
+                        if (amount > cash) continue; // :184-188
+                        pw[2 * b + (j >> 1)] |= num_shares << (16 * (j & 1) + 4 * k);
+                        cash = dm_sub(cash, amount);
+                    }
+                }
+            }
+        }
+
+        double value = 0.0;
+        if (a.do_sell || a.do_net_worth)
+        {
+#pragma unroll
+            for (int b = 0; b < (NW + 1) / 2; ++b)
+            {
+                const uint32_t w0 = pw[2 * b], w1 = (2 * b + 1 < NW) ? pw[2 * b + 1] : 0u;
+                if (!(w0 | w1)) continue;
+                uint4 l1 = make_uint4(~0u, ~0u, ~0u, ~0u);
+                if (a.do_sell) l1 = philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_sell);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                {
+                    if (2 * b + h >= NW) break;
+                    uint32_t w = h ? w1 : w0;
+                    uint32_t rest = w;
+                    while (rest)
+                    {
+                        const uint32_t k = (__ffs(rest) - 1) >> 2; // nibble index 0..7, ascending StockId
+                        const uint32_t n_sh = (w >> (4 * k)) & 0xfu;
+                        rest &= ~(0xfu << (4 * k));
+                        const uint32_t s = 16u * b + 8u * h + k;
+                        bool sell = false;
+                        if (a.do_sell && byte_of(l1, 8u * h + k) < a.sell_t1)
+                            sell = bernoulli(philox4x32_10(uid, s, a.step, 1u, a.rk_sell).x, a.sell_thr2);
+                        const double worth = dm_mul(static_cast<double>(n_sh), s_price[s]);
+                        if (sell)
+                        {
+                            cash = dm_add(cash, worth); // :232-233
+                            w &= ~(0xfu << (4 * k));
+                        }
+                        else
+                            value = dm_add(value, worth);
+                    }
+                    pw[2 * b + h] = w;
+                }
+            }
+        }
+
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            if (pw[w] != pw0[w]) a.portfolio[static_cast<uint64_t>(w) * a.n_cap + row] = pw[w];
+        if (a.do_buy || a.do_sell) a.cash[row] = cash;
+        if (a.do_net_worth) a.net_worth[row] = dm_add(cash, value); // :261
+    }
+}
+
+__global__ void stocks_price_change_kernel(TradersArgs a)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.num_stocks) return;
+    const uint32_t fl = a.stock_flags[s];
+    if (!(fl & 1u) || (fl & a.bit_delisted)) return; // Without<StockDelisted> (:142)
+    const uint4 r = philox4x32_10(s, 0u, a.step, 0u, a.rk_price);
+    const double change = dm_add(a.change_mean, dm_mul(a.change_std_dev, det_normal(r.x, r.y, r.z, r.w)));
+    double p = dm_add(a.price[s], change);
+    p = p > 0.0 ? p : 0.0; // .max(0.0) (:155)
+    a.price[s] = p;
+    if (p < 2.220446049250313e-16) a.stock_flags[s] = static_cast<uint8_t>(fl | a.bit_delisted); // f64::EPSILON (:157-161)
+}
+
+__global__ void fill_f64_kernel(double* p, double v, uint64_t n)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gstride) p[i] = v;
+}
+__global__ void iota_u64_kernel(uint64_t* p, uint64_t n)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gstride) p[i] = i;
+}
+
+inline int blocks_for(uint64_t items, int threads, int per_sm)
+{
+    uint64_t b = (items + threads - 1) / threads;
+    const uint64_t cap = static_cast<uint64_t>(kNumSMs) * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+} // namespace
+
+void launch_traders_step(const TradersArgs& a, cudaStream_t st)
+{
+    const uint32_t nw = (a.num_stocks + 7) >> 3;
+    const int blocks = blocks_for(a.n, kThreads, 16);
+    if (nw <= 4)
+        traders_step_kernel<4><<<blocks, kThreads, 0, st>>>(a);
+    else if (nw <= 8)
+        traders_step_kernel<8><<<blocks, kThreads, 0, st>>>(a);
+    else if (nw <= 14)
+        traders_step_kernel<14><<<blocks, kThreads, 0, st>>>(a);
+    else
+        traders_step_kernel<32><<<blocks, kThreads, 0, st>>>(a);
+}
+void launch_stocks_price_change(const TradersArgs& a, cudaStream_t st)
+{
+    stocks_price_change_kernel<<<(a.num_stocks + 127) / 128, 128, 0, st>>>(a);
+}
+void launch_fill_f64(double* p, double v, uint64_t n, cudaStream_t st)
+{
+    fill_f64_kernel<<<blocks_for(n, 256, 16), 256, 0, st>>>(p, v, n);
+}
+void launch_iota_u64(uint64_t* p, uint64_t n, cudaStream_t st)
+{
+    iota_u64_kernel<<<blocks_for(n, 256, 16), 256, 0, st>>>(p, n);
+}
+
+} // namespace incerto

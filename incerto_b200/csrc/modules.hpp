@@ -81,6 +81,15 @@ struct AirModule
     uint64_t* d_acc = nullptr;            // [0] conflicts of the last step (pairs counted twice), [1] aircraft indexed
 };
 
+struct TradersModule
+{
+    bool active = false;
+    int table_traders = -1, table_stocks = -1;
+    incerto_traders_params p{};
+    bool do_buy = false, do_sell = false, do_net_worth = false, do_price = false;
+    uint32_t num_stocks_cap = 0; // portfolio capacity in stocks (fixed at build)
+};
+
 struct CoinModule
 {
     bool active = false;
@@ -95,6 +104,7 @@ struct Sim::Modules
     CoinModule coin;
     PandemicModule pandemic;
     AirModule air;
+    TradersModule traders;
     std::vector<StepOp> program;
     uint32_t* d_step = nullptr; // device mirror of StepNumber
 };
@@ -123,6 +133,13 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps);
 int32_t air_spawn_device(Sim& s, const HostSpawn& sp, Table& t, uint64_t row_offset);
 void air_free(Sim& s);
 int32_t air_reset(Sim& s);
+
+// module_traders.cu
+int32_t traders_layout(Sim& s, const std::vector<uint64_t>& rows);
+int32_t traders_bind(Sim& s);
+int32_t traders_step(Sim& s, uint64_t first_step, uint32_t nsteps);
+int32_t traders_spawn_device(Sim& s, const HostSpawn& sp, Table& t, uint64_t row_offset);
+int32_t traders_read_portfolio(Sim& s, int table, uint8_t* out, size_t out_size, size_t* written);
 
 // comm.cpp
 int32_t comm_unique_id(uint8_t out[128]);

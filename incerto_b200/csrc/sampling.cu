@@ -1180,6 +1180,14 @@ int32_t incerto_sim_read_component(incerto_sim* s, incerto_component component, 
             written += rows * abi_bytes;
             continue;
         }
+        if (ci.managed_bytes)
+        {
+            if (!S.mods->traders.active || S.mods->traders.p.portfolio != component) return INCERTO_ERR_UNSUPPORTED;
+            size_t w = 0;
+            INC_TRY(traders_read_portfolio(S, static_cast<int>(ti), o + written, out_size - written, &w));
+            written += w;
+            continue;
+        }
         std::vector<uint8_t> fl(t.n);
         INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, S.stream));
         std::vector<uint32_t> uid;
@@ -1212,6 +1220,36 @@ int32_t incerto_sim_read_component(incerto_sim* s, incerto_component component, 
                 std::memcpy(o + written, &data[r * rb], abi_bytes);
             written += abi_bytes;
             if (uids_out) uids_out[k++] = t.d_uid ? uid[r] : r;
+        }
+    }
+    return INCERTO_OK;
+}
+
+int32_t incerto_sim_read_marker(incerto_sim* s, incerto_component marker, incerto_component rows_of, uint8_t* out,
+                                size_t out_size)
+{
+    INC_SIM(s);
+    if (marker < 0 || rows_of < 0 || marker >= static_cast<int>(S.comps.size()) ||
+        rows_of >= static_cast<int>(S.comps.size()) || !out || S.comps[marker].dtype != INCERTO_MARKER ||
+        S.comps[rows_of].dtype == INCERTO_MARKER)
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    INC_TRY(incerto_sim_synchronize(s));
+    size_t written = 0;
+    for (auto& t : S.tables)
+    {
+        if (!t.has(rows_of) || !t.n || !t.d_flags) continue;
+        std::vector<uint8_t> fl(t.n);
+        INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, S.stream));
+        INC_CUDA(cudaStreamSynchronize(S.stream));
+        for (uint64_t r = 0; r < t.n; ++r)
+        {
+            if (!(fl[r] & kAliveBit)) continue;
+            if (written >= out_size)
+            {
+                set_error("read_marker: output buffer too small");
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            out[written++] = (fl[r] >> S.comps[marker].marker_bit) & 1u;
         }
     }
     return INCERTO_OK;

@@ -212,6 +212,43 @@ def PeopleInfectedMayRecover(person, position, infected, grid_size: int, chance:
     return System(F.SYS_PANDEMIC_RECOVER, F.PandemicParams(person.handle, position.handle, infected.handle, grid_size, chance))
 
 
+# examples/traders.rs:140-263
+@dataclass(frozen=True)
+class TraderComponents:
+    """The component handles the four traders systems share (Trader{cash, portfolio}, TraderNetWorth, StockPrice ...)."""
+    trader_id: Component
+    cash: Component
+    portfolio: Component
+    net_worth: Component
+    stock_id: Component
+    stock_price: Component
+    stock_delisted: Component
+
+    def _params(self, **kw) -> "F.TradersParams":
+        p = F.TradersParams(self.trader_id.handle, self.cash.handle, self.portfolio.handle, self.net_worth.handle,
+                            self.stock_id.handle, self.stock_price.handle, self.stock_delisted.handle)
+        p.buy_shares_min, p.buy_shares_max = 1, 5
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+
+def TradersMayBuyShares(tc: TraderComponents, chance_buy: float = 0.01, shares=(1, 5)) -> System:
+    return System(F.SYS_TRADERS_BUY, tc._params(chance_buy=chance_buy, buy_shares_min=shares[0], buy_shares_max=shares[1]))
+
+
+def TradersMaySellShares(tc: TraderComponents, chance_sell: float = 0.005) -> System:
+    return System(F.SYS_TRADERS_SELL, tc._params(chance_sell=chance_sell))
+
+
+def TradersCalculateNetWorth(tc: TraderComponents) -> System:
+    return System(F.SYS_TRADERS_NET_WORTH, tc._params())
+
+
+def StocksPriceChange(tc: TraderComponents, mean: float = 0.001, std_dev: float = 0.2) -> System:
+    return System(F.SYS_STOCKS_PRICE_CHANGE, tc._params(price_change_mean=mean, price_change_std_dev=std_dev))
+
+
 # examples/air_traffic_3d.rs:93-162
 def CheckConflicts(position, target_altitude, airspace_size: int, airspace_height: int) -> System:
     return System(F.SYS_AIR_CHECK_CONFLICTS, F.AirParams(position.handle, target_altitude.handle, airspace_size,
@@ -543,7 +580,13 @@ class Simulation:
             if rows_of is None:
                 raise ValueError("read_component of a marker needs rows_of=<a data component of the same archetype>")
             n = self.num_entities(rows_of)
-            out = np.zeros((n, 1), dtype=np.uint8)
+            out = np.zeros(n, dtype=np.uint8)
+            _check(self._lib.incerto_sim_read_marker(self._h, component.handle, rows_of.handle,
+                                                     out.ctypes.data_as(C.c_void_p), out.nbytes))
+            if with_uids:
+                _, uids = self.read_component(rows_of, with_uids=True)
+                return out, uids
+            return out
         else:
             n = self.num_entities(component)
             out = np.zeros((n, component.lanes), dtype=component.np_dtype)
@@ -552,6 +595,14 @@ class Simulation:
                                                     out.nbytes, uids.ctypes.data_as(C.POINTER(C.c_uint64))))
         out = out[:, 0] if out.shape[1] == 1 else out
         return (out, uids) if with_uids else out
+
+    def read_portfolio(self, portfolio: Component, rows_of: Component, num_stocks: int) -> np.ndarray:
+        """Trader.portfolio (engine-managed): #shares per (live trader, stock); 0 = not owned."""
+        n = self.num_entities(rows_of)
+        out = np.zeros((n, num_stocks), dtype=np.uint8)
+        _check(self._lib.incerto_sim_read_component(self._h, portfolio.handle, out.ctypes.data_as(C.c_void_p),
+                                                    out.nbytes, None))
+        return out
 
     def last_run_stats(self) -> tuple[float, int]:
         ms, n = C.c_double(), C.c_uint64()

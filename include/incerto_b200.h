@@ -478,6 +478,10 @@ int32_t incerto_sim_step_number(incerto_sim* s, uint64_t* out); /* StepNumber, s
 int32_t incerto_sim_num_entities(incerto_sim* s, incerto_component component, uint64_t* out);
 int32_t incerto_sim_read_component(incerto_sim* s, incerto_component component, void* out, size_t out_size,
                                    uint64_t* uids_out /* may be NULL */);
+/* Presence (0/1) of `marker` on every live row of the tables holding the data component `rows_of`,
+ * in the row order of incerto_sim_read_component(rows_of). */
+int32_t incerto_sim_read_marker(incerto_sim* s, incerto_component marker, incerto_component rows_of, uint8_t* out,
+                                size_t out_size);
 /* Device time (ms, CUDA events on the engine's stream) and kernel launches of
  * the last incerto_sim_run / run_async+synchronize. */
 int32_t incerto_sim_last_run_stats(incerto_sim* s, double* device_ms, uint64_t* kernel_launches);

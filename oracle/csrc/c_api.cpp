@@ -9,6 +9,7 @@
 #include "library.hpp"
 #include "pandemic.hpp"
 #include "philox.hpp"
+#include "traders.hpp"
 
 using namespace oracle;
 
@@ -233,6 +234,67 @@ uint64_t oracle_air_series(void* h, uint64_t* out, uint64_t cap)
     for (size_t i = 0; i < s.series.size() && i < cap; ++i) out[i] = s.series[i];
     return s.series.size();
 }
+
+// ------------------------------------------------------------------ traders
+void* oracle_traders_new(uint64_t seed, uint32_t replica, uint64_t num_traders, uint32_t num_stocks, double cash,
+                         double p_buy, double p_sell, uint32_t shares_min, uint32_t shares_max, double price,
+                         double mean, double std_dev, uint32_t systems_mask /* 1 buy 2 sell 4 net worth 8 price */)
+{
+    TradersParams p;
+    p.num_traders = num_traders;
+    p.num_stocks = num_stocks;
+    p.initial_cash = cash;
+    p.chance_buy = p_buy;
+    p.chance_sell = p_sell;
+    p.shares_min = shares_min;
+    p.shares_max = shares_max;
+    p.initial_price = price;
+    p.change_mean = mean;
+    p.change_std_dev = std_dev;
+    p.buy = systems_mask & 1;
+    p.sell = systems_mask & 2;
+    p.net_worth = systems_mask & 4;
+    p.price_change = systems_mask & 8;
+    TradersSim* s = new TradersSim(p, seed, replica);
+    s->spawn_traders();
+    s->spawn_stocks();
+    return s;
+}
+void oracle_traders_free(void* h) { delete static_cast<TradersSim*>(h); }
+void oracle_traders_set_prices(void* h, const double* prices)
+{
+    TradersSim& s = *static_cast<TradersSim*>(h);
+    for (size_t i = 0; i < s.price.size(); ++i) s.price[i] = prices[i];
+}
+void oracle_traders_run(void* h, uint64_t steps) { static_cast<TradersSim*>(h)->run(steps); }
+// cash, net worth: num_traders each; shares: num_traders x num_stocks; price, delisted: num_stocks
+void oracle_traders_state(void* h, double* cash, double* net_worth, uint8_t* shares, double* price, uint8_t* delisted)
+{
+    TradersSim& s = *static_cast<TradersSim*>(h);
+    const size_t ns = s.price.size();
+    for (size_t t = 0; t < s.traders.size(); ++t)
+    {
+        cash[t] = s.traders[t].cash;
+        net_worth[t] = s.net_worth[t];
+        for (size_t k = 0; k < ns; ++k) shares[t * ns + k] = 0;
+        for (auto& kv : s.traders[t].portfolio) shares[t * ns + kv.first] = static_cast<uint8_t>(kv.second);
+    }
+    for (size_t k = 0; k < ns; ++k)
+    {
+        price[k] = s.price[k];
+        delisted[k] = s.delisted[k];
+    }
+}
+// net worth of one trader at every recorded step
+uint64_t oracle_traders_series(void* h, uint64_t trader, double* out, uint64_t cap)
+{
+    TradersSim& s = *static_cast<TradersSim*>(h);
+    for (size_t i = 0; i < s.series.size() && i < cap; ++i) out[i] = s.series[i][trader];
+    return s.series.size();
+}
+double oracle_det_log(double x) { return det_log(x); }
+double oracle_det_cos2pi(double u) { return det_cos2pi(u); }
+double oracle_det_normal(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) { return det_normal(w0, w1, w2, w3); }
 
 // ------------------------------------------------------- library: aggregators
 #define ORACLE_AGG(T, NAME)                                                                          \

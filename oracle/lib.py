@@ -91,6 +91,26 @@ def load() -> C.CDLL:
     lib.oracle_air_state.restype = None
     lib.oracle_air_series.argtypes = [vp, u64p, C.c_uint64]
     lib.oracle_air_series.restype = C.c_uint64
+    f64p = C.POINTER(C.c_double)
+    lib.oracle_traders_new.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_double,
+                                       C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32]
+    lib.oracle_traders_new.restype = vp
+    lib.oracle_traders_free.argtypes = [vp]
+    lib.oracle_traders_free.restype = None
+    lib.oracle_traders_set_prices.argtypes = [vp, f64p]
+    lib.oracle_traders_set_prices.restype = None
+    lib.oracle_traders_run.argtypes = [vp, C.c_uint64]
+    lib.oracle_traders_run.restype = None
+    lib.oracle_traders_state.argtypes = [vp, f64p, f64p, u8p, f64p, u8p]
+    lib.oracle_traders_state.restype = None
+    lib.oracle_traders_series.argtypes = [vp, C.c_uint64, f64p, C.c_uint64]
+    lib.oracle_traders_series.restype = C.c_uint64
+    lib.oracle_det_log.argtypes = [C.c_double]
+    lib.oracle_det_log.restype = C.c_double
+    lib.oracle_det_cos2pi.argtypes = [C.c_double]
+    lib.oracle_det_cos2pi.restype = C.c_double
+    lib.oracle_det_normal.argtypes = [C.c_uint32] * 4
+    lib.oracle_det_normal.restype = C.c_double
     for name, ct in (("u8", C.c_uint8), ("u16", C.c_uint16), ("u32", C.c_uint32), ("u64", C.c_uint64),
                      ("i8", C.c_int8), ("i16", C.c_int16), ("i32", C.c_int32), ("i64", C.c_int64),
                      ("f32", C.c_float), ("f64", C.c_double)):

@@ -52,6 +52,7 @@ extern "C" {
     pub fn incerto_sim_step_number(s: *mut incerto_sim, out: *mut u64) -> i32;
     pub fn incerto_sim_num_entities(s: *mut incerto_sim, component: incerto_component, out: *mut u64) -> i32;
     pub fn incerto_sim_read_component(s: *mut incerto_sim, component: incerto_component, out: *mut c_void, out_size: usize, uids_out: *mut u64) -> i32;
+    pub fn incerto_sim_read_marker(s: *mut incerto_sim, marker: incerto_component, rows_of: incerto_component, out: *mut u8, out_size: usize) -> i32;
     pub fn incerto_sim_last_run_stats(s: *mut incerto_sim, device_ms: *mut f64, kernel_launches: *mut u64) -> i32;
     pub fn incerto_sim_set_profiling(s: *mut incerto_sim, enabled: u32) -> i32;
     pub fn incerto_sim_kernel_stats(s: *mut incerto_sim, out: *mut incerto_kernel_stat, capacity: u32, n_out: *mut u32) -> i32;

@@ -24,6 +24,8 @@ SOURCES = [
     "module_forest.cu",
     "module_pandemic.cu",
     "kernels_pandemic.cu",
+    "module_spatial.cu",
+    "kernels_spatial.cu",
     "module_traders.cu",
     "kernels_traders.cu",
     "module_air.cu",

@@ -44,6 +44,7 @@ AGG_SUM, AGG_COUNT, AGG_MINIMUM, AGG_MAXIMUM, AGG_MEAN, AGG_MEDIAN, AGG_PERCENTI
 AGG_COIN_ODDS, AGG_FIRE_STATS, AGG_PANDEMIC_STATS, AGG_AIR_CONFLICTS = 16, 17, 18, 19
 
 CELL_BURNED, CELL_HEALTHY, CELL_EMPTY = 0, 0x40, 0x80
+DISEASE_HEALTHY, DISEASE_INFECTIOUS, DISEASE_RECOVERED = 0, 0x80, 0x81   # Exposed{n} = n
 
 component_t = C.c_int32
 
@@ -107,6 +108,24 @@ class AirParams(C.Structure):
 class SpawnAircraftParams(C.Structure):
     _fields_ = [("position", component_t), ("target_altitude", component_t), ("num_aircraft", C.c_uint64),
                 ("airspace_size", C.c_int32), ("airspace_height", C.c_int32)]
+
+
+class SpatialParams(C.Structure):
+    _fields_ = [("position", component_t), ("disease_state", component_t), ("social_distancing", component_t),
+                ("quarantined", component_t), ("contact_history", component_t), ("grid_size", C.c_int32),
+                ("infection_radius", C.c_int32), ("chance_infect_distance_1", C.c_double),
+                ("chance_infect_distance_2", C.c_double), ("chance_recover", C.c_double), ("chance_die", C.c_double),
+                ("incubation_period", C.c_uint32), ("crowding_threshold", C.c_uint32),
+                ("contact_quarantine_duration", C.c_uint32), ("quarantine_center_x", C.c_int32),
+                ("quarantine_center_y", C.c_int32), ("quarantine_radius", C.c_int32),
+                ("contact_history_clear_above", C.c_uint32), ("chance_attempt_move", C.c_double)]
+
+
+class SpawnSpatialParams(C.Structure):
+    _fields_ = [("position", component_t), ("disease_state", component_t), ("social_distancing", component_t),
+                ("quarantined", component_t), ("contact_history", component_t), ("initial_population", C.c_uint64),
+                ("grid_size", C.c_int32), ("social_distance_compliance", C.c_double),
+                ("chance_start_infected", C.c_double), ("incubation_period", C.c_uint32)]
 
 
 class TradersParams(C.Structure):

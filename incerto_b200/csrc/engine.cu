@@ -41,6 +41,7 @@ Sim::~Sim()
     forest_free(*this);
     pandemic_free(*this);
     air_free(*this);
+    spatial_free(*this);
     comm_free(*this);
     for (auto& t : tables)
     {
@@ -295,6 +296,20 @@ static int32_t device_spawn_signature(Sim& s, const HostSpawn& sp, std::vector<i
         n = p.initial_population;
         return INCERTO_OK;
     }
+    case INCERTO_SPAWN_SPATIAL_POPULATION:
+    {
+        if (sp.params.size() != sizeof(incerto_spawn_spatial_params)) return INCERTO_ERR_INVALID_ARGUMENT;
+        incerto_spawn_spatial_params p;
+        std::memcpy(&p, sp.params.data(), sizeof(p));
+        auto bad = [&](int c) { return c < 0 || c >= static_cast<int>(s.comps.size()); };
+        if (bad(p.position) || bad(p.disease_state) || bad(p.social_distancing) || bad(p.quarantined) || bad(p.contact_history))
+            return INCERTO_ERR_INVALID_ARGUMENT;
+        s.comps[p.social_distancing].exists = true;
+        sig = {p.position, p.disease_state, p.quarantined, p.contact_history};
+        std::sort(sig.begin(), sig.end());
+        n = p.initial_population;
+        return INCERTO_OK;
+    }
     case INCERTO_SPAWN_TRADERS:
     {
         if (sp.params.size() != sizeof(incerto_spawn_traders_params)) return INCERTO_ERR_INVALID_ARGUMENT;
@@ -367,6 +382,7 @@ static int32_t run_spawners(Sim& s, bool first_time)
         spawn_table[i] = ti;
     }
     INC_TRY(traders_layout(s, rows)); // the managed portfolio's width depends on the number of stocks
+    INC_TRY(spatial_layout(s));
     // allocate
     for (size_t ti = 0; ti < s.tables.size(); ++ti)
     {
@@ -454,6 +470,12 @@ static int32_t run_spawners(Sim& s, bool first_time)
             if (sp.kind == INCERTO_SPAWN_PANDEMIC_PEOPLE)
             {
                 INC_TRY(pandemic_spawn_device(s, sp, t, off));
+                cursor[ti] += n;
+                continue;
+            }
+            if (sp.kind == INCERTO_SPAWN_SPATIAL_POPULATION)
+            {
+                INC_TRY(spatial_spawn_device(s, sp, t, off));
                 cursor[ti] += n;
                 continue;
             }
@@ -685,6 +707,24 @@ static int32_t bind_generic_systems(Sim& s)
                 StepOp op;
                 op.name = "pandemic_step";
                 op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return pandemic_step(sim, first_step, nsteps); };
+                prog.push_back(op);
+            }
+            break;
+        }
+        case INCERTO_SYS_SPATIAL_INCUBATION:
+        case INCERTO_SYS_SPATIAL_TRANSMISSION:
+        case INCERTO_SYS_SPATIAL_RECOVERY_DEATH:
+        case INCERTO_SYS_SPATIAL_CONTACT_HISTORY:
+        case INCERTO_SYS_SPATIAL_CONTACT_TRACING:
+        case INCERTO_SYS_SPATIAL_QUARANTINE:
+        case INCERTO_SYS_SPATIAL_MOVE:
+        {
+            if (!s.mods->spatial.active)
+            {
+                INC_TRY(spatial_bind(s));
+                StepOp op;
+                op.name = "spatial_step";
+                op.fn = [](Sim& sim, uint64_t first_step, uint32_t nsteps) { return spatial_step(sim, first_step, nsteps); };
                 prog.push_back(op);
             }
             break;
@@ -1088,6 +1128,7 @@ int32_t incerto_sim_reset(incerto_sim* s, uint32_t replica)
     if (S.mods->forest.active) INC_TRY(forest_reset_after_spawn(S));
     if (S.mods->pandemic.active) INC_TRY(pandemic_reset(S));
     if (S.mods->air.active) INC_TRY(air_reset(S));
+    if (S.mods->spatial.active) INC_TRY(spatial_reset(S));
     for (auto& g : S.grids)
     {
         g.built_step = ~0ull;

@@ -90,6 +90,20 @@ struct TradersModule
     uint32_t num_stocks_cap = 0; // portfolio capacity in stocks (fixed at build)
 };
 
+struct SpatialModule
+{
+    bool active = false;
+    int table = -1, grid = -1;
+    incerto_spatial_params p{};
+    uint32_t systems = 0;          // bit k: system kind 40 + k registered
+    uint8_t* d_aux = nullptr;      // per person: ContactHistory length | pending grid op
+    uint32_t* d_count = nullptr;   // persons per cell (PreUpdate snapshot)
+    uint32_t* d_src_bits = nullptr;
+    uint32_t* d_src_head = nullptr;
+    uint32_t* d_src_next = nullptr;
+    uint32_t* d_mark = nullptr;
+};
+
 struct CoinModule
 {
     bool active = false;
@@ -105,6 +119,7 @@ struct Sim::Modules
     PandemicModule pandemic;
     AirModule air;
     TradersModule traders;
+    SpatialModule spatial;
     std::vector<StepOp> program;
     uint32_t* d_step = nullptr; // device mirror of StepNumber
 };
@@ -140,6 +155,16 @@ int32_t traders_bind(Sim& s);
 int32_t traders_step(Sim& s, uint64_t first_step, uint32_t nsteps);
 int32_t traders_spawn_device(Sim& s, const HostSpawn& sp, Table& t, uint64_t row_offset);
 int32_t traders_read_portfolio(Sim& s, int table, uint8_t* out, size_t out_size, size_t* written);
+
+// module_spatial.cu
+int32_t spatial_layout(Sim& s);
+int32_t spatial_bind(Sim& s);
+int32_t spatial_reset(Sim& s);
+int32_t spatial_step(Sim& s, uint64_t first_step, uint32_t nsteps);
+int32_t spatial_spawn_device(Sim& s, const HostSpawn& sp, Table& t, uint64_t row_offset);
+int32_t spatial_read_history(Sim& s, int table, uint8_t* out, size_t out_size, size_t* written);
+int32_t spatial_stats_now(Sim& s, uint64_t initial_population, uint8_t* d_raw);
+void spatial_free(Sim& s);
 
 // comm.cpp
 int32_t comm_unique_id(uint8_t out[128]);

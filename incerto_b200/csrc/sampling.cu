@@ -157,6 +157,16 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
         INC_CUDA(cudaStreamSynchronize(s.stream));
         return INCERTO_OK;
     }
+    if (a.kind == INCERTO_AGG_PANDEMIC_STATS)
+    {
+        SpatialModule& sm = s.mods->spatial;
+        if (!sm.active || sm.table != ti || a.component != sm.p.disease_state)
+        {
+            set_error("PANDEMIC_STATS is sampled on the disease_state column of the pandemic_spatial systems");
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+        return spatial_stats_now(s, a.param, d_raw);
+    }
     if (a.kind == INCERTO_AGG_AIR_CONFLICTS)
     {
         AirModule& am = s.mods->air;
@@ -446,6 +456,15 @@ static int32_t aggregate_finalize(const Sim& s, const AggSpec& a, const uint8_t*
         store_as<uint64_t>(out, twice / 2); // "Divide by 2 since each conflict is counted twice", air_traffic_3d.rs:160
         return INCERTO_OK;
     }
+    if (a.kind == INCERTO_AGG_PANDEMIC_STATS)
+    {
+        incerto_pandemic_stats ps;
+        std::memcpy(&ps, raws, sizeof(ps));
+        if (count_out) *count_out = ps.total_population;
+        if (!ps.total_population) return INCERTO_ERR_AGGREGATE_NO_ENTITIES;
+        std::memcpy(out, &ps, sizeof(ps));
+        return INCERTO_OK;
+    }
     if (a.kind == INCERTO_AGG_FIRE_STATS)
     {
         incerto_fire_stats fs;
@@ -547,7 +566,7 @@ int32_t series_sample_step(Sim& s, uint64_t step)
         const size_t rs = raw_size(se.agg.kind);
         INC_TRY(aggregate_launch(s, se.agg, tabs[0], se.d_values + slot * rs));
         // count: first u64 of GenericRaw; second u64 of coin odds
-        const size_t count_off = is_generic_kind(se.agg.kind) ? 0 : ((se.agg.kind == INCERTO_AGG_COIN_ODDS || se.agg.kind == INCERTO_AGG_AIR_CONFLICTS) ? 8 : 32);
+        const size_t count_off = is_generic_kind(se.agg.kind) ? 0 : ((se.agg.kind == INCERTO_AGG_COIN_ODDS || se.agg.kind == INCERTO_AGG_AIR_CONFLICTS) ? 8 : (se.agg.kind == INCERTO_AGG_PANDEMIC_STATS ? 40 : 32));
         INC_CUDA(cudaMemcpyAsync(se.d_counts + slot, se.d_values + slot * rs + count_off, 8, cudaMemcpyDeviceToDevice,
                                  s.stream));
         se.n_slots = std::max(se.n_slots, slot + 1);
@@ -1182,9 +1201,13 @@ int32_t incerto_sim_read_component(incerto_sim* s, incerto_component component, 
         }
         if (ci.managed_bytes)
         {
-            if (!S.mods->traders.active || S.mods->traders.p.portfolio != component) return INCERTO_ERR_UNSUPPORTED;
             size_t w = 0;
-            INC_TRY(traders_read_portfolio(S, static_cast<int>(ti), o + written, out_size - written, &w));
+            if (S.mods->traders.active && S.mods->traders.p.portfolio == component)
+                INC_TRY(traders_read_portfolio(S, static_cast<int>(ti), o + written, out_size - written, &w));
+            else if (S.mods->spatial.active && S.mods->spatial.p.contact_history == component)
+                INC_TRY(spatial_read_history(S, static_cast<int>(ti), o + written, out_size - written, &w));
+            else
+                return INCERTO_ERR_UNSUPPORTED;
             written += w;
             continue;
         }

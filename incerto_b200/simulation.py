@@ -212,6 +212,56 @@ def PeopleInfectedMayRecover(person, position, infected, grid_size: int, chance:
     return System(F.SYS_PANDEMIC_RECOVER, F.PandemicParams(person.handle, position.handle, infected.handle, grid_size, chance))
 
 
+# examples/pandemic_spatial.rs:316-625
+@dataclass(frozen=True)
+class SpatialComponents:
+    """Person{disease_state, social_distancing}, Quarantined, ContactHistory, GridPosition2D handles + the constants
+    of examples/pandemic_spatial.rs:28-58 shared by its seven systems."""
+    position: Component
+    disease_state: Component
+    social_distancing: Component
+    quarantined: Component
+    contact_history: Component
+    grid_size: int = 40
+    infection_radius: int = 2
+    chance_infect_distance_1: float = 0.15
+    chance_infect_distance_2: float = 0.05
+    chance_recover: float = 0.03
+    chance_die: float = 0.001
+    incubation_period: int = 5
+    crowding_threshold: int = 8
+    contact_quarantine_duration: int = 14
+    quarantine_center: tuple | None = None     # (GRID_SIZE / 2, GRID_SIZE / 2)
+    quarantine_radius: int = 8
+    contact_history_clear_above: int = 20
+    chance_attempt_move: float = 0.5
+
+    def _params(self) -> "F.SpatialParams":
+        cx, cy = self.quarantine_center or (self.grid_size // 2, self.grid_size // 2)
+        p = F.SpatialParams()
+        p.position, p.disease_state = self.position.handle, self.disease_state.handle
+        p.social_distancing, p.quarantined = self.social_distancing.handle, self.quarantined.handle
+        p.contact_history = self.contact_history.handle
+        p.grid_size, p.infection_radius = self.grid_size, self.infection_radius
+        p.chance_infect_distance_1, p.chance_infect_distance_2 = self.chance_infect_distance_1, self.chance_infect_distance_2
+        p.chance_recover, p.chance_die = self.chance_recover, self.chance_die
+        p.incubation_period, p.crowding_threshold = self.incubation_period, self.crowding_threshold
+        p.contact_quarantine_duration = self.contact_quarantine_duration
+        p.quarantine_center_x, p.quarantine_center_y, p.quarantine_radius = cx, cy, self.quarantine_radius
+        p.contact_history_clear_above = self.contact_history_clear_above
+        p.chance_attempt_move = self.chance_attempt_move
+        return p
+
+
+def PeopleMoveWithSocialDistancing(sc: SpatialComponents) -> System: return System(F.SYS_SPATIAL_MOVE, sc._params())
+def DiseaseIncubationProgression(sc: SpatialComponents) -> System: return System(F.SYS_SPATIAL_INCUBATION, sc._params())
+def SpatialDiseaseTransmission(sc: SpatialComponents) -> System: return System(F.SYS_SPATIAL_TRANSMISSION, sc._params())
+def DiseaseRecoveryAndDeath(sc: SpatialComponents) -> System: return System(F.SYS_SPATIAL_RECOVERY_DEATH, sc._params())
+def UpdateContactHistory(sc: SpatialComponents) -> System: return System(F.SYS_SPATIAL_CONTACT_HISTORY, sc._params())
+def ProcessContactTracing(sc: SpatialComponents) -> System: return System(F.SYS_SPATIAL_CONTACT_TRACING, sc._params())
+def UpdateQuarantineStatus(sc: SpatialComponents) -> System: return System(F.SYS_SPATIAL_QUARANTINE, sc._params())
+
+
 # examples/traders.rs:140-263
 @dataclass(frozen=True)
 class TraderComponents:
@@ -603,6 +653,14 @@ class Simulation:
         _check(self._lib.incerto_sim_read_component(self._h, portfolio.handle, out.ctypes.data_as(C.c_void_p),
                                                     out.nbytes, None))
         return out
+
+    def read_contact_history(self, contact_history: Component, rows_of: Component) -> list[set]:
+        """ContactHistory.recent_contacts (engine-managed) of every live person as a set of (x, y)."""
+        n = self.num_entities(rows_of)
+        out = np.zeros((n, 21), dtype=np.uint32)
+        _check(self._lib.incerto_sim_read_component(self._h, contact_history.handle, out.ctypes.data_as(C.c_void_p),
+                                                    out.nbytes, None))
+        return [set((int(k) & 0xffff, int(k) >> 16) for k in row[1:1 + row[0]]) for row in out]
 
     def last_run_stats(self) -> tuple[float, int]:
         ms, n = C.c_double(), C.c_uint64()

@@ -8,6 +8,7 @@
 #include "forest_fire.hpp"
 #include "library.hpp"
 #include "pandemic.hpp"
+#include "pandemic_spatial.hpp"
 #include "philox.hpp"
 #include "traders.hpp"
 
@@ -232,6 +233,85 @@ uint64_t oracle_air_series(void* h, uint64_t* out, uint64_t cap)
 {
     AirSim& s = *static_cast<AirSim*>(h);
     for (size_t i = 0; i < s.series.size() && i < cap; ++i) out[i] = s.series[i];
+    return s.series.size();
+}
+
+// -------------------------------------------------------- pandemic_spatial
+// params: 12 doubles / ints flattened, see oracle/spatial.py
+void* oracle_spatial_new(uint64_t seed, uint32_t replica, uint64_t population, int32_t grid_size, const double* prob /*6*/,
+                         const int32_t* ints /*9*/, uint32_t systems)
+{
+    SpatialParams p;
+    p.initial_population = population;
+    p.grid_size = grid_size;
+    p.chance_start_infected = prob[0];
+    p.chance_infect_1 = prob[1];
+    p.chance_infect_2 = prob[2];
+    p.chance_recover = prob[3];
+    p.chance_die = prob[4];
+    p.social_compliance = prob[5];
+    p.chance_attempt_move = prob[6];
+    p.infection_radius = ints[0];
+    p.incubation_period = static_cast<uint32_t>(ints[1]);
+    p.crowding_threshold = static_cast<uint32_t>(ints[2]);
+    p.quarantine_duration = static_cast<uint32_t>(ints[3]);
+    p.zone_x = ints[4];
+    p.zone_y = ints[5];
+    p.zone_radius = ints[6];
+    p.history_clear_above = static_cast<uint32_t>(ints[7]);
+    p.systems = systems;
+    return new SpatialSim(p, seed, replica);
+}
+void oracle_spatial_free(void* h) { delete static_cast<SpatialSim*>(h); }
+void oracle_spatial_spawn(void* h) { static_cast<SpatialSim*>(h)->spawn_population(); }
+void oracle_spatial_spawn_explicit(void* h, uint64_t n, const int32_t* xy, const uint8_t* disease, const uint8_t* social)
+{
+    SpatialSim& s = *static_cast<SpatialSim*>(h);
+    for (uint64_t i = 0; i < n; ++i) s.push_person(xy[2 * i], xy[2 * i + 1], disease[i], social[i]);
+}
+int oracle_spatial_run(void* h, uint64_t steps)
+{
+    try
+    {
+        static_cast<SpatialSim*>(h)->run(steps);
+    }
+    catch (const std::out_of_range&)
+    {
+        return 34;
+    }
+    return 0;
+}
+uint64_t oracle_spatial_num_slots(void* h) { return static_cast<SpatialSim*>(h)->position.size(); }
+// per spawn slot; history: 21 u32 per slot = len, then the packed (x | y << 16) keys in ascending order
+void oracle_spatial_state(void* h, int32_t* xy, uint8_t* alive, uint8_t* disease, uint8_t* social, uint32_t* quarantined,
+                          uint32_t* history)
+{
+    SpatialSim& s = *static_cast<SpatialSim*>(h);
+    for (size_t i = 0; i < s.position.size(); ++i)
+    {
+        xy[2 * i] = s.position[i].x;
+        xy[2 * i + 1] = s.position[i].y;
+        alive[i] = s.alive[i];
+        disease[i] = s.disease[i];
+        social[i] = s.social[i];
+        quarantined[i] = s.quarantined[i];
+        if (history)
+        {
+            uint32_t* hrow = history + 21 * i;
+            std::vector<uint32_t> keys;
+            for (auto& loc : s.history[i]) keys.push_back(static_cast<uint32_t>(loc.first) | (static_cast<uint32_t>(loc.second) << 16));
+            std::sort(keys.begin(), keys.end());
+            hrow[0] = static_cast<uint32_t>(keys.size());
+            for (size_t k = 0; k < 20; ++k) hrow[1 + k] = k < keys.size() ? keys[k] : 0;
+        }
+    }
+}
+void oracle_spatial_stats(void* h, uint64_t out6[6]) { static_cast<SpatialSim*>(h)->stats(out6); }
+uint64_t oracle_spatial_series(void* h, uint64_t* out /* len * 6 */, uint64_t cap)
+{
+    SpatialSim& s = *static_cast<SpatialSim*>(h);
+    for (size_t i = 0; i < s.series.size() && i < cap; ++i)
+        for (int k = 0; k < 6; ++k) out[6 * i + k] = s.series[i][k];
     return s.series.size();
 }
 

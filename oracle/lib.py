@@ -92,6 +92,24 @@ def load() -> C.CDLL:
     lib.oracle_air_series.argtypes = [vp, u64p, C.c_uint64]
     lib.oracle_air_series.restype = C.c_uint64
     f64p = C.POINTER(C.c_double)
+    lib.oracle_spatial_new.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, f64p, i32p, C.c_uint32]
+    lib.oracle_spatial_new.restype = vp
+    lib.oracle_spatial_free.argtypes = [vp]
+    lib.oracle_spatial_free.restype = None
+    lib.oracle_spatial_spawn.argtypes = [vp]
+    lib.oracle_spatial_spawn.restype = None
+    lib.oracle_spatial_spawn_explicit.argtypes = [vp, C.c_uint64, i32p, u8p, u8p]
+    lib.oracle_spatial_spawn_explicit.restype = None
+    lib.oracle_spatial_run.argtypes = [vp, C.c_uint64]
+    lib.oracle_spatial_run.restype = C.c_int
+    lib.oracle_spatial_num_slots.argtypes = [vp]
+    lib.oracle_spatial_num_slots.restype = C.c_uint64
+    lib.oracle_spatial_state.argtypes = [vp, i32p, u8p, u8p, u8p, u32p, u32p]
+    lib.oracle_spatial_state.restype = None
+    lib.oracle_spatial_stats.argtypes = [vp, u64p]
+    lib.oracle_spatial_stats.restype = None
+    lib.oracle_spatial_series.argtypes = [vp, u64p, C.c_uint64]
+    lib.oracle_spatial_series.restype = C.c_uint64
     lib.oracle_traders_new.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_double,
                                        C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32]
     lib.oracle_traders_new.restype = vp

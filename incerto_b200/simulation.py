@@ -359,6 +359,8 @@ class Spawner:
         for comp, val in columns.items():
             if comp.dtype == F.MARKER:
                 cols[comp] = None if val is None else [np.asarray(val, dtype=np.uint8).reshape(n, 1)]
+            elif val is None:
+                cols[comp] = None      # Default::default(): zeros / empty engine-managed container
             else:
                 cols[comp] = [np.ascontiguousarray(np.asarray(val, dtype=comp.np_dtype)).reshape(n, comp.lanes)]
         self._calls.append((n, cols))

@@ -43,9 +43,62 @@ __device__ __forceinline__ uint32_t bytes_below(uint32_t w, uint32_t t)
     return __vcmpltu4(w, t * 0x01010101u);
 }
 
+// bit k of the result: byte k of w is < t
+__device__ __forceinline__ uint32_t bytes_below_bits(uint32_t w, uint32_t t)
+{
+    const uint32_t m = bytes_below(w, t) & 0x08040201u;
+    return (m * 0x01010101u) >> 24; // the four selected bits land in the top byte without carries
+}
+// bit k of the result: nibble k of w is non-zero
+__device__ __forceinline__ uint32_t nibbles_nonzero_bits(uint32_t w)
+{
+    uint32_t y = (w | (w >> 1) | (w >> 2) | (w >> 3)) & 0x11111111u;
+    y = (y | (y >> 3)) & 0x03030303u;
+    y = (y | (y >> 6)) & 0x000f000fu;
+    return (y | (y >> 12)) & 0xffu;
+}
+
+template <int NW>
+__device__ __forceinline__ uint32_t nibble_at(const uint32_t (&pw)[NW], uint32_t s)
+{
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k)
+        if (static_cast<uint32_t>(k) == (s >> 3)) w = pw[k];
+    return (w >> (4 * (s & 7u))) & 0xfu;
+}
+template <int NW>
+__device__ __forceinline__ void nibble_set(uint32_t (&pw)[NW], uint32_t s, uint32_t v)
+{
+    const uint32_t sh = 4 * (s & 7u);
+#pragma unroll
+    for (int k = 0; k < NW; ++k)
+        if (static_cast<uint32_t>(k) == (s >> 3)) pw[k] = (pw[k] & ~(0xfu << sh)) | (v << sh);
+}
+// lowest set bit of a multi-word mask, cleared on return; -1 when empty
+template <int NC>
+__device__ __forceinline__ int pop_lowest(unsigned long long (&m)[NC])
+{
+    int s = -1;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if (s < 0 && m[c])
+        {
+            s = 64 * c + __ffsll(static_cast<long long>(m[c])) - 1;
+            m[c] &= m[c] - 1;
+        }
+    return s;
+}
+
+// One thread = one trader.  The level-1 draws of all stocks are taken first (one Philox call per 16 stocks,
+// no divergence) and reduced to candidate bit masks; the rare level-2 events are then handled by a short loop
+// in ascending StockId order, so that a warp executes the expensive path max-events-per-lane times instead of
+// once per stock position.
 template <int NW>
 __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
 {
+    constexpr int NB = (NW + 1) / 2;  // 16-stock blocks
+    constexpr int NC = (NW + 7) / 8;  // 64-stock candidate words
     __shared__ double s_price[kTradersMaxStocks];
     __shared__ uint32_t s_listed[kTradersMaxStocks / 32]; // bit s: stock s exists and is not delisted
     for (uint32_t i = threadIdx.x; i < kTradersMaxStocks / 32; i += blockDim.x) s_listed[i] = 0;
@@ -75,72 +128,71 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
 
         if (a.do_buy)
         {
+            // candidates: level-1 byte below T1, stock listed, not owned yet (:176-180)
+            unsigned long long cand[NC];
 #pragma unroll
-            for (int b = 0; b < (NW + 1) / 2; ++b)
+            for (int c = 0; c < NC; ++c) cand[c] = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
             {
                 if (static_cast<uint32_t>(b) >= nblk) break;
                 const uint4 l1 = philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_buy);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    // candidates: level-1 byte below T1, listed, not owned yet
-                    uint32_t m = bytes_below(word_of(l1, j), a.buy_t1) & 0x01010101u;
-                    if (!m) continue;
-                    const uint32_t s0 = 16u * b + 4u * j;
-                    const uint32_t listed4 = (s_listed[s0 >> 5] >> (s0 & 31)) & 0xfu;
-                    const uint32_t nib4 = (pw[2 * b + (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                    {
-                        if (!((m >> (8 * k)) & 1u) || !((listed4 >> k) & 1u) || ((nib4 >> (4 * k)) & 0xfu)) continue;
-                        const uint32_t s = s0 + k;
-                        const uint4 l2 = philox4x32_10(uid, s, a.step, 1u, a.rk_buy);
-                        if (!bernoulli(l2.x, a.buy_thr2)) continue;
-                        const uint32_t num_shares = a.shares_min + uniform_below(l2.y, a.shares_range);
-                        const double amount = dm_mul(static_cast<double>(num_shares), s_price[s]);
-                        if (amount > cash) continue; // :184-188
-                        pw[2 * b + (j >> 1)] |= num_shares << (16 * (j & 1) + 4 * k);
-                        cash = dm_sub(cash, amount);
-                    }
-                }
+                const uint32_t hit = bytes_below_bits(l1.x, a.buy_t1) | (bytes_below_bits(l1.y, a.buy_t1) << 4) |
+                                     (bytes_below_bits(l1.z, a.buy_t1) << 8) | (bytes_below_bits(l1.w, a.buy_t1) << 12);
+                const uint32_t listed = (s_listed[b >> 1] >> (16 * (b & 1))) & 0xffffu;
+                const uint32_t owned = nibbles_nonzero_bits(pw[2 * b]) | ((2 * b + 1 < NW ? nibbles_nonzero_bits(pw[2 * b + 1]) : 0u) << 8);
+                cand[b >> 2] |= static_cast<unsigned long long>(hit & listed & ~owned) << (16 * (b & 3));
+            }
+            for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))
+            {
+                const uint4 l2 = philox4x32_10(uid, static_cast<uint32_t>(s), a.step, 1u, a.rk_buy);
+                if (!bernoulli(l2.x, a.buy_thr2)) continue;
+                const uint32_t num_shares = a.shares_min + uniform_below(l2.y, a.shares_range);
+                const double amount = dm_mul(static_cast<double>(num_shares), s_price[s]);
+                if (amount > cash) continue; // :184-188
+                nibble_set<NW>(pw, static_cast<uint32_t>(s), num_shares);
+                cash = dm_sub(cash, amount);
             }
         }
 
         double value = 0.0;
-        if (a.do_sell || a.do_net_worth)
+        if (a.do_sell)
         {
+            // candidates: owned and level-1 byte below T1 (:216-223)
+            unsigned long long cand[NC];
 #pragma unroll
-            for (int b = 0; b < (NW + 1) / 2; ++b)
+            for (int c = 0; c < NC; ++c) cand[c] = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
             {
-                const uint32_t w0 = pw[2 * b], w1 = (2 * b + 1 < NW) ? pw[2 * b + 1] : 0u;
-                if (!(w0 | w1)) continue;
-                uint4 l1 = make_uint4(~0u, ~0u, ~0u, ~0u);
-                if (a.do_sell) l1 = philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_sell);
+                const uint32_t owned = nibbles_nonzero_bits(pw[2 * b]) | ((2 * b + 1 < NW ? nibbles_nonzero_bits(pw[2 * b + 1]) : 0u) << 8);
+                if (!owned) continue;
+                const uint4 l1 = philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_sell);
+                const uint32_t hit = bytes_below_bits(l1.x, a.sell_t1) | (bytes_below_bits(l1.y, a.sell_t1) << 4) |
+                                     (bytes_below_bits(l1.z, a.sell_t1) << 8) | (bytes_below_bits(l1.w, a.sell_t1) << 12);
+                cand[b >> 2] |= static_cast<unsigned long long>(hit & owned) << (16 * (b & 3));
+            }
+            for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))
+            {
+                if (!bernoulli(philox4x32_10(uid, static_cast<uint32_t>(s), a.step, 1u, a.rk_sell).x, a.sell_thr2)) continue;
+                const uint32_t n_sh = nibble_at<NW>(pw, static_cast<uint32_t>(s));
+                cash = dm_add(cash, dm_mul(static_cast<double>(n_sh), s_price[s])); // :229-233, ascending StockId
+                nibble_set<NW>(pw, static_cast<uint32_t>(s), 0u);
+            }
+        }
+        if (a.do_net_worth)
+        {
+            // :250-261 portfolio value summed in ascending StockId order
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+            for (int w = 0; w < NW; ++w)
+            {
+                uint32_t rest = pw[w];
+                while (rest)
                 {
-                    if (2 * b + h >= NW) break;
-                    uint32_t w = h ? w1 : w0;
-                    uint32_t rest = w;
-                    while (rest)
-                    {
-                        const uint32_t k = (__ffs(rest) - 1) >> 2; // nibble index 0..7, ascending StockId
-                        const uint32_t n_sh = (w >> (4 * k)) & 0xfu;
-                        rest &= ~(0xfu << (4 * k));
-                        const uint32_t s = 16u * b + 8u * h + k;
-                        bool sell = false;
-                        if (a.do_sell && byte_of(l1, 8u * h + k) < a.sell_t1)
-                            sell = bernoulli(philox4x32_10(uid, s, a.step, 1u, a.rk_sell).x, a.sell_thr2);
-                        const double worth = dm_mul(static_cast<double>(n_sh), s_price[s]);
-                        if (sell)
-                        {
-                            cash = dm_add(cash, worth); // :232-233
-                            w &= ~(0xfu << (4 * k));
-                        }
-                        else
-                            value = dm_add(value, worth);
-                    }
-                    pw[2 * b + h] = w;
+                    const uint32_t k = (__ffs(rest) - 1) >> 2;
+                    const uint32_t n_sh = (rest >> (4 * k)) & 0xfu;
+                    rest &= ~(0xfu << (4 * k));
+                    value = dm_add(value, dm_mul(static_cast<double>(n_sh), s_price[8 * w + k]));
                 }
             }
         }

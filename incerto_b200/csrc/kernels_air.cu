@@ -11,9 +11,12 @@
 // Algorithmic bytes per aircraft-update: 18 (position 8 r + 8 w, target 2 r).
 //
 // The airspace is sparse (reference density 15 / 4000 cells), so the reference's HashMap<pos, HashSet>
-// becomes a device hash table of per-cell occupancy counts rebuilt every step (no dense cell table):
-// open addressing, 64-bit slots tag:8 | key:32 | count:24.  The tag changes every step, which makes last
-// step's entries read as empty: the table is only cleared when the tag wraps (every 255 steps).
+// becomes, per step: (1) a hashed occupancy bitmap set by every aircraft - an exact "nobody there" answer
+// for almost every neighbour cell -, (2) an exact hash table of per-cell counts holding only the aircraft that
+// saw a set bit next to them (open addressing, 64-bit slots tag:8 | key:32 | count:24; the tag changes every
+// step so that last step's entries read as empty and the table is cleared only when the tag wraps, every
+// 255 steps), (3) the conflict count: exact lookups for the flagged neighbour cells only.  Two aircraft in
+// face-adjacent cells always flag each other (the bitmap has no false negatives), so both are in the table.
 //
 // Draw contract:
 //   spawn  aircraft uid: a = philox(key[ASPW], (uid,0,0,0)), b = philox(key[ASPW], (uid,0,0,1));
@@ -86,8 +89,34 @@ __global__ void __launch_bounds__(kThreads) air_spawn_kernel(AirArgs a, int16_t*
     }
 }
 
-// PreUpdate: spatial_grid_update_system (spatial_grid.rs:434-443) as a full rebuild of the occupancy index
-__global__ void __launch_bounds__(kThreads) air_index_kernel(AirArgs a)
+__device__ __forceinline__ bool cell_of(const AirArgs& a, const uint2& p, int& gx, int& gy, int& gz, uint32_t& key)
+{
+    gx = lane16(p.x, 0) - a.bmin[0];
+    gy = lane16(p.x, 1) - a.bmin[1];
+    gz = lane16(p.y, 0) - a.bmin[2];
+    if (gx < 0 || gx >= a.ext[0] || gy < 0 || gy >= a.ext[1] || gz < 0 || gz >= a.ext[2]) return false;
+    key = (static_cast<uint32_t>(gx) * a.ext[1] + static_cast<uint32_t>(gy)) * a.ext[2] + static_cast<uint32_t>(gz);
+    return true;
+}
+__device__ __forceinline__ uint32_t bit_of(const AirArgs& a, uint32_t key) { return (key * 0x85EBCA6Bu) >> a.bits_shift; }
+
+// the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds, spatial_grid.rs:337-340),
+// in the fixed order -x +x -y +y -z +z
+__device__ __forceinline__ uint32_t neighbour_keys(const AirArgs& a, int gx, int gy, int gz, uint32_t key, uint32_t (&nk)[6])
+{
+    const uint32_t sx = static_cast<uint32_t>(a.ext[1]) * a.ext[2], sy = a.ext[2];
+    nk[0] = key - sx;
+    nk[1] = key + sx;
+    nk[2] = key - sy;
+    nk[3] = key + sy;
+    nk[4] = key - 1;
+    nk[5] = key + 1;
+    return (gx > 0 ? 1u : 0u) | (gx < a.ext[0] - 1 ? 2u : 0u) | (gy > 0 ? 4u : 0u) | (gy < a.ext[1] - 1 ? 8u : 0u) |
+           (gz > 0 ? 16u : 0u) | (gz < a.ext[2] - 1 ? 32u : 0u);
+}
+
+// PreUpdate, pass 1: spatial_grid_update_system (spatial_grid.rs:434-443) - every aircraft sets the bit of its cell
+__global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
 {
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -99,16 +128,42 @@ __global__ void __launch_bounds__(kThreads) air_index_kernel(AirArgs a)
     for (uint64_t i = first; i < a.n; i += gstride)
     {
         if (a.flags && !(a.flags[i] & 1u)) continue;
-        const uint2 p = a.pos[i];
-        const int x = lane16(p.x, 0) - a.bmin[0], y = lane16(p.x, 1) - a.bmin[1], z = lane16(p.y, 0) - a.bmin[2];
-        if (x < 0 || x >= a.ext[0] || y < 0 || y >= a.ext[1] || z < 0 || z >= a.ext[2])
+        int gx, gy, gz;
+        uint32_t key;
+        if (!cell_of(a, a.pos[i], gx, gy, gz, key))
         {
             // "entity at position {position:?} outside spatial grid bounds" (spatial_grid.rs:276-279)
             if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u)
                 a.error[1] = static_cast<uint32_t>(i);
             continue;
         }
-        index_insert(a, (static_cast<uint32_t>(x) * a.ext[1] + static_cast<uint32_t>(y)) * a.ext[2] + static_cast<uint32_t>(z));
+        const uint32_t h = bit_of(a, key);
+        atomicOr(&a.bits[h >> 5], 1u << (h & 31));
+    }
+}
+
+// PreUpdate, pass 2: aircraft with a possibly occupied neighbour cell enter the exact per-cell index
+__global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride)
+    {
+        uint32_t mask = 0;
+        int gx, gy, gz;
+        uint32_t key;
+        if ((!a.flags || (a.flags[i] & 1u)) && cell_of(a, a.pos[i], gx, gy, gz, key))
+        {
+            uint32_t nk[6];
+            const uint32_t valid = neighbour_keys(a, gx, gy, gz, key, nk);
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+            {
+                const uint32_t h = bit_of(a, nk[k]);
+                if (((valid >> k) & 1u) && ((a.bits[h >> 5] >> (h & 31)) & 1u)) mask |= 1u << k;
+            }
+            if (mask) index_insert(a, key);
+        }
+        a.cand[i] = static_cast<uint8_t>(mask);
     }
 }
 
@@ -123,19 +178,21 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
         const uint64_t row0 = q * 2;
         const bool full = row0 + 2 <= a.n;
         uint2 p[2];
-        uint32_t t2;
+        uint32_t t2, c2 = 0;
         if (full)
         {
             const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
             p[0] = make_uint2(v.x, v.y);
             p[1] = make_uint2(v.z, v.w);
             t2 = *reinterpret_cast<const uint32_t*>(a.target + row0);
+            if (a.do_check) c2 = *reinterpret_cast<const uint16_t*>(a.cand + row0);
         }
         else
         {
             p[0] = a.pos[row0];
             p[1] = p[0];
             t2 = static_cast<uint16_t>(a.target[row0]);
+            if (a.do_check) c2 = a.cand[row0];
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k)
@@ -146,20 +203,23 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
             int x = lane16(p[k].x, 0), y = lane16(p[k].x, 1), z = lane16(p[k].y, 0);
             if (a.do_check)
             {
-                // neighbors_of filters the neighbour cells by the grid bounds (:337-340); aircraft outside
-                // the bounds were already reported by the index kernel
-                const int gx = x - a.bmin[0], gy = y - a.bmin[1], gz = z - a.bmin[2];
-                if (gx >= 0 && gx < a.ext[0] && gy >= 0 && gy < a.ext[1] && gz >= 0 && gz < a.ext[2])
+                int gx, gy, gz;
+                uint32_t key;
+                if (cell_of(a, p[k], gx, gy, gz, key)) // aircraft outside the bounds were reported by the bits kernel
                 {
-                    const uint32_t key = (static_cast<uint32_t>(gx) * a.ext[1] + static_cast<uint32_t>(gy)) * a.ext[2] + static_cast<uint32_t>(gz);
-                    const uint32_t sx = static_cast<uint32_t>(a.ext[1]) * a.ext[2], sy = a.ext[2];
-                    if (gx > 0) conflicts += index_count(a, key - sx);
-                    if (gx < a.ext[0] - 1) conflicts += index_count(a, key + sx);
-                    if (gy > 0) conflicts += index_count(a, key - sy);
-                    if (gy < a.ext[1] - 1) conflicts += index_count(a, key + sy);
-                    if (gz > 0) conflicts += index_count(a, key - 1);
-                    if (gz < a.ext[2] - 1) conflicts += index_count(a, key + 1);
                     indexed += 1;
+                    uint32_t mask = (c2 >> (8 * k)) & 0xffu;
+                    if (mask)
+                    {
+                        uint32_t nk[6];
+                        neighbour_keys(a, gx, gy, gz, key, nk);
+                        while (mask)
+                        {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            conflicts += index_count(a, j == 0 ? nk[0] : (j == 1 ? nk[1] : (j == 2 ? nk[2] : (j == 3 ? nk[3] : (j == 4 ? nk[4] : nk[5])))));
+                        }
+                    }
                 }
             }
             if (a.do_move)
@@ -215,7 +275,8 @@ void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out,
 {
     air_spawn_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a, target_out, flags_out);
 }
-void launch_air_index(const AirArgs& a, cudaStream_t st) { air_index_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
+void launch_air_bits(const AirArgs& a, cudaStream_t st) { air_bits_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
+void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
     air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);

@@ -28,11 +28,17 @@ struct AirArgs
     uint32_t slot_shift; // 32 - log2(slots)
     uint32_t tag;       // 1..255, changes every step; slots with another tag are empty
     uint64_t* acc;      // [0] conflicts of this step (each pair counted twice), [1] aircraft indexed
+    // occupancy pre-filter: one bit per hashed cell (no false negatives); only aircraft that see a set bit
+    // in one of their six face-neighbour cells enter the exact index above
+    uint32_t* bits;
+    uint32_t bits_shift; // 32 - log2(number of bits)
+    uint8_t* cand;       // per row: which of the six neighbour cells (-x +x -y +y -z +z) showed a set bit
     uint32_t* error;
 };
 
 void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out, cudaStream_t st);
-void launch_air_index(const AirArgs& a, cudaStream_t st);
+void launch_air_bits(const AirArgs& a, cudaStream_t st);
+void launch_air_candidates(const AirArgs& a, cudaStream_t st);
 void launch_air_step(const AirArgs& a, cudaStream_t st);
 
 } // namespace incerto

@@ -89,13 +89,19 @@ int32_t air_bind(Sim& s)
             // per-cell counts are 24 bit; more aircraft than that could in principle share one cell
             if (t.n >= (1ull << 31)) return INCERTO_ERR_UNSUPPORTED;
         }
-        uint64_t want = std::max<uint64_t>(1024, t.n + t.n / 2);
+        uint64_t want = std::max<uint64_t>(1024, 2 * t.n);
         uint32_t bits = 10;
         while ((1ull << bits) < want) ++bits;
         am.n_slots = 1u << bits;
         am.slot_bits = bits;
         INC_CUDA(cudaMalloc(&am.d_slots, static_cast<size_t>(am.n_slots) * 8));
         INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
+        // pre-filter bitmap: >= 32 bits per aircraft (at most ~3 % of the bits set)
+        uint32_t fb = 16;
+        while ((1ull << fb) < 32 * t.n && fb < 32) ++fb;
+        am.filter_bits = fb;
+        INC_CUDA(cudaMalloc(&am.d_bits, (1ull << fb) / 8));
+        INC_CUDA(cudaMalloc(&am.d_cand, std::max<uint64_t>(t.n, 2)));
     }
     return INCERTO_OK;
 }
@@ -113,6 +119,10 @@ void air_free(Sim& s)
     AirModule& am = s.mods->air;
     cudaFree(am.d_slots);
     cudaFree(am.d_acc);
+    cudaFree(am.d_bits);
+    cudaFree(am.d_cand);
+    am.d_bits = nullptr;
+    am.d_cand = nullptr;
     am.d_slots = nullptr;
     am.d_acc = nullptr;
 }
@@ -146,6 +156,9 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.slot_shift = 32 - am.slot_bits;
     a.tag = static_cast<uint32_t>(step % 255) + 1;
     a.acc = am.d_acc;
+    a.bits = am.d_bits;
+    a.bits_shift = 32 - am.filter_bits;
+    a.cand = am.d_cand;
     a.error = s.d_error;
 }
 
@@ -164,11 +177,18 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
         {
             // the tag of 255 steps ago comes round again: drop those entries first
             if (step % 255 == 0) INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
-            KTimer kt(s, "air_index", 8.0 * t.n);
-            launch_air_index(a, s.stream);
+            INC_CUDA(cudaMemsetAsync(am.d_bits, 0, (1ull << am.filter_bits) / 8, s.stream));
+            {
+                KTimer kt(s, "air_bits", 8.0 * t.n);
+                launch_air_bits(a, s.stream);
+            }
+            {
+                KTimer kt(s, "air_candidates", 9.0 * t.n);
+                launch_air_candidates(a, s.stream);
+            }
         }
         {
-            KTimer kt(s, "air_step", (am.do_move ? 18.0 : 8.0) * t.n);
+            KTimer kt(s, "air_step", (am.do_move ? 18.0 : 8.0) * t.n + (am.do_check ? 1.0 : 0.0) * t.n);
             launch_air_step(a, s.stream);
         }
         INC_CUDA(cudaGetLastError());

@@ -73,152 +73,210 @@ __device__ __forceinline__ void mark_cell(const SpatialArgs& a, uint32_t key, ui
     if (old != 0u && old != id && old != kMany) a.mark[cell] = kMany;
 }
 
+// Rare, long work (walking a contact history, probing 13 cells) is done by the whole warp for one person at
+// a time - one load per lane - instead of by one lane with 31 idle: the warp's persons needing it are taken
+// from a ballot.
 __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a)
 {
-    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const uint32_t G = static_cast<uint32_t>(a.G);
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t base = warp0 * 32; base < a.n; base += nwarps * 32)
     {
-        const uint32_t fl = a.flags[i];
-        const uint32_t ax = a.aux[i];
+        const uint64_t i = base + lane;
+        const bool valid = i < a.n;
+        uint32_t fl = 0, ax = 0, p = 0, q = 0, d = 0;
+        if (valid)
+        {
+            fl = a.flags[i];
+            ax = a.aux[i];
+            p = a.pos[i];
+            q = a.quar[i];
+            d = a.disease[i];
+        }
         const uint32_t op = ax >> 5;
         uint32_t len = ax & 31u;
-        const uint32_t p = a.pos[i];
         const uint32_t x = p & 0xffffu, y = p >> 16;
-        if (!(fl & 1u))
-        {
-            if (op == OP_DIED)
-            {
-                // spatial_grid_cleanup_system (spatial_grid.rs:446-455)
-                atomicSub(&a.count[x * G + y], 1u);
-                a.aux[i] = 0;
-            }
-            continue;
-        }
         const uint32_t cell = x * G + y;
+        bool alive = valid && (fl & 1u);
+        if (valid && !alive && op == OP_DIED)
+        {
+            // spatial_grid_cleanup_system (spatial_grid.rs:446-455)
+            atomicSub(&a.count[cell], 1u);
+            a.aux[i] = 0;
+        }
         // spatial_grid_update_system (spatial_grid.rs:434-443) for Changed<GridPosition>
-        if (op == OP_NEW)
+        if (alive && op == OP_NEW)
         {
             if (x >= G || y >= G)
             {
                 if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u) a.error[1] = static_cast<uint32_t>(i);
-                continue;
+                alive = false; // left untouched
             }
-            atomicAdd(&a.count[cell], 1u);
+            else
+                atomicAdd(&a.count[cell], 1u);
         }
-        else if (op >= OP_UP && op <= OP_DOWN)
+        const bool moved = alive && op >= OP_UP && op <= OP_DOWN;
+        if (moved)
         {
             const uint32_t old = op == OP_UP ? cell + 1 : (op == OP_DOWN ? cell - 1 : (op == OP_LEFT ? cell + G : cell - G));
             atomicSub(&a.count[old], 1u);
             atomicAdd(&a.count[cell], 1u);
         }
-        const bool moved = op >= OP_UP && op <= OP_DOWN;
-        const bool free_ = a.quar[i] == 0;
-        uint32_t d = a.disease[i];
+        const bool free_ = q == 0;
         const uint32_t d0 = d;
-        const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
-        // :414-433
-        if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
-        // :446-459 the infectious, non-quarantined people are the sources of this step
-        if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
-        {
-            atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
-            const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
-            a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
-        }
-        // :521-541
+        const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
         bool dying = false;
-        if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
+        if (alive)
         {
-            const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
-            if (bernoulli(r.x, a.thr_die))
-                dying = true;
-            else if (bernoulli(r.y, a.thr_recover))
-                d = INCERTO_DISEASE_RECOVERED;
-        }
-        // :544-562 a person who did not move already remembers this cell (it was inserted last step), unless that
-        // insert emptied the set
-        if (a.systems & 8u)
-        {
-            if (len == 0)
+            // :414-433
+            if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
+            // :446-459 the infectious, non-quarantined people are the sources of this step
+            if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
             {
-                a.hist[i] = p;
-                len = 1;
+                atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
+                const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
+                a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
             }
-            else if (moved)
+            // :521-541
+            if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
             {
-                bool found = false;
-                for (uint32_t k = 0; k < len; ++k) found = found || a.hist[static_cast<uint64_t>(k) * a.n_cap + i] == p;
+                const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
+                if (bernoulli(r.x, a.thr_die))
+                    dying = true;
+                else if (bernoulli(r.y, a.thr_recover))
+                    d = INCERTO_DISEASE_RECOVERED;
+            }
+        }
+        // :544-562 update_contact_history: a person who did not move already remembers this cell (it was inserted
+        // last step) unless that insert emptied the set; :565-608 scatter side of the tracing: every cell a
+        // non-quarantined person remembers is stamped with its id
+        const bool need_hist = alive && (a.systems & 8u) && (len == 0 || moved);
+        const bool need_mark = alive && (a.systems & 16u) && free_;
+        uint32_t work = __ballot_sync(kFullMask, need_hist || need_mark);
+        while (work)
+        {
+            const int src = __ffs(work) - 1;
+            work &= work - 1;
+            const uint64_t bi = base + static_cast<uint32_t>(src);
+            uint32_t blen = __shfl_sync(kFullMask, len, src);
+            const uint32_t bp = __shfl_sync(kFullMask, p, src);
+            const uint32_t bid = __shfl_sync(kFullMask, uid, src) + 1u;
+            const bool bhist = __shfl_sync(kFullMask, static_cast<int>(need_hist), src) != 0;
+            const bool bmark = __shfl_sync(kFullMask, static_cast<int>(need_mark), src) != 0;
+            uint32_t h = lane < blen ? a.hist[static_cast<uint64_t>(lane) * a.n_cap + bi] : 0u;
+            if (bhist)
+            {
+                const bool found = __any_sync(kFullMask, lane < blen && h == bp);
                 if (!found)
                 {
-                    if (len >= a.history_cap)
-                        len = 0; // the insert made the set larger than 20: clear() (:555-558)
+                    if (blen >= a.history_cap)
+                        blen = 0; // the insert made the set larger than 20: clear() (:555-558)
                     else
                     {
-                        a.hist[static_cast<uint64_t>(len) * a.n_cap + i] = p;
-                        len += 1;
+                        if (lane == blen)
+                        {
+                            a.hist[static_cast<uint64_t>(lane) * a.n_cap + bi] = bp;
+                            h = bp;
+                        }
+                        blen += 1;
                     }
                 }
             }
+            if (bmark && lane < blen) mark_cell(a, h, bid);
+            if (static_cast<int>(lane) == src) len = blen;
         }
-        // :565-608, scatter side: every cell this non-quarantined person remembers
-        if ((a.systems & 16u) && free_)
-            for (uint32_t k = 0; k < len; ++k) mark_cell(a, a.hist[static_cast<uint64_t>(k) * a.n_cap + i], uid + 1u);
-        if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
-        a.aux[i] = static_cast<uint8_t>(len | ((dying ? OP_DYING : OP_NONE) << 5));
+        if (alive)
+        {
+            if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
+            const uint32_t nax = len | ((dying ? OP_DYING : OP_NONE) << 5);
+            if (nax != ax) a.aux[i] = static_cast<uint8_t>(nax);
+        }
     }
+}
+
+// (dx, dy) of the 13 cells within Manhattan distance 2, one per lane
+__device__ __forceinline__ void offset13(uint32_t lane, int& dx, int& dy)
+{
+    // lane: 0 -> (0,0); 1..4 -> distance 1; 5..12 -> distance 2
+    const int t[13][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-2, 0}, {2, 0}, {0, -2}, {0, 2}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
+    dx = 0;
+    dy = 0;
+#pragma unroll
+    for (int k = 0; k < 13; ++k)
+        if (lane == static_cast<uint32_t>(k))
+        {
+            dx = t[k][0];
+            dy = t[k][1];
+        }
 }
 
 __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs a)
 {
-    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const int G = a.G;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    int odx, ody;
+    offset13(lane, odx, ody);
+    const uint32_t odist = static_cast<uint32_t>((odx < 0 ? -odx : odx) + (ody < 0 ? -ody : ody));
+    const bool olane = lane < 13u && odist <= a.radius; // beyond distance 2 the chance is 0.0 (:498)
+    const uint64_t othr = odist <= 1u ? a.thr_infect1 : a.thr_infect2;
+    for (uint64_t base = warp0 * 32; base < a.n; base += nwarps * 32)
     {
-        uint32_t fl = a.flags[i];
-        if (!(fl & 1u)) continue;
-        const uint32_t ax = a.aux[i];
+        const uint64_t i = base + lane;
+        uint32_t fl = 0, ax = 0, q = 0, d = 0, p = 0;
+        if (i < a.n)
+        {
+            fl = a.flags[i];
+            ax = a.aux[i];
+            q = a.quar[i];
+            d = a.disease[i];
+            p = a.pos[i];
+        }
+        const bool alive = (fl & 1u) != 0;
         const bool dying = (ax >> 5) == OP_DYING;
-        uint32_t q = a.quar[i];
-        const uint32_t q0 = q;
+        const uint32_t q0 = q, d0 = d;
         const bool free_ = q == 0;
-        uint32_t d = a.disease[i];
-        const uint32_t d0 = d;
-        uint32_t p = a.pos[i];
         const int x = static_cast<int>(p & 0xffffu), y = static_cast<int>(p >> 16);
         const uint32_t cell = static_cast<uint32_t>(x) * G + static_cast<uint32_t>(y);
-        const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
+        const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
 
-        // :461-508 gather side of the transmission: sources within Manhattan distance <= radius
-        if ((a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY)
+        // :461-508 gather side of the transmission: the warp probes the 13 cells around one healthy,
+        // non-quarantined person at a time
+        uint32_t work = __ballot_sync(kFullMask, alive && (a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY);
+        while (work)
         {
-            const int R = static_cast<int>(a.radius < 2u ? a.radius : 2u); // beyond distance 2 the chance is 0.0 (:498)
-            bool exposed = false;
-            for (int dx = -R; dx <= R; ++dx)
+            const int src = __ffs(work) - 1;
+            work &= work - 1;
+            const int bx = __shfl_sync(kFullMask, x, src), by = __shfl_sync(kFullMask, y, src);
+            const uint32_t buid = __shfl_sync(kFullMask, uid, src);
+            const int cx = bx + odx, cy = by + ody;
+            bool hit = false;
+            uint32_t c = 0;
+            if (olane && cx >= 0 && cx < G && cy >= 0 && cy < G)
             {
-                const int cx = x + dx;
-                if (cx < 0 || cx >= G) continue;
-                const int span = R - (dx < 0 ? -dx : dx);
-                for (int dy = -span; dy <= span; ++dy)
+                c = static_cast<uint32_t>(cx) * G + static_cast<uint32_t>(cy);
+                hit = (a.src_bits[c >> 5] >> (c & 31)) & 1u;
+            }
+            if (!__any_sync(kFullMask, hit)) continue;
+            bool exposed = false;
+            if (hit)
+            {
+                const uint32_t h = a.src_head[c];
+                uint32_t cur = ((h >> kSpatialRowBits) == a.tag) ? (h & kRowMask) : kRowMask;
+                for (uint32_t guard = 0; cur != kRowMask && guard <= kRowMask; ++guard)
                 {
-                    const int cy = y + dy;
-                    if (cy < 0 || cy >= G) continue;
-                    const uint32_t c = static_cast<uint32_t>(cx) * G + static_cast<uint32_t>(cy);
-                    if (!((a.src_bits[c >> 5] >> (c & 31)) & 1u)) continue;
-                    const uint32_t dist = static_cast<uint32_t>((dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy));
-                    const uint64_t thr = dist <= 1u ? a.thr_infect1 : a.thr_infect2;
-                    const uint32_t h = a.src_head[c];
-                    uint32_t cur = ((h >> kSpatialRowBits) == a.tag) ? (h & kRowMask) : kRowMask;
-                    for (uint32_t guard = 0; cur != kRowMask && guard <= kRowMask; ++guard)
-                    {
-                        const uint32_t suid = a.uid ? a.uid[cur] : cur;
-                        exposed = exposed || bernoulli(philox4x32_10(uid, suid, a.step, 0u, a.rk_transmit).x, thr);
-                        cur = a.src_next[cur];
-                    }
+                    const uint32_t suid = a.uid ? a.uid[cur] : cur;
+                    exposed = exposed || bernoulli(philox4x32_10(buid, suid, a.step, 0u, a.rk_transmit).x, othr);
+                    cur = a.src_next[cur];
                 }
             }
-            if (exposed) d = a.incubation; // :510-517
+            exposed = __any_sync(kFullMask, exposed);
+            if (exposed && static_cast<int>(lane) == src) d = a.incubation; // :510-517
         }
+        if (!alive) continue;
 
         // :580-606 gather side of the tracing
         bool quarantine = false;
@@ -236,40 +294,35 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
             if (bernoulli(r.x, a.thr_attempt)) // :332
             {
                 const bool social = (fl & a.bit_social) != 0;
-                const int nx[4] = {x, x - 1, x + 1, x}, ny[4] = {y - 1, y, y, y + 1}; // up, left, right, down (:338-343)
-                uint32_t best[4], best_count[4], nbest = 0, min_crowding = 0xffffffffu;
+                // candidates in the order up, left, right, down (:338-343); bit k of `ok`: candidate k passes
+                // the bounds (:348-355) and quarantine-zone (:360-371) filters
+                uint32_t ok = 0, cnt[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                 {
-                    if (nx[k] < 0 || nx[k] >= G || ny[k] < 0 || ny[k] >= G) continue;
-                    const int zd = (nx[k] > a.zone_x ? nx[k] - a.zone_x : a.zone_x - nx[k]) + (ny[k] > a.zone_y ? ny[k] - a.zone_y : a.zone_y - ny[k]);
-                    if (zd <= a.zone_radius && social) continue; // :360-371
-                    const uint32_t people = a.count[static_cast<uint32_t>(nx[k]) * G + static_cast<uint32_t>(ny[k])];
-                    if (social)
-                    {
-                        if (people < min_crowding)
-                        {
-                            min_crowding = people;
-                            nbest = 0;
-                        }
-                        else if (people != min_crowding)
-                            continue;
-                    }
-                    best[nbest] = static_cast<uint32_t>(k);
-                    best_count[nbest] = people;
-                    ++nbest;
+                    const int nx = k == 1 ? x - 1 : (k == 2 ? x + 1 : x), ny = k == 0 ? y - 1 : (k == 3 ? y + 1 : y);
+                    if (nx < 0 || nx >= G || ny < 0 || ny >= G) continue;
+                    const int zd = (nx > a.zone_x ? nx - a.zone_x : a.zone_x - nx) + (ny > a.zone_y ? ny - a.zone_y : a.zone_y - ny);
+                    if (zd <= a.zone_radius && social) continue;
+                    ok |= 1u << k;
+                    cnt[k] = a.count[static_cast<uint32_t>(nx) * G + static_cast<uint32_t>(ny)];
                 }
-                if (nbest)
+                if (social)
                 {
-                    const uint32_t c = uniform_below(r.y, nbest); // best_moves.choose (:401)
-                    uint32_t dir = best[0], people = best_count[0];
+                    // keep the least crowded candidates (:377-390)
+                    uint32_t mn = 0xffffffffu;
 #pragma unroll
-                    for (int k = 1; k < 4; ++k)
-                        if (static_cast<uint32_t>(k) == c)
-                        {
-                            dir = best[k];
-                            people = best_count[k];
-                        }
+                    for (int k = 0; k < 4; ++k)
+                        if ((ok >> k) & 1u) mn = min(mn, cnt[k]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (cnt[k] != mn) ok &= ~(1u << k);
+                }
+                if (ok)
+                {
+                    const uint32_t pick = uniform_below(r.y, static_cast<uint32_t>(__popc(ok))); // best_moves.choose (:401)
+                    const uint32_t dir = __fns(ok, 0, static_cast<int>(pick) + 1);
+                    const uint32_t people = dir == 0 ? cnt[0] : (dir == 1 ? cnt[1] : (dir == 2 ? cnt[2] : cnt[3]));
                     if (people < a.crowding) // :403-408
                     {
                         const int mx = dir == 1 ? x - 1 : (dir == 2 ? x + 1 : x), my = dir == 0 ? y - 1 : (dir == 3 ? y + 1 : y);

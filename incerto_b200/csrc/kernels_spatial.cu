@@ -73,144 +73,230 @@ __device__ __forceinline__ void mark_cell(const SpatialArgs& a, uint32_t key, ui
     if (old != 0u && old != id && old != kMany) a.mark[cell] = kMany;
 }
 
-// Rare, long work (walking a contact history, probing 13 cells) is done by the whole warp for one person at
-// a time - one load per lane - instead of by one lane with 31 idle: the warp's persons needing it are taken
-// from a ballot.
+// ---- eight persons per lane: byte columns travel as one 64-bit word, positions as two 128-bit words
+constexpr unsigned long long kOnes = 0x0101010101010101ull;
+
+// 0x01 in every byte of x that is zero (exact per byte)
+__device__ __forceinline__ unsigned long long zero_bytes(unsigned long long x)
+{
+    const unsigned long long m = 0x7f7f7f7f7f7f7f7full;
+    const unsigned long long t = ~(((x & m) + m) | x | m); // 0x80 where the byte is zero
+    return t >> 7;
+}
+// bit k of the result = bit 0 of byte k
+__device__ __forceinline__ uint32_t collect_lsb(unsigned long long x)
+{
+    return static_cast<uint32_t>(((x & kOnes) * 0x0102040810204080ull) >> 56);
+}
+__device__ __forceinline__ uint32_t byte_at(unsigned long long v, uint32_t k) { return static_cast<uint32_t>(v >> (8 * k)) & 0xffu; }
+__device__ __forceinline__ unsigned long long byte_put(unsigned long long v, uint32_t k, uint32_t b)
+{
+    return (v & ~(0xffull << (8 * k))) | (static_cast<unsigned long long>(b) << (8 * k));
+}
+__device__ __forceinline__ uint32_t word_at(const uint32_t (&w)[8], uint32_t k)
+{
+    uint32_t r = w[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+        if (k == static_cast<uint32_t>(j)) r = w[j];
+    return r;
+}
+
+struct Tile8
+{
+    unsigned long long fl, ax, q, d;
+    uint32_t pos[8];
+};
+
+__device__ __forceinline__ void load_tile(const SpatialArgs& a, uint64_t i0, Tile8& t)
+{
+    if (i0 + 8 <= a.n)
+    {
+        t.fl = *reinterpret_cast<const unsigned long long*>(a.flags + i0);
+        t.ax = *reinterpret_cast<const unsigned long long*>(a.aux + i0);
+        t.q = *reinterpret_cast<const unsigned long long*>(a.quar + i0);
+        t.d = *reinterpret_cast<const unsigned long long*>(a.disease + i0);
+        const uint4 p0 = *reinterpret_cast<const uint4*>(a.pos + i0), p1 = *reinterpret_cast<const uint4*>(a.pos + i0 + 4);
+        t.pos[0] = p0.x;
+        t.pos[1] = p0.y;
+        t.pos[2] = p0.z;
+        t.pos[3] = p0.w;
+        t.pos[4] = p1.x;
+        t.pos[5] = p1.y;
+        t.pos[6] = p1.z;
+        t.pos[7] = p1.w;
+        return;
+    }
+    t.fl = t.ax = t.q = t.d = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+        t.pos[k] = 0;
+        if (i0 + k < a.n)
+        {
+            t.fl |= static_cast<unsigned long long>(a.flags[i0 + k]) << (8 * k);
+            t.ax |= static_cast<unsigned long long>(a.aux[i0 + k]) << (8 * k);
+            t.q |= static_cast<unsigned long long>(a.quar[i0 + k]) << (8 * k);
+            t.d |= static_cast<unsigned long long>(a.disease[i0 + k]) << (8 * k);
+            t.pos[k] = a.pos[i0 + k];
+        }
+    }
+}
+__device__ __forceinline__ void store_bytes(uint8_t* col, uint64_t i0, uint64_t n, unsigned long long v)
+{
+    if (i0 + 8 <= n)
+        *reinterpret_cast<unsigned long long*>(col + i0) = v;
+    else
+        for (int k = 0; k < 8 && i0 + k < n; ++k) col[i0 + k] = static_cast<uint8_t>(v >> (8 * k));
+}
+
+// Streaming pass with a rare slow path.  A lane owns eight consecutive persons (128 bytes in flight per lane);
+// byte-parallel tests pick the persons that need any work this step - in the steady state most people are
+// quarantined, healthy and standing still, and need none -, the warp then serves one such person per lane and
+// iteration.  The longer work of such a person (reading its contact history, probing 13 cells) is a fully
+// unrolled set of independent predicated loads, so that its latencies overlap.
 __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a)
 {
     const uint32_t G = static_cast<uint32_t>(a.G);
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-    for (uint64_t base = warp0 * 32; base < a.n; base += nwarps * 32)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats_acc)
+        for (int k = 0; k < 4; ++k) a.stats_acc[k] = 0;
+    for (uint64_t base = warp0 * 256; base < a.n; base += nwarps * 256)
     {
-        const uint64_t i = base + lane;
-        const bool valid = i < a.n;
-        uint32_t fl = 0, ax = 0, p = 0, q = 0, d = 0;
-        if (valid)
+        const uint64_t i0 = base + lane * 8;
+        Tile8 t;
+        load_tile(a, i0, t);
+        const unsigned long long ax0 = t.ax, d0 = t.d;
+        const unsigned long long opbits = t.ax & (0xe0ull * kOnes);
+        const unsigned long long alive8 = t.fl & kOnes;
+        const unsigned long long op_nz = zero_bytes(opbits) ^ kOnes;
+        const unsigned long long died = zero_bytes(opbits ^ ((OP_DIED << 5) * kOnes));
+        const unsigned long long free8 = zero_bytes(t.q);
+        const unsigned long long d_active = (zero_bytes(t.d) | zero_bytes(t.d ^ (0x81ull * kOnes))) ^ kOnes; // exposed or infectious
+        const unsigned long long len0 = zero_bytes(t.ax & (0x1full * kOnes));
+        unsigned long long want = alive8 & (op_nz | d_active);
+        if (a.systems & 16u) want |= alive8 & free8;
+        if (a.systems & 8u) want |= alive8 & len0;
+        want |= (alive8 ^ kOnes) & died;
+        uint32_t todo = collect_lsb(want);
+        if (i0 >= a.n) todo = 0;
+        while (__any_sync(kFullMask, todo != 0))
         {
-            fl = a.flags[i];
-            ax = a.aux[i];
-            p = a.pos[i];
-            q = a.quar[i];
-            d = a.disease[i];
-        }
-        const uint32_t op = ax >> 5;
-        uint32_t len = ax & 31u;
-        const uint32_t x = p & 0xffffu, y = p >> 16;
-        const uint32_t cell = x * G + y;
-        bool alive = valid && (fl & 1u);
-        if (valid && !alive && op == OP_DIED)
-        {
-            // spatial_grid_cleanup_system (spatial_grid.rs:446-455)
-            atomicSub(&a.count[cell], 1u);
-            a.aux[i] = 0;
-        }
-        // spatial_grid_update_system (spatial_grid.rs:434-443) for Changed<GridPosition>
-        if (alive && op == OP_NEW)
-        {
-            if (x >= G || y >= G)
+            const bool active = todo != 0;
+            const uint32_t k = active ? static_cast<uint32_t>(__ffs(todo) - 1) : 0u;
+            todo &= todo - 1;
+            const uint64_t i = i0 + k;
+            const uint32_t fl = byte_at(t.fl, k), ax = byte_at(t.ax, k), q = byte_at(t.q, k);
+            uint32_t d = byte_at(t.d, k);
+            const uint32_t p = word_at(t.pos, k);
+            const uint32_t op = ax >> 5;
+            uint32_t len = ax & 31u;
+            const uint32_t x = p & 0xffffu, y = p >> 16;
+            const uint32_t cell = x * G + y;
+            bool alive = active && (fl & 1u);
+            if (active && !alive && op == OP_DIED)
             {
-                if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u) a.error[1] = static_cast<uint32_t>(i);
-                alive = false; // left untouched
+                // spatial_grid_cleanup_system (spatial_grid.rs:446-455)
+                atomicSub(&a.count[cell], 1u);
+                t.ax = byte_put(t.ax, k, 0u);
             }
-            else
-                atomicAdd(&a.count[cell], 1u);
-        }
-        const bool moved = alive && op >= OP_UP && op <= OP_DOWN;
-        if (moved)
-        {
-            const uint32_t old = op == OP_UP ? cell + 1 : (op == OP_DOWN ? cell - 1 : (op == OP_LEFT ? cell + G : cell - G));
-            atomicSub(&a.count[old], 1u);
-            atomicAdd(&a.count[cell], 1u);
-        }
-        const bool free_ = q == 0;
-        const uint32_t d0 = d;
-        const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
-        bool dying = false;
-        if (alive)
-        {
-            // :414-433
-            if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
-            // :446-459 the infectious, non-quarantined people are the sources of this step
-            if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
+            // spatial_grid_update_system (spatial_grid.rs:434-443) for Changed<GridPosition>
+            if (alive && op == OP_NEW)
             {
-                atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
-                const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
-                a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
-            }
-            // :521-541
-            if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
-            {
-                const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
-                if (bernoulli(r.x, a.thr_die))
-                    dying = true;
-                else if (bernoulli(r.y, a.thr_recover))
-                    d = INCERTO_DISEASE_RECOVERED;
-            }
-        }
-        // :544-562 update_contact_history: a person who did not move already remembers this cell (it was inserted
-        // last step) unless that insert emptied the set; :565-608 scatter side of the tracing: every cell a
-        // non-quarantined person remembers is stamped with its id
-        const bool need_hist = alive && (a.systems & 8u) && (len == 0 || moved);
-        const bool need_mark = alive && (a.systems & 16u) && free_;
-        uint32_t work = __ballot_sync(kFullMask, need_hist || need_mark);
-        while (work)
-        {
-            const int src = __ffs(work) - 1;
-            work &= work - 1;
-            const uint64_t bi = base + static_cast<uint32_t>(src);
-            uint32_t blen = __shfl_sync(kFullMask, len, src);
-            const uint32_t bp = __shfl_sync(kFullMask, p, src);
-            const uint32_t bid = __shfl_sync(kFullMask, uid, src) + 1u;
-            const bool bhist = __shfl_sync(kFullMask, static_cast<int>(need_hist), src) != 0;
-            const bool bmark = __shfl_sync(kFullMask, static_cast<int>(need_mark), src) != 0;
-            uint32_t h = lane < blen ? a.hist[static_cast<uint64_t>(lane) * a.n_cap + bi] : 0u;
-            if (bhist)
-            {
-                const bool found = __any_sync(kFullMask, lane < blen && h == bp);
-                if (!found)
+                if (x >= G || y >= G)
                 {
-                    if (blen >= a.history_cap)
-                        blen = 0; // the insert made the set larger than 20: clear() (:555-558)
-                    else
-                    {
-                        if (lane == blen)
-                        {
-                            a.hist[static_cast<uint64_t>(lane) * a.n_cap + bi] = bp;
-                            h = bp;
-                        }
-                        blen += 1;
-                    }
+                    if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u) a.error[1] = static_cast<uint32_t>(i);
+                    alive = false; // left untouched
+                }
+                else
+                    atomicAdd(&a.count[cell], 1u);
+            }
+            const bool moved = alive && op >= OP_UP && op <= OP_DOWN;
+            if (moved)
+            {
+                const uint32_t old = op == OP_UP ? cell + 1 : (op == OP_DOWN ? cell - 1 : (op == OP_LEFT ? cell + G : cell - G));
+                atomicSub(&a.count[old], 1u);
+                atomicAdd(&a.count[cell], 1u);
+            }
+            const bool free_ = q == 0;
+            const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
+            bool dying = false;
+            if (alive)
+            {
+                // :414-433
+                if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
+                // :446-459 the infectious, non-quarantined people are the sources of this step
+                if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
+                {
+                    atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
+                    const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
+                    a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
+                }
+                // :521-541
+                if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
+                {
+                    const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
+                    if (bernoulli(r.x, a.thr_die))
+                        dying = true;
+                    else if (bernoulli(r.y, a.thr_recover))
+                        d = INCERTO_DISEASE_RECOVERED;
                 }
             }
-            if (bmark && lane < blen) mark_cell(a, h, bid);
-            if (static_cast<int>(lane) == src) len = blen;
+            // :544-562 update_contact_history: a person who did not move already remembers this cell (it was
+            // inserted last step) unless that insert emptied the set; :565-608 scatter side of the tracing: every
+            // cell a non-quarantined person remembers is stamped with its id
+            const bool need_hist = alive && (a.systems & 8u) && (len == 0 || moved);
+            const bool need_mark = alive && (a.systems & 16u) && free_;
+            if (need_hist || need_mark)
+            {
+                // all remembered cells at once: independent, predicated loads (slot-major: coalesced across lanes)
+                uint32_t hv[kSpatialHistorySlots];
+                bool found = false;
+#pragma unroll
+                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                {
+                    hv[s2] = 0xffffffffu;
+                    if (s2 < len) hv[s2] = a.hist[static_cast<uint64_t>(s2) * a.n_cap + i];
+                    found = found || hv[s2] == p;
+                }
+                if (need_hist && !found)
+                {
+                    if (len >= a.history_cap)
+                        len = 0; // the insert made the set larger than 20: clear() (:555-558)
+                    else
+                    {
+                        a.hist[static_cast<uint64_t>(len) * a.n_cap + i] = p;
+#pragma unroll
+                        for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                            if (s2 == len) hv[s2] = p;
+                        len += 1;
+                    }
+                }
+                if (need_mark)
+                {
+#pragma unroll
+                    for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                        if (s2 < len) mark_cell(a, hv[s2], uid + 1u);
+                }
+            }
+            if (alive)
+            {
+                t.d = byte_put(t.d, k, d);
+                t.ax = byte_put(t.ax, k, len | ((dying ? OP_DYING : OP_NONE) << 5));
+            }
         }
-        if (alive)
+        if (i0 < a.n)
         {
-            if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
-            const uint32_t nax = len | ((dying ? OP_DYING : OP_NONE) << 5);
-            if (nax != ax) a.aux[i] = static_cast<uint8_t>(nax);
+            if (t.d != d0) store_bytes(a.disease, i0, a.n, t.d);
+            if (t.ax != ax0) store_bytes(a.aux, i0, a.n, t.ax);
         }
     }
 }
 
-// (dx, dy) of the 13 cells within Manhattan distance 2, one per lane
-__device__ __forceinline__ void offset13(uint32_t lane, int& dx, int& dy)
-{
-    // lane: 0 -> (0,0); 1..4 -> distance 1; 5..12 -> distance 2
-    const int t[13][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-2, 0}, {2, 0}, {0, -2}, {0, 2}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
-    dx = 0;
-    dy = 0;
-#pragma unroll
-    for (int k = 0; k < 13; ++k)
-        if (lane == static_cast<uint32_t>(k))
-        {
-            dx = t[k][0];
-            dy = t[k][1];
-        }
-}
+// (dx, dy) of the 13 cells within Manhattan distance 2: index 0 -> distance 0, 1..4 -> distance 1, 5..12 -> distance 2
+__device__ constexpr int kOff13[13][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-2, 0}, {2, 0}, {0, -2}, {0, 2}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
 
 __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs a)
 {
@@ -218,147 +304,232 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-    int odx, ody;
-    offset13(lane, odx, ody);
-    const uint32_t odist = static_cast<uint32_t>((odx < 0 ? -odx : odx) + (ody < 0 ? -ody : ody));
-    const bool olane = lane < 13u && odist <= a.radius; // beyond distance 2 the chance is 0.0 (:498)
-    const uint64_t othr = odist <= 1u ? a.thr_infect1 : a.thr_infect2;
-    for (uint64_t base = warp0 * 32; base < a.n; base += nwarps * 32)
+    uint32_t st[4] = {0, 0, 0, 0}; // PandemicStats of the state after this step: healthy, exposed, infectious, recovered
+    for (uint64_t base = warp0 * 256; base < a.n; base += nwarps * 256)
     {
-        const uint64_t i = base + lane;
-        uint32_t fl = 0, ax = 0, q = 0, d = 0, p = 0;
-        if (i < a.n)
+        const uint64_t i0 = base + lane * 8;
+        Tile8 t;
+        load_tile(a, i0, t);
+        const unsigned long long fl0 = t.fl, ax0 = t.ax, q0 = t.q, d0 = t.d;
+        const unsigned long long alive8 = t.fl & kOnes;
+        const unsigned long long free8 = zero_bytes(t.q);
+        const unsigned long long dying8 = zero_bytes((t.ax & (0xe0ull * kOnes)) ^ ((OP_DYING << 5) * kOnes));
+        // update_quarantine_status (:611-625) for everybody at once: n > 1 -> n - 1, n == 1 -> removed at the flush.
+        // (people quarantined at this flush were not quarantined during the step: disjoint from these)
+        if (a.systems & 32u) t.q -= alive8 & (free8 ^ kOnes);
+        uint32_t todo = collect_lsb(alive8 & (free8 | dying8));
+        if (i0 >= a.n) todo = 0;
+        bool pos_changed = false;
+        while (__any_sync(kFullMask, todo != 0))
         {
-            fl = a.flags[i];
-            ax = a.aux[i];
-            q = a.quar[i];
-            d = a.disease[i];
-            p = a.pos[i];
-        }
-        const bool alive = (fl & 1u) != 0;
-        const bool dying = (ax >> 5) == OP_DYING;
-        const uint32_t q0 = q, d0 = d;
-        const bool free_ = q == 0;
-        const int x = static_cast<int>(p & 0xffffu), y = static_cast<int>(p >> 16);
-        const uint32_t cell = static_cast<uint32_t>(x) * G + static_cast<uint32_t>(y);
-        const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
+            const bool active = todo != 0;
+            const uint32_t k = active ? static_cast<uint32_t>(__ffs(todo) - 1) : 0u;
+            todo &= todo - 1;
+            const uint64_t i = i0 + k;
+            uint32_t fl = byte_at(t.fl, k);
+            const uint32_t ax = byte_at(t.ax, k);
+            uint32_t q = byte_at(q0, k), d = byte_at(t.d, k);
+            uint32_t p = word_at(t.pos, k);
+            const bool alive = active;
+            const bool dying = (ax >> 5) == OP_DYING;
+            const bool free_ = q == 0;
+            const int x = static_cast<int>(p & 0xffffu), y = static_cast<int>(p >> 16);
+            const uint32_t cell = static_cast<uint32_t>(x) * G + static_cast<uint32_t>(y);
+            const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
 
-        // :461-508 gather side of the transmission: the warp probes the 13 cells around one healthy,
-        // non-quarantined person at a time
-        uint32_t work = __ballot_sync(kFullMask, alive && (a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY);
-        while (work)
-        {
-            const int src = __ffs(work) - 1;
-            work &= work - 1;
-            const int bx = __shfl_sync(kFullMask, x, src), by = __shfl_sync(kFullMask, y, src);
-            const uint32_t buid = __shfl_sync(kFullMask, uid, src);
-            const int cx = bx + odx, cy = by + ody;
-            bool hit = false;
-            uint32_t c = 0;
-            if (olane && cx >= 0 && cx < G && cy >= 0 && cy < G)
+            // :461-508 gather side of the transmission: probe the 13 cells within Manhattan distance 2 (independent,
+            // predicated bit loads), then walk the source lists of the few cells that hold a source
+            if (alive && (a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY)
             {
-                c = static_cast<uint32_t>(cx) * G + static_cast<uint32_t>(cy);
-                hit = (a.src_bits[c >> 5] >> (c & 31)) & 1u;
-            }
-            if (!__any_sync(kFullMask, hit)) continue;
-            bool exposed = false;
-            if (hit)
-            {
-                const uint32_t h = a.src_head[c];
-                uint32_t cur = ((h >> kSpatialRowBits) == a.tag) ? (h & kRowMask) : kRowMask;
-                for (uint32_t guard = 0; cur != kRowMask && guard <= kRowMask; ++guard)
-                {
-                    const uint32_t suid = a.uid ? a.uid[cur] : cur;
-                    exposed = exposed || bernoulli(philox4x32_10(buid, suid, a.step, 0u, a.rk_transmit).x, othr);
-                    cur = a.src_next[cur];
-                }
-            }
-            exposed = __any_sync(kFullMask, exposed);
-            if (exposed && static_cast<int>(lane) == src) d = a.incubation; // :510-517
-        }
-        if (!alive) continue;
-
-        // :580-606 gather side of the tracing
-        bool quarantine = false;
-        if ((a.systems & 16u) && free_)
-        {
-            const uint32_t m = a.mark[cell];
-            quarantine = m != 0u && m != uid + 1u;
-        }
-
-        // :316-411 (a person despawned at this flush is left where it is: its move is unobservable)
-        uint32_t newop = OP_NONE;
-        if ((a.systems & 64u) && free_ && !dying)
-        {
-            const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_move);
-            if (bernoulli(r.x, a.thr_attempt)) // :332
-            {
-                const bool social = (fl & a.bit_social) != 0;
-                // candidates in the order up, left, right, down (:338-343); bit k of `ok`: candidate k passes
-                // the bounds (:348-355) and quarantine-zone (:360-371) filters
-                uint32_t ok = 0, cnt[4] = {0, 0, 0, 0};
+                uint32_t hits = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int c13 = 0; c13 < 13; ++c13)
                 {
-                    const int nx = k == 1 ? x - 1 : (k == 2 ? x + 1 : x), ny = k == 0 ? y - 1 : (k == 3 ? y + 1 : y);
-                    if (nx < 0 || nx >= G || ny < 0 || ny >= G) continue;
-                    const int zd = (nx > a.zone_x ? nx - a.zone_x : a.zone_x - nx) + (ny > a.zone_y ? ny - a.zone_y : a.zone_y - ny);
-                    if (zd <= a.zone_radius && social) continue;
-                    ok |= 1u << k;
-                    cnt[k] = a.count[static_cast<uint32_t>(nx) * G + static_cast<uint32_t>(ny)];
-                }
-                if (social)
-                {
-                    // keep the least crowded candidates (:377-390)
-                    uint32_t mn = 0xffffffffu;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if ((ok >> k) & 1u) mn = min(mn, cnt[k]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (cnt[k] != mn) ok &= ~(1u << k);
-                }
-                if (ok)
-                {
-                    const uint32_t pick = uniform_below(r.y, static_cast<uint32_t>(__popc(ok))); // best_moves.choose (:401)
-                    const uint32_t dir = __fns(ok, 0, static_cast<int>(pick) + 1);
-                    const uint32_t people = dir == 0 ? cnt[0] : (dir == 1 ? cnt[1] : (dir == 2 ? cnt[2] : cnt[3]));
-                    if (people < a.crowding) // :403-408
+                    const int dx = kOff13[c13][0], dy = kOff13[c13][1];
+                    const int cx = x + dx, cy = y + dy;
+                    const uint32_t dist = static_cast<uint32_t>((dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy));
+                    if (dist <= a.radius && cx >= 0 && cx < G && cy >= 0 && cy < G)
                     {
-                        const int mx = dir == 1 ? x - 1 : (dir == 2 ? x + 1 : x), my = dir == 0 ? y - 1 : (dir == 3 ? y + 1 : y);
-                        p = static_cast<uint32_t>(mx) | (static_cast<uint32_t>(my) << 16);
-                        newop = dir + 1;
+                        const uint32_t c = static_cast<uint32_t>(cx) * G + static_cast<uint32_t>(cy);
+                        hits |= ((a.src_bits[c >> 5] >> (c & 31)) & 1u) << c13;
+                    }
+                }
+                bool exposed = false;
+                while (hits)
+                {
+                    const int c13 = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    int dx = 0, dy = 0;
+#pragma unroll
+                    for (int j = 0; j < 13; ++j)
+                        if (c13 == j)
+                        {
+                            dx = kOff13[j][0];
+                            dy = kOff13[j][1];
+                        }
+                    const uint32_t c = static_cast<uint32_t>(x + dx) * G + static_cast<uint32_t>(y + dy);
+                    const uint64_t thr = c13 <= 4 ? a.thr_infect1 : a.thr_infect2; // distance 0 | 1, else 2 (:495-499)
+                    const uint32_t h = a.src_head[c];
+                    uint32_t cur = ((h >> kSpatialRowBits) == a.tag) ? (h & kRowMask) : kRowMask;
+                    for (uint32_t guard = 0; cur != kRowMask && guard <= kRowMask; ++guard)
+                    {
+                        const uint32_t suid = a.uid ? a.uid[cur] : cur;
+                        exposed = exposed || bernoulli(philox4x32_10(uid, suid, a.step, 0u, a.rk_transmit).x, thr);
+                        cur = a.src_next[cur];
+                    }
+                }
+                if (exposed) d = a.incubation; // :510-517
+            }
+            if (!alive) continue;
+
+            // :580-606 gather side of the tracing
+            bool quarantine = false;
+            if ((a.systems & 16u) && free_)
+            {
+                const uint32_t m = a.mark[cell];
+                quarantine = m != 0u && m != uid + 1u;
+            }
+
+            // :316-411 (a person despawned at this flush is left where it is: its move is unobservable)
+            uint32_t newop = OP_NONE;
+            if ((a.systems & 64u) && free_ && !dying)
+            {
+                const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_move);
+                if (bernoulli(r.x, a.thr_attempt)) // :332
+                {
+                    const bool social = (fl & a.bit_social) != 0;
+                    // candidates in the order up, left, right, down (:338-343); bit k of `ok`: candidate k passes
+                    // the bounds (:348-355) and quarantine-zone (:360-371) filters
+                    uint32_t ok = 0, cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                    {
+                        const int nx = c == 1 ? x - 1 : (c == 2 ? x + 1 : x), ny = c == 0 ? y - 1 : (c == 3 ? y + 1 : y);
+                        if (nx < 0 || nx >= G || ny < 0 || ny >= G) continue;
+                        const int zd = (nx > a.zone_x ? nx - a.zone_x : a.zone_x - nx) + (ny > a.zone_y ? ny - a.zone_y : a.zone_y - ny);
+                        if (zd <= a.zone_radius && social) continue;
+                        ok |= 1u << c;
+                        cnt[c] = a.count[static_cast<uint32_t>(nx) * G + static_cast<uint32_t>(ny)];
+                    }
+                    if (social)
+                    {
+                        // keep the least crowded candidates (:377-390)
+                        uint32_t mn = 0xffffffffu;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if ((ok >> c) & 1u) mn = min(mn, cnt[c]);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (cnt[c] != mn) ok &= ~(1u << c);
+                    }
+                    if (ok)
+                    {
+                        const uint32_t pick = uniform_below(r.y, static_cast<uint32_t>(__popc(ok))); // best_moves.choose (:401)
+                        const uint32_t dir = __fns(ok, 0, static_cast<int>(pick) + 1);
+                        const uint32_t people = dir == 0 ? cnt[0] : (dir == 1 ? cnt[1] : (dir == 2 ? cnt[2] : cnt[3]));
+                        if (people < a.crowding) // :403-408
+                        {
+                            const int mx = dir == 1 ? x - 1 : (dir == 2 ? x + 1 : x), my = dir == 0 ? y - 1 : (dir == 3 ? y + 1 : y);
+                            p = static_cast<uint32_t>(mx) | (static_cast<uint32_t>(my) << 16);
+                            newop = dir + 1;
+                        }
                     }
                 }
             }
-        }
 
-        // end of Update: despawn (:530), try_insert(Quarantined) (:600-603), update_quarantine_status (:611-625)
-        if (dying)
-        {
-            fl &= ~1u;
-            newop = OP_DIED;
-            a.flags[i] = static_cast<uint8_t>(fl);
+            // end of Update: despawn (:530), try_insert(Quarantined) (:600-603)
+            if (dying)
+            {
+                fl &= ~1u;
+                newop = OP_DIED;
+                t.fl = byte_put(t.fl, k, fl);
+            }
+            else if (quarantine)
+                t.q = byte_put(t.q, k, a.quarantine_duration);
+            t.d = byte_put(t.d, k, d);
+            if (newop >= OP_UP && newop <= OP_DOWN)
+            {
+                pos_changed = true;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (k == static_cast<uint32_t>(j)) t.pos[j] = p;
+            }
+            t.ax = byte_put(t.ax, k, (ax & 31u) | (newop << 5));
         }
-        else if (quarantine)
-            q = a.quarantine_duration;
-        else if ((a.systems & 32u) && q > 0u)
-            q = q > 1u ? q - 1u : 0u;
-        if (q != q0) a.quar[i] = static_cast<uint8_t>(q);
-        if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
-        if (newop >= OP_UP && newop <= OP_DOWN) a.pos[i] = p;
-        if (newop != (ax >> 5)) a.aux[i] = static_cast<uint8_t>((ax & 31u) | (newop << 5));
+        if (i0 < a.n)
+        {
+            if (t.fl != fl0) store_bytes(a.flags, i0, a.n, t.fl);
+            if (t.q != q0) store_bytes(a.quar, i0, a.n, t.q);
+            if (t.d != d0) store_bytes(a.disease, i0, a.n, t.d);
+            if (t.ax != ax0) store_bytes(a.aux, i0, a.n, t.ax);
+            if (pos_changed)
+            {
+                if (i0 + 8 <= a.n)
+                {
+                    *reinterpret_cast<uint4*>(a.pos + i0) = make_uint4(t.pos[0], t.pos[1], t.pos[2], t.pos[3]);
+                    *reinterpret_cast<uint4*>(a.pos + i0 + 4) = make_uint4(t.pos[4], t.pos[5], t.pos[6], t.pos[7]);
+                }
+                else
+                    for (int j = 0; j < 8 && i0 + j < a.n; ++j) a.pos[i0 + j] = t.pos[j];
+            }
+            // fused PandemicStats (:107-138) of the post-flush state
+            const unsigned long long al = t.fl & kOnes;
+            const unsigned long long healthy = zero_bytes(t.d) & al, infectious = zero_bytes(t.d ^ (0x80ull * kOnes)) & al,
+                                     recovered = zero_bytes(t.d ^ (0x81ull * kOnes)) & al;
+            st[0] += __popcll(healthy);
+            st[2] += __popcll(infectious);
+            st[3] += __popcll(recovered);
+            st[1] += __popcll(al) - __popcll(healthy) - __popcll(infectious) - __popcll(recovered);
+        }
+    }
+    if (a.stats_acc)
+    {
+        __shared__ uint32_t smem[4 * 32];
+        block_sum<uint32_t, 4>(st, smem);
+        if (threadIdx.x == 0)
+            for (int k = 0; k < 4; ++k)
+                if (st[k]) atomicAdd(reinterpret_cast<unsigned long long*>(&a.stats_acc[k]), static_cast<unsigned long long>(st[k]));
     }
 }
 
-// PandemicStats: counts by disease state among the live persons
+// out6 <- PandemicStats from the counts accumulated by the interact kernel
+__global__ void spatial_stats_finalize_kernel(const uint64_t* acc, uint64_t initial_population, uint64_t* out6)
+{
+    const uint64_t alive = acc[0] + acc[1] + acc[2] + acc[3];
+    out6[0] = acc[0];
+    out6[1] = acc[1];
+    out6[2] = acc[2];
+    out6[3] = acc[3];
+    out6[4] = initial_population - alive; // dead_count: INITIAL_POPULATION - components.len() (:134)
+    out6[5] = alive;
+}
+
+// PandemicStats: counts by disease state among the live persons (standalone: 16 persons per thread and load)
 __global__ void __launch_bounds__(kThreads) spatial_stats_kernel(const uint8_t* __restrict__ disease, const uint8_t* __restrict__ flags,
                                                                  uint64_t n, uint64_t initial_population, uint64_t* out6,
                                                                  uint32_t* partial, uint32_t* ticket)
 {
     uint32_t v[4] = {0, 0, 0, 0}; // healthy, exposed, infectious, recovered
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gstride)
+    const uint64_t nvec = n / 16;
+    for (uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < nvec; j += gstride)
+    {
+        const uint4 f = ld_stream_v4(flags + 16 * j), d = ld_stream_v4(disease + 16 * j);
+        const unsigned long long fw[2] = {f.x | (static_cast<unsigned long long>(f.y) << 32), f.z | (static_cast<unsigned long long>(f.w) << 32)};
+        const unsigned long long dw[2] = {d.x | (static_cast<unsigned long long>(d.y) << 32), d.z | (static_cast<unsigned long long>(d.w) << 32)};
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {
+            const unsigned long long al = fw[h] & kOnes;
+            const uint32_t he = __popcll(zero_bytes(dw[h]) & al), in = __popcll(zero_bytes(dw[h] ^ (0x80ull * kOnes)) & al),
+                           re = __popcll(zero_bytes(dw[h] ^ (0x81ull * kOnes)) & al);
+            v[0] += he;
+            v[2] += in;
+            v[3] += re;
+            v[1] += __popcll(al) - he - in - re;
+        }
+    }
+    for (uint64_t i = nvec * 16 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gstride)
     {
         if (!(flags[i] & 1u)) continue;
         const uint32_t d = disease[i];
@@ -401,8 +572,12 @@ inline int blocks_for(uint64_t items)
 } // namespace
 
 void launch_spatial_spawn(const SpatialArgs& a, cudaStream_t st) { spatial_spawn_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
-void launch_spatial_prepare(const SpatialArgs& a, cudaStream_t st) { spatial_prepare_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
-void launch_spatial_interact(const SpatialArgs& a, cudaStream_t st) { spatial_interact_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
+void launch_spatial_prepare(const SpatialArgs& a, cudaStream_t st) { spatial_prepare_kernel<<<blocks_for((a.n + 7) / 8), kThreads, 0, st>>>(a); }
+void launch_spatial_interact(const SpatialArgs& a, cudaStream_t st) { spatial_interact_kernel<<<blocks_for((a.n + 7) / 8), kThreads, 0, st>>>(a); }
+void launch_spatial_stats_finalize(const uint64_t* acc, uint64_t initial_population, uint64_t* out6, cudaStream_t st)
+{
+    spatial_stats_finalize_kernel<<<1, 1, 0, st>>>(acc, initial_population, out6);
+}
 void launch_spatial_stats(const uint8_t* disease, const uint8_t* flags, uint64_t n, uint64_t initial_population,
                           uint64_t* out6, void* scratch, uint32_t* ticket, cudaStream_t st)
 {

@@ -35,12 +35,14 @@ struct SpatialArgs
     uint32_t* src_next; // per row: next source in the same cell
     uint32_t tag;       // 1..63
     uint32_t* mark;     // per cell: 0, uid + 1 of the only non-quarantined person remembering it, or 0xffffffff (several)
+    uint64_t* stats_acc; // healthy, exposed, infectious, recovered of the post-flush state (zeroed by prepare, summed by interact)
     uint32_t* error;
 };
 
 void launch_spatial_spawn(const SpatialArgs& a, cudaStream_t st);
 void launch_spatial_prepare(const SpatialArgs& a, cudaStream_t st);
 void launch_spatial_interact(const SpatialArgs& a, cudaStream_t st);
+void launch_spatial_stats_finalize(const uint64_t* acc, uint64_t initial_population, uint64_t* out6, cudaStream_t st);
 // PandemicStats (examples/pandemic_spatial.rs:107-138): out6 = healthy, exposed, infectious, recovered, dead, total
 void launch_spatial_stats(const uint8_t* disease, const uint8_t* flags, uint64_t n, uint64_t initial_population,
                           uint64_t* out6, void* scratch, uint32_t* ticket, cudaStream_t st);

@@ -107,6 +107,7 @@ int32_t spatial_bind(Sim& s)
     INC_CUDA(cudaMalloc(&sm.d_src_head, cells * 4));
     INC_CUDA(cudaMalloc(&sm.d_src_next, n * 4));
     INC_CUDA(cudaMalloc(&sm.d_mark, cells * 4));
+    INC_CUDA(cudaMalloc(&sm.d_stats_acc, 64));
     return spatial_reset(s);
 }
 
@@ -120,6 +121,7 @@ int32_t spatial_reset(Sim& s)
     INC_CUDA(cudaMemsetAsync(sm.d_aux, 6u << 5, std::max<uint64_t>(t.n_spawned, 1), s.stream)); // OP_NEW, empty history
     INC_CUDA(cudaMemsetAsync(sm.d_count, 0, cells * 4, s.stream));
     INC_CUDA(cudaMemsetAsync(sm.d_src_head, 0, cells * 4, s.stream));
+    sm.stats_valid = false;
     return INCERTO_OK;
 }
 
@@ -132,6 +134,8 @@ void spatial_free(Sim& s)
     cudaFree(sm.d_src_head);
     cudaFree(sm.d_src_next);
     cudaFree(sm.d_mark);
+    cudaFree(sm.d_stats_acc);
+    sm.d_stats_acc = nullptr;
     sm.d_aux = nullptr;
     sm.d_count = sm.d_src_bits = sm.d_src_head = sm.d_src_next = sm.d_mark = nullptr;
 }
@@ -175,6 +179,7 @@ static void spatial_fill(Sim& s, SpatialModule& sm, SpatialArgs& a, Table& t, ui
     a.src_next = sm.d_src_next;
     a.tag = static_cast<uint32_t>(step % 63) + 1;
     a.mark = sm.d_mark;
+    a.stats_acc = sm.d_stats_acc;
     a.error = s.d_error;
 }
 
@@ -207,6 +212,7 @@ int32_t spatial_step(Sim& s, uint64_t first_step, uint32_t nsteps)
         }
         INC_CUDA(cudaGetLastError());
         if (sm.systems & 4u) t.all_alive = false;
+        sm.stats_valid = true; // the interact kernel left the PandemicStats counts of the post-flush state
     }
     return INCERTO_OK;
 }
@@ -280,6 +286,13 @@ int32_t spatial_stats_now(Sim& s, uint64_t initial_population, uint8_t* d_raw)
     SpatialModule& sm = s.mods->spatial;
     if (sm.table < 0) return INCERTO_ERR_AGGREGATE_NO_ENTITIES;
     Table& t = s.tables[sm.table];
+    if (sm.stats_valid)
+    {
+        KTimer kt(s, "spatial_stats_fused", 0.0);
+        launch_spatial_stats_finalize(sm.d_stats_acc, initial_population, reinterpret_cast<uint64_t*>(d_raw), s.stream);
+        INC_CUDA(cudaGetLastError());
+        return INCERTO_OK;
+    }
     INC_TRY(ensure_scratch(s, 64 * kNumSMs * 8 + 4096));
     KTimer kt(s, "spatial_stats", 2.0 * t.n);
     launch_spatial_stats(static_cast<const uint8_t*>(t.col(sm.p.disease_state)->d), t.d_flags, t.n, initial_population,

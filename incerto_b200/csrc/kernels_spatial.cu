@@ -39,7 +39,6 @@ namespace
 
 constexpr int kThreads = 256;
 constexpr uint32_t kRowMask = (1u << kSpatialRowBits) - 1;
-constexpr uint32_t kMany = 0xffffffffu;
 // pending ops carried in aux bits 5-7 from one step's flush to the next PreUpdate
 enum : uint32_t
 {
@@ -66,11 +65,14 @@ __global__ void __launch_bounds__(kThreads) spatial_spawn_kernel(SpatialArgs a)
     }
 }
 
+// mark word of a cell: number of non-quarantined people remembering it (high half) | sum of their ids (low half).
+// One fire-and-forget 64-bit reduction per mark; a person's history is a set, so nobody marks a cell twice.
+// The reader only needs "somebody other than me": count >= 2, or count == 1 and the sum is not my id (with a
+// single marker the sum cannot have carried into the count).
 __device__ __forceinline__ void mark_cell(const SpatialArgs& a, uint32_t key, uint32_t id)
 {
     const uint32_t cell = (key & 0xffffu) * static_cast<uint32_t>(a.G) + (key >> 16);
-    const uint32_t old = atomicCAS(&a.mark[cell], 0u, id);
-    if (old != 0u && old != id && old != kMany) a.mark[cell] = kMany;
+    atomicAdd(&a.mark[cell], (1ull << 32) | id);
 }
 
 // ---- eight persons per lane: byte columns travel as one 64-bit word, positions as two 128-bit words
@@ -386,8 +388,9 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
             bool quarantine = false;
             if ((a.systems & 16u) && free_)
             {
-                const uint32_t m = a.mark[cell];
-                quarantine = m != 0u && m != uid + 1u;
+                const unsigned long long m = a.mark[cell];
+                const uint32_t markers = static_cast<uint32_t>(m >> 32);
+                quarantine = markers >= 2u || (markers == 1u && static_cast<uint32_t>(m) != uid + 1u);
             }
 
             // :316-411 (a person despawned at this flush is left where it is: its move is unobservable)

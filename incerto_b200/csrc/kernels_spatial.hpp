@@ -34,7 +34,7 @@ struct SpatialArgs
     uint32_t* src_head; // tag:6 | row:26 of the list head
     uint32_t* src_next; // per row: next source in the same cell
     uint32_t tag;       // 1..63
-    uint32_t* mark;     // per cell: 0, uid + 1 of the only non-quarantined person remembering it, or 0xffffffff (several)
+    unsigned long long* mark; // per cell: markers (non-quarantined people remembering it) << 32 | sum of their uid + 1
     uint64_t* stats_acc; // healthy, exposed, infectious, recovered of the post-flush state (zeroed by prepare, summed by interact)
     uint32_t* error;
 };

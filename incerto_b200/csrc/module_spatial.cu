@@ -106,7 +106,7 @@ int32_t spatial_bind(Sim& s)
     INC_CUDA(cudaMalloc(&sm.d_src_bits, (cells / 32 + 1) * 4));
     INC_CUDA(cudaMalloc(&sm.d_src_head, cells * 4));
     INC_CUDA(cudaMalloc(&sm.d_src_next, n * 4));
-    INC_CUDA(cudaMalloc(&sm.d_mark, cells * 4));
+    INC_CUDA(cudaMalloc(&sm.d_mark, cells * 8));
     INC_CUDA(cudaMalloc(&sm.d_stats_acc, 64));
     return spatial_reset(s);
 }
@@ -137,7 +137,8 @@ void spatial_free(Sim& s)
     cudaFree(sm.d_stats_acc);
     sm.d_stats_acc = nullptr;
     sm.d_aux = nullptr;
-    sm.d_count = sm.d_src_bits = sm.d_src_head = sm.d_src_next = sm.d_mark = nullptr;
+    sm.d_count = sm.d_src_bits = sm.d_src_head = sm.d_src_next = nullptr;
+    sm.d_mark = nullptr;
 }
 
 static void spatial_fill(Sim& s, SpatialModule& sm, SpatialArgs& a, Table& t, uint64_t step)
@@ -200,7 +201,7 @@ int32_t spatial_step(Sim& s, uint64_t first_step, uint32_t nsteps)
             INC_CUDA(cudaMemsetAsync(sm.d_src_bits, 0, (cells / 32 + 1) * 4, s.stream));
             if (step % 63 == 0) INC_CUDA(cudaMemsetAsync(sm.d_src_head, 0, cells * 4, s.stream)); // the tag comes round again
         }
-        if (sm.systems & 16u) INC_CUDA(cudaMemsetAsync(sm.d_mark, 0, cells * 4, s.stream));
+        if (sm.systems & 16u) INC_CUDA(cudaMemsetAsync(sm.d_mark, 0, cells * 8, s.stream));
         {
             // pos 4 + disease 1 + flags 1 + quarantine 1 + aux 1 read, aux 1 written; history and tables on top
             KTimer kt(s, "spatial_prepare", 9.0 * t.n);

@@ -104,7 +104,7 @@ struct SpatialModule
     uint32_t* d_src_bits = nullptr;
     uint32_t* d_src_head = nullptr;
     uint32_t* d_src_next = nullptr;
-    uint32_t* d_mark = nullptr;
+    unsigned long long* d_mark = nullptr;
     uint64_t* d_stats_acc = nullptr; // PandemicStats counts of the state after the last step (fused into the interact kernel)
     bool stats_valid = false;
 };

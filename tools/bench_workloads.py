@@ -136,6 +136,35 @@ def air():
     print("   conflicts of the last step:", sim.sample_aggregate(ib.AirConflicts(target)))
 
 
+def cpu():
+    """The CPU oracle (structure-faithful C++ restatement of the Bevy systems, 1 thread - Bevy runs each system's loop on
+    one core) on bounded samples of the same workloads: the baseline the GPU numbers are reported beside."""
+    import time
+    from oracle.air import AirOracle
+    from oracle.forest import ForestOracle, coin_toss_run
+    from oracle.pandemic import PandemicOracle
+    from oracle.spatial import SpatialConfig, SpatialOracle
+    from oracle.traders import TradersOracle
+
+    def timed(name, n, steps, make, note=""):
+        o = make()
+        t0 = time.perf_counter()
+        o.run(steps) if hasattr(o, "run") else None
+        dt = time.perf_counter() - t0
+        print(f"cpu {name}: n={n} steps={steps}: {n * steps / dt / 1e6:.2f} M updates/s on 1 core ({dt:.1f} s){note}", flush=True)
+
+    t0 = time.perf_counter()
+    coin_toss_run(SEED, 0, 1_000_000, 0.5, 1, 20)
+    dt = time.perf_counter() - t0
+    print(f"cpu coin_toss: n=1000000 steps=20: {20e6 / dt / 1e6:.2f} M updates/s on 1 core ({dt:.1f} s)", flush=True)
+    timed("forest_fire 1024x1024", 1024 * 1024, 10, lambda: ForestOracle(SEED, 0, 1024, 1024).spawn())
+    timed("pandemic G=707", 200_000, 20, lambda: PandemicOracle(SEED, 0, 200_000, 707, nested_loop=False).spawn(),
+          " [per-cell buckets; the reference's O(infected x healthy) double loop is far slower]")
+    timed("pandemic_spatial G=400", 200_000, 30, lambda: SpatialOracle(SEED, 0, SpatialConfig(population=200_000, grid_size=400)).spawn())
+    timed("traders 100 stocks", 20_000, 50, lambda: TradersOracle(SEED, 0, 20_000, 100))
+    timed("air_traffic_3d 2309x2309x10", 200_000, 20, lambda: AirOracle(SEED, 0, 200_000, 2309, 10).spawn())
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     if "--scale" in sys.argv:

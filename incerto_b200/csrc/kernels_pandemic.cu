@@ -48,176 +48,254 @@ __global__ void __launch_bounds__(kThreads) pandemic_spawn_kernel(PandemicArgs a
     }
 }
 
+constexpr int kRows = 8; // consecutive rows per thread: two 128-bit position loads, one 64-bit flags load
+
+struct Rows8
+{
+    uint32_t p[kRows];
+    unsigned long long f; // flags bytes
+};
+
+__device__ __forceinline__ void load_rows(const PandemicArgs& a, uint64_t row0, bool need_pos, Rows8& r)
+{
+    if (row0 + kRows <= a.n)
+    {
+        r.f = *reinterpret_cast<const unsigned long long*>(a.flags + row0);
+        if (need_pos)
+        {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(a.pos + row0), v1 = *reinterpret_cast<const uint4*>(a.pos + row0 + 4);
+            r.p[0] = v0.x;
+            r.p[1] = v0.y;
+            r.p[2] = v0.z;
+            r.p[3] = v0.w;
+            r.p[4] = v1.x;
+            r.p[5] = v1.y;
+            r.p[6] = v1.z;
+            r.p[7] = v1.w;
+        }
+        return;
+    }
+    r.f = 0;
+#pragma unroll
+    for (int k = 0; k < kRows; ++k)
+    {
+        r.p[k] = 0;
+        if (row0 + k < a.n)
+        {
+            r.f |= static_cast<unsigned long long>(a.flags[row0 + k]) << (8 * k);
+            if (need_pos) r.p[k] = a.pos[row0 + k];
+        }
+    }
+}
+
 // people_move + building the per-cell lists of infected people for the interaction kernel.
-// One thread = 4 consecutive rows (one 128-bit position load/store, one Philox call when uid == row).
+// One thread = 8 consecutive rows (two Philox calls when uid == row).  All memory operations of the tile are issued
+// before any result is consumed: the returning exchanges that link the infected into their cells overlap.
 __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
 {
-    const uint64_t nquads = (a.n + 3) >> 2;
+    const uint64_t ntiles = (a.n + kRows - 1) / kRows;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const uint32_t G = a.grid_size;
     const uint32_t tag = (a.step & 0xffu) << 24;
-    for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += gstride)
+    for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < ntiles; q += gstride)
     {
-        const uint64_t row0 = q * 4;
-        const bool full = row0 + 4 <= a.n;
-        uint32_t p[4] = {0, 0, 0, 0};
-        uint32_t f4 = 0;
-        if (full)
+        const uint64_t row0 = q * kRows;
+        const bool full = row0 + kRows <= a.n;
+        Rows8 r;
+        load_rows(a, row0, true, r);
+        uint32_t w[kRows];
+        if (a.do_move)
         {
-            const uint4 pv = *reinterpret_cast<const uint4*>(a.pos + row0);
-            p[0] = pv.x;
-            p[1] = pv.y;
-            p[2] = pv.z;
-            p[3] = pv.w;
-            f4 = *reinterpret_cast<const uint32_t*>(a.flags + row0);
-        }
-        else
-        {
-            for (uint64_t k = 0; row0 + k < a.n; ++k)
+            if (a.uid == nullptr)
             {
-                p[k] = a.pos[row0 + k];
-                f4 |= static_cast<uint32_t>(a.flags[row0 + k]) << (8 * k);
+                const uint4 r0 = philox4x32_10(static_cast<uint32_t>(2 * q), 0u, a.step, 0u, a.rk_move);
+                const uint4 r1 = philox4x32_10(static_cast<uint32_t>(2 * q + 1), 0u, a.step, 0u, a.rk_move);
+                w[0] = r0.x;
+                w[1] = r0.y;
+                w[2] = r0.z;
+                w[3] = r0.w;
+                w[4] = r1.x;
+                w[5] = r1.y;
+                w[6] = r1.z;
+                w[7] = r1.w;
+            }
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < kRows; ++k)
+                {
+                    w[k] = 0;
+                    if ((r.f >> (8 * k)) & 1ull)
+                    {
+                        const uint32_t u = a.uid[row0 + k];
+                        w[k] = word_of(philox4x32_10(u >> 2, 0u, a.step, 0u, a.rk_move), u & 3u);
+                    }
+                }
             }
         }
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (a.do_move && a.uid == nullptr) r = philox4x32_10(static_cast<uint32_t>(q), 0u, a.step, 0u, a.rk_move);
+        uint32_t old[kRows];
+        uint32_t linked = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < kRows; ++k)
         {
-            const uint32_t fl = (f4 >> (8 * k)) & 0xffu;
+            const uint32_t fl = static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu;
+            old[k] = 0;
             if (!(fl & 1u)) continue; // despawned
-            uint32_t x = p[k] & 0xffffu, y = p[k] >> 16;
+            uint32_t x = r.p[k] & 0xffffu, y = r.p[k] >> 16;
             if (a.do_move)
             {
-                uint32_t w;
-                if (a.uid == nullptr)
-                    w = k == 0 ? r.x : (k == 1 ? r.y : (k == 2 ? r.z : r.w));
-                else
-                {
-                    const uint32_t u = a.uid[row0 + k];
-                    w = word_of(philox4x32_10(u >> 2, 0u, a.step, 0u, a.rk_move), u & 3u);
-                }
                 // :121 stay put; :125 x axis else y axis; :128/:147 negative else positive direction; saturating
-                if (w & 0x80000000u)
+                if (w[k] & 0x80000000u)
                 {
-                    const bool neg = !(w & 0x20000000u);
-                    if (!(w & 0x40000000u))
+                    const bool neg = !(w[k] & 0x20000000u);
+                    if (!(w[k] & 0x40000000u))
                         x = neg ? (x > 0 ? x - 1 : x) : (x < G - 1 ? x + 1 : x);
                     else
                         y = neg ? (y > 0 ? y - 1 : y) : (y < G - 1 ? y + 1 : y);
                 }
-                p[k] = x | (y << 16);
+                r.p[k] = x | (y << 16);
             }
             if (a.do_infect && (fl & a.bit_infected))
             {
                 // per-cell list of infected people (order irrelevant: the draws are keyed by the pair)
                 const uint32_t cell = x * G + y;
-                const uint32_t row = static_cast<uint32_t>(row0 + k);
                 atomicOr(&a.cell_bits[cell >> 5], 1u << (cell & 31));
-                const uint32_t old = atomicExch(&a.cell_head[cell], tag | row);
-                a.next_infected[row] = ((old & 0xff000000u) == tag) ? (old & 0x00ffffffu) : 0x00ffffffu;
+                old[k] = atomicExch(&a.cell_head[cell], tag | static_cast<uint32_t>(row0 + k));
+                linked |= 1u << k;
             }
         }
         if (a.do_move)
         {
             if (full)
-                *reinterpret_cast<uint4*>(a.pos + row0) = make_uint4(p[0], p[1], p[2], p[3]);
+            {
+                *reinterpret_cast<uint4*>(a.pos + row0) = make_uint4(r.p[0], r.p[1], r.p[2], r.p[3]);
+                *reinterpret_cast<uint4*>(a.pos + row0 + 4) = make_uint4(r.p[4], r.p[5], r.p[6], r.p[7]);
+            }
             else
-                for (uint64_t k = 0; row0 + k < a.n; ++k) a.pos[row0 + k] = p[k];
+                for (uint64_t k = 0; row0 + k < a.n; ++k) a.pos[row0 + k] = r.p[k];
         }
+#pragma unroll
+        for (int k = 0; k < kRows; ++k)
+            if ((linked >> k) & 1u)
+                a.next_infected[row0 + k] = ((old[k] & 0xff000000u) == tag) ? (old[k] & 0x00ffffffu) : 0x00ffffffu;
     }
 }
 
+// warp-wide exclusive prefix sum of a small per-lane count; total returned through `total`
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, uint32_t& total)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t y = __shfl_up_sync(kFullMask, x, o);
+        if (lane >= static_cast<uint32_t>(o)) x += y;
+    }
+    total = __shfl_sync(kFullMask, x, 31);
+    return x - v;
+}
+
 // people_infect_others + people_infected_may_die + people_infected_may_recover + the command flush.
+// A warp streams 256 rows (8 per lane, packed loads).  The rows with real work - the infected (fate draws) and
+// the healthy standing in a cell that holds an infected person (pair draws) - are rare and scattered, so they are
+// first compacted into a per-warp queue in shared memory and then dealt out one per lane: the Philox paths run
+// with full warps instead of once per row position with two or three lanes active.
 __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArgs a)
 {
-    const uint64_t nquads = (a.n + 3) >> 2;
-    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    __shared__ uint32_t s_queue[kThreads / 32][2][32 * kRows]; // item = row | flags << 24 (rows < 2^24)
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     const uint32_t G = a.grid_size;
     const uint32_t tag = (a.step & 0xffu) << 24;
-    for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += gstride)
+    const bool fate = (a.do_die | a.do_recover) != 0;
+    for (uint64_t base = warp0 * (32 * kRows); base < a.n; base += nwarps * (32 * kRows))
     {
-        const uint64_t row0 = q * 4;
-        const bool full = row0 + 4 <= a.n;
-        uint32_t f4 = 0;
-        if (full)
-            f4 = *reinterpret_cast<const uint32_t*>(a.flags + row0);
-        else
-            for (uint64_t k = 0; row0 + k < a.n; ++k) f4 |= static_cast<uint32_t>(a.flags[row0 + k]) << (8 * k);
-        if (!(f4 & 0x01010101u)) continue;
-        uint32_t p[4] = {0, 0, 0, 0};
-        if (a.do_infect)
+        const uint64_t row0 = base + lane * kRows;
+        Rows8 r;
+        r.f = 0;
+        if (row0 < a.n) load_rows(a, row0, a.do_infect != 0, r);
+        // healthy people: is anybody infected standing in my cell?  (all eight bit loads first)
+        uint32_t hit = 0, sick = 0;
         {
-            if (full)
-            {
-                const uint4 pv = *reinterpret_cast<const uint4*>(a.pos + row0);
-                p[0] = pv.x;
-                p[1] = pv.y;
-                p[2] = pv.z;
-                p[3] = pv.w;
-            }
-            else
-                for (uint64_t k = 0; row0 + k < a.n; ++k) p[k] = a.pos[row0 + k];
-        }
-        uint32_t nf4 = f4;
+            uint32_t bw[kRows];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < kRows; ++k)
+            {
+                const uint32_t fl = static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu;
+                bw[k] = 0;
+                if (fl & 1u)
+                {
+                    if (fl & a.bit_infected)
+                        sick |= 1u << k;
+                    else if (a.do_infect)
+                    {
+                        const uint32_t cell = (r.p[k] & 0xffffu) * G + (r.p[k] >> 16);
+                        bw[k] = (a.cell_bits[cell >> 5] >> (cell & 31)) & 1u;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) hit |= bw[k] << k;
+        }
+        if (!fate) sick = 0;
+        uint32_t n_sick, n_hit;
+        uint32_t o_sick = warp_exclusive_scan(__popc(sick), n_sick);
+        uint32_t o_hit = warp_exclusive_scan(__popc(hit), n_hit);
+        if (!(n_sick | n_hit)) continue;
+#pragma unroll
+        for (int k = 0; k < kRows; ++k)
         {
-            const uint32_t fl = (f4 >> (8 * k)) & 0xffu;
-            if (!(fl & 1u)) continue;
-            const uint32_t row = static_cast<uint32_t>(row0 + k);
+            const uint32_t item = static_cast<uint32_t>(row0 + k) | ((static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu) << 24);
+            if ((sick >> k) & 1u) s_queue[warp][0][o_sick++] = item;
+            if ((hit >> k) & 1u) s_queue[warp][1][o_hit++] = item;
+        }
+        __syncwarp();
+        for (uint32_t j = lane; j < n_sick; j += 32)
+        {
+            const uint32_t item = s_queue[warp][0][j];
+            const uint32_t row = item & 0x00ffffffu, fl = item >> 24;
             const uint32_t uid = a.uid ? a.uid[row] : row;
-            uint32_t nfl = fl;
-            if (fl & a.bit_infected)
+            bool l1_die = true, l1_rec = true;
+            if (a.fate_two_level)
             {
-                if (a.do_die | a.do_recover)
-                {
-                    bool l1_die = true, l1_rec = true;
-                    if (a.fate_two_level)
-                    {
-                        const uint4 l1 = philox4x32_10(uid >> 3, 0u, a.step, 0u, a.rk_fate);
-                        l1_die = byte_of(l1, 2 * (uid & 7u)) == 0;
-                        l1_rec = byte_of(l1, 2 * (uid & 7u) + 1) == 0;
-                    }
-                    if ((l1_die && a.do_die) || (l1_rec && a.do_recover))
-                    {
-                        const uint4 l2 = philox4x32_10(uid, 0u, a.step, 1u, a.rk_fate);
-                        const bool die = a.do_die && l1_die && bernoulli(l2.x, a.thr_die);
-                        const bool rec = a.do_recover && l1_rec && bernoulli(l2.y, a.thr_recover);
-                        if (rec) nfl &= ~a.bit_infected;   // commands.entity(e).remove::<Infected>() (:220)
-                        if (die) nfl = 0;                   // commands.entity(e).despawn() (:203) wins
-                    }
-                }
+                const uint4 l1 = philox4x32_10(uid >> 3, 0u, a.step, 0u, a.rk_fate);
+                l1_die = byte_of(l1, 2 * (uid & 7u)) == 0;
+                l1_rec = byte_of(l1, 2 * (uid & 7u) + 1) == 0;
             }
-            else if (a.do_infect)
+            if ((l1_die && a.do_die) || (l1_rec && a.do_recover))
             {
-                const uint32_t x = p[k] & 0xffffu, y = p[k] >> 16;
-                const uint32_t cell = x * G + y;
-                if ((a.cell_bits[cell >> 5] >> (cell & 31)) & 1u)
-                {
-                    uint32_t h = a.cell_head[cell];
-                    uint32_t cur = ((h & 0xff000000u) == tag) ? (h & 0x00ffffffu) : 0x00ffffffu;
-                    bool infected = false;
-                    // (the guard only bounds the walk should the list ever be corrupt: never hang the device)
-                    for (uint32_t guard = 0; cur != 0x00ffffffu && guard < 0x01000000u; ++guard)
-                    {
-                        const uint32_t iuid = a.uid ? a.uid[cur] : cur;
-                        const uint4 r = philox4x32_10(uid, iuid, a.step, 0u, a.rk_infect);
-                        infected = infected || bernoulli(r.x, a.thr_infect); // :184-188; every pair draws
-                        cur = a.next_infected[cur];
-                    }
-                    if (infected) nfl |= a.bit_infected; // commands.entity(healthy).insert(Infected) (:187)
-                }
+                const uint4 l2 = philox4x32_10(uid, 0u, a.step, 1u, a.rk_fate);
+                const bool die = a.do_die && l1_die && bernoulli(l2.x, a.thr_die);
+                const bool rec = a.do_recover && l1_rec && bernoulli(l2.y, a.thr_recover);
+                uint32_t nfl = fl;
+                if (rec) nfl &= ~a.bit_infected;   // commands.entity(e).remove::<Infected>() (:220)
+                if (die) nfl = 0;                   // commands.entity(e).despawn() (:203) wins
+                if (nfl != fl) a.flags[row] = static_cast<uint8_t>(nfl);
             }
-            nf4 = (nf4 & ~(0xffu << (8 * k))) | (nfl << (8 * k));
         }
-        if (nf4 != f4)
+        for (uint32_t j = lane; j < n_hit; j += 32)
         {
-            if (full)
-                *reinterpret_cast<uint32_t*>(a.flags + row0) = nf4;
-            else
-                for (uint64_t k = 0; row0 + k < a.n; ++k) a.flags[row0 + k] = static_cast<uint8_t>(nf4 >> (8 * k));
+            const uint32_t item = s_queue[warp][1][j];
+            const uint32_t row = item & 0x00ffffffu, fl = item >> 24;
+            const uint32_t uid = a.uid ? a.uid[row] : row;
+            const uint32_t p = a.pos[row];
+            const uint32_t cell = (p & 0xffffu) * G + (p >> 16);
+            const uint32_t h = a.cell_head[cell];
+            uint32_t cur = ((h & 0xff000000u) == tag) ? (h & 0x00ffffffu) : 0x00ffffffu;
+            bool infected = false;
+            // (the guard only bounds the walk should the list ever be corrupt: never hang the device)
+            for (uint32_t guard = 0; cur != 0x00ffffffu && guard < 0x01000000u; ++guard)
+            {
+                const uint32_t iuid = a.uid ? a.uid[cur] : cur;
+                const uint4 rr = philox4x32_10(uid, iuid, a.step, 0u, a.rk_infect);
+                infected = infected || bernoulli(rr.x, a.thr_infect); // :184-188; every pair draws
+                cur = a.next_infected[cur];
+            }
+            if (infected) a.flags[row] = static_cast<uint8_t>(fl | a.bit_infected); // commands.entity(healthy).insert(Infected) (:187)
         }
+        __syncwarp();
     }
 }
 
@@ -238,11 +316,11 @@ void launch_pandemic_spawn(const PandemicArgs& a, cudaStream_t st)
 }
 void launch_pandemic_move(const PandemicArgs& a, cudaStream_t st)
 {
-    pandemic_move_kernel<<<blocks_for((a.n + 3) / 4), kThreads, 0, st>>>(a);
+    pandemic_move_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
 }
 void launch_pandemic_interact(const PandemicArgs& a, cudaStream_t st)
 {
-    pandemic_interact_kernel<<<blocks_for((a.n + 3) / 4), kThreads, 0, st>>>(a);
+    pandemic_interact_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
 }
 
 } // namespace incerto

@@ -8,6 +8,9 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <cstdlib>
+
+#include "kernels_grid.hpp"
 #include "modules.hpp"
 
 namespace incerto
@@ -166,6 +169,29 @@ static void resolve_timers(Sim& s)
         cudaEventDestroy(p.b);
     }
     g_pending.clear();
+}
+
+int32_t live_rows_by_uid(Sim& s, Table& t, std::vector<uint32_t>& rows, std::vector<uint32_t>& uids)
+{
+    rows.clear();
+    uids.clear();
+    if (!t.n || !t.d_flags) return INCERTO_OK;
+    std::vector<uint8_t> fl(t.n);
+    std::vector<uint32_t> uid;
+    INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, s.stream));
+    if (t.d_uid)
+    {
+        uid.resize(t.n);
+        INC_CUDA(cudaMemcpyAsync(uid.data(), t.d_uid, t.n * 4, cudaMemcpyDeviceToHost, s.stream));
+    }
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    for (uint64_t r = 0; r < t.n; ++r)
+        if (fl[r] & kAliveBit) rows.push_back(static_cast<uint32_t>(r));
+    if (t.d_uid)
+        std::sort(rows.begin(), rows.end(), [&](uint32_t a, uint32_t b) { return uid[a] < uid[b]; });
+    uids.reserve(rows.size());
+    for (uint32_t r : rows) uids.push_back(t.d_uid ? uid[r] : r);
+    return INCERTO_OK;
 }
 
 int table_for_components(Sim& s, const std::vector<int>& comps)
@@ -553,6 +579,94 @@ static int32_t run_spawners(Sim& s, bool first_time)
         }
     }
     return INCERTO_OK;
+}
+
+// ------------------------------------------------------------ row order
+// Store the rows of a table in cell order (counting sort on the linearised cell key of `pos_comp`): entities that
+// are close in space become close in memory, so that the per-cell tables the spatial workloads scatter into and
+// gather from are touched sector by sector instead of at random.  Entities keep their uid (= spawn ordinal): every
+// draw is keyed by it, so results do not depend on the row order.  Columns in `zero_comps` are known to be all
+// zero (freshly spawned engine-managed containers) and are left alone.
+int32_t table_sort_by_cell(Sim& s, int ti, int pos_comp, const GridDesc& g, const std::vector<int>& zero_comps)
+{
+    if (const char* e = std::getenv("INCERTO_B200_NO_ROW_SORT"))
+        if (e[0] == '1') return INCERTO_OK;
+    Table& t = s.tables[ti];
+    if (t.n < 2 || t.n != t.n_spawned || !t.all_alive) return INCERTO_OK;
+    Column* pc = t.col(pos_comp);
+    if (!pc) return INCERTO_OK;
+    const uint64_t n_cells = static_cast<uint64_t>(g.ext[0]) * g.ext[1] * g.ext[2];
+    if (n_cells == 0 || n_cells >= (1ull << 32)) return INCERTO_OK;
+    uint32_t *d_start = nullptr, *d_cursor = nullptr, *d_perm = nullptr, *d_scan = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_start);
+        cudaFree(d_cursor);
+        cudaFree(d_scan);
+        cudaFree(d_perm);
+    };
+    if (cudaMalloc(&d_start, (n_cells + 1) * 4) != cudaSuccess || cudaMalloc(&d_cursor, n_cells * 4) != cudaSuccess ||
+        cudaMalloc(&d_perm, t.n * 4) != cudaSuccess || cudaMalloc(&d_scan, scan_scratch_bytes(n_cells) + 256) != cudaSuccess)
+    {
+        cudaGetLastError();
+        cleanup();
+        return INCERTO_OK; // not enough memory for the temporary index: keep the spawn order
+    }
+    // rows outside the bounds raise the grid's error flag: remember it, sort nothing (the first run reports it)
+    launch_grid_build(g, static_cast<const int16_t*>(pc->d), s.comps[pos_comp].stride(), nullptr, 0, t.n, d_start, d_cursor,
+                      d_perm, d_scan, s.d_error, s.stream);
+    uint32_t total = 0;
+    cudaError_t ce = cudaMemcpyAsync(&total, d_start + n_cells, 4, cudaMemcpyDeviceToHost, s.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s.stream);
+    if (ce != cudaSuccess || total != t.n)
+    {
+        cudaMemsetAsync(s.d_error, 0, 64, s.stream); // the workload's own index kernel raises it again, at run time
+        cleanup();
+        return ce == cudaSuccess ? INCERTO_OK : cuda_fail(ce, "table_sort_by_cell", __FILE__, __LINE__);
+    }
+    KTimer kt(s, "table_sort_by_cell", 0.0);
+    auto permute = [&](void*& buf, size_t row_bytes) -> int32_t {
+        void* nb = nullptr;
+        INC_CUDA(cudaMalloc(&nb, t.n * row_bytes));
+        launch_gather_rows(buf, nb, static_cast<uint32_t>(row_bytes), d_perm, t.n, s.stream);
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+        INC_CUDA(cudaFree(buf));
+        buf = nb;
+        return INCERTO_OK;
+    };
+    int32_t st = INCERTO_OK;
+    for (auto& c : t.cols)
+    {
+        if (std::find(zero_comps.begin(), zero_comps.end(), c.comp) != zero_comps.end()) continue;
+        if (s.comps[c.comp].managed_bytes)
+        {
+            st = INCERTO_ERR_UNSUPPORTED;
+            set_error("table_sort_by_cell: cannot reorder a populated engine-managed column");
+            break;
+        }
+        if ((st = permute(c.d, c.row_bytes)) != INCERTO_OK) break;
+    }
+    if (st == INCERTO_OK)
+    {
+        void* f = t.d_flags;
+        st = permute(f, 1);
+        t.d_flags = static_cast<uint8_t*>(f);
+    }
+    if (st == INCERTO_OK)
+    {
+        if (t.d_uid)
+        {
+            void* u = t.d_uid;
+            st = permute(u, 4);
+            t.d_uid = static_cast<uint32_t*>(u);
+        }
+        else
+        {
+            t.d_uid = d_perm; // uid of row i = its spawn-order row
+            d_perm = nullptr;
+        }
+    }
+    cleanup();
+    return st;
 }
 
 // ------------------------------------------------------------ step program

@@ -269,6 +269,8 @@ struct RowFilter
 RowFilter row_filter(const Sim& s, const Table& t, const FilterSpec& f);
 int32_t validate_filter(const Sim& s, const FilterSpec& f);
 KernelStat& kstat(Sim& s, const char* name);
+// live rows of a table in ascending uid order (the order every host-side reader reports entities in), with their uids
+int32_t live_rows_by_uid(Sim& s, Table& t, std::vector<uint32_t>& rows, std::vector<uint32_t>& uids);
 
 // scoped kernel timing (only when profiling is on)
 struct KTimer

@@ -54,6 +54,9 @@ void launch_flush(uint8_t* p, size_t bytes, uint32_t value, cudaStream_t st);
 // step counter kept on the device so that captured step programs need no new arguments
 void launch_step_increment(uint32_t* d_step, cudaStream_t st);
 
+// dst row i = src row perm[i] (row reordering of a column)
+void launch_gather_rows(const void* src, void* dst, uint32_t row_bytes, const uint32_t* perm, uint64_t n, cudaStream_t st);
+
 // stream compaction of a table by its alive bit (ballot + prefix sum)
 // d_block_counts: >= ceil(n/1024)+1 u32; returns nothing; new_n is read back from d_block_counts[nblocks].
 void launch_compact_offsets(const uint8_t* flags, uint64_t n, uint32_t* d_block_counts, cudaStream_t st);

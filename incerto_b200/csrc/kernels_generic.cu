@@ -8,6 +8,8 @@
 //   Simulation::sample          src/simulation.rs:43-65 (identifier scan)
 #include <cfloat>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.hpp"
 #include "../../include/incerto_b200.h"
@@ -668,6 +670,40 @@ void launch_flush(uint8_t* p, size_t bytes, uint32_t value, cudaStream_t st)
 }
 
 void launch_step_increment(uint32_t* d_step, cudaStream_t st) { step_increment_kernel<<<1, 1, 0, st>>>(d_step); }
+
+namespace
+{
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, const uint32_t* __restrict__ perm, uint64_t n)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gstride) dst[i] = src[perm[i]];
+}
+__global__ void gather_rows_bytes_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t row_bytes,
+                                         const uint32_t* __restrict__ perm, uint64_t n)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gstride)
+        for (uint32_t b = 0; b < row_bytes; ++b) dst[i * row_bytes + b] = src[static_cast<uint64_t>(perm[i]) * row_bytes + b];
+}
+} // namespace
+
+// dst row i = src row perm[i]; uid_old == nullptr means the identity
+void launch_gather_rows(const void* src, void* dst, uint32_t row_bytes, const uint32_t* perm, uint64_t n, cudaStream_t st)
+{
+    if (!n) return;
+    const int blocks = static_cast<int>(std::min<uint64_t>((n + 255) / 256, static_cast<uint64_t>(kNumSMs) * 16));
+    switch (row_bytes)
+    {
+    case 1: gather_rows_kernel<uint8_t><<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), perm, n); break;
+    case 2: gather_rows_kernel<uint16_t><<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), perm, n); break;
+    case 4: gather_rows_kernel<uint32_t><<<blocks, 256, 0, st>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), perm, n); break;
+    case 8: gather_rows_kernel<uint2><<<blocks, 256, 0, st>>>(static_cast<const uint2*>(src), static_cast<uint2*>(dst), perm, n); break;
+    case 16: gather_rows_kernel<uint4><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), perm, n); break;
+    default:
+        gather_rows_bytes_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), row_bytes, perm, n);
+    }
+}
 
 void launch_compact_offsets(const uint8_t* flags, uint64_t n, uint32_t* d_block_counts, cudaStream_t st)
 {

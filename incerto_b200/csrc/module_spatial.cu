@@ -1,6 +1,7 @@
 // pandemic_spatial module: host side of kernels_spatial.cu (examples/pandemic_spatial.rs).
 #include <algorithm>
 
+#include "kernels_grid.hpp"
 #include "kernels_spatial.hpp"
 #include "modules.hpp"
 
@@ -122,7 +123,14 @@ int32_t spatial_reset(Sim& s)
     INC_CUDA(cudaMemsetAsync(sm.d_count, 0, cells * 4, s.stream));
     INC_CUDA(cudaMemsetAsync(sm.d_src_head, 0, cells * 4, s.stream));
     sm.stats_valid = false;
-    return INCERTO_OK;
+    // rows in cell order: the per-cell tables are then touched sector by sector (people move one cell at a time and
+    // mostly sit in quarantine, so the order stays good for hundreds of steps)
+    GridDesc g;
+    g.dim = 2;
+    g.bmin[0] = g.bmin[1] = g.bmin[2] = 0;
+    g.ext[0] = g.ext[1] = sm.p.grid_size;
+    g.ext[2] = 1;
+    return table_sort_by_cell(s, sm.table, sm.p.position, g, {sm.p.contact_history});
 }
 
 void spatial_free(Sim& s)
@@ -257,16 +265,16 @@ int32_t spatial_read_history(Sim& s, int table, uint8_t* out, size_t out_size, s
     Table& t = s.tables[table];
     Column* c = t.col(sm.p.contact_history);
     std::vector<uint32_t> h(static_cast<size_t>(kSpatialHistorySlots) * t.n_spawned);
-    std::vector<uint8_t> fl(t.n), aux(t.n);
+    std::vector<uint8_t> aux(t.n);
+    std::vector<uint32_t> rows, uids;
+    INC_TRY(live_rows_by_uid(s, t, rows, uids));
     INC_CUDA(cudaMemcpyAsync(h.data(), c->d, h.size() * 4, cudaMemcpyDeviceToHost, s.stream));
-    INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, s.stream));
     INC_CUDA(cudaMemcpyAsync(aux.data(), sm.d_aux, t.n, cudaMemcpyDeviceToHost, s.stream));
     INC_CUDA(cudaStreamSynchronize(s.stream));
     size_t w = 0;
     const size_t rec = (kSpatialHistorySlots + 1) * 4;
-    for (uint64_t r = 0; r < t.n; ++r)
+    for (uint32_t r : rows)
     {
-        if (!(fl[r] & kAliveBit)) continue;
         if (w + rec > out_size)
         {
             set_error("read_component: output buffer too small");

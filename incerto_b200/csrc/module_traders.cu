@@ -247,14 +247,13 @@ int32_t traders_read_portfolio(Sim& s, int table, uint8_t* out, size_t out_size,
     Column* c = t.col(tm.p.portfolio);
     const uint32_t ns = tm.num_stocks_cap, words = (ns + 7) / 8;
     std::vector<uint32_t> h(static_cast<size_t>(words) * t.n_spawned);
-    std::vector<uint8_t> fl(t.n);
+    std::vector<uint32_t> rows, uids;
+    INC_TRY(live_rows_by_uid(s, t, rows, uids));
     INC_CUDA(cudaMemcpyAsync(h.data(), c->d, h.size() * 4, cudaMemcpyDeviceToHost, s.stream));
-    INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, s.stream));
     INC_CUDA(cudaStreamSynchronize(s.stream));
     size_t w = 0;
-    for (uint64_t r = 0; r < t.n; ++r)
+    for (uint32_t r : rows)
     {
-        if (!(fl[r] & kAliveBit)) continue;
         if (w + ns > out_size)
         {
             set_error("read_component: output buffer too small");

@@ -129,6 +129,10 @@ struct Sim::Modules
     uint32_t* d_step = nullptr; // device mirror of StepNumber
 };
 
+// engine.cu
+struct GridDesc;
+int32_t table_sort_by_cell(Sim& s, int table, int pos_comp, const GridDesc& g, const std::vector<int>& zero_comps);
+
 // module_forest.cu
 int32_t forest_spawn_device(Sim& s, const HostSpawn& sp);
 int32_t forest_bind(Sim& s);

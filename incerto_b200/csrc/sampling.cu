@@ -1211,13 +1211,13 @@ int32_t incerto_sim_read_component(incerto_sim* s, incerto_component component, 
             written += w;
             continue;
         }
-        std::vector<uint8_t> fl(t.n);
-        INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, S.stream));
-        std::vector<uint32_t> uid;
-        if (t.d_uid)
+        std::vector<uint32_t> rows, uids;
+        INC_TRY(live_rows_by_uid(S, t, rows, uids));
+        std::vector<uint8_t> fl;
+        if (ci.dtype == INCERTO_MARKER)
         {
-            uid.resize(t.n);
-            INC_CUDA(cudaMemcpyAsync(uid.data(), t.d_uid, t.n * 4, cudaMemcpyDeviceToHost, S.stream));
+            fl.resize(t.n);
+            INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, S.stream));
         }
         std::vector<uint8_t> data;
         size_t rb = 0;
@@ -1229,9 +1229,9 @@ int32_t incerto_sim_read_component(incerto_sim* s, incerto_component component, 
             INC_CUDA(cudaMemcpyAsync(data.data(), c->d, data.size(), cudaMemcpyDeviceToHost, S.stream));
         }
         INC_CUDA(cudaStreamSynchronize(S.stream));
-        for (uint64_t r = 0; r < t.n; ++r)
+        for (size_t j = 0; j < rows.size(); ++j)
         {
-            if (!(fl[r] & kAliveBit)) continue;
+            const uint32_t r = rows[j];
             if (written + abi_bytes > out_size)
             {
                 set_error("read_component: output buffer too small");
@@ -1242,7 +1242,7 @@ int32_t incerto_sim_read_component(incerto_sim* s, incerto_component component, 
             else
                 std::memcpy(o + written, &data[r * rb], abi_bytes);
             written += abi_bytes;
-            if (uids_out) uids_out[k++] = t.d_uid ? uid[r] : r;
+            if (uids_out) uids_out[k++] = uids[j];
         }
     }
     return INCERTO_OK;
@@ -1261,12 +1261,13 @@ int32_t incerto_sim_read_marker(incerto_sim* s, incerto_component marker, incert
     for (auto& t : S.tables)
     {
         if (!t.has(rows_of) || !t.n || !t.d_flags) continue;
+        std::vector<uint32_t> rows, uids;
+        INC_TRY(live_rows_by_uid(S, t, rows, uids));
         std::vector<uint8_t> fl(t.n);
         INC_CUDA(cudaMemcpyAsync(fl.data(), t.d_flags, t.n, cudaMemcpyDeviceToHost, S.stream));
         INC_CUDA(cudaStreamSynchronize(S.stream));
-        for (uint64_t r = 0; r < t.n; ++r)
+        for (uint32_t r : rows)
         {
-            if (!(fl[r] & kAliveBit)) continue;
             if (written >= out_size)
             {
                 set_error("read_marker: output buffer too small");
@@ -1457,10 +1458,20 @@ int32_t incerto_sim_grid_position_of(incerto_sim* s, incerto_grid g, uint64_t ui
         }
         return INCERTO_ERR_ENTITY_IDENTIFIER_NOT_FOUND;
     }
-    if (t.d_uid || uid >= t.n) return INCERTO_ERR_UNSUPPORTED;
+    uint64_t row = uid;
+    if (t.d_uid)
+    {
+        std::vector<uint32_t> rows, uids;
+        INC_TRY(live_rows_by_uid(S, t, rows, uids));
+        auto it = std::lower_bound(uids.begin(), uids.end(), static_cast<uint32_t>(uid));
+        if (uid >= (1ull << 32) || it == uids.end() || *it != uid) return INCERTO_ERR_ENTITY_IDENTIFIER_NOT_FOUND;
+        row = rows[it - uids.begin()];
+    }
+    else if (uid >= t.n)
+        return INCERTO_ERR_ENTITY_IDENTIFIER_NOT_FOUND;
     int16_t p[4];
     Column* c = t.col(G->position);
-    INC_CUDA(cudaMemcpy(p, static_cast<uint8_t*>(c->d) + uid * c->row_bytes, c->row_bytes, cudaMemcpyDeviceToHost));
+    INC_CUDA(cudaMemcpy(p, static_cast<uint8_t*>(c->d) + row * c->row_bytes, c->row_bytes, cudaMemcpyDeviceToHost));
     for (uint32_t d = 0; d < G->dim; ++d) out_pos[d] = p[d];
     return INCERTO_OK;
 }

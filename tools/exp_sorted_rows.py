@@ -31,7 +31,7 @@ def spatial(n, G, sort):
     sim = b.build()
     sim.run(20)
     sim.set_profiling(True)
-    sim.run(50)
+    sim.run(45)
     print(f"spatial n={n} G={G} sorted={sort}")
     for k in sim.kernel_stats():
         if k["device_ms"] > 0:
@@ -63,7 +63,9 @@ def pandemic(n, G, sort):
 
 
 if __name__ == "__main__":
+    import sys
+    n, G = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (20_000_000, 4000)
     for s in (False, True):
-        spatial(20_000_000, 4000, s)
+        spatial(n, G, s)
     for s in (False, True):
         pandemic(10_000_000, 5000, s)

@@ -91,19 +91,6 @@ __device__ __forceinline__ uint32_t collect_lsb(unsigned long long x)
     return static_cast<uint32_t>(((x & kOnes) * 0x0102040810204080ull) >> 56);
 }
 __device__ __forceinline__ uint32_t byte_at(unsigned long long v, uint32_t k) { return static_cast<uint32_t>(v >> (8 * k)) & 0xffu; }
-__device__ __forceinline__ unsigned long long byte_put(unsigned long long v, uint32_t k, uint32_t b)
-{
-    return (v & ~(0xffull << (8 * k))) | (static_cast<unsigned long long>(b) << (8 * k));
-}
-__device__ __forceinline__ uint32_t word_at(const uint32_t (&w)[8], uint32_t k)
-{
-    uint32_t r = w[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j)
-        if (k == static_cast<uint32_t>(j)) r = w[j];
-    return r;
-}
-
 struct Tile8
 {
     unsigned long long fl, ax, q, d;
@@ -152,15 +139,61 @@ __device__ __forceinline__ void store_bytes(uint8_t* col, uint64_t i0, uint64_t 
         for (int k = 0; k < 8 && i0 + k < n; ++k) col[i0 + k] = static_cast<uint8_t>(v >> (8 * k));
 }
 
+// warp-wide exclusive prefix sum of a small per-lane count; the total is returned through `total`
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, uint32_t& total)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t y = __shfl_up_sync(kFullMask, x, o);
+        if (lane >= static_cast<uint32_t>(o)) x += y;
+    }
+    total = __shfl_sync(kFullMask, x, 31);
+    return x - v;
+}
+
+// The persons of a 256-row warp tile that need any work this step, compacted: row, its four state bytes
+// (flags | aux << 8 | quarantine << 16 | disease << 24) and its position.
+struct WorkQueue
+{
+    uint32_t row[kThreads / 32][256];
+    uint32_t bytes[kThreads / 32][256];
+    uint32_t pos[kThreads / 32][256];
+};
+
+__device__ __forceinline__ uint32_t enqueue(WorkQueue& wq, uint32_t warp, const Tile8& t, uint64_t i0, uint32_t todo)
+{
+    uint32_t total;
+    uint32_t off = warp_exclusive_scan(__popc(todo), total);
+    if (total)
+    {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if ((todo >> k) & 1u)
+            {
+                wq.row[warp][off] = static_cast<uint32_t>(i0 + k);
+                wq.bytes[warp][off] = byte_at(t.fl, k) | (byte_at(t.ax, k) << 8) | (byte_at(t.q, k) << 16) | (byte_at(t.d, k) << 24);
+                wq.pos[warp][off] = t.pos[k];
+                ++off;
+            }
+    }
+    __syncwarp();
+    return total;
+}
+
 // Streaming pass with a rare slow path.  A lane owns eight consecutive persons (128 bytes in flight per lane);
 // byte-parallel tests pick the persons that need any work this step - in the steady state most people are
-// quarantined, healthy and standing still, and need none -, the warp then serves one such person per lane and
-// iteration.  The longer work of such a person (reading its contact history, probing 13 cells) is a fully
-// unrolled set of independent predicated loads, so that its latencies overlap.
+// quarantined, healthy and standing still, and need none.  Those are compacted into a per-warp queue in shared
+// memory and dealt out one per lane, so that the per-person code (draws, history, marks) runs with full warps;
+// the longer work of a person (reading its contact history, probing 13 cells) is a fully unrolled set of
+// independent predicated loads, so that its latencies overlap.  Results go back by byte stores.
 __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a)
 {
+    __shared__ WorkQueue wq;
     const uint32_t G = static_cast<uint32_t>(a.G);
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats_acc)
@@ -169,8 +202,8 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
     {
         const uint64_t i0 = base + lane * 8;
         Tile8 t;
-        load_tile(a, i0, t);
-        const unsigned long long ax0 = t.ax, d0 = t.d;
+        t.fl = t.ax = t.q = t.d = 0;
+        if (i0 < a.n) load_tile(a, i0, t);
         const unsigned long long opbits = t.ax & (0xe0ull * kOnes);
         const unsigned long long alive8 = t.fl & kOnes;
         const unsigned long long op_nz = zero_bytes(opbits) ^ kOnes;
@@ -182,40 +215,36 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
         if (a.systems & 16u) want |= alive8 & free8;
         if (a.systems & 8u) want |= alive8 & len0;
         want |= (alive8 ^ kOnes) & died;
-        uint32_t todo = collect_lsb(want);
-        if (i0 >= a.n) todo = 0;
-        while (__any_sync(kFullMask, todo != 0))
+        const uint32_t total = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(want) : 0u);
+        for (uint32_t j = lane; j < total; j += 32)
         {
-            const bool active = todo != 0;
-            const uint32_t k = active ? static_cast<uint32_t>(__ffs(todo) - 1) : 0u;
-            todo &= todo - 1;
-            const uint64_t i = i0 + k;
-            const uint32_t fl = byte_at(t.fl, k), ax = byte_at(t.ax, k), q = byte_at(t.q, k);
-            uint32_t d = byte_at(t.d, k);
-            const uint32_t p = word_at(t.pos, k);
+            const uint64_t i = wq.row[warp][j];
+            const uint32_t bytes = wq.bytes[warp][j], p = wq.pos[warp][j];
+            const uint32_t fl = bytes & 0xffu, ax = (bytes >> 8) & 0xffu, q = (bytes >> 16) & 0xffu;
+            uint32_t d = bytes >> 24;
+            const uint32_t d0 = d;
             const uint32_t op = ax >> 5;
             uint32_t len = ax & 31u;
             const uint32_t x = p & 0xffffu, y = p >> 16;
             const uint32_t cell = x * G + y;
-            bool alive = active && (fl & 1u);
-            if (active && !alive && op == OP_DIED)
+            if (!(fl & 1u))
             {
-                // spatial_grid_cleanup_system (spatial_grid.rs:446-455)
+                // spatial_grid_cleanup_system (spatial_grid.rs:446-455): despawned at the last flush
                 atomicSub(&a.count[cell], 1u);
-                t.ax = byte_put(t.ax, k, 0u);
+                a.aux[i] = 0;
+                continue;
             }
             // spatial_grid_update_system (spatial_grid.rs:434-443) for Changed<GridPosition>
-            if (alive && op == OP_NEW)
+            if (op == OP_NEW)
             {
                 if (x >= G || y >= G)
                 {
                     if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u) a.error[1] = static_cast<uint32_t>(i);
-                    alive = false; // left untouched
+                    continue; // left untouched
                 }
-                else
-                    atomicAdd(&a.count[cell], 1u);
+                atomicAdd(&a.count[cell], 1u);
             }
-            const bool moved = alive && op >= OP_UP && op <= OP_DOWN;
+            const bool moved = op >= OP_UP && op <= OP_DOWN;
             if (moved)
             {
                 const uint32_t old = op == OP_UP ? cell + 1 : (op == OP_DOWN ? cell - 1 : (op == OP_LEFT ? cell + G : cell - G));
@@ -223,37 +252,34 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
                 atomicAdd(&a.count[cell], 1u);
             }
             const bool free_ = q == 0;
-            const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
+            const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
             bool dying = false;
-            if (alive)
+            // :414-433
+            if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
+            // :446-459 the infectious, non-quarantined people are the sources of this step
+            if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
             {
-                // :414-433
-                if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
-                // :446-459 the infectious, non-quarantined people are the sources of this step
-                if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
-                {
-                    atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
-                    const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
-                    a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
-                }
-                // :521-541
-                if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
-                {
-                    const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
-                    if (bernoulli(r.x, a.thr_die))
-                        dying = true;
-                    else if (bernoulli(r.y, a.thr_recover))
-                        d = INCERTO_DISEASE_RECOVERED;
-                }
+                atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
+                const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
+                a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
+            }
+            // :521-541
+            if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
+            {
+                const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
+                if (bernoulli(r.x, a.thr_die))
+                    dying = true;
+                else if (bernoulli(r.y, a.thr_recover))
+                    d = INCERTO_DISEASE_RECOVERED;
             }
             // :544-562 update_contact_history: a person who did not move already remembers this cell (it was
             // inserted last step) unless that insert emptied the set; :565-608 scatter side of the tracing: every
             // cell a non-quarantined person remembers is stamped with its id
-            const bool need_hist = alive && (a.systems & 8u) && (len == 0 || moved);
-            const bool need_mark = alive && (a.systems & 16u) && free_;
+            const bool need_hist = (a.systems & 8u) && (len == 0 || moved);
+            const bool need_mark = (a.systems & 16u) && free_;
             if (need_hist || need_mark)
             {
-                // all remembered cells at once: independent, predicated loads (slot-major: coalesced across lanes)
+                // all remembered cells at once: independent, predicated loads (slot-major)
                 uint32_t hv[kSpatialHistorySlots];
                 bool found = false;
 #pragma unroll
@@ -283,17 +309,11 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
                         if (s2 < len) mark_cell(a, hv[s2], uid + 1u);
                 }
             }
-            if (alive)
-            {
-                t.d = byte_put(t.d, k, d);
-                t.ax = byte_put(t.ax, k, len | ((dying ? OP_DYING : OP_NONE) << 5));
-            }
+            if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
+            const uint32_t nax = len | ((dying ? OP_DYING : OP_NONE) << 5);
+            if (nax != ax) a.aux[i] = static_cast<uint8_t>(nax);
         }
-        if (i0 < a.n)
-        {
-            if (t.d != d0) store_bytes(a.disease, i0, a.n, t.d);
-            if (t.ax != ax0) store_bytes(a.aux, i0, a.n, t.ax);
-        }
+        __syncwarp();
     }
 }
 
@@ -302,8 +322,9 @@ __device__ constexpr int kOff13[13][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 
 
 __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs a)
 {
+    __shared__ WorkQueue wq;
     const int G = a.G;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     uint32_t st[4] = {0, 0, 0, 0}; // PandemicStats of the state after this step: healthy, exposed, infectious, recovered
@@ -311,37 +332,49 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
     {
         const uint64_t i0 = base + lane * 8;
         Tile8 t;
-        load_tile(a, i0, t);
-        const unsigned long long fl0 = t.fl, ax0 = t.ax, q0 = t.q, d0 = t.d;
+        t.fl = t.ax = t.q = t.d = 0;
+        if (i0 < a.n) load_tile(a, i0, t);
         const unsigned long long alive8 = t.fl & kOnes;
         const unsigned long long free8 = zero_bytes(t.q);
         const unsigned long long dying8 = zero_bytes((t.ax & (0xe0ull * kOnes)) ^ ((OP_DYING << 5) * kOnes));
-        // update_quarantine_status (:611-625) for everybody at once: n > 1 -> n - 1, n == 1 -> removed at the flush.
-        // (people quarantined at this flush were not quarantined during the step: disjoint from these)
-        if (a.systems & 32u) t.q -= alive8 & (free8 ^ kOnes);
-        uint32_t todo = collect_lsb(alive8 & (free8 | dying8));
-        if (i0 >= a.n) todo = 0;
-        bool pos_changed = false;
-        while (__any_sync(kFullMask, todo != 0))
+        const unsigned long long busy8 = alive8 & (free8 | dying8); // everybody else only counts its quarantine down
+        // update_quarantine_status (:611-625) for all the quarantined at once: n > 1 -> n - 1, n == 1 -> removed at
+        // the flush.  (People quarantined at this flush were not quarantined during the step: disjoint from these.)
+        if ((a.systems & 32u) && i0 < a.n)
         {
-            const bool active = todo != 0;
-            const uint32_t k = active ? static_cast<uint32_t>(__ffs(todo) - 1) : 0u;
-            todo &= todo - 1;
-            const uint64_t i = i0 + k;
-            uint32_t fl = byte_at(t.fl, k);
-            const uint32_t ax = byte_at(t.ax, k);
-            uint32_t q = byte_at(q0, k), d = byte_at(t.d, k);
-            uint32_t p = word_at(t.pos, k);
-            const bool alive = active;
+            const unsigned long long nq = t.q - (alive8 & (free8 ^ kOnes));
+            if (nq != t.q) store_bytes(a.quar, i0, a.n, nq);
+        }
+        {
+            // fused PandemicStats (:107-138): the people whose state this kernel does not touch any further
+            const unsigned long long al = alive8 & (busy8 ^ kOnes);
+            const unsigned long long healthy = zero_bytes(t.d) & al, infectious = zero_bytes(t.d ^ (0x80ull * kOnes)) & al,
+                                     recovered = zero_bytes(t.d ^ (0x81ull * kOnes)) & al;
+            st[0] += __popcll(healthy);
+            st[2] += __popcll(infectious);
+            st[3] += __popcll(recovered);
+            st[1] += __popcll(al) - __popcll(healthy) - __popcll(infectious) - __popcll(recovered);
+        }
+        // the packed quarantine store above is ordered before the byte stores below by the barrier inside enqueue()
+        const uint32_t total = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(busy8) : 0u);
+        for (uint32_t j = lane; j < total; j += 32)
+        {
+            const uint64_t i = wq.row[warp][j];
+            const uint32_t bytes = wq.bytes[warp][j];
+            uint32_t p = wq.pos[warp][j];
+            uint32_t fl = bytes & 0xffu;
+            const uint32_t ax = (bytes >> 8) & 0xffu, q = (bytes >> 16) & 0xffu;
+            uint32_t d = bytes >> 24;
+            const uint32_t d0 = d;
             const bool dying = (ax >> 5) == OP_DYING;
             const bool free_ = q == 0;
             const int x = static_cast<int>(p & 0xffffu), y = static_cast<int>(p >> 16);
             const uint32_t cell = static_cast<uint32_t>(x) * G + static_cast<uint32_t>(y);
-            const uint32_t uid = (alive && a.uid) ? a.uid[i] : static_cast<uint32_t>(i);
+            const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
 
             // :461-508 gather side of the transmission: probe the 13 cells within Manhattan distance 2 (independent,
             // predicated bit loads), then walk the source lists of the few cells that hold a source
-            if (alive && (a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY)
+            if ((a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY)
             {
                 uint32_t hits = 0;
 #pragma unroll
@@ -363,11 +396,11 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
                     hits &= hits - 1;
                     int dx = 0, dy = 0;
 #pragma unroll
-                    for (int j = 0; j < 13; ++j)
-                        if (c13 == j)
+                    for (int k = 0; k < 13; ++k)
+                        if (c13 == k)
                         {
-                            dx = kOff13[j][0];
-                            dy = kOff13[j][1];
+                            dx = kOff13[k][0];
+                            dy = kOff13[k][1];
                         }
                     const uint32_t c = static_cast<uint32_t>(x + dx) * G + static_cast<uint32_t>(y + dy);
                     const uint64_t thr = c13 <= 4 ? a.thr_infect1 : a.thr_infect2; // distance 0 | 1, else 2 (:495-499)
@@ -382,7 +415,6 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
                 }
                 if (exposed) d = a.incubation; // :510-517
             }
-            if (!alive) continue;
 
             // :580-606 gather side of the tracing
             bool quarantine = false;
@@ -440,50 +472,28 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
                 }
             }
 
-            // end of Update: despawn (:530), try_insert(Quarantined) (:600-603)
+            // end of Update: despawn (:530), try_insert(Quarantined) (:600-603); a quarantined dying person had its
+            // counter decremented above, which nobody can observe
             if (dying)
             {
                 fl &= ~1u;
                 newop = OP_DIED;
-                t.fl = byte_put(t.fl, k, fl);
+                a.flags[i] = static_cast<uint8_t>(fl);
             }
             else if (quarantine)
-                t.q = byte_put(t.q, k, a.quarantine_duration);
-            t.d = byte_put(t.d, k, d);
-            if (newop >= OP_UP && newop <= OP_DOWN)
+                a.quar[i] = static_cast<uint8_t>(a.quarantine_duration);
+            if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
+            if (newop >= OP_UP && newop <= OP_DOWN) a.pos[i] = p;
+            if (newop != (ax >> 5)) a.aux[i] = static_cast<uint8_t>((ax & 31u) | (newop << 5));
+            if (fl & 1u)
             {
-                pos_changed = true;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (k == static_cast<uint32_t>(j)) t.pos[j] = p;
+                st[0] += d == INCERTO_DISEASE_HEALTHY;
+                st[1] += d >= 1u && d < 0x80u;
+                st[2] += d == INCERTO_DISEASE_INFECTIOUS;
+                st[3] += d == INCERTO_DISEASE_RECOVERED;
             }
-            t.ax = byte_put(t.ax, k, (ax & 31u) | (newop << 5));
         }
-        if (i0 < a.n)
-        {
-            if (t.fl != fl0) store_bytes(a.flags, i0, a.n, t.fl);
-            if (t.q != q0) store_bytes(a.quar, i0, a.n, t.q);
-            if (t.d != d0) store_bytes(a.disease, i0, a.n, t.d);
-            if (t.ax != ax0) store_bytes(a.aux, i0, a.n, t.ax);
-            if (pos_changed)
-            {
-                if (i0 + 8 <= a.n)
-                {
-                    *reinterpret_cast<uint4*>(a.pos + i0) = make_uint4(t.pos[0], t.pos[1], t.pos[2], t.pos[3]);
-                    *reinterpret_cast<uint4*>(a.pos + i0 + 4) = make_uint4(t.pos[4], t.pos[5], t.pos[6], t.pos[7]);
-                }
-                else
-                    for (int j = 0; j < 8 && i0 + j < a.n; ++j) a.pos[i0 + j] = t.pos[j];
-            }
-            // fused PandemicStats (:107-138) of the post-flush state
-            const unsigned long long al = t.fl & kOnes;
-            const unsigned long long healthy = zero_bytes(t.d) & al, infectious = zero_bytes(t.d ^ (0x80ull * kOnes)) & al,
-                                     recovered = zero_bytes(t.d ^ (0x81ull * kOnes)) & al;
-            st[0] += __popcll(healthy);
-            st[2] += __popcll(infectious);
-            st[3] += __popcll(recovered);
-            st[1] += __popcll(al) - __popcll(healthy) - __popcll(infectious) - __popcll(recovered);
-        }
+        __syncwarp();
     }
     if (a.stats_acc)
     {

@@ -98,7 +98,12 @@ __device__ __forceinline__ bool cell_of(const AirArgs& a, const uint2& p, int& g
     key = (static_cast<uint32_t>(gx) * a.ext[1] + static_cast<uint32_t>(gy)) * a.ext[2] + static_cast<uint32_t>(gz);
     return true;
 }
-__device__ __forceinline__ uint32_t bit_of(const AirArgs& a, uint32_t key) { return (key * 0x85EBCA6Bu) >> a.bits_shift; }
+// bit of a cell in the pre-filter: runs of 256 consecutive cell keys (the z column of ~25 adjacent y) share one
+// hashed 32-byte sector, so the own cell and its +-z / +-y neighbours are usually answered by one sector
+__device__ __forceinline__ uint32_t bit_of(const AirArgs& a, uint32_t key)
+{
+    return ((((key >> 8) * 0x85EBCA6Bu) >> a.bits_shift) << 8) | (key & 255u);
+}
 
 // the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds, spatial_grid.rs:337-340),
 // in the fixed order -x +x -y +y -z +z

@@ -2,6 +2,7 @@
 #include <algorithm>
 
 #include "kernels_air.hpp"
+#include "kernels_grid.hpp"
 #include "modules.hpp"
 
 namespace incerto
@@ -37,6 +38,8 @@ static int32_t air_check(Sim& s, AirModule& am, const incerto_air_params& p)
     s.comps[p.target_altitude].exists = true;
     return INCERTO_OK;
 }
+
+static int32_t air_sort_rows(Sim& s);
 
 int32_t air_bind(Sim& s)
 {
@@ -103,7 +106,23 @@ int32_t air_bind(Sim& s)
         INC_CUDA(cudaMalloc(&am.d_bits, (1ull << fb) / 8));
         INC_CUDA(cudaMalloc(&am.d_cand, std::max<uint64_t>(t.n, 2)));
     }
-    return INCERTO_OK;
+    return air_sort_rows(s);
+}
+
+// rows in (x, y) column order: neighbouring aircraft then probe neighbouring sectors of the pre-filter
+static int32_t air_sort_rows(Sim& s)
+{
+    AirModule& am = s.mods->air;
+    if (am.table < 0 || am.grid < 0 || !am.do_check) return INCERTO_OK;
+    const GridInst& gi = s.grids[am.grid];
+    GridDesc g;
+    g.dim = 2; // z (lane 2) is ignored: one sort bin per column
+    for (int d = 0; d < 3; ++d)
+    {
+        g.bmin[d] = d < 2 ? gi.bmin[d] : 0;
+        g.ext[d] = d < 2 ? gi.bmax[d] - gi.bmin[d] + 1 : 1;
+    }
+    return table_sort_by_cell(s, am.table, am.comp_pos, g, {});
 }
 
 int32_t air_reset(Sim& s)
@@ -111,7 +130,7 @@ int32_t air_reset(Sim& s)
     AirModule& am = s.mods->air;
     if (am.d_slots) INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
     if (am.d_acc) INC_CUDA(cudaMemsetAsync(am.d_acc, 0, 64, s.stream));
-    return INCERTO_OK;
+    return air_sort_rows(s);
 }
 
 void air_free(Sim& s)
@@ -157,7 +176,7 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.tag = static_cast<uint32_t>(step % 255) + 1;
     a.acc = am.d_acc;
     a.bits = am.d_bits;
-    a.bits_shift = 32 - am.filter_bits;
+    a.bits_shift = 32 - (am.filter_bits - 8); // 256-bit sectors are hashed, the low 8 key bits index inside
     a.cand = am.d_cand;
     a.error = s.d_error;
 }

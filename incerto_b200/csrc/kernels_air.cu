@@ -120,17 +120,12 @@ __device__ __forceinline__ uint32_t neighbour_keys(const AirArgs& a, int gx, int
            (gz > 0 ? 16u : 0u) | (gz < a.ext[2] - 1 ? 32u : 0u);
 }
 
-// PreUpdate, pass 1: spatial_grid_update_system (spatial_grid.rs:434-443) - every aircraft sets the bit of its cell
+// PreUpdate, pass 1: spatial_grid_update_system (spatial_grid.rs:434-443) - every aircraft sets the bit of its cell.
+// Only launched when the previous step did not already leave the bitmap behind (first step, after a reset).
 __global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
 {
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (first == 0)
-    {
-        a.acc[0] = 0;
-        a.acc[1] = 0;
-    }
-    for (uint64_t i = first; i < a.n; i += gstride)
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride)
     {
         if (a.flags && !(a.flags[i] & 1u)) continue;
         int gx, gy, gz;
@@ -147,28 +142,58 @@ __global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
     }
 }
 
-// PreUpdate, pass 2: aircraft with a possibly occupied neighbour cell enter the exact per-cell index
+// PreUpdate, pass 2: aircraft with a possibly occupied neighbour cell enter the exact per-cell index.
+// One thread = 2 consecutive rows (one 128-bit position load, twelve independent bit probes in flight).
 __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
 {
+    const uint64_t npairs = (a.n + 1) >> 1;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride)
+    const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (first == 0)
     {
-        uint32_t mask = 0;
-        int gx, gy, gz;
-        uint32_t key;
-        if ((!a.flags || (a.flags[i] & 1u)) && cell_of(a, a.pos[i], gx, gy, gz, key))
+        a.acc[0] = 0;
+        a.acc[1] = 0;
+        if (a.acc[2])
         {
-            uint32_t nk[6];
-            const uint32_t valid = neighbour_keys(a, gx, gy, gz, key, nk);
-#pragma unroll
-            for (int k = 0; k < 6; ++k)
-            {
-                const uint32_t h = bit_of(a, nk[k]);
-                if (((valid >> k) & 1u) && ((a.bits[h >> 5] >> (h & 31)) & 1u)) mask |= 1u << k;
-            }
-            if (mask) index_insert(a, key);
+            // an aircraft left the grid bounds in the last step: the reference panics in this PreUpdate (spatial_grid.rs:276-279)
+            if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u) a.error[1] = static_cast<uint32_t>(a.acc[2] - 1);
+            a.acc[2] = 0;
         }
-        a.cand[i] = static_cast<uint8_t>(mask);
+    }
+    for (uint64_t q = first; q < npairs; q += gstride)
+    {
+        const uint64_t row0 = q * 2;
+        const bool full = row0 + 2 <= a.n;
+        uint2 p[2];
+        if (full)
+        {
+            const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
+            p[0] = make_uint2(v.x, v.y);
+            p[1] = make_uint2(v.z, v.w);
+        }
+        else
+            p[0] = p[1] = a.pos[row0];
+        uint32_t key[2] = {0, 0}, probe[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            int gx, gy, gz;
+            if ((k == 1 && !full) || (a.flags && !(a.flags[row0 + k] & 1u)) || !cell_of(a, p[k], gx, gy, gz, key[k])) continue;
+            uint32_t nk[6];
+            const uint32_t valid = neighbour_keys(a, gx, gy, gz, key[k], nk);
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+            {
+                const uint32_t h = bit_of(a, nk[j]);
+                if ((valid >> j) & 1u) probe[k] |= ((a.bits[h >> 5] >> (h & 31)) & 1u) << j;
+            }
+        }
+        if (probe[0]) index_insert(a, key[0]);
+        if (probe[1]) index_insert(a, key[1]);
+        if (full)
+            *reinterpret_cast<uint16_t*>(a.cand + row0) = static_cast<uint16_t>(probe[0] | (probe[1] << 8));
+        else
+            a.cand[row0] = static_cast<uint8_t>(probe[0]);
     }
 }
 
@@ -242,6 +267,19 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
                 }
                 p[k] = make_uint2((static_cast<uint32_t>(x) & 0xffffu) | (static_cast<uint32_t>(y) << 16),
                                   (static_cast<uint32_t>(z) & 0xffffu) | (p[k].y & 0xffff0000u));
+            }
+            if (a.bits_next)
+            {
+                // the next PreUpdate's first pass, done here while the new position is in registers
+                int gx, gy, gz;
+                uint32_t key;
+                if (cell_of(a, p[k], gx, gy, gz, key))
+                {
+                    const uint32_t h = bit_of(a, key);
+                    atomicOr(&a.bits_next[h >> 5], 1u << (h & 31));
+                }
+                else
+                    atomicMax(reinterpret_cast<unsigned long long*>(&a.acc[2]), static_cast<unsigned long long>(row + 1));
             }
         }
         if (a.do_move)

@@ -27,10 +27,11 @@ struct AirArgs
     uint32_t slot_mask; // slots - 1 (power of two)
     uint32_t slot_shift; // 32 - log2(slots)
     uint32_t tag;       // 1..255, changes every step; slots with another tag are empty
-    uint64_t* acc;      // [0] conflicts of this step (each pair counted twice), [1] aircraft indexed
+    uint64_t* acc;      // [0] conflicts of this step (each pair counted twice), [1] aircraft indexed, [2] row + 1 of an aircraft that left the bounds
     // occupancy pre-filter: one bit per hashed cell (no false negatives); only aircraft that see a set bit
     // in one of their six face-neighbour cells enter the exact index above
     uint32_t* bits;
+    uint32_t* bits_next; // bitmap of the next step, filled by the step kernel from the moved positions (nullptr: not wanted)
     uint32_t bits_shift; // 32 - log2(number of bits)
     uint8_t* cand;       // per row: which of the six neighbour cells (-x +x -y +y -z +z) showed a set bit
     uint32_t* error;

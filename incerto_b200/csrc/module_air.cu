@@ -104,6 +104,7 @@ int32_t air_bind(Sim& s)
         while ((1ull << fb) < 32 * t.n && fb < 32) ++fb;
         am.filter_bits = fb;
         INC_CUDA(cudaMalloc(&am.d_bits, (1ull << fb) / 8));
+        INC_CUDA(cudaMalloc(&am.d_bits_next, (1ull << fb) / 8));
         INC_CUDA(cudaMalloc(&am.d_cand, std::max<uint64_t>(t.n, 2)));
     }
     return air_sort_rows(s);
@@ -130,6 +131,7 @@ int32_t air_reset(Sim& s)
     AirModule& am = s.mods->air;
     if (am.d_slots) INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
     if (am.d_acc) INC_CUDA(cudaMemsetAsync(am.d_acc, 0, 64, s.stream));
+    am.bits_ready = false;
     return air_sort_rows(s);
 }
 
@@ -139,6 +141,8 @@ void air_free(Sim& s)
     cudaFree(am.d_slots);
     cudaFree(am.d_acc);
     cudaFree(am.d_bits);
+    cudaFree(am.d_bits_next);
+    am.d_bits_next = nullptr;
     cudaFree(am.d_cand);
     am.d_bits = nullptr;
     am.d_cand = nullptr;
@@ -176,6 +180,7 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.tag = static_cast<uint32_t>(step % 255) + 1;
     a.acc = am.d_acc;
     a.bits = am.d_bits;
+    a.bits_next = am.do_check ? am.d_bits_next : nullptr;
     a.bits_shift = 32 - (am.filter_bits - 8); // 256-bit sectors are hashed, the low 8 key bits index inside
     a.cand = am.d_cand;
     a.error = s.d_error;
@@ -196,11 +201,13 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
         {
             // the tag of 255 steps ago comes round again: drop those entries first
             if (step % 255 == 0) INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
-            INC_CUDA(cudaMemsetAsync(am.d_bits, 0, (1ull << am.filter_bits) / 8, s.stream));
+            if (!am.bits_ready)
             {
+                INC_CUDA(cudaMemsetAsync(am.d_bits, 0, (1ull << am.filter_bits) / 8, s.stream));
                 KTimer kt(s, "air_bits", 8.0 * t.n);
                 launch_air_bits(a, s.stream);
             }
+            INC_CUDA(cudaMemsetAsync(am.d_bits_next, 0, (1ull << am.filter_bits) / 8, s.stream));
             {
                 KTimer kt(s, "air_candidates", 9.0 * t.n);
                 launch_air_candidates(a, s.stream);
@@ -211,6 +218,11 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
             launch_air_step(a, s.stream);
         }
         INC_CUDA(cudaGetLastError());
+        if (am.do_check)
+        {
+            std::swap(am.d_bits, am.d_bits_next); // the step kernel left the next PreUpdate's bitmap behind
+            am.bits_ready = true;
+        }
     }
     return INCERTO_OK;
 }

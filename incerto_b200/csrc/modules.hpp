@@ -79,6 +79,8 @@ struct AirModule
     unsigned long long* d_slots = nullptr; // per-step occupancy hash (kernels_air.cu)
     uint32_t n_slots = 0, slot_bits = 0;
     uint32_t* d_bits = nullptr;           // hashed occupancy bitmap (pre-filter), 2^filter_bits bits
+    uint32_t* d_bits_next = nullptr;      // the same for the next step, filled by the step kernel
+    bool bits_ready = false;              // d_bits already describes the current positions
     uint32_t filter_bits = 0;
     uint8_t* d_cand = nullptr;            // per row: neighbour cells that showed a set bit
     uint64_t* d_acc = nullptr;            // [0] conflicts of the last step (pairs counted twice), [1] aircraft indexed

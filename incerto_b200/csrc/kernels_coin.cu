@@ -136,6 +136,66 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The same aggregate for unfiltered u32 columns, 4 entities per lane and load.  Every entity of a run normally has
+// the same num_tosses (= the steps taken): when a whole warp agrees on it, the 128 ratios are summed as
+// (sum of heads) / tosses - one exact integer sum and one division instead of 128 f64 divisions (the kernel is
+// otherwise bound by the fp64 pipe).  The result differs from the entity-by-entity sum only by rounding, which the
+// aggregate's contract already leaves open: the reference sums in arbitrary query order (traits.rs:16-19).
+__global__ void __launch_bounds__(256)
+    coin_odds_quad_kernel(const uint32_t* __restrict__ heads, const uint32_t* __restrict__ tosses, uint64_t n, double* out,
+                          double* partials, uint32_t* ticket)
+{
+    double sum = 0.0;
+    double cnt = 0.0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    const uint64_t nfull = n / 128; // whole warp tiles of 128 entities
+    for (uint64_t w = warp0; w < nfull; w += nwarps)
+    {
+        const uint64_t i = w * 128 + lane * 4;
+        const uint4 h = ld_stream_v4(heads + i), t = ld_stream_v4(tosses + i);
+        const bool same = t.x == t.y && t.x == t.z && t.x == t.w && t.x == __shfl_sync(kFullMask, t.x, 0);
+        if (__all_sync(kFullMask, same))
+        {
+            const unsigned long long hs = warp_sum(static_cast<unsigned long long>(h.x) + h.y + h.z + h.w);
+            if (lane == 0) sum += static_cast<double>(hs) / static_cast<double>(t.x);
+        }
+        else
+            sum += static_cast<double>(h.x) / static_cast<double>(t.x) + static_cast<double>(h.y) / static_cast<double>(t.y) +
+                   static_cast<double>(h.z) / static_cast<double>(t.z) + static_cast<double>(h.w) / static_cast<double>(t.w);
+        cnt += 4.0;
+    }
+    for (uint64_t i = nfull * 128 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    {
+        sum += static_cast<double>(heads[i]) / static_cast<double>(tosses[i]);
+        cnt += 1.0;
+    }
+    double v[2] = {sum, cnt};
+    __shared__ double smem[64];
+    block_sum<double, 2>(v, smem);
+    if (threadIdx.x == 0)
+    {
+        partials[2 * blockIdx.x] = v[0];
+        partials[2 * blockIdx.x + 1] = v[1];
+    }
+    if (last_block_arrives(ticket, gridDim.x))
+    {
+        if (threadIdx.x == 0)
+        {
+            double s2 = 0.0, c = 0.0;
+            for (uint32_t b = 0; b < gridDim.x; ++b)
+            {
+                s2 += partials[2 * b];
+                c += partials[2 * b + 1];
+            }
+            out[0] = s2;
+            reinterpret_cast<uint64_t*>(out)[1] = static_cast<uint64_t>(c);
+        }
+    }
+}
+
 inline int coin_blocks(uint64_t work_items)
 {
     uint64_t b = (work_items + kCoinThreads - 1) / kCoinThreads;
@@ -172,9 +232,16 @@ void launch_coin_odds(const void* heads, const void* tosses, int dtype, const ui
     if (b < 1) b = 1;
     if (b > static_cast<uint64_t>(kNumSMs) * 8) b = kNumSMs * 8;
     if (dtype == INCERTO_U32)
-        coin_odds_kernel<uint32_t><<<static_cast<int>(b), 256, 0, st>>>(
+    {
+        if (flags == nullptr && n >= 128)
+            coin_odds_quad_kernel<<<static_cast<int>(b), 256, 0, st>>>(static_cast<const uint32_t*>(heads),
+                                                                       static_cast<const uint32_t*>(tosses), n, out,
+                                                                       static_cast<double*>(scratch), ticket);
+        else
+            coin_odds_kernel<uint32_t><<<static_cast<int>(b), 256, 0, st>>>(
             static_cast<const uint32_t*>(heads), static_cast<const uint32_t*>(tosses), flags, need_set, need_clear,
             n, out, static_cast<double*>(scratch), ticket);
+    }
     else
         coin_odds_kernel<uint64_t><<<static_cast<int>(b), 256, 0, st>>>(
             static_cast<const uint64_t*>(heads), static_cast<const uint64_t*>(tosses), flags, need_set, need_clear,

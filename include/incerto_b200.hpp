@@ -116,6 +116,12 @@ inline Aggregate Median(Component c) { return Aggregate{c, {}, INCERTO_AGG_MEDIA
 inline Aggregate Percentile(Component c, uint32_t p) { return Aggregate{c, {}, INCERTO_AGG_PERCENTILE, p}; } // :107-135
 inline Aggregate CoinOdds(Component heads, Component tosses) { return Aggregate{heads, tosses, INCERTO_AGG_COIN_ODDS}; }
 inline Aggregate FireStats(Component cell) { return Aggregate{cell, {}, INCERTO_AGG_FIRE_STATS}; }
+// examples/pandemic_spatial.rs:107-138 (param = INITIAL_POPULATION) and the conflicts / 2 of air_traffic_3d.rs:130-161
+inline Aggregate PandemicStats(Component disease_state, uint64_t initial_population)
+{
+    return Aggregate{disease_state, {}, INCERTO_AGG_PANDEMIC_STATS, 0, initial_population};
+}
+inline Aggregate AirConflicts(Component c) { return Aggregate{c, {}, INCERTO_AGG_AIR_CONFLICTS}; }
 
 // src/spawner.rs:3-12 — bulk form: n entities, one column per component
 class Spawner
@@ -200,6 +206,16 @@ class Simulation // src/simulation.rs:17-259
         if (rs != sizeof(Out) && ts.len_) throw std::logic_error("record size mismatch");
         ts.values_ = static_cast<const Out*>(v);
         return ts;
+    }
+    // column contents of the live entities in uid (= spawn) order; `out` holds n * lanes values
+    template <typename T>
+    std::vector<T> read_component(Component c, uint32_t values_per_entity = 0)
+    {
+        uint64_t n = 0;
+        check(incerto_sim_num_entities(h_, c.handle, &n));
+        std::vector<T> out(n * (values_per_entity ? values_per_entity : c.lanes));
+        if (n) check(incerto_sim_read_component(h_, c.handle, out.data(), out.size() * sizeof(T), nullptr));
+        return out;
     }
     uint64_t step_number()
     {

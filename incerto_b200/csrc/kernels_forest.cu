@@ -40,8 +40,11 @@ constexpr int kTX = 32;  // chunks (16 cells) along y per CTA
 #ifndef INCERTO_FOREST_TY
 #define INCERTO_FOREST_TY 4
 #endif
-constexpr int kTY = INCERTO_FOREST_TY;   // column quads (warps) per CTA
-constexpr int kColsPerThread = 4;
+constexpr int kTY = INCERTO_FOREST_TY;   // column groups (warps) per CTA
+#ifndef INCERTO_FOREST_COLS
+#define INCERTO_FOREST_COLS 4
+#endif
+constexpr int kColsPerThread = INCERTO_FOREST_COLS; // adjacent columns per thread
 #ifndef INCERTO_FOREST_MIN_BLOCKS
 #define INCERTO_FOREST_MIN_BLOCKS 10
 #endif
@@ -58,6 +61,7 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t v)
     return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
 }
 
+constexpr int kEventQueue = 512;   // rare events of one warp tile handled per round
 constexpr int kMaxNear = 64;       // overlay entities within one cell of a CTA tile
 
 struct ForestConst
@@ -165,7 +169,9 @@ __device__ __forceinline__ bool overlay_marked(const ForestConst& c, const NearO
     return false;
 }
 
-// The vectorised body: each thread owns 4 adjacent columns x 16 cells.
+// The vectorised body: each thread owns kColsPerThread (4) adjacent columns x 16 cells.  (Wider threads were tried:
+// 8 / 16 / 24 columns are slower - 135 / 159 / 198 us against 127 us at 16384^2 - the level-1 Philox call per 16
+// cells dominates the instruction count and does not amortise; profiles/r01_forest_variant_sweep2.txt.)
 //  * streaming path, fully unrolled and register resident: 128-bit loads of the chunk and its W/E
 //    neighbours, a warp-uniform "is there any fire around" vote that skips progression/spread work for the
 //    (vast majority of) warps far from the front, the level-1 regrowth draw (one Philox call per 16 cells),
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
 
     const uint32_t ign = ignited_value(a);
     Delta dl;
-    uint32_t ev[kColsPerThread] = {0, 0, 0, 0}; // per column: bit 8b+k = spread candidate, bit 8b+4+k = regrowth
+    uint32_t ev[kColsPerThread] = {};           // per column: bit 8b+k = spread candidate, bit 8b+4+k = regrowth
                                                 // draw owed, for cell 4k+b of the chunk
     uint8_t* q0 = a.next + (p0 - a.cur);
     if (!fire) // warp-uniform, and by far the common case: no progression, no spread — the chunk is copied
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             uint32_t next = __shfl_down_sync(kFullMask, B[0] & 1u, 1);
             if (lane == 0) prev = (edge >> (j - 1)) & 1u;
             if (lane == 31) next = (edge >> (j - 1)) & 1u;
-            if (lx0 - 1 + j > c.slab_w) continue; // warp-uniform; only in the last, partial column quad
+            if (lx0 - 1 + j > c.slab_w) continue; // warp-uniform; only in the last, partial column group
             uint32_t nw[4] = {cw[0], cw[1], cw[2], cw[3]};
             // ---- progression of cells already burning (:340-349); Burning{1} -> Burned leaves the burning count
             if (a.do_progress)
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         }
     }
 
-    // ---- regrowth (:354-365): only EMPTY cells draw.  The four level-1 Philox calls of the thread's columns
+    // ---- regrowth (:354-365): only EMPTY cells draw.  The level-1 Philox calls of the thread's columns
     // sit in one basic block so that their dependent multiply chains interleave.
     if (a.do_regrow)
     {
@@ -341,17 +347,43 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     }
 
     // ================= rare events: patch single cells of the buffer just written =================
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half)
+    // Events are rare and scattered over the lanes (an empty cell that passed the level-1 regrowth draw, a healthy
+    // cell at a fire front), and each costs a Philox call: the warp compacts them into a shared-memory queue and
+    // deals them out one per lane, so that the expensive path runs once per 32 events instead of once per event
+    // position of the busiest lane.  The queue is bounded; leftovers go through another round.
+    __shared__ uint16_t s_evq[kTY][kEventQueue];
+    for (;;)
     {
-        uint64_t evs = half ? (static_cast<uint64_t>(ev[2]) | (static_cast<uint64_t>(ev[3]) << 32))
-                            : (static_cast<uint64_t>(ev[0]) | (static_cast<uint64_t>(ev[1]) << 32));
-        while (evs)
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < kColsPerThread; ++j) mine += __popc(ev[j]);
+        if (!__any_sync(kFullMask, mine != 0)) break;
+        // exclusive prefix sum of the per-lane event counts
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
         {
-            const int bit = __ffsll(static_cast<long long>(evs)) - 1;
-            evs &= evs - 1;
-            const uint32_t lx = lx0 + 2 * half + (bit >> 5);
-            const uint32_t y = y0 + 4 * (bit & 3) + ((bit >> 3) & 3);
+            const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= static_cast<uint32_t>(o)) incl += up;
+        }
+        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        uint32_t slot = incl - mine;
+#pragma unroll
+        for (int j = 0; j < kColsPerThread; ++j)
+            while (ev[j] && slot < kEventQueue)
+            {
+                const uint32_t bit = __ffs(ev[j]) - 1;
+                ev[j] &= ev[j] - 1;
+                s_evq[threadIdx.y][slot++] = static_cast<uint16_t>((lane << 10) | (static_cast<uint32_t>(j) << 5) | bit);
+            }
+        __syncwarp(); // also orders the owners' vector stores of `next` before the byte patches below
+        const uint32_t n_ev = total < kEventQueue ? total : kEventQueue;
+        for (uint32_t k = lane; k < n_ev; k += 32)
+        {
+            const uint32_t item = s_evq[threadIdx.y][k];
+            const uint32_t bit = item & 31u;
+            const uint32_t lx = lx0 + ((item >> 5) & 31u);
+            const uint32_t y = (blockIdx.x * kTX + (item >> 10)) * 16 + 4 * (bit & 3) + ((bit >> 3) & 3);
             const size_t off = static_cast<size_t>(lx) * c.pitch + y;
             const uint32_t uid = (static_cast<uint32_t>(a.x_begin) + lx - 1) * H + y;
             if (!(bit & 4))
@@ -392,6 +424,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
                 }
             }
         }
+        __syncwarp();
     }
     // (c) cells an overlay entity can influence, and the overlay entities living in this thread's tile
     if (n_near && chunk_ok)

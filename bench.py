@@ -118,7 +118,7 @@ def e2e_job(ib, F, np, W, H, device, host_state, host_pos, steps):
     b.add_entity_spawner(lambda s: s.spawn_batch(n, {pos: host_pos, cell: host_state}))
     b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.001))
     b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
-    sim = b.build()
+    sim = b.build(borrow_spawn_buffers=True)   # the spawner's staging arrays are read in place (no host-side copy)
     sim.run(steps)
     ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
     fs = sim.sample_aggregate(ib.FireStatsOf(cell))

@@ -171,7 +171,8 @@ class KernelStat(C.Structure):
 SYMBOLS = [
     "incerto_last_error_message", "incerto_abi_version", "incerto_builder_register_component",
     "incerto_builder_new", "incerto_builder_free", "incerto_builder_set_seed", "incerto_builder_set_device",
-    "incerto_builder_set_row_partition", "incerto_builder_add_entity_spawner", "incerto_builder_add_device_spawner",
+    "incerto_builder_set_row_partition", "incerto_builder_add_entity_spawner", "incerto_builder_add_entity_spawner_borrowed",
+    "incerto_builder_add_device_spawner",
     "incerto_builder_add_systems", "incerto_builder_add_spatial_grid",
     "incerto_builder_record_aggregate_time_series", "incerto_builder_record_time_series", "incerto_builder_build",
     "incerto_sim_run", "incerto_sim_run_async", "incerto_sim_synchronize", "incerto_sim_destroy", "incerto_sim_reset",
@@ -210,6 +211,7 @@ def load() -> C.CDLL:
     lib.incerto_builder_set_row_partition.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.incerto_builder_register_component.argtypes = [vp, C.c_char_p, C.c_int, C.c_uint32, C.POINTER(component_t)]
     lib.incerto_builder_add_entity_spawner.argtypes = [vp, C.c_uint64, C.POINTER(ColumnData), C.c_uint32]
+    lib.incerto_builder_add_entity_spawner_borrowed.argtypes = [vp, C.c_uint64, C.POINTER(ColumnData), C.c_uint32]
     lib.incerto_builder_add_device_spawner.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
     lib.incerto_builder_add_systems.argtypes = [vp, C.POINTER(SystemDesc), C.c_uint32]
     lib.incerto_builder_add_spatial_grid.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int32), component_t, component_t,

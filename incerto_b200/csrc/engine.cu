@@ -534,7 +534,7 @@ static int32_t run_spawners(Sim& s, bool first_time)
                 for (auto& f : flags) f |= bit;
             else
                 for (uint64_t r = 0; r < n; ++r)
-                    if (c.data[r]) flags[r] |= bit;
+                    if (c.bytes()[r]) flags[r] |= bit;
         }
         INC_CUDA(cudaMemcpyAsync(t.d_flags + off, flags.data(), n, cudaMemcpyHostToDevice, s.stream));
         for (auto& c : sp.cols)
@@ -554,14 +554,14 @@ static int32_t run_spawners(Sim& s, bool first_time)
             {
                 // 3 lanes are padded to a stride of 4 on the device
                 std::vector<uint8_t> padded(n * 4 * es, 0);
-                for (uint64_t r = 0; r < n; ++r) std::memcpy(&padded[r * 4 * es], &c.data[r * 3 * es], 3 * es);
+                for (uint64_t r = 0; r < n; ++r) std::memcpy(&padded[r * 4 * es], c.bytes() + r * 3 * es, 3 * es);
                 INC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(col->d) + off * col->row_bytes, padded.data(),
                                          padded.size(), cudaMemcpyHostToDevice, s.stream));
                 INC_CUDA(cudaStreamSynchronize(s.stream));
             }
             else
             {
-                INC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(col->d) + off * col->row_bytes, c.data.data(),
+                INC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(col->d) + off * col->row_bytes, c.bytes(),
                                          n * col->row_bytes, cudaMemcpyHostToDevice, s.stream));
             }
         }
@@ -1043,13 +1043,14 @@ int32_t incerto_builder_register_component(incerto_builder* b, const char* name,
     return INCERTO_OK;
 }
 
-int32_t incerto_builder_add_entity_spawner(incerto_builder* b, uint64_t n, const incerto_column_data* columns,
-                                           uint32_t n_columns)
+static int32_t add_entity_spawner(incerto_builder* b, uint64_t n, const incerto_column_data* columns, uint32_t n_columns,
+                                  bool borrow)
 {
     INC_BUILDER(b);
     if (n_columns && !columns) return INCERTO_ERR_INVALID_ARGUMENT;
     HostSpawn sp;
     sp.n = n;
+    sp.borrowed = borrow;
     for (uint32_t i = 0; i < n_columns; ++i)
     {
         const int c = columns[i].component;
@@ -1070,17 +1071,35 @@ int32_t incerto_builder_add_entity_spawner(incerto_builder* b, uint64_t n, const
         col.has_data = columns[i].data != nullptr;
         if (ci.dtype == INCERTO_MARKER)
         {
-            if (col.has_data) col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + n);
+            if (col.has_data && borrow)
+                col.ext = static_cast<const uint8_t*>(columns[i].data);
+            else if (col.has_data)
+                col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + n);
         }
         else
         {
             const size_t bytes = n * dtype_size(ci.dtype) * ci.lanes;
-            if (n && col.has_data) col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + bytes);
+            if (n && col.has_data && borrow)
+                col.ext = static_cast<const uint8_t*>(columns[i].data);
+            else if (n && col.has_data)
+                col.data.assign(static_cast<const uint8_t*>(columns[i].data), static_cast<const uint8_t*>(columns[i].data) + bytes);
         }
         sp.cols.push_back(std::move(col));
     }
     S.spawns.push_back(std::move(sp));
     return INCERTO_OK;
+}
+
+int32_t incerto_builder_add_entity_spawner(incerto_builder* b, uint64_t n, const incerto_column_data* columns,
+                                           uint32_t n_columns)
+{
+    return add_entity_spawner(b, n, columns, n_columns, false);
+}
+
+int32_t incerto_builder_add_entity_spawner_borrowed(incerto_builder* b, uint64_t n, const incerto_column_data* columns,
+                                                    uint32_t n_columns)
+{
+    return add_entity_spawner(b, n, columns, n_columns, true);
 }
 
 int32_t incerto_builder_add_device_spawner(incerto_builder* b, uint32_t kind, const void* params, uint32_t params_size)
@@ -1175,6 +1194,9 @@ int32_t incerto_builder_build(incerto_builder* b, incerto_sim** out)
     INC_TRY(bind_generic_systems(S));
     INC_TRY(grids_allocate(S));
     INC_CUDA(cudaStreamSynchronize(S.stream));
+    for (auto& sp : S.spawns)
+        if (sp.borrowed)
+            for (auto& c : sp.cols) c.ext = nullptr; // the caller's buffers are only promised until here
     *out = reinterpret_cast<incerto_sim*>(B->sim.release());
     return INCERTO_OK;
 }
@@ -1232,6 +1254,12 @@ int32_t incerto_sim_reset(incerto_sim* s, uint32_t replica)
 {
     INC_SIM(s);
     INC_CUDA(cudaSetDevice(S.device));
+    for (auto& sp : S.spawns)
+        if (sp.borrowed)
+        {
+            set_error("reset: the entities were spawned from borrowed buffers (add_entity_spawner_borrowed), which are gone");
+            return INCERTO_ERR_UNSUPPORTED;
+        }
     INC_CUDA(cudaStreamSynchronize(S.stream));
     S.replica = replica;
     S.step = 1;

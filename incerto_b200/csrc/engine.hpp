@@ -122,9 +122,12 @@ struct HostSpawn
     {
         int comp;
         bool has_data;
-        std::vector<uint8_t> data;
+        std::vector<uint8_t> data;      // owned copy (incerto_builder_add_entity_spawner)
+        const uint8_t* ext = nullptr;   // or the caller's buffer, valid until build returns (..._borrowed)
+        const uint8_t* bytes() const { return ext ? ext : data.data(); }
     };
     std::vector<Col> cols;
+    bool borrowed = false; // the data is gone after build: the simulation cannot be reset
 };
 
 struct SystemInst

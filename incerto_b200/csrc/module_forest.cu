@@ -277,7 +277,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
             if (s.comps[c.comp].dtype != INCERTO_MARKER) ++ndata;
         }
         if (!pcol || !ccol || ndata != 2) continue;
-        pieces.push_back(Piece{pcol->data.data(), ccol->data.data(), sp.n});
+        pieces.push_back(Piece{pcol->bytes(), ccol->bytes(), sp.n});
         total += sp.n;
     }
     if (total != t.n_spawned || total < cells)
@@ -300,58 +300,88 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
             y = q[2 * r + 1];
         }
     };
-    std::vector<uint8_t> st(total);
+    // The dense prefix is checked column by column with branch-free loops the host compiler vectorises (a 4096^2
+    // grid is 16.8 M rows: this check is on the end-to-end path of every host-spawned job): the first row of
+    // column x must be (x, 0) and every following row must add exactly one to y.
     std::vector<int32_t> ov_x, ov_y;
+    const uint8_t* dense_states = nullptr; // the states of the dense prefix, when one spawn call holds them all
+    std::vector<uint8_t> st;               // otherwise (several pieces): gathered here
+    if (!pieces.empty() && pieces[0].n >= cells)
+        dense_states = pieces[0].st;
+    else
+        st.resize(cells);
+    std::vector<uint8_t> ov_states;
     {
         uint64_t g = 0; // global row
-        int32_t ex = 0, ey = 0; // expected position of the next dense row
+        uint32_t bad_state = 0;
         for (auto& pz : pieces)
         {
-            std::memcpy(st.data() + g, pz.st, pz.n);
-            for (uint64_t r = 0; r < pz.n; ++r, ++g)
+            const uint64_t n_dense = g < cells ? std::min<uint64_t>(pz.n, cells - g) : 0;
+            if (n_dense)
             {
-                int32_t x, y;
-                pos_at(pz, r, x, y);
-                if (g < cells)
+                if (!dense_states) std::memcpy(st.data() + g, pz.st, n_dense);
+                uint32_t bad = 0;
+                if (wide)
                 {
-                    if (x != ex || y != ey)
+                    const int32_t* q = reinterpret_cast<const int32_t*>(pz.pos);
+                    for (uint64_t r = 0; r < n_dense; ++r)
                     {
-                        set_error("forest: cells must be spawned in x-major order (for x {for y}) as forest_fire.rs:239-257 does");
-                        return INCERTO_ERR_UNSUPPORTED;
-                    }
-                    if (++ey == fm.H)
-                    {
-                        ey = 0;
-                        ++ex;
+                        const uint64_t gg = g + r;
+                        bad |= static_cast<uint32_t>(q[2 * r] != static_cast<int32_t>(gg / fm.H)) |
+                               static_cast<uint32_t>(q[2 * r + 1] != static_cast<int32_t>(gg % fm.H));
                     }
                 }
                 else
                 {
-                    if (x < 0 || x >= fm.W || y < 0 || y >= fm.H)
+                    // packed (x | y << 16): within a column consecutive rows differ by 0x10000
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(pz.pos);
+                    uint64_t r = 0;
+                    while (r < n_dense)
                     {
-                        set_error("entity at position (%d, %d) outside spatial grid bounds", x, y); // spatial_grid.rs:276-279
-                        return INCERTO_ERR_OUT_OF_BOUNDS;
+                        const uint64_t gg = g + r;
+                        const uint32_t x = static_cast<uint32_t>(gg / fm.H), y = static_cast<uint32_t>(gg % fm.H);
+                        const uint64_t run = std::min<uint64_t>(n_dense - r, static_cast<uint64_t>(fm.H) - y);
+                        bad |= static_cast<uint32_t>(q[r] != ((x & 0xffffu) | (y << 16)));
+                        uint32_t acc = 0;
+                        for (uint64_t k = 1; k < run; ++k) acc |= (q[r + k] - q[r + k - 1]) ^ 0x10000u;
+                        bad |= acc;
+                        r += run;
                     }
-                    ov_x.push_back(x);
-                    ov_y.push_back(y);
+                }
+                if (bad)
+                {
+                    set_error("forest: cells must be spawned in x-major order (for x {for y}) as forest_fire.rs:239-257 does");
+                    return INCERTO_ERR_UNSUPPORTED;
                 }
             }
+            // state codes: BURNED 0, BURNING 1..63, HEALTHY 0x40, EMPTY 0x80
+            for (uint64_t r = 0; r < pz.n; ++r)
+            {
+                const uint8_t v = pz.st[r];
+                bad_state |= static_cast<uint32_t>(!(v <= 63 || v == INCERTO_CELL_HEALTHY || v == INCERTO_CELL_EMPTY));
+            }
+            for (uint64_t r = n_dense; r < pz.n; ++r)
+            {
+                int32_t x, y;
+                pos_at(pz, r, x, y);
+                if (x < 0 || x >= fm.W || y < 0 || y >= fm.H)
+                {
+                    set_error("entity at position (%d, %d) outside spatial grid bounds", x, y); // spatial_grid.rs:276-279
+                    return INCERTO_ERR_OUT_OF_BOUNDS;
+                }
+                ov_x.push_back(x);
+                ov_y.push_back(y);
+                ov_states.push_back(pz.st[r]);
+            }
+            g += pz.n;
         }
-    }
-    {
-        // state codes: BURNED 0, BURNING 1..63, HEALTHY 0x40, EMPTY 0x80
-        bool ok = true;
-        for (uint64_t i = 0; i < total && ok; ++i)
-        {
-            const uint8_t v = st[i];
-            ok = v <= 63 || v == INCERTO_CELL_HEALTHY || v == INCERTO_CELL_EMPTY;
-        }
-        if (!ok)
+        if (bad_state)
         {
             set_error("forest: invalid cell state code");
             return INCERTO_ERR_INVALID_ARGUMENT;
         }
     }
+    const uint8_t* dense = dense_states ? dense_states : st.data();
     fm.n_overlay = static_cast<uint32_t>(total - cells);
     if (fm.n_overlay > 256)
     {
@@ -363,7 +393,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     for (int i = 0; i < 2; ++i) INC_CUDA(cudaMemsetAsync(fm.d_alloc[i], 0, fm.slab_bytes + 2 * kLead, s.stream));
     const int32_t lo = std::max(fm.x_begin - 1, 0), hi = std::min(fm.x_end + 1, fm.W);
     INC_CUDA(cudaMemcpy2DAsync(fm.d_slab[0] + static_cast<size_t>(lo - (fm.x_begin - 1)) * fm.pitch, fm.pitch,
-                               st.data() + static_cast<size_t>(lo) * fm.H, fm.H, fm.H, hi - lo, cudaMemcpyHostToDevice,
+                               dense + static_cast<size_t>(lo) * fm.H, fm.H, fm.H, hi - lo, cudaMemcpyHostToDevice,
                                s.stream));
     INC_CUDA(cudaStreamSynchronize(s.stream));
     fm.cur = 0;
@@ -373,7 +403,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     {
         fm.h_ov_pos[2 * k] = static_cast<int16_t>(ov_x[k]);
         fm.h_ov_pos[2 * k + 1] = static_cast<int16_t>(ov_y[k]);
-        ovst[k] = st[cells + k];
+        ovst[k] = ov_states[k];
     }
     INC_TRY(forest_upload_overlays(s, fm, ovst));
     // the generic columns are no longer needed

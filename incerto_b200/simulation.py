@@ -443,8 +443,11 @@ class SimulationBuilder:
                                                             sample_interval))
         return self
 
-    def build(self) -> "Simulation":                                            # :295-305
+    def build(self, borrow_spawn_buffers: bool = False) -> "Simulation":          # :295-305
+        """`borrow_spawn_buffers`: hand the spawners' staging arrays to the engine without a copy (they live until this
+        call returns); the simulation then cannot be `reset`."""
         # spawners run in insertion order
+        keep_all = []
         for sp in self._spawners:
             if isinstance(sp, DeviceSpawner):
                 _check(self._lib.incerto_builder_add_device_spawner(
@@ -464,7 +467,10 @@ class SimulationBuilder:
                         a = np.ascontiguousarray(chunks[0] if len(chunks) == 1 else np.concatenate(chunks, axis=0))
                         keep.append(a)
                         arr[i].data = a.ctypes.data_as(C.c_void_p)
-                _check(self._lib.incerto_builder_add_entity_spawner(self._h, n, arr, len(cols)))
+                keep_all.append(keep)
+                add = (self._lib.incerto_builder_add_entity_spawner_borrowed if borrow_spawn_buffers
+                       else self._lib.incerto_builder_add_entity_spawner)
+                _check(add(self._h, n, arr, len(cols)))
         out = C.c_void_p()
         h, self._h = self._h, None
         code = self._lib.incerto_builder_build(h, C.byref(out))   # consumes the builder, also on failure

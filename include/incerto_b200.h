@@ -124,6 +124,11 @@ typedef struct incerto_column_data
 int32_t incerto_builder_add_entity_spawner(incerto_builder* b, uint64_t n, const incerto_column_data* columns,
                                            uint32_t n_columns);
 
+/* The same without the copy: the column buffers must stay valid and unchanged until incerto_builder_build
+ * returns (a spawner closure's staging buffers do).  A simulation built this way cannot be `reset`. */
+int32_t incerto_builder_add_entity_spawner_borrowed(incerto_builder* b, uint64_t n, const incerto_column_data* columns,
+                                                    uint32_t n_columns);
+
 /* Built-in device-side spawners: the examples' spawn functions restated with
  * the Philox contract so that populations too large to upload are created in
  * HBM directly. */

@@ -26,6 +26,7 @@ extern "C" {
     pub fn incerto_builder_set_row_partition(b: *mut incerto_builder, rank: u32, world: u32) -> i32;
     pub fn incerto_builder_register_component(b: *mut incerto_builder, name: *const c_char, dtype: i32, lanes: u32, out: *mut incerto_component) -> i32;
     pub fn incerto_builder_add_entity_spawner(b: *mut incerto_builder, n: u64, columns: *const incerto_column_data, n_columns: u32) -> i32;
+    pub fn incerto_builder_add_entity_spawner_borrowed(b: *mut incerto_builder, n: u64, columns: *const incerto_column_data, n_columns: u32) -> i32;
     pub fn incerto_builder_add_device_spawner(b: *mut incerto_builder, kind: u32, params: *const c_void, params_size: u32) -> i32;
     pub fn incerto_builder_add_systems(b: *mut incerto_builder, systems: *const incerto_system_desc, n: u32) -> i32;
     pub fn incerto_builder_add_spatial_grid(b: *mut incerto_builder, dim: u32, bounds: *const i32, position: incerto_component, component: incerto_component, out: *mut incerto_grid) -> i32;

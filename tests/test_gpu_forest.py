@@ -160,3 +160,31 @@ def test_full_size_properties():
     st = sim.read_component(cell)
     assert stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell))) == tuple(vals[-1])
     assert int((st == HEALTHY).sum()) == vals[-1, 0] and int((st == EMPTY).sum()) == vals[-1, 3]
+
+
+def test_borrowed_spawn_buffers_give_the_same_result_and_refuse_reset():
+    """incerto_builder_add_entity_spawner_borrowed: no host-side copy of the spawn columns; reset is refused."""
+    W, H = 40, 24
+    rng = np.random.default_rng(4)
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.int16), np.arange(H, dtype=np.int16), indexing="ij")
+    host_pos = np.concatenate([np.stack([xs.ravel(), ys.ravel()], 1), np.array([[3, 3], [20, 11]], np.int16)])
+    host_state = np.concatenate([np.where(rng.random(W * H) < 0.7, F.CELL_HEALTHY, F.CELL_EMPTY).astype(np.uint8),
+                                 np.array([3, 3], np.uint8)])
+    out = []
+    for borrow in (False, True):
+        b = ib.SimulationBuilder(seed=SEED)
+        pos = b.component("GridPosition2D", F.I16, lanes=2)
+        cell = b.component("ForestCell.state", F.U8)
+        b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
+        b.add_entity_spawner(lambda s: s.spawn_batch(len(host_state), {pos: host_pos, cell: host_state}))
+        b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.01))
+        sim = b.build(borrow_spawn_buffers=borrow)
+        sim.run(40)
+        out.append(sim.read_component(cell))
+        if borrow:
+            with pytest.raises(ib.EngineError) as e:
+                sim.reset(1)
+            assert e.value.code == F.ERR_UNSUPPORTED
+        else:
+            sim.reset(0)
+    assert np.array_equal(out[0], out[1]) and (out[0] == F.CELL_BURNED).any()

@@ -74,6 +74,13 @@ __device__ __forceinline__ void mark_cell(const SpatialArgs& a, uint32_t key, ui
     const uint32_t cell = (key & 0xffffu) * static_cast<uint32_t>(a.G) + (key >> 16);
     atomicAdd(&a.mark[cell], (1ull << 32) | id);
 }
+// the exact inverse: the mark table is kept incrementally (a person's marks are added when it becomes free,
+// extended when it remembers a new cell, and taken back when it is quarantined, forgets everything or dies)
+__device__ __forceinline__ void unmark_cell(const SpatialArgs& a, uint32_t key, uint32_t id)
+{
+    const uint32_t cell = (key & 0xffffu) * static_cast<uint32_t>(a.G) + (key >> 16);
+    atomicAdd(&a.mark[cell], 0ull - ((1ull << 32) | id));
+}
 
 // ---- eight persons per lane: byte columns travel as one 64-bit word, positions as two 128-bit words
 constexpr unsigned long long kOnes = 0x0101010101010101ull;
@@ -161,9 +168,11 @@ struct WorkQueue
     uint32_t row[kThreads / 32][256];
     uint32_t bytes[kThreads / 32][256];
     uint32_t pos[kThreads / 32][256];
+    uint8_t marked[kThreads / 32][256]; // prepare only: the person's marks are in the mark table
 };
 
-__device__ __forceinline__ uint32_t enqueue(WorkQueue& wq, uint32_t warp, const Tile8& t, uint64_t i0, uint32_t todo)
+__device__ __forceinline__ uint32_t enqueue(WorkQueue& wq, uint32_t warp, const Tile8& t, uint64_t i0, uint32_t todo,
+                                            uint32_t marked_bits = 0)
 {
     uint32_t total;
     uint32_t off = warp_exclusive_scan(__popc(todo), total);
@@ -176,6 +185,7 @@ __device__ __forceinline__ uint32_t enqueue(WorkQueue& wq, uint32_t warp, const 
                 wq.row[warp][off] = static_cast<uint32_t>(i0 + k);
                 wq.bytes[warp][off] = byte_at(t.fl, k) | (byte_at(t.ax, k) << 8) | (byte_at(t.q, k) << 16) | (byte_at(t.d, k) << 24);
                 wq.pos[warp][off] = t.pos[k];
+                wq.marked[warp][off] = static_cast<uint8_t>((marked_bits >> k) & 1u);
                 ++off;
             }
     }
@@ -211,11 +221,14 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
         const unsigned long long free8 = zero_bytes(t.q);
         const unsigned long long d_active = (zero_bytes(t.d) | zero_bytes(t.d ^ (0x81ull * kOnes))) ^ kOnes; // exposed or infectious
         const unsigned long long len0 = zero_bytes(t.ax & (0x1full * kOnes));
+        // one bit per person: its marks are in the mark table (a tile of 8 persons = one byte)
+        const uint32_t mk = ((a.systems & 16u) && i0 < a.n) ? a.marked[i0 >> 3] : 0u;
+        const unsigned long long marked8 = zero_bytes((mk * kOnes) & 0x8040201008040201ull) ^ kOnes;
         unsigned long long want = alive8 & (op_nz | d_active);
-        if (a.systems & 16u) want |= alive8 & free8;
+        if (a.systems & 16u) want |= alive8 & (free8 ^ marked8); // became free: add its marks; quarantined: take them back
         if (a.systems & 8u) want |= alive8 & len0;
         want |= (alive8 ^ kOnes) & died;
-        const uint32_t total = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(want) : 0u);
+        const uint32_t total = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(want) : 0u, mk);
         for (uint32_t j = lane; j < total; j += 32)
         {
             const uint64_t i = wq.row[warp][j];
@@ -227,7 +240,38 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
             uint32_t len = ax & 31u;
             const uint32_t x = p & 0xffffu, y = p >> 16;
             const uint32_t cell = x * G + y;
-            if (!(fl & 1u))
+            bool marked = wq.marked[warp][j] != 0;
+            const bool alive = (fl & 1u) != 0;
+            const bool free_ = q == 0;
+            const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
+            const bool moved = alive && op >= OP_UP && op <= OP_DOWN;
+            // :544-562 update_contact_history: a person who did not move already remembers this cell (it was
+            // inserted last step) unless that insert emptied the set
+            const bool need_hist = alive && (a.systems & 8u) && (len == 0 || moved);
+            // :565-608 scatter side of the tracing, kept incrementally: the mark table holds the remembered cells of
+            // exactly the non-quarantined live people
+            const bool take_back = marked && !(alive && free_);
+            const bool put_all = alive && (a.systems & 16u) && free_ && !marked;
+            uint32_t hv[kSpatialHistorySlots];
+            if (need_hist || take_back || put_all)
+            {
+                // all remembered cells at once: independent, predicated loads (slot-major)
+#pragma unroll
+                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                {
+                    hv[s2] = 0xffffffffu;
+                    if (s2 < len) hv[s2] = a.hist[static_cast<uint64_t>(s2) * a.n_cap + i];
+                }
+            }
+            if (take_back)
+            {
+                // quarantined at the last flush, or despawned: its marks (the set as it was while it was free) go
+#pragma unroll
+                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                    if (s2 < len) unmark_cell(a, hv[s2], uid + 1u);
+                marked = false;
+            }
+            if (!alive)
             {
                 // spatial_grid_cleanup_system (spatial_grid.rs:446-455): despawned at the last flush
                 atomicSub(&a.count[cell], 1u);
@@ -244,15 +288,12 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
                 }
                 atomicAdd(&a.count[cell], 1u);
             }
-            const bool moved = op >= OP_UP && op <= OP_DOWN;
             if (moved)
             {
                 const uint32_t old = op == OP_UP ? cell + 1 : (op == OP_DOWN ? cell - 1 : (op == OP_LEFT ? cell + G : cell - G));
                 atomicSub(&a.count[old], 1u);
                 atomicAdd(&a.count[cell], 1u);
             }
-            const bool free_ = q == 0;
-            const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
             bool dying = false;
             // :414-433
             if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
@@ -272,27 +313,24 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
                 else if (bernoulli(r.y, a.thr_recover))
                     d = INCERTO_DISEASE_RECOVERED;
             }
-            // :544-562 update_contact_history: a person who did not move already remembers this cell (it was
-            // inserted last step) unless that insert emptied the set; :565-608 scatter side of the tracing: every
-            // cell a non-quarantined person remembers is stamped with its id
-            const bool need_hist = (a.systems & 8u) && (len == 0 || moved);
-            const bool need_mark = (a.systems & 16u) && free_;
-            if (need_hist || need_mark)
+            if (need_hist)
             {
-                // all remembered cells at once: independent, predicated loads (slot-major)
-                uint32_t hv[kSpatialHistorySlots];
                 bool found = false;
 #pragma unroll
-                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
-                {
-                    hv[s2] = 0xffffffffu;
-                    if (s2 < len) hv[s2] = a.hist[static_cast<uint64_t>(s2) * a.n_cap + i];
-                    found = found || hv[s2] == p;
-                }
-                if (need_hist && !found)
+                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2) found = found || hv[s2] == p;
+                if (!found)
                 {
                     if (len >= a.history_cap)
-                        len = 0; // the insert made the set larger than 20: clear() (:555-558)
+                    {
+                        // the insert made the set larger than 20: clear() (:555-558)
+                        if (marked)
+                        {
+#pragma unroll
+                            for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                                if (s2 < len) unmark_cell(a, hv[s2], uid + 1u);
+                        }
+                        len = 0;
+                    }
                     else
                     {
                         a.hist[static_cast<uint64_t>(len) * a.n_cap + i] = p;
@@ -300,14 +338,25 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
                         for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
                             if (s2 == len) hv[s2] = p;
                         len += 1;
+                        if (marked) mark_cell(a, p, uid + 1u);
                     }
                 }
-                if (need_mark)
-                {
+            }
+            if (put_all)
+            {
 #pragma unroll
-                    for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
-                        if (s2 < len) mark_cell(a, hv[s2], uid + 1u);
-                }
+                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                    if (s2 < len) mark_cell(a, hv[s2], uid + 1u);
+                marked = true;
+            }
+            if (marked != (wq.marked[warp][j] != 0))
+            {
+                // flip this person's bit (rare: once per quarantine / release)
+                uint32_t* word = reinterpret_cast<uint32_t*>(a.marked) + (i >> 5);
+                if (marked)
+                    atomicOr(word, 1u << (i & 31));
+                else
+                    atomicAnd(word, ~(1u << (i & 31)));
             }
             if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
             const uint32_t nax = len | ((dying ? OP_DYING : OP_NONE) << 5);

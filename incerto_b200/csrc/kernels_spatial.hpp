@@ -35,6 +35,7 @@ struct SpatialArgs
     uint32_t* src_next; // per row: next source in the same cell
     uint32_t tag;       // 1..63
     unsigned long long* mark; // per cell: markers (non-quarantined people remembering it) << 32 | sum of their uid + 1
+    uint8_t* marked;          // 1 bit per row: this person's remembered cells are currently in `mark`
     uint64_t* stats_acc; // healthy, exposed, infectious, recovered of the post-flush state (zeroed by prepare, summed by interact)
     uint32_t* error;
 };

@@ -108,6 +108,7 @@ int32_t spatial_bind(Sim& s)
     INC_CUDA(cudaMalloc(&sm.d_src_head, cells * 4));
     INC_CUDA(cudaMalloc(&sm.d_src_next, n * 4));
     INC_CUDA(cudaMalloc(&sm.d_mark, cells * 8));
+    INC_CUDA(cudaMalloc(&sm.d_marked, (n / 32 + 2) * 4));
     INC_CUDA(cudaMalloc(&sm.d_stats_acc, 64));
     return spatial_reset(s);
 }
@@ -122,6 +123,8 @@ int32_t spatial_reset(Sim& s)
     INC_CUDA(cudaMemsetAsync(sm.d_aux, 6u << 5, std::max<uint64_t>(t.n_spawned, 1), s.stream)); // OP_NEW, empty history
     INC_CUDA(cudaMemsetAsync(sm.d_count, 0, cells * 4, s.stream));
     INC_CUDA(cudaMemsetAsync(sm.d_src_head, 0, cells * 4, s.stream));
+    INC_CUDA(cudaMemsetAsync(sm.d_mark, 0, cells * 8, s.stream)); // kept incrementally from here on
+    INC_CUDA(cudaMemsetAsync(sm.d_marked, 0, (std::max<uint64_t>(t.n_spawned, 1) / 32 + 2) * 4, s.stream));
     sm.stats_valid = false;
     // rows in cell order: the per-cell tables are then touched sector by sector (people move one cell at a time and
     // mostly sit in quarantine, so the order stays good for hundreds of steps)
@@ -143,6 +146,8 @@ void spatial_free(Sim& s)
     cudaFree(sm.d_src_next);
     cudaFree(sm.d_mark);
     cudaFree(sm.d_stats_acc);
+    cudaFree(sm.d_marked);
+    sm.d_marked = nullptr;
     sm.d_stats_acc = nullptr;
     sm.d_aux = nullptr;
     sm.d_count = sm.d_src_bits = sm.d_src_head = sm.d_src_next = nullptr;
@@ -188,6 +193,7 @@ static void spatial_fill(Sim& s, SpatialModule& sm, SpatialArgs& a, Table& t, ui
     a.src_next = sm.d_src_next;
     a.tag = static_cast<uint32_t>(step % 63) + 1;
     a.mark = sm.d_mark;
+    a.marked = sm.d_marked;
     a.stats_acc = sm.d_stats_acc;
     a.error = s.d_error;
 }
@@ -209,7 +215,6 @@ int32_t spatial_step(Sim& s, uint64_t first_step, uint32_t nsteps)
             INC_CUDA(cudaMemsetAsync(sm.d_src_bits, 0, (cells / 32 + 1) * 4, s.stream));
             if (step % 63 == 0) INC_CUDA(cudaMemsetAsync(sm.d_src_head, 0, cells * 4, s.stream)); // the tag comes round again
         }
-        if (sm.systems & 16u) INC_CUDA(cudaMemsetAsync(sm.d_mark, 0, cells * 8, s.stream));
         {
             // pos 4 + disease 1 + flags 1 + quarantine 1 + aux 1 read, aux 1 written; history and tables on top
             KTimer kt(s, "spatial_prepare", 9.0 * t.n);

@@ -107,6 +107,7 @@ struct SpatialModule
     uint32_t* d_src_head = nullptr;
     uint32_t* d_src_next = nullptr;
     unsigned long long* d_mark = nullptr;
+    uint8_t* d_marked = nullptr;   // 1 bit per person: its marks are in d_mark
     uint64_t* d_stats_acc = nullptr; // PandemicStats counts of the state after the last step (fused into the interact kernel)
     bool stats_valid = false;
 };

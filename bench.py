@@ -285,13 +285,18 @@ def main():
                 "l2_resident": {"achieved": 2.0 * per_rank_cells * warm_steps / (warm_ms * 1e-3) / 1e9,
                                 "note": "same kernel, state left in L2 between steps (CUDA-graph replay); not an HBM figure"}}
 
+    halo = None
+    if world > 1:
+        names = {k["name"] for k in sim.kernel_stats() if k["launches"]}
+        halo = ("peer-memory stores over NVLink (CUDA IPC) + mailbox stamps" if "forest_halo_push_peer" in names
+                else "NCCL send/recv")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "systems": "fire_spread + burn_progression + regrowth + FireStats series/1",
                    "l2": "flushed between timed steps (512 MB written, untimed)", "seed": hex(SEED),
-                   "parallelism": "1 GPU" if world == 1 else f"row partition x{world} + NCCL halo"},
+                   "parallelism": "1 GPU" if world == 1 else f"row partition x{world}, halo transport: {halo}"},
         "roofline": roofline,
         "value_l2_resident": value_warm,
         "gpu_launches": int(launches),

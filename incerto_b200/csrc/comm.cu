@@ -20,6 +20,7 @@ struct NcclApi
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -55,6 +56,7 @@ static int32_t nccl_load()
     INC_SYM(CommInitRank, "ncclCommInitRank")
     INC_SYM(CommDestroy, "ncclCommDestroy")
     INC_SYM(AllReduce, "ncclAllReduce")
+    INC_SYM(AllGather, "ncclAllGather")
     INC_SYM(Send, "ncclSend")
     INC_SYM(Recv, "ncclRecv")
     INC_SYM(GroupStart, "ncclGroupStart")
@@ -134,6 +136,18 @@ int32_t comm_allreduce(Sim& s, void* d_buf, uint32_t n, int is_f64, uint32_t op)
     return INCERTO_OK;
 }
 
+// every rank contributes `bytes` bytes; d_recv holds world * bytes
+int32_t comm_allgather_bytes(Sim& s, const void* d_send, void* d_recv, size_t bytes)
+{
+    if (!s.comm)
+    {
+        set_error("no communicator attached");
+        return INCERTO_ERR_COMM;
+    }
+    INC_NCCL(g_nccl.AllGather(d_send, d_recv, bytes, ncclUint8, s.comm->comm, s.stream));
+    return INCERTO_OK;
+}
+
 int32_t comm_halo(Sim& s, const void* const* d_send_lo, void* const* d_recv_lo, const void* const* d_send_hi,
                   void* const* d_recv_hi, const size_t* bytes, uint32_t n_msgs)
 {
@@ -178,7 +192,10 @@ int32_t incerto_sim_attach_comm(incerto_sim* s, const uint8_t unique_id[128], ui
 {
     Sim* S = reinterpret_cast<Sim*>(s);
     if (!S || !unique_id || world == 0 || rank >= world) return INCERTO_ERR_INVALID_ARGUMENT;
-    return comm_attach(*S, unique_id, rank, world);
+    INC_TRY(comm_attach(*S, unique_id, rank, world));
+    // row-partitioned forest: try to map the neighbours' slabs (CUDA IPC over NVLink) so that the halo columns can
+    // be stored straight into their memory; NCCL send/recv stays as the fallback transport
+    return forest_peer_setup(*S);
 }
 
 static int32_t allreduce_host(Sim& S, void* values, uint32_t n, int is_f64, uint32_t op)

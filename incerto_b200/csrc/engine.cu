@@ -1266,6 +1266,7 @@ int32_t incerto_sim_reset(incerto_sim* s, uint32_t replica)
     const uint32_t one = 1;
     INC_CUDA(cudaMemcpyAsync(S.mods->d_step, &one, sizeof(one), cudaMemcpyHostToDevice, S.stream));
     series_clear(S);
+    if (S.mods->forest.active) INC_TRY(forest_peer_quiesce(S));
     INC_TRY(run_spawners(S, false));
     if (S.mods->forest.active) INC_TRY(forest_reset_after_spawn(S));
     if (S.mods->pandemic.active) INC_TRY(pandemic_reset(S));

@@ -119,6 +119,12 @@ int forest_step_grid_blocks(int32_t slab_w, int32_t H);
 uint32_t forest_pitch(int32_t H);            // bytes per column: H rounded up to whole CTA tiles
 uint32_t forest_alloc_cols(int32_t slab_w);  // columns allocated: slab_w rounded up to whole CTA tiles + 2 halos
 void forest_tile_shape(uint32_t* cols, uint32_t* rows);
+// halo transport over peer memory: store my two boundary columns (+ overlay states) into the neighbours' halo columns
+// and then publish `stamp` in their mailboxes; and its counterpart, wait until both neighbours published `need`
+void launch_forest_halo_push(const uint8_t* col_lo, uint8_t* peer_lo, const uint8_t* col_hi, uint8_t* peer_hi,
+                             uint32_t col_bytes, const uint8_t* ov, uint8_t* peer_ov_lo, uint8_t* peer_ov_hi, uint32_t n_ov,
+                             uint32_t* peer_mail_lo, uint32_t* peer_mail_hi, uint32_t stamp, cudaStream_t st);
+void launch_forest_halo_wait(const uint32_t* mail, uint32_t need_lo, uint32_t need_hi, uint32_t* error, cudaStream_t st);
 void launch_forest_spawn(uint8_t* cells, int32_t W, int32_t H, int32_t x_begin, int32_t x_end, PhiloxKey key,
                          uint64_t thr_density, cudaStream_t st);
 // FireStats of the owned columns of a pitched slab (standalone sample_aggregate)

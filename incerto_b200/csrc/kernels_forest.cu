@@ -631,6 +631,63 @@ void forest_tile_shape(uint32_t* cols, uint32_t* rows)
     *rows = kTX * 16;
 }
 
+namespace
+{
+// block 0 serves the lower neighbour, block 1 the upper one.  The stores go over NVLink into the neighbour's HBM; the
+// system-scope fence orders them before the mailbox stamp the neighbour's wait kernel polls.
+__global__ void __launch_bounds__(256)
+    forest_halo_push_kernel(const uint8_t* col_lo, uint8_t* peer_lo, const uint8_t* col_hi, uint8_t* peer_hi, uint32_t col_bytes,
+                            const uint8_t* ov, uint8_t* peer_ov_lo, uint8_t* peer_ov_hi, uint32_t n_ov, uint32_t* peer_mail_lo,
+                            uint32_t* peer_mail_hi, uint32_t stamp)
+{
+    const uint8_t* src = blockIdx.x == 0 ? col_lo : col_hi;
+    uint8_t* dst = blockIdx.x == 0 ? peer_lo : peer_hi;
+    uint8_t* ov_dst = blockIdx.x == 0 ? peer_ov_lo : peer_ov_hi;
+    // the lower neighbour knows me as its upper one (mailbox slot 1) and vice versa (slot 0)
+    uint32_t* mail = blockIdx.x == 0 ? peer_mail_lo + 1 : peer_mail_hi;
+    if (!dst) return; // no neighbour on this side
+    for (uint32_t i = threadIdx.x; i < col_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (uint32_t i = threadIdx.x; i < n_ov; i += blockDim.x) ov_dst[i] = ov[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        *reinterpret_cast<volatile uint32_t*>(mail) = stamp;
+        __threadfence_system();
+    }
+}
+
+__global__ void forest_halo_wait_kernel(const uint32_t* mail, uint32_t need_lo, uint32_t need_hi, uint32_t* error)
+{
+    const volatile uint32_t* m = mail;
+    const long long t0 = clock64();
+    // stamps only grow; wrap-around-safe comparison
+    while (static_cast<int32_t>(m[0] - need_lo) < 0 || static_cast<int32_t>(m[1] - need_hi) < 0)
+    {
+        __nanosleep(200);
+        if (clock64() - t0 > 20000000000ll) // ~10 s: a neighbour died; never hang the device
+        {
+            if (atomicCAS(error, 0u, static_cast<uint32_t>(39 /* INCERTO_ERR_COMM */)) == 0u) error[1] = m[0] | (m[1] << 16);
+            return;
+        }
+    }
+    __threadfence_system();
+}
+} // namespace
+
+void launch_forest_halo_push(const uint8_t* col_lo, uint8_t* peer_lo, const uint8_t* col_hi, uint8_t* peer_hi,
+                             uint32_t col_bytes, const uint8_t* ov, uint8_t* peer_ov_lo, uint8_t* peer_ov_hi, uint32_t n_ov,
+                             uint32_t* peer_mail_lo, uint32_t* peer_mail_hi, uint32_t stamp, cudaStream_t st)
+{
+    forest_halo_push_kernel<<<2, 256, 0, st>>>(col_lo, peer_lo, col_hi, peer_hi, col_bytes, ov, peer_ov_lo, peer_ov_hi, n_ov,
+                                               peer_mail_lo, peer_mail_hi, stamp);
+}
+void launch_forest_halo_wait(const uint32_t* mail, uint32_t need_lo, uint32_t need_hi, uint32_t* error, cudaStream_t st)
+{
+    forest_halo_wait_kernel<<<1, 1, 0, st>>>(mail, need_lo, need_hi, error);
+}
+
 int forest_step_grid_blocks(int32_t slab_w, int32_t H)
 {
     const uint32_t chunks = forest_pitch(H) / 16;

@@ -3,6 +3,7 @@
 //
 // Reference: examples/forest_fire.rs (spawn :234-279, systems :282-365, stats :104-134).
 #include <algorithm>
+#include <cstdlib>
 
 #include "modules.hpp"
 
@@ -65,9 +66,112 @@ static int32_t forest_alloc(Sim& s, ForestModule& fm)
 
 void forest_graph_free(ForestModule& fm);
 
+void forest_peer_free(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    for (void*& p : fm.ipc_opened)
+    {
+        if (p) cudaIpcCloseMemHandle(p);
+        p = nullptr;
+    }
+    cudaFree(fm.d_mail);
+    fm.d_mail = nullptr;
+    fm.peer = false;
+    fm.peer_alloc_lo[0] = fm.peer_alloc_lo[1] = fm.peer_alloc_hi[0] = fm.peer_alloc_hi[1] = nullptr;
+    fm.peer_ov_lo = fm.peer_ov_hi = nullptr;
+    fm.peer_mail_lo = fm.peer_mail_hi = nullptr;
+    fm.pushes = 0;
+}
+
+// Map the neighbours' slabs through CUDA IPC (handles exchanged with one NCCL all-gather).  Any failure leaves the NCCL
+// send/recv transport in place: `fm.peer` tells which one runs.
+int32_t forest_peer_setup(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    if (!fm.active || s.part_world <= 1 || !s.comm || !fm.d_alloc[0]) return INCERTO_OK;
+    forest_peer_free(s);
+    struct Pack
+    {
+        cudaIpcMemHandle_t alloc[2], ov_lo, ov_hi, mail;
+        uint32_t ok, slab_w, pad[2];
+    };
+    const char* env = std::getenv("INCERTO_B200_HALO");
+    const bool want = !(env && std::strcmp(env, "nccl") == 0);
+    Pack mine;
+    std::memset(&mine, 0, sizeof(mine));
+    INC_CUDA(cudaMalloc(&fm.d_mail, 64));
+    INC_CUDA(cudaMemsetAsync(fm.d_mail, 0, 64, s.stream));
+    mine.ok = want && cudaIpcGetMemHandle(&mine.alloc[0], fm.d_alloc[0]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.alloc[1], fm.d_alloc[1]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.ov_lo, fm.d_ov_lo) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.ov_hi, fm.d_ov_hi) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.mail, fm.d_mail) == cudaSuccess;
+    cudaGetLastError();
+    mine.slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    // all-gather the packs (device buffers), read them back
+    const size_t all = sizeof(Pack) * s.part_world;
+    INC_TRY(ensure_scratch(s, sizeof(Pack) + all + 256));
+    uint8_t* d_send = s.d_scratch;
+    uint8_t* d_recv = s.d_scratch + ((sizeof(Pack) + 255) & ~static_cast<size_t>(255));
+    INC_CUDA(cudaMemcpyAsync(d_send, &mine, sizeof(Pack), cudaMemcpyHostToDevice, s.stream));
+    INC_TRY(comm_allgather_bytes(s, d_send, d_recv, sizeof(Pack)));
+    std::vector<Pack> packs(s.part_world);
+    INC_CUDA(cudaMemcpyAsync(packs.data(), d_recv, all, cudaMemcpyDeviceToHost, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    bool ok = true;
+    for (auto& p : packs) ok = ok && p.ok;
+    int n_open = 0;
+    auto open = [&](const cudaIpcMemHandle_t& h) -> void* {
+        void* p = nullptr;
+        if (!ok) return nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+            cudaGetLastError();
+            ok = false;
+            return nullptr;
+        }
+        fm.ipc_opened[n_open++] = p;
+        return p;
+    };
+    if (s.part_rank > 0)
+    {
+        const Pack& p = packs[s.part_rank - 1];
+        fm.peer_alloc_lo[0] = static_cast<uint8_t*>(open(p.alloc[0]));
+        fm.peer_alloc_lo[1] = static_cast<uint8_t*>(open(p.alloc[1]));
+        fm.peer_ov_lo = static_cast<uint8_t*>(open(p.ov_hi));
+        fm.peer_mail_lo = static_cast<uint32_t*>(open(p.mail));
+        fm.peer_slab_w_lo = p.slab_w;
+    }
+    if (s.part_rank + 1 < s.part_world)
+    {
+        const Pack& p = packs[s.part_rank + 1];
+        fm.peer_alloc_hi[0] = static_cast<uint8_t*>(open(p.alloc[0]));
+        fm.peer_alloc_hi[1] = static_cast<uint8_t*>(open(p.alloc[1]));
+        fm.peer_ov_hi = static_cast<uint8_t*>(open(p.ov_lo));
+        fm.peer_mail_hi = static_cast<uint32_t*>(open(p.mail));
+    }
+    // everybody must agree on the transport: a second tiny all-gather of the outcome
+    uint32_t flag = ok ? 1u : 0u;
+    INC_CUDA(cudaMemcpyAsync(d_send, &flag, 4, cudaMemcpyHostToDevice, s.stream));
+    INC_TRY(comm_allgather_bytes(s, d_send, d_recv, 4));
+    std::vector<uint32_t> flags(s.part_world);
+    INC_CUDA(cudaMemcpyAsync(flags.data(), d_recv, 4 * s.part_world, cudaMemcpyDeviceToHost, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    for (uint32_t f : flags) ok = ok && f;
+    if (!ok)
+    {
+        forest_peer_free(s);
+        return INCERTO_OK; // NCCL send/recv it is
+    }
+    fm.peer = true;
+    fm.pushes = 0;
+    return INCERTO_OK;
+}
+
 void forest_free(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
+    forest_peer_free(s);
     forest_graph_free(fm);
     for (int i = 0; i < 2; ++i)
     {
@@ -486,6 +590,17 @@ int32_t forest_bind(Sim& s)
     return INCERTO_OK;
 }
 
+// reset() with the peer-memory halo transport: before this rank respawns, the boundary columns its neighbours pushed
+// after their last step must have landed (they target the buffers about to be rewritten) ...
+int32_t forest_peer_quiesce(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    if (!fm.peer || !s.comm || !fm.pushes) return INCERTO_OK;
+    launch_forest_halo_wait(fm.d_mail, fm.peer_mail_lo ? fm.pushes : 0u, fm.peer_mail_hi ? fm.pushes : 0u, s.d_error, s.stream);
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    return INCERTO_OK;
+}
+
 int32_t forest_reset_after_spawn(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
@@ -496,6 +611,14 @@ int32_t forest_reset_after_spawn(Sim& s)
         if (sp.device_kind && sp.kind == INCERTO_SPAWN_FOREST_GRID) device_spawned = true;
     if (!device_spawned) INC_TRY(forest_adopt_host_table(s, fm));
     (void)t;
+    if (fm.peer && s.comm)
+    {
+        // ... and nobody may step (and push into a neighbour) before every rank has respawned: a collective as barrier
+        INC_TRY(ensure_scratch(s, 64));
+        INC_CUDA(cudaMemsetAsync(s.d_scratch, 0, 8, s.stream));
+        INC_TRY(comm_allreduce(s, s.d_scratch, 1, 0, 0));
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+    }
     return INCERTO_OK;
 }
 
@@ -507,6 +630,21 @@ int32_t forest_halo_exchange(Sim& s)
     // `cur` already points at the buffer the step just produced
     uint8_t* slab = fm.d_slab[fm.cur];
     const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    if (fm.peer)
+    {
+        // peer-memory transport: my boundary columns go straight into the neighbours' halo columns of the same
+        // buffer (all ranks flip `cur` in lock step), then the step stamp lands in their mailboxes
+        uint8_t* dst_lo = fm.peer_alloc_lo[fm.cur] ? fm.peer_alloc_lo[fm.cur] + kLead + static_cast<size_t>(fm.peer_slab_w_lo + 1) * fm.pitch : nullptr;
+        uint8_t* dst_hi = fm.peer_alloc_hi[fm.cur] ? fm.peer_alloc_hi[fm.cur] + kLead : nullptr;
+        fm.pushes += 1;
+        KTimer kt(s, "forest_halo_push_peer", 2.0 * fm.pitch);
+        launch_forest_halo_push(slab + static_cast<size_t>(1) * fm.pitch, dst_lo, slab + static_cast<size_t>(slab_w) * fm.pitch, dst_hi,
+                                fm.pitch, fm.d_ov[fm.cur], fm.peer_ov_lo, fm.peer_ov_hi, fm.n_overlay, fm.peer_mail_lo,
+                                fm.peer_mail_hi, fm.pushes, s.stream);
+        INC_CUDA(cudaGetLastError());
+        return INCERTO_OK;
+    }
+    KTimer kt(s, "forest_halo_nccl", 2.0 * fm.pitch);
     const void* send_lo[2] = {slab + static_cast<size_t>(1) * fm.pitch, fm.d_ov[fm.cur]};
     void* recv_lo[2] = {slab, fm.d_ov_lo};
     const void* send_hi[2] = {slab + static_cast<size_t>(slab_w) * fm.pitch, fm.d_ov[fm.cur]};
@@ -643,6 +781,11 @@ int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps)
     }
     for (; done < nsteps; ++done)
     {
+        if (fm.peer && s.comm && fm.pushes)
+        {
+            // the halo columns this step reads were stored by the neighbours after their previous step
+            launch_forest_halo_wait(fm.d_mail, fm.peer_mail_lo ? fm.pushes : 0u, fm.peer_mail_hi ? fm.pushes : 0u, s.d_error, s.stream);
+        }
         INC_TRY(forest_launch_one(s));
         INC_TRY(forest_halo_exchange(s));
     }

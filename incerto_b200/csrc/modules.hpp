@@ -52,6 +52,19 @@ struct ForestModule
     int graph_cur = 0;
     const void* graph_series_values = nullptr;
     uint64_t graph_series_capacity = 0;
+    // halo transport over peer memory (row partition): the neighbours' slabs, overlay inboxes and mailboxes mapped
+    // through CUDA IPC; `peer` stays false when that is not possible and NCCL send/recv is used instead
+    bool peer = false;
+    uint8_t* peer_alloc_lo[2] = {nullptr, nullptr}; // lower neighbour's d_alloc[0/1]
+    uint8_t* peer_alloc_hi[2] = {nullptr, nullptr};
+    uint8_t* peer_ov_lo = nullptr;   // lower neighbour's d_ov_hi (my overlay states are its upper neighbour's)
+    uint8_t* peer_ov_hi = nullptr;   // upper neighbour's d_ov_lo
+    uint32_t* peer_mail_lo = nullptr; // lower neighbour's mailbox
+    uint32_t* peer_mail_hi = nullptr;
+    uint32_t* d_mail = nullptr;      // [0] steps pushed by the lower neighbour, [1] by the upper one
+    uint32_t peer_slab_w_lo = 0;     // lower neighbour's slab width (to find its upper halo column)
+    uint32_t pushes = 0;             // steps whose boundary I pushed so far
+    void* ipc_opened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct PandemicModule
@@ -146,6 +159,9 @@ int32_t forest_read_cells(Sim& s, uint8_t* out_rows); // W*H + overlays, uid ord
 int32_t forest_stats_now(Sim& s, uint64_t out5[5]);
 void forest_free(Sim& s);
 int32_t forest_halo_exchange(Sim& s);
+int32_t forest_peer_setup(Sim& s);
+int32_t forest_peer_quiesce(Sim& s);
+void forest_peer_free(Sim& s);
 
 // module_pandemic.cu
 int32_t pandemic_bind(Sim& s);
@@ -183,6 +199,7 @@ int32_t comm_unique_id(uint8_t out[128]);
 int32_t comm_attach(Sim& s, const uint8_t id[128], uint32_t rank, uint32_t world);
 void comm_free(Sim& s);
 int32_t comm_allreduce(Sim& s, void* d_buf, uint32_t n, int is_f64, uint32_t op);
+int32_t comm_allgather_bytes(Sim& s, const void* d_send, void* d_recv, size_t bytes);
 // send `bytes_lo` from d_send_lo to rank-1 and `bytes_hi` from d_send_hi to rank+1, receive likewise
 int32_t comm_halo(Sim& s, const void* const* d_send_lo, void* const* d_recv_lo, const void* const* d_send_hi,
                   void* const* d_recv_hi, const size_t* bytes, uint32_t n_msgs);

@@ -15,6 +15,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 W, H, steps = 64 * world, 96, 80
+RESET = "--reset" in sys.argv
 b = ib.SimulationBuilder(seed=SEED, device=local)
 pos = b.component("GridPosition2D", F.I16, lanes=2)
 cell = b.component("ForestCell.state", F.U8)
@@ -26,7 +27,14 @@ b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
 sim = b.build()
 sim.attach_comm(D.share_unique_id(dist, ib.comm_unique_id, rank), rank, world)
 sim.run(steps)
-o = ForestOracle(SEED, 0, W, H, density=0.85, p_regrow=0.004, fires=6).spawn().run(steps)
+replica = 0
+if RESET:
+    # reset under another replica key and run again (exercises the quiesce + barrier of the peer transport)
+    replica = 3
+    sim.reset(replica)
+    sim.run(steps)
+transport = "peer" if any(k["name"] == "forest_halo_push_peer" and k["launches"] for k in sim.kernel_stats()) else "nccl"
+o = ForestOracle(SEED, replica, W, H, density=0.85, p_regrow=0.004, fires=6).spawn().run(steps)
 want = o.cells()[0]
 xb, xe = ib.partition_range(W, rank, world)
 got = sim.read_component(cell)[:(xe - xb) * H]
@@ -35,7 +43,7 @@ fs = sim.sample_aggregate(ib.FireStatsOf(cell))          # all-reduced over the 
 stats_ok = (fs.healthy_count, fs.burning_count, fs.burned_count, fs.empty_count, fs.total_cells) == tuple(int(v) for v in o.stats())
 ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
 series_ok = np.array_equal(np.array([(v.healthy_count, v.burning_count, v.burned_count, v.empty_count, v.total_cells) for v in ts.values()], dtype=np.uint64), o.series())
-print(f"rank {rank}/{world}: slab parity {ok}, all-reduced stats {stats_ok}, series {series_ok}, burned {int(o.stats()[2])}", flush=True)
+print(f"rank {rank}/{world}: halo transport {transport}, slab parity {ok}, all-reduced stats {stats_ok}, series {series_ok}, burned {int(o.stats()[2])}", flush=True)
 flag = torch.tensor([int(ok and stats_ok and series_ok)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

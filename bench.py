@@ -229,27 +229,19 @@ def main():
             torch.cuda.synchronize()
 
     # ---- warm-up
-    for _ in range(args.warmup):
-        sim.flush_l2()
-        sim.run(1)
+    sim.run_cold(args.warmup)
     barrier()
 
-    # ---- timed: K steps, each from a cold L2, device-timed by the engine's CUDA events around the step
+    # ---- timed: K steps, each from a cold L2 (flush kernel in between, not timed), all enqueued back to back on
+    # the engine's stream with a CUDA event pair around every step; the device time is the sum over the steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms = 0.0
-    launches = 0
-    step_ms = []
-    for _ in range(args.steps):
-        sim.flush_l2()
-        sim.run(1)                     # records events around the step on the engine's stream and synchronises
-        ms, ln = sim.last_run_stats()
-        total_ms += ms
-        launches += ln
-        step_ms.append(ms)
+    sim.run_cold(args.steps)
+    total_ms, launches = sim.last_run_stats()
     barrier()
     clocks = sampler.stop() if rank == 0 else {}
+    kernel_ms = total_ms / args.steps   # this rank's own average step (the roofline of its kernel)
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -269,7 +261,6 @@ def main():
     # ---- roofline of the dominant kernel (forest_step): algorithmic 2 B per cell-update
     peak, peak_src = measured_peak_gbs()
     per_rank_cells = cells / world
-    kernel_ms = statistics.mean(step_ms)
     achieved = 2.0 * per_rank_cells / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "forest_step_traffic.json")
@@ -288,7 +279,9 @@ def main():
     halo = None
     if world > 1:
         names = {k["name"] for k in sim.kernel_stats() if k["launches"]}
-        halo = ("peer-memory stores over NVLink (CUDA IPC) + mailbox stamps" if "forest_halo_push_peer" in names
+        halo = ("fused into the step kernel: boundary warps store into the neighbours' slabs over NVLink (CUDA IPC), "
+                "mailbox stamps" if "forest_step_fused_halo" in names
+                else "peer-memory stores over NVLink (CUDA IPC) + mailbox stamps, separate kernels" if "forest_halo_push_peer" in names
                 else "NCCL send/recv")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -887,6 +887,8 @@ void series_clear(Sim& s);
 int32_t grids_allocate(Sim& s);
 int32_t grids_rebuild_for_step(Sim& s, uint64_t step, bool last_of_run);
 
+static int32_t do_run_enqueue(Sim& s, uint64_t num_steps);
+
 static int32_t do_run(Sim& s, uint64_t num_steps)
 {
     INC_CUDA(cudaSetDevice(s.device));
@@ -896,6 +898,16 @@ static int32_t do_run(Sim& s, uint64_t num_steps)
     for (auto& op : s.mods->program)
         if (op.prepare) INC_TRY(op.prepare(s, num_steps));
     INC_CUDA(cudaEventRecord(s.ev_begin, s.stream));
+    INC_TRY(do_run_enqueue(s, num_steps));
+    INC_CUDA(cudaEventRecord(s.ev_end, s.stream));
+    s.run_pending = true;
+    series_after_run(s);
+    return INCERTO_OK;
+}
+
+// the steps themselves, enqueued on the engine's stream
+static int32_t do_run_enqueue(Sim& s, uint64_t num_steps)
+{
     auto& prog = s.mods->program;
     bool all_multi = !prog.empty();
     bool device_bump = false;
@@ -948,9 +960,6 @@ static int32_t do_run(Sim& s, uint64_t num_steps)
         }
         remaining -= k;
     }
-    INC_CUDA(cudaEventRecord(s.ev_end, s.stream));
-    s.run_pending = true;
-    series_after_run(s);
     return INCERTO_OK;
 }
 
@@ -1221,6 +1230,63 @@ int32_t incerto_sim_run_async(incerto_sim* s, uint64_t num_steps)
 {
     INC_SIM(s);
     return do_run(S, num_steps);
+}
+
+// Bench hygiene in one call: `num_steps` steps, each started from a flushed L2, everything enqueued back to back (no
+// host round trip between the steps, so the ranks of a partitioned grid stay in lock step on the device); the device
+// time reported by incerto_sim_last_run_stats is the sum over the steps of the CUDA-event time around each step alone.
+int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps)
+{
+    INC_SIM(s);
+    INC_CUDA(cudaSetDevice(S.device));
+    if (num_steps == 0 || num_steps > 65536) return INCERTO_ERR_INVALID_ARGUMENT;
+    if (S.run_pending) INC_TRY(incerto_sim_synchronize(s));
+    INC_TRY(incerto_sim_flush_l2(s)); // allocates the flush buffer on first use
+    std::vector<cudaEvent_t> ev(2 * num_steps, nullptr);
+    int32_t rc = INCERTO_OK;
+    auto fail = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == INCERTO_OK)
+        {
+            set_error("run_cold: %s", cudaGetErrorString(e));
+            rc = INCERTO_ERR_CUDA;
+        }
+    };
+    for (auto& e : ev) fail(cudaEventCreate(&e));
+    if (S.comm && rc == INCERTO_OK) rc = ensure_scratch(S, 64);
+    const uint64_t launches0 = S.launches;
+    if (rc == INCERTO_OK) rc = series_prepare(S, S.step, num_steps);
+    for (auto& op : S.mods->program)
+        if (rc == INCERTO_OK && op.prepare) rc = op.prepare(S, 1);
+    for (uint64_t i = 0; i < num_steps && rc == INCERTO_OK; ++i)
+    {
+        rc = incerto_sim_flush_l2(s);
+        if (rc != INCERTO_OK) break;
+        if (S.comm)
+        {
+            // ranks of a partitioned grid: line them up again after the (untimed) flush, whose duration differs from
+            // GPU to GPU — otherwise that skew would be charged to the step as time spent waiting for the neighbour
+            rc = comm_allreduce(S, S.d_scratch, 1, 0, 0);
+            if (rc != INCERTO_OK) break;
+        }
+        fail(cudaEventRecord(ev[2 * i], S.stream));
+        if (rc == INCERTO_OK) rc = do_run_enqueue(S, 1);
+        fail(cudaEventRecord(ev[2 * i + 1], S.stream));
+    }
+    fail(cudaStreamSynchronize(S.stream));
+    double total = 0.0;
+    for (uint64_t i = 0; i < num_steps && rc == INCERTO_OK; ++i)
+    {
+        float ms = 0.f;
+        fail(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+        total += ms;
+    }
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    series_after_run(S);
+    if (rc != INCERTO_OK) return rc;
+    S.last_ms = total;
+    S.last_launches = S.launches - launches0;
+    return incerto_sim_synchronize(s); // resolves the per-kernel timers and checks the device error flag
 }
 
 int32_t incerto_sim_synchronize(incerto_sim* s)

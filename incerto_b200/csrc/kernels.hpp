@@ -112,9 +112,26 @@ struct ForestArgs
     uint64_t* series_counts;
     uint64_t series_interval, series_capacity;
 };
+// Halo transport fused into the step kernel (row partition, neighbours' slabs mapped through CUDA IPC).  A stamp k in
+// my mailbox says "that neighbour finished step k: the buffer that step wrote is complete".  The CTAs that read a halo
+// column wait for the stamp of the previous step and then PULL the neighbour's boundary column over NVLink into their
+// own halo column (nothing on the writer's side but one system-scope fence and the stamp, issued by the last block);
+// they are scheduled first, so that the wait and the NVLink round trip overlap with the rest of the grid.  The
+// neighbour cannot overwrite what is being pulled: the warps that write its boundary column are the ones that wait
+// for MY stamp of this step.
+struct ForestPeer
+{
+    const uint32_t* mail = nullptr;      // my mailbox: [0] last step stamped by the lower neighbour, [1] by the upper one
+    uint32_t need_lo = 0, need_hi = 0;   // stamp the neighbour's buffer must carry (0: first step, halos spawned locally)
+    const uint8_t* src_lo = nullptr;     // lower neighbour's last own column in the buffer this step reads
+    const uint8_t* src_hi = nullptr;     // upper neighbour's first own column
+    uint32_t* mail_lo = nullptr;         // my slot in the lower / upper neighbour's mailbox
+    uint32_t* mail_hi = nullptr;
+    uint32_t stamp = 0;
+};
 void launch_forest_step(const ForestArgs& a, cudaStream_t st);
 void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
-                           cudaStream_t st);
+                           cudaStream_t st, const ForestPeer* peer = nullptr);
 int forest_step_grid_blocks(int32_t slab_w, int32_t H);
 uint32_t forest_pitch(int32_t H);            // bytes per column: H rounded up to whole CTA tiles
 uint32_t forest_alloc_cols(int32_t slab_w);  // columns allocated: slab_w rounded up to whole CTA tiles + 2 halos

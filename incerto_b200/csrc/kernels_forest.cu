@@ -76,6 +76,7 @@ struct ForestConst
     const uint32_t* near_bits; // one bit per CTA tile: an overlay entity lies within one cell of the tile
     uint32_t* error;
     PhiloxRoundKeys rk_spread, rk_regrow; // key schedules of the two streams, as constant operands
+    ForestPeer peer;         // fused halo transport (all null without it)
 };
 
 __device__ __forceinline__ uint32_t ignited_value(const ForestArgs& a)
@@ -188,7 +189,11 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // The slab is padded to whole CTA tiles (pitch a multiple of 512 B, columns a multiple of 32 plus the
     // two halo columns; pad bytes are BURNED = inert), so no load or store below needs a bounds predicate.
     const uint32_t cy = blockIdx.x * kTX + threadIdx.x;
-    const uint32_t lx0 = 1 + (blockIdx.y * kTY + threadIdx.y) * kColsPerThread;
+    // column group of this CTA.  With the fused halo transport the two boundary groups come first in launch order
+    // (groups 1 and last swapped): they wait for the neighbours while the rest of the grid works.
+    uint32_t by = blockIdx.y;
+    if (c.peer.mail && gridDim.y > 2) by = by == 1 ? gridDim.y - 1 : (by == gridDim.y - 1 ? 1 : by);
+    const uint32_t lx0 = 1 + (by * kTY + threadIdx.y) * kColsPerThread;
     const uint32_t lane = threadIdx.x; // blockDim.x == 32: one warp per threadIdx.y
     const uint32_t tid = threadIdx.y * kTX + threadIdx.x;
     const uint32_t y0 = cy * 16;
@@ -199,6 +204,45 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     __shared__ int32_t s_delta[3];
     if (tid < 3) s_delta[tid] = 0;
     if (tid == 0) s_done = 0;
+
+    // ---- fused halo transport: the CTAs that read a halo column wait for the neighbour's stamp of the previous step
+    // and pull its boundary column into their own halo column (CTA-uniform; nothing else in this grid depends on
+    // these CTAs, so they may spin)
+    if (c.peer.mail)
+    {
+        const bool wait_lo = by == 0 && c.peer.need_lo, wait_hi = by == gridDim.y - 1 && c.peer.need_hi;
+        if (wait_lo || wait_hi)
+        {
+            if (tid == 0)
+            {
+                const volatile uint32_t* m = c.peer.mail;
+                const long long t0 = clock64();
+                // stamps only grow; wrap-around-safe comparison
+                while ((wait_lo && static_cast<int32_t>(m[0] - c.peer.need_lo) < 0) ||
+                       (wait_hi && static_cast<int32_t>(m[1] - c.peer.need_hi) < 0))
+                {
+                    __nanosleep(64);
+                    if (clock64() - t0 > 20000000000ll) // ~10 s: a neighbour died; never hang the device
+                    {
+                        if (c.error) atomicCAS(c.error, 0u, 39u); // INCERTO_ERR_COMM
+                        break;
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (threadIdx.y == 0)
+            {
+                uint8_t* mine = const_cast<uint8_t*>(a.cur);
+                if (wait_lo)
+                    *reinterpret_cast<uint4*>(mine + y0) = __ldcv(reinterpret_cast<const uint4*>(c.peer.src_lo + y0));
+                if (wait_hi)
+                    *reinterpret_cast<uint4*>(mine + static_cast<size_t>(c.slab_w + 1) * c.pitch + y0) =
+                        __ldcv(reinterpret_cast<const uint4*>(c.peer.src_hi + y0));
+            }
+            __syncthreads();
+        }
+    }
 
     // ---- loads first: columns lx0-1 .. lx0+4
     const uint8_t* p0 = a.cur + static_cast<size_t>(lx0 - 1) * c.pitch + y0;
@@ -226,13 +270,13 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     bool any_near = false;
     if (nov)
     {
-        const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+        const uint32_t tile = by * gridDim.x + blockIdx.x;
         any_near = (c.near_bits[tile >> 5] >> (tile & 31)) & 1u;
     }
     __syncthreads(); // s_done is initialised; all warps are still in step here, so this barrier is cheap
     if (any_near) // CTA-uniform
     {
-        const int tx0 = a.x_begin + static_cast<int>(blockIdx.y * kTY * kColsPerThread);
+        const int tx0 = a.x_begin + static_cast<int>(by * kTY * kColsPerThread);
         const int ty0 = static_cast<int>(blockIdx.x * kTX * 16);
         if (tid == 0) nr.n = 0;
         __syncthreads();
@@ -485,6 +529,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // Completion without a trailing block barrier (warps finish at very different times because of the
     // rare-event loops): every warp arrives on a shared counter; the last warp of the block pushes the
     // block's deltas to the running totals and takes the grid ticket; the last block publishes.
+    if (c.peer.mail_lo || c.peer.mail_hi) __syncwarp(); // lane 0 speaks for the whole warp's stores (the neighbours pull them)
     if (lane != 0) return;
     __threadfence_block();
     if (atomicAdd(&s_done, 1u) != kTY - 1) return;
@@ -494,13 +539,23 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         if (h) atomicAdd(run + 0, static_cast<unsigned long long>(static_cast<long long>(h)));
         if (b) atomicAdd(run + 1, static_cast<unsigned long long>(static_cast<long long>(b)));
         if (e) atomicAdd(run + 2, static_cast<unsigned long long>(static_cast<long long>(e)));
-        if (h | b | e) __threadfence(); // the totals are updated before this block is counted
+        // the totals are updated before this block is counted; with the fused halo transport so are the block's
+        // cells and overlay states, which a neighbour may pull as soon as the last block has stamped
+        const bool pulled = (c.peer.mail_lo || c.peer.mail_hi) && (by == 0 || by == gridDim.y - 1 || any_near);
+        if ((h | b | e) || pulled) __threadfence();
     }
     const uint32_t nblocks = gridDim.x * gridDim.y;
     const uint32_t t = atomicAdd(a.ticket, 1u);
     if (t != nblocks - 1) return;
     *a.ticket = 0u; // ready for the next launch
     __threadfence();
+    if (c.peer.mail_lo || c.peer.mail_hi)
+    {
+        // every block has arrived (each fenced its stores before taking the ticket): publish the step's stamp
+        __threadfence_system();
+        if (c.peer.mail_lo) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_lo) = c.peer.stamp;
+        if (c.peer.mail_hi) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_hi) = c.peer.stamp;
+    }
 
     // ================= last block: publish the step's FireStats =================
     unsigned long long* run = reinterpret_cast<unsigned long long*>(a.stats_run);
@@ -594,9 +649,10 @@ __global__ void __launch_bounds__(256)
 
 // Extended launch: the engine passes the neighbour overlay arrays separately.
 void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
-                           cudaStream_t st)
+                           cudaStream_t st, const ForestPeer* peer)
 {
     ForestConst c;
+    if (peer) c.peer = *peer;
     c.a = a;
     c.slab_w = static_cast<uint32_t>(a.x_end - a.x_begin);
     c.pitch = forest_pitch(a.H);

@@ -10,6 +10,7 @@
 namespace incerto
 {
 
+static constexpr size_t kOvSlot = 256; // bytes per overlay inbox slot (at most 256 overlay entities)
 static constexpr size_t kLead = 256; // bytes before column 0 / after the last column (reads of y-1 / y+1 bytes)
 
 static void forest_partition(const Sim& s, ForestModule& fm)
@@ -52,8 +53,10 @@ static int32_t forest_alloc(Sim& s, ForestModule& fm)
     const size_t nov = std::max<uint32_t>(fm.n_overlay, 1);
     INC_CUDA(cudaMalloc(&fm.d_ov_pos, nov * 2 * sizeof(int16_t)));
     for (int i = 0; i < 2; ++i) INC_CUDA(cudaMalloc(&fm.d_ov[i], nov));
-    INC_CUDA(cudaMalloc(&fm.d_ov_lo, nov));
-    INC_CUDA(cudaMalloc(&fm.d_ov_hi, nov));
+    // inboxes of the neighbours' overlay states: two slots each (the peer-memory transports alternate by step parity,
+    // so that a neighbour one step ahead never overwrites what this rank still reads); NCCL only uses slot 0
+    INC_CUDA(cudaMalloc(&fm.d_ov_lo, 2 * kOvSlot));
+    INC_CUDA(cudaMalloc(&fm.d_ov_hi, 2 * kOvSlot));
     INC_CUDA(cudaMalloc(&fm.d_ov_owner, nov));
     {
         uint32_t tc, tr;
@@ -79,6 +82,7 @@ void forest_peer_free(Sim& s)
     fm.peer = false;
     fm.peer_alloc_lo[0] = fm.peer_alloc_lo[1] = fm.peer_alloc_hi[0] = fm.peer_alloc_hi[1] = nullptr;
     fm.peer_ov_lo = fm.peer_ov_hi = nullptr;
+    fm.peer_ovs_lo[0] = fm.peer_ovs_lo[1] = fm.peer_ovs_hi[0] = fm.peer_ovs_hi[1] = nullptr;
     fm.peer_mail_lo = fm.peer_mail_hi = nullptr;
     fm.pushes = 0;
 }
@@ -92,17 +96,21 @@ int32_t forest_peer_setup(Sim& s)
     forest_peer_free(s);
     struct Pack
     {
-        cudaIpcMemHandle_t alloc[2], ov_lo, ov_hi, mail;
+        cudaIpcMemHandle_t alloc[2], ov[2], ov_lo, ov_hi, mail;
         uint32_t ok, slab_w, pad[2];
     };
+    // INCERTO_B200_HALO = nccl | peer (separate wait / push kernels) | fused (default: inside the step kernel)
     const char* env = std::getenv("INCERTO_B200_HALO");
     const bool want = !(env && std::strcmp(env, "nccl") == 0);
+    fm.fused = !(env && std::strcmp(env, "peer") == 0);
     Pack mine;
     std::memset(&mine, 0, sizeof(mine));
     INC_CUDA(cudaMalloc(&fm.d_mail, 64));
     INC_CUDA(cudaMemsetAsync(fm.d_mail, 0, 64, s.stream));
     mine.ok = want && cudaIpcGetMemHandle(&mine.alloc[0], fm.d_alloc[0]) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.alloc[1], fm.d_alloc[1]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.ov[0], fm.d_ov[0]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.ov[1], fm.d_ov[1]) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.ov_lo, fm.d_ov_lo) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.ov_hi, fm.d_ov_hi) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.mail, fm.d_mail) == cudaSuccess;
@@ -139,6 +147,8 @@ int32_t forest_peer_setup(Sim& s)
         fm.peer_alloc_lo[0] = static_cast<uint8_t*>(open(p.alloc[0]));
         fm.peer_alloc_lo[1] = static_cast<uint8_t*>(open(p.alloc[1]));
         fm.peer_ov_lo = static_cast<uint8_t*>(open(p.ov_hi));
+        fm.peer_ovs_lo[0] = static_cast<uint8_t*>(open(p.ov[0]));
+        fm.peer_ovs_lo[1] = static_cast<uint8_t*>(open(p.ov[1]));
         fm.peer_mail_lo = static_cast<uint32_t*>(open(p.mail));
         fm.peer_slab_w_lo = p.slab_w;
     }
@@ -148,6 +158,8 @@ int32_t forest_peer_setup(Sim& s)
         fm.peer_alloc_hi[0] = static_cast<uint8_t*>(open(p.alloc[0]));
         fm.peer_alloc_hi[1] = static_cast<uint8_t*>(open(p.alloc[1]));
         fm.peer_ov_hi = static_cast<uint8_t*>(open(p.ov_lo));
+        fm.peer_ovs_hi[0] = static_cast<uint8_t*>(open(p.ov[0]));
+        fm.peer_ovs_hi[1] = static_cast<uint8_t*>(open(p.ov[1]));
         fm.peer_mail_hi = static_cast<uint32_t*>(open(p.mail));
     }
     // everybody must agree on the transport: a second tiny all-gather of the outcome
@@ -236,7 +248,7 @@ static int32_t forest_upload_overlays(Sim& s, ForestModule& fm, const std::vecto
         INC_CUDA(cudaMemcpyAsync(fm.d_ov_pos, fm.h_ov_pos.data(), fm.n_overlay * 2 * sizeof(int16_t),
                                  cudaMemcpyHostToDevice, s.stream));
         INC_CUDA(cudaMemcpyAsync(fm.d_ov_owner, fm.h_ov_owner.data(), fm.n_overlay, cudaMemcpyHostToDevice, s.stream));
-        for (uint8_t* p : {fm.d_ov[0], fm.d_ov[1], fm.d_ov_lo, fm.d_ov_hi})
+        for (uint8_t* p : {fm.d_ov[0], fm.d_ov[1], fm.d_ov_lo, fm.d_ov_hi, fm.d_ov_lo + kOvSlot, fm.d_ov_hi + kOvSlot})
             INC_CUDA(cudaMemcpyAsync(p, states.data(), fm.n_overlay, cudaMemcpyHostToDevice, s.stream));
         INC_CUDA(cudaStreamSynchronize(s.stream));
     }
@@ -630,6 +642,7 @@ int32_t forest_halo_exchange(Sim& s)
     // `cur` already points at the buffer the step just produced
     uint8_t* slab = fm.d_slab[fm.cur];
     const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
+    if (fm.peer && fm.fused) return INCERTO_OK; // the step kernel did it (forest_launch_one)
     if (fm.peer)
     {
         // peer-memory transport: my boundary columns go straight into the neighbours' halo columns of the same
@@ -639,8 +652,9 @@ int32_t forest_halo_exchange(Sim& s)
         fm.pushes += 1;
         KTimer kt(s, "forest_halo_push_peer", 2.0 * fm.pitch);
         launch_forest_halo_push(slab + static_cast<size_t>(1) * fm.pitch, dst_lo, slab + static_cast<size_t>(slab_w) * fm.pitch, dst_hi,
-                                fm.pitch, fm.d_ov[fm.cur], fm.peer_ov_lo, fm.peer_ov_hi, fm.n_overlay, fm.peer_mail_lo,
-                                fm.peer_mail_hi, fm.pushes, s.stream);
+                                fm.pitch, fm.d_ov[fm.cur], fm.peer_ov_lo ? fm.peer_ov_lo + (fm.pushes & 1u) * kOvSlot : nullptr,
+                                fm.peer_ov_hi ? fm.peer_ov_hi + (fm.pushes & 1u) * kOvSlot : nullptr, fm.n_overlay,
+                                fm.peer_mail_lo, fm.peer_mail_hi, fm.pushes, s.stream);
         INC_CUDA(cudaGetLastError());
         return INCERTO_OK;
     }
@@ -696,10 +710,31 @@ static int32_t forest_launch_one(Sim& s)
         a.series_interval = se.interval;
         a.series_capacity = se.capacity;
     }
+    // the neighbours' overlay states of the previous step: the peer-memory transports alternate two inbox slots
+    const size_t ov_slot = (fm.peer && s.comm) ? (fm.pushes & 1u) * kOvSlot : 0;
+    ForestPeer pr;
+    const bool fused = fm.peer && fm.fused && s.comm;
+    const uint8_t* ov_lo = fm.d_ov_lo + ov_slot;
+    const uint8_t* ov_hi = fm.d_ov_hi + ov_slot;
+    if (fused)
+    {
+        // pull protocol (kernels.hpp: ForestPeer): this step reads the neighbours' boundary columns and overlay states
+        // straight from the buffers their previous step wrote
+        pr.mail = fm.d_mail;
+        pr.need_lo = fm.peer_mail_lo ? fm.pushes : 0u;
+        pr.need_hi = fm.peer_mail_hi ? fm.pushes : 0u;
+        pr.stamp = ++fm.pushes;
+        pr.src_lo = fm.peer_alloc_lo[fm.cur] ? fm.peer_alloc_lo[fm.cur] + kLead + static_cast<size_t>(fm.peer_slab_w_lo) * fm.pitch : nullptr;
+        pr.src_hi = fm.peer_alloc_hi[fm.cur] ? fm.peer_alloc_hi[fm.cur] + kLead + fm.pitch : nullptr;
+        pr.mail_lo = fm.peer_mail_lo ? fm.peer_mail_lo + 1 : nullptr; // the lower neighbour knows me as its upper one
+        pr.mail_hi = fm.peer_mail_hi;
+        if (pr.need_lo && fm.peer_ovs_lo[fm.cur]) ov_lo = fm.peer_ovs_lo[fm.cur];
+        if (pr.need_hi && fm.peer_ovs_hi[fm.cur]) ov_hi = fm.peer_ovs_hi[fm.cur];
+    }
     {
         // 2 B per cell-update (1 B read + 1 B written)
-        KTimer kt(s, "forest_step", 2.0 * slab_w * fm.H);
-        launch_forest_step_ex(a, fm.d_ov_lo, fm.d_ov_hi, fm.d_ov_owner, s.stream);
+        KTimer kt(s, fused ? "forest_step_fused_halo" : "forest_step", 2.0 * slab_w * fm.H);
+        launch_forest_step_ex(a, ov_lo, ov_hi, fm.d_ov_owner, s.stream, fused ? &pr : nullptr);
     }
     INC_CUDA(cudaGetLastError());
     fm.cur = 1 - fm.cur;
@@ -781,7 +816,7 @@ int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps)
     }
     for (; done < nsteps; ++done)
     {
-        if (fm.peer && s.comm && fm.pushes)
+        if (fm.peer && !fm.fused && s.comm && fm.pushes)
         {
             // the halo columns this step reads were stored by the neighbours after their previous step
             launch_forest_halo_wait(fm.d_mail, fm.peer_mail_lo ? fm.pushes : 0u, fm.peer_mail_hi ? fm.pushes : 0u, s.d_error, s.stream);

@@ -55,16 +55,19 @@ struct ForestModule
     // halo transport over peer memory (row partition): the neighbours' slabs, overlay inboxes and mailboxes mapped
     // through CUDA IPC; `peer` stays false when that is not possible and NCCL send/recv is used instead
     bool peer = false;
+    bool fused = true;               // the step kernel itself waits / pushes / stamps (else: separate kernels)
     uint8_t* peer_alloc_lo[2] = {nullptr, nullptr}; // lower neighbour's d_alloc[0/1]
     uint8_t* peer_alloc_hi[2] = {nullptr, nullptr};
     uint8_t* peer_ov_lo = nullptr;   // lower neighbour's d_ov_hi (my overlay states are its upper neighbour's)
     uint8_t* peer_ov_hi = nullptr;   // upper neighbour's d_ov_lo
+    uint8_t* peer_ovs_lo[2] = {nullptr, nullptr}; // the neighbours' own overlay state arrays d_ov[0/1] (pulled by the fused transport)
+    uint8_t* peer_ovs_hi[2] = {nullptr, nullptr};
     uint32_t* peer_mail_lo = nullptr; // lower neighbour's mailbox
     uint32_t* peer_mail_hi = nullptr;
     uint32_t* d_mail = nullptr;      // [0] steps pushed by the lower neighbour, [1] by the upper one
     uint32_t peer_slab_w_lo = 0;     // lower neighbour's slab width (to find its upper halo column)
     uint32_t pushes = 0;             // steps whose boundary I pushed so far
-    void* ipc_opened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* ipc_opened[12] = {};
 };
 
 struct PandemicModule

@@ -688,6 +688,11 @@ class Simulation:
     def flush_l2(self) -> None:
         _check(self._lib.incerto_sim_flush_l2(self._h))
 
+    def run_cold(self, num_steps: int) -> None:
+        """`num_steps` steps, each from a flushed L2, enqueued back to back; `last_run_stats()` then holds the sum of
+        the per-step device times (the flushes are not timed)."""
+        _check(self._lib.incerto_sim_run_cold(self._h, num_steps))
+
     def halo_export(self, side: int) -> np.ndarray:
         n = C.c_size_t()
         buf = np.zeros(1 << 16, dtype=np.uint8)

@@ -503,6 +503,12 @@ int32_t incerto_sim_set_profiling(incerto_sim* s, uint32_t enabled);
 int32_t incerto_sim_kernel_stats(incerto_sim* s, incerto_kernel_stat* out, uint32_t capacity, uint32_t* n_out);
 /* Write >= 2x L2 worth of HBM so the next kernel starts cold (bench hygiene). */
 int32_t incerto_sim_flush_l2(incerto_sim* s);
+/* Bench hygiene in one call: `num_steps` steps of Simulation::run (src/simulation.rs:25-31), each started from a
+ * flushed L2 and all enqueued back to back (no host round trip between the steps, so the ranks of a row-partitioned
+ * grid stay in lock step on the device).  incerto_sim_last_run_stats then reports the SUM over the steps of the
+ * CUDA-event time around each step alone (the flushes are not timed; with a communicator attached an untimed
+ * all-reduce lines the ranks up again after each flush). */
+int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps);
 
 /* ----------------------------------------------------------------- multi-GPU */
 /* Attach an NCCL communicator (one process per GPU).  `unique_id` is the

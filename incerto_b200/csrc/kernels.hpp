@@ -129,9 +129,9 @@ struct ForestPeer
     uint32_t* mail_hi = nullptr;
     uint32_t stamp = 0;
 };
-void launch_forest_step(const ForestArgs& a, cudaStream_t st);
-void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
-                           cudaStream_t st, const ForestPeer* peer = nullptr);
+cudaError_t launch_forest_step(const ForestArgs& a, cudaStream_t st);
+cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
+                                  cudaStream_t st, const ForestPeer* peer = nullptr);
 int forest_step_grid_blocks(int32_t slab_w, int32_t H);
 uint32_t forest_pitch(int32_t H);            // bytes per column: H rounded up to whole CTA tiles
 uint32_t forest_alloc_cols(int32_t slab_w);  // columns allocated: slab_w rounded up to whole CTA tiles + 2 halos

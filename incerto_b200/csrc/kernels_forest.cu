@@ -28,6 +28,8 @@
 //     byte (uid & 15) of philox(key[REGROW], (uid >> 4, 0, step, 0)) == 0
 //     AND word (uid & 3) of philox(key[REGROW], (uid >> 2, 0, step, 1)) < floor(256*p*2^32)
 //   regrow, p*256 > 1: word (uid & 3) of philox(key[REGROW], (uid >> 2, 0, step, 1)) < floor(p*2^32)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
@@ -60,6 +62,23 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t v)
     // 0x80 in every byte of v that is zero
     return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
 }
+
+#ifdef INCERTO_FOREST_TRACE
+// developer instrumentation (tools/trace_forest.py): per warp {start, loads consumed, end} in globaltimer ns + SM id
+__device__ unsigned long long g_forest_trace[4 * (1 << 18)];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t smid()
+{
+    uint32_t v;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(v));
+    return v;
+}
+#endif
 
 constexpr int kEventQueue = 512;   // rare events of one warp tile handled per round
 constexpr int kMaxNear = 64;       // overlay entities within one cell of a CTA tile
@@ -200,6 +219,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     const uint32_t H = static_cast<uint32_t>(a.H);
     constexpr bool chunk_ok = true;
 
+#ifdef INCERTO_FOREST_TRACE
+    const unsigned long long tr_start = gtime();
+#endif
     __shared__ uint32_t s_done; // warps of this block that finished (see the end of the kernel)
     __shared__ int32_t s_delta[3];
     if (tid < 3) s_delta[tid] = 0;
@@ -308,6 +330,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
 #pragma unroll
     for (int j = 0; j < kColsPerThread + 2; ++j) ob |= (v[j].x | v[j].y | v[j].z | v[j].w) & 0x3f3f3f3fu;
     const bool fire = __any_sync(kFullMask, ob != 0);
+#ifdef INCERTO_FOREST_TRACE
+    const unsigned long long tr_loaded = gtime();
+#endif
 
     const uint32_t ign = ignited_value(a);
     Delta dl;
@@ -529,6 +554,16 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // Completion without a trailing block barrier (warps finish at very different times because of the
     // rare-event loops): every warp arrives on a shared counter; the last warp of the block pushes the
     // block's deltas to the running totals and takes the grid ticket; the last block publishes.
+#ifdef INCERTO_FOREST_TRACE
+    if (lane == 0)
+    {
+        const uint32_t w = ((blockIdx.y * gridDim.x + blockIdx.x) * kTY + threadIdx.y) & ((1u << 18) - 1);
+        g_forest_trace[4 * w + 0] = tr_start;
+        g_forest_trace[4 * w + 1] = tr_loaded;
+        g_forest_trace[4 * w + 2] = gtime();
+        g_forest_trace[4 * w + 3] = smid();
+    }
+#endif
     if (c.peer.mail_lo || c.peer.mail_hi) __syncwarp(); // lane 0 speaks for the whole warp's stores (the neighbours pull them)
     if (lane != 0) return;
     __threadfence_block();
@@ -648,8 +683,8 @@ __global__ void __launch_bounds__(256)
 } // namespace
 
 // Extended launch: the engine passes the neighbour overlay arrays separately.
-void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
-                           cudaStream_t st, const ForestPeer* peer)
+cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
+                                  cudaStream_t st, const ForestPeer* peer)
 {
     ForestConst c;
     if (peer) c.peer = *peer;
@@ -672,9 +707,10 @@ void launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint
         forest_step_kernel<true><<<grid, block, 0, st>>>(c);
     else
         forest_step_kernel<false><<<grid, block, 0, st>>>(c);
+    return cudaGetLastError();
 }
 
-void launch_forest_step(const ForestArgs& a, cudaStream_t st) { launch_forest_step_ex(a, nullptr, nullptr, nullptr, st); }
+cudaError_t launch_forest_step(const ForestArgs& a, cudaStream_t st) { return launch_forest_step_ex(a, nullptr, nullptr, nullptr, st); }
 
 uint32_t forest_pitch(int32_t H) { return (static_cast<uint32_t>(H) + kTX * 16 - 1) / (kTX * 16) * (kTX * 16); }
 uint32_t forest_alloc_cols(int32_t slab_w)
@@ -774,3 +810,10 @@ void launch_forest_stats(const uint8_t* slab, int32_t H, int32_t slab_w, uint64_
 }
 
 } // namespace incerto
+
+#ifdef INCERTO_FOREST_TRACE
+extern "C" int incerto_debug_forest_trace(unsigned long long* out, unsigned long long n_words)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, incerto::g_forest_trace, n_words * sizeof(unsigned long long)));
+}
+#endif

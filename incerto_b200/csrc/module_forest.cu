@@ -734,9 +734,8 @@ static int32_t forest_launch_one(Sim& s)
     {
         // 2 B per cell-update (1 B read + 1 B written)
         KTimer kt(s, fused ? "forest_step_fused_halo" : "forest_step", 2.0 * slab_w * fm.H);
-        launch_forest_step_ex(a, ov_lo, ov_hi, fm.d_ov_owner, s.stream, fused ? &pr : nullptr);
+        INC_CUDA(launch_forest_step_ex(a, ov_lo, ov_hi, fm.d_ov_owner, s.stream, fused ? &pr : nullptr));
     }
-    INC_CUDA(cudaGetLastError());
     fm.cur = 1 - fm.cur;
     return INCERTO_OK;
 }

@@ -188,3 +188,23 @@ def test_borrowed_spawn_buffers_give_the_same_result_and_refuse_reset():
         else:
             sim.reset(0)
     assert np.array_equal(out[0], out[1]) and (out[0] == F.CELL_BURNED).any()
+
+
+def test_run_cold_is_run_with_a_flushed_l2_before_every_step():
+    """incerto_sim_run_cold (the bench's timed loop): same states, same series, same step counter as run(n); the
+    device time it reports is the sum of the per-step event times."""
+    W, H, steps = 96, 80, 25
+    a, _, cell_a = build_device_forest(W, H, density=0.85, p_regrow=0.004, fires=5)
+    b, _, cell_b = build_device_forest(W, H, density=0.85, p_regrow=0.004, fires=5)
+    a.run(steps)
+    b.run_cold(10)
+    b.run_cold(steps - 10)
+    ms, launches = b.last_run_stats()
+    assert launches == steps - 10 and ms > 0
+    assert a.step_number() == b.step_number() == steps + 1
+    assert np.array_equal(a.read_component(cell_a), b.read_component(cell_b))
+    ta, tb = a.get_aggregate_time_series(ib.FireStatsOf(cell_a)), b.get_aggregate_time_series(ib.FireStatsOf(cell_b))
+    assert ta.len() == tb.len() == steps
+    assert [stats_tuple(v) for v in ta.values()] == [stats_tuple(v) for v in tb.values()]
+    o = ForestOracle(SEED, 0, W, H, density=0.85, p_regrow=0.004, fires=5).spawn().run(steps)
+    assert np.array_equal(b.read_component(cell_b), o.cells()[0])

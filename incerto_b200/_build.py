@@ -96,7 +96,7 @@ def build(verbose: bool = False, force: bool = False, extra_flags: list[str] | N
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB):
         # libcudart is linked statically (nvcc default); NCCL is dlopen-ed at attach time
-        run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+        run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"])
     return LIB
 
 

@@ -5,6 +5,8 @@
 //   Simulation::run                                                src/simulation.rs:25-31
 //   StepNumberPlugin                                               src/plugins/step_number.rs:6-23
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdarg>
 #include <cstdio>
 
@@ -114,6 +116,16 @@ int32_t ensure_pinned(Sim& s, size_t bytes)
     INC_CUDA(cudaMallocHost(&s.h_pinned, bytes));
     s.pinned_bytes = bytes;
     return INCERTO_OK;
+}
+
+void stage_mark(const char* what)
+{
+    static const bool on = std::getenv("INCERTO_B200_TIMING") != nullptr;
+    if (!on) return;
+    static auto last = std::chrono::steady_clock::now();
+    const auto now = std::chrono::steady_clock::now();
+    if (what) std::fprintf(stderr, "[incerto_b200 timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
 }
 
 KernelStat& kstat(Sim& s, const char* name)
@@ -1164,6 +1176,7 @@ int32_t incerto_builder_build(incerto_builder* b, incerto_sim** out)
         set_error("device ordinal %d out of range (%d devices)", S.device, ndev);
         return INCERTO_ERR_INVALID_ARGUMENT;
     }
+    stage_mark(nullptr);
     INC_CUDA(cudaSetDevice(S.device));
     INC_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     INC_CUDA(cudaEventCreate(&S.ev_begin));
@@ -1176,7 +1189,6 @@ int32_t incerto_builder_build(incerto_builder* b, incerto_sim** out)
     const uint32_t one = 1;
     INC_CUDA(cudaMemcpyAsync(S.mods->d_step, &one, sizeof(one), cudaMemcpyHostToDevice, S.stream));
     INC_TRY(ensure_scratch(S, 1u << 20));
-    INC_TRY(ensure_pinned(S, 1u << 16));
     S.step = 1; // SimulationBuilder::new runs one empty update (simulation_builder.rs:50)
 
     // components named by grids and series "exist" like the query state of a bevy system
@@ -1199,10 +1211,13 @@ int32_t incerto_builder_build(incerto_builder* b, incerto_sim** out)
         for (int c : se.agg.filter.with) S.comps[c].exists = true;
         for (int c : se.agg.filter.without) S.comps[c].exists = true;
     }
+    stage_mark("build: stream, scratch");
     INC_TRY(run_spawners(S, true));
+    stage_mark("build: run_spawners");
     INC_TRY(bind_generic_systems(S));
     INC_TRY(grids_allocate(S));
     INC_CUDA(cudaStreamSynchronize(S.stream));
+    stage_mark("build: bind, grids, sync");
     for (auto& sp : S.spawns)
         if (sp.borrowed)
             for (auto& c : sp.cols) c.ext = nullptr; // the caller's buffers are only promised until here

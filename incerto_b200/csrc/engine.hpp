@@ -276,6 +276,9 @@ KernelStat& kstat(Sim& s, const char* name);
 int32_t live_rows_by_uid(Sim& s, Table& t, std::vector<uint32_t>& rows, std::vector<uint32_t>& uids);
 
 // scoped kernel timing (only when profiling is on)
+// developer aid: with INCERTO_B200_TIMING=1 the host-side stages of build() report their wall time on stderr
+void stage_mark(const char* what);
+
 struct KTimer
 {
     Sim& s;

@@ -4,6 +4,7 @@
 // Reference: examples/forest_fire.rs (spawn :234-279, systems :282-365, stats :104-134).
 #include <algorithm>
 #include <cstdlib>
+#include <thread>
 
 #include "modules.hpp"
 
@@ -345,10 +346,31 @@ int32_t forest_spawn_device(Sim& s, const HostSpawn& sp)
     return INCERTO_OK;
 }
 
+// OR of fn(begin, end) over [0, n) split into contiguous ranges, one per host thread (small inputs stay on the caller)
+template <class Fn>
+static uint32_t host_parallel_or(uint64_t n, Fn fn)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    const uint64_t nt = std::min<uint64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), n / (1u << 20));
+    if (nt <= 1) return fn(0, n);
+    std::vector<uint32_t> res(nt, 0u);
+    std::vector<std::thread> th;
+    for (uint64_t i = 0; i < nt; ++i)
+        th.emplace_back([&, i] { res[i] = fn(n * i / nt, n * (i + 1) / nt); });
+    uint32_t r = 0;
+    for (uint64_t i = 0; i < nt; ++i)
+    {
+        th[i].join();
+        r |= res[i];
+    }
+    return r;
+}
+
 // Host-spawned forest: find the dense x-major prefix among the spawned rows and
 // move the cell column into the pitched slab.
 static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
 {
+    stage_mark("(before forest adopt)");
     Table& t = s.tables[fm.table];
     const ComponentInfo& pc = s.comps[fm.comp_pos];
     const ComponentInfo& cc = s.comps[fm.comp_cell];
@@ -427,7 +449,32 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     else
         st.resize(cells);
     std::vector<uint8_t> ov_states;
+    // pass A (cheap): the rows after the dense prefix are overlay entities
     {
+        uint64_t g = 0; // global row
+        for (auto& pz : pieces)
+        {
+            const uint64_t n_dense = g < cells ? std::min<uint64_t>(pz.n, cells - g) : 0;
+            for (uint64_t r = n_dense; r < pz.n; ++r)
+            {
+                int32_t x, y;
+                pos_at(pz, r, x, y);
+                if (x < 0 || x >= fm.W || y < 0 || y >= fm.H)
+                {
+                    set_error("entity at position (%d, %d) outside spatial grid bounds", x, y); // spatial_grid.rs:276-279
+                    return INCERTO_ERR_OUT_OF_BOUNDS;
+                }
+                ov_x.push_back(x);
+                ov_y.push_back(y);
+                ov_states.push_back(pz.st[r]);
+            }
+            g += pz.n;
+        }
+    }
+    // pass B (streams every row: 5 bytes per cell): order of the dense prefix and validity of the state codes.
+    // Returns 0, 1 (order) or 2 (state code); runs beside the allocation + upload below when the states can be
+    // uploaded straight from the caller's buffer.
+    auto verify = [&]() -> int {
         uint64_t g = 0; // global row
         uint32_t bad_state = 0;
         for (auto& pz : pieces)
@@ -449,54 +496,73 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
                 }
                 else
                 {
-                    // packed (x | y << 16): within a column consecutive rows differ by 0x10000
+                    // packed (x | y << 16): within a column consecutive rows differ by 0x10000.  The rows are split
+                    // over a few host threads.
                     const uint32_t* q = reinterpret_cast<const uint32_t*>(pz.pos);
-                    uint64_t r = 0;
-                    while (r < n_dense)
-                    {
-                        const uint64_t gg = g + r;
-                        const uint32_t x = static_cast<uint32_t>(gg / fm.H), y = static_cast<uint32_t>(gg % fm.H);
-                        const uint64_t run = std::min<uint64_t>(n_dense - r, static_cast<uint64_t>(fm.H) - y);
-                        bad |= static_cast<uint32_t>(q[r] != ((x & 0xffffu) | (y << 16)));
-                        uint32_t acc = 0;
-                        for (uint64_t k = 1; k < run; ++k) acc |= (q[r + k] - q[r + k - 1]) ^ 0x10000u;
-                        bad |= acc;
-                        r += run;
-                    }
+                    auto check_rows = [&](uint64_t r, uint64_t r_end) {
+                        uint32_t b = 0;
+                        while (r < r_end)
+                        {
+                            const uint64_t gg = g + r;
+                            const uint32_t x = static_cast<uint32_t>(gg / fm.H), y = static_cast<uint32_t>(gg % fm.H);
+                            const uint64_t run = std::min<uint64_t>(r_end - r, static_cast<uint64_t>(fm.H) - y);
+                            b |= static_cast<uint32_t>(q[r] != ((x & 0xffffu) | (y << 16)));
+                            uint32_t acc = 0;
+                            for (uint64_t k = 1; k < run; ++k) acc |= (q[r + k] - q[r + k - 1]) ^ 0x10000u;
+                            b |= acc;
+                            r += run;
+                        }
+                        return b;
+                    };
+                    bad |= host_parallel_or(n_dense, check_rows);
                 }
-                if (bad)
-                {
-                    set_error("forest: cells must be spawned in x-major order (for x {for y}) as forest_fire.rs:239-257 does");
-                    return INCERTO_ERR_UNSUPPORTED;
-                }
+                if (bad) return 1;
             }
             // state codes: BURNED 0, BURNING 1..63, HEALTHY 0x40, EMPTY 0x80
-            for (uint64_t r = 0; r < pz.n; ++r)
             {
-                const uint8_t v = pz.st[r];
-                bad_state |= static_cast<uint32_t>(!(v <= 63 || v == INCERTO_CELL_HEALTHY || v == INCERTO_CELL_EMPTY));
-            }
-            for (uint64_t r = n_dense; r < pz.n; ++r)
-            {
-                int32_t x, y;
-                pos_at(pz, r, x, y);
-                if (x < 0 || x >= fm.W || y < 0 || y >= fm.H)
-                {
-                    set_error("entity at position (%d, %d) outside spatial grid bounds", x, y); // spatial_grid.rs:276-279
-                    return INCERTO_ERR_OUT_OF_BOUNDS;
-                }
-                ov_x.push_back(x);
-                ov_y.push_back(y);
-                ov_states.push_back(pz.st[r]);
+                const uint8_t* stp = pz.st;
+                bad_state |= host_parallel_or(pz.n, [stp](uint64_t r, uint64_t r_end) {
+                    uint32_t b = 0;
+                    for (; r < r_end; ++r)
+                    {
+                        const uint8_t v = stp[r];
+                        b |= static_cast<uint32_t>(!(v <= 63 || v == INCERTO_CELL_HEALTHY || v == INCERTO_CELL_EMPTY));
+                    }
+                    return b;
+                });
             }
             g += pz.n;
         }
-        if (bad_state)
+        return bad_state ? 2 : 0;
+    };
+    auto verdict = [&](int v) -> int32_t {
+        if (v == 1)
+        {
+            set_error("forest: cells must be spawned in x-major order (for x {for y}) as forest_fire.rs:239-257 does");
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+        if (v == 2)
         {
             set_error("forest: invalid cell state code");
             return INCERTO_ERR_INVALID_ARGUMENT;
         }
-    }
+        return INCERTO_OK;
+    };
+    int verified = -1;
+    std::thread checker;
+    if (dense_states)
+        checker = std::thread([&] { verified = verify(); });
+    else
+        INC_TRY(verdict(verify()));
+    struct Joiner
+    {
+        std::thread& t;
+        ~Joiner()
+        {
+            if (t.joinable()) t.join();
+        }
+    } joiner{checker};
+    stage_mark("forest adopt: host checks");
     const uint8_t* dense = dense_states ? dense_states : st.data();
     fm.n_overlay = static_cast<uint32_t>(total - cells);
     if (fm.n_overlay > 256)
@@ -512,6 +578,12 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
                                dense + static_cast<size_t>(lo) * fm.H, fm.H, fm.H, hi - lo, cudaMemcpyHostToDevice,
                                s.stream));
     INC_CUDA(cudaStreamSynchronize(s.stream));
+    if (checker.joinable())
+    {
+        checker.join();
+        INC_TRY(verdict(verified));
+    }
+    stage_mark("forest adopt: alloc, H2D");
     fm.cur = 0;
     fm.h_ov_pos.resize(2 * static_cast<size_t>(fm.n_overlay));
     std::vector<uint8_t> ovst(std::max<uint32_t>(fm.n_overlay, 1), 0);
@@ -534,7 +606,9 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     t.dense_h = fm.H;
     t.x_begin = fm.x_begin;
     t.x_end = fm.x_end;
+    stage_mark("forest adopt: overlays, frees");
     INC_TRY(forest_init_stats(s, fm, ovst));
+    stage_mark("forest adopt: init stats");
     return INCERTO_OK;
 }
 

@@ -208,3 +208,40 @@ def test_run_cold_is_run_with_a_flushed_l2_before_every_step():
     assert [stats_tuple(v) for v in ta.values()] == [stats_tuple(v) for v in tb.values()]
     o = ForestOracle(SEED, 0, W, H, density=0.85, p_regrow=0.004, fires=5).spawn().run(steps)
     assert np.array_equal(b.read_component(cell_b), o.cells()[0])
+
+
+@pytest.mark.parametrize("W,H", [(24, 40), (1100, 1024)])   # the big one takes the multi-threaded host check
+@pytest.mark.parametrize("borrow", [False, True])
+def test_host_spawn_is_verified(W, H, borrow):
+    """A host-spawned forest must be the dense x-major grid of forest_fire.rs:239-257 with valid state codes, and an
+    entity outside the grid bounds is refused as the reference's SpatialGrid does (spatial_grid.rs:276-279)."""
+    from incerto_b200.simulation import EngineError
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H), indexing="ij")
+    xy = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int16)
+    st = np.full(W * H, HEALTHY, np.uint8)
+
+    def build(xy_, st_):
+        b = ib.SimulationBuilder(seed=SEED)
+        pos = b.component("GridPosition2D", F.I16, lanes=2)
+        cell = b.component("ForestCell.state", F.U8)
+        b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
+        b.add_entity_spawner(lambda s: s.spawn_batch(len(st_), {pos: xy_, cell: st_}))
+        b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.004))
+        return b.build(borrow_spawn_buffers=borrow), cell
+
+    sim, cell = build(xy, st)
+    assert np.array_equal(sim.read_component(cell), st)
+    swapped = xy.copy()
+    k = (W * H * 3) // 4 + 5                       # two rows in the wrong order, far into the grid
+    swapped[[k, k + 1]] = swapped[[k + 1, k]]
+    with pytest.raises(EngineError) as e:
+        build(swapped, st)
+    assert e.value.code == F.ERR_UNSUPPORTED and "x-major" in str(e.value)
+    bad = st.copy()
+    bad[W * H - 7] = 0x41                           # not a ForestCell state code
+    with pytest.raises(EngineError) as e:
+        build(xy, bad)
+    assert e.value.code == F.ERR_INVALID_ARGUMENT
+    with pytest.raises(EngineError) as e:
+        build(np.concatenate([xy, np.array([[W, 0]], np.int16)]), np.concatenate([st, np.array([3], np.uint8)]))
+    assert e.value.code == F.ERR_OUT_OF_BOUNDS

@@ -22,7 +22,7 @@ for it in range(3):
     b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.001))
     b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
     t.append(time.perf_counter())
-    sim = b.build()
+    sim = b.build(borrow_spawn_buffers=True)
     t.append(time.perf_counter())
     sim.run(500)
     t.append(time.perf_counter())
@@ -34,34 +34,3 @@ for it in range(3):
     print("builder %.1f ms | build() %.1f ms | run(500) %.1f ms | series+aggregate %.1f ms | destroy %.1f ms | total %.1f ms" %
           tuple([(t[i + 1] - t[i]) * 1e3 for i in range(5)] + [(t[-1] - t[0]) * 1e3]))
 
-# finer: time the C calls inside build()
-import ctypes as C
-lib = F.load()
-orig_add, orig_build = lib.incerto_builder_add_entity_spawner, lib.incerto_builder_build
-acc = {"add": 0.0, "build": 0.0}
-class Timed:
-    def __init__(self, fn, key): self.fn, self.key = fn, key
-    def __call__(self, *a):
-        t0 = time.perf_counter(); r = self.fn(*a); acc[self.key] += time.perf_counter() - t0; return r
-b = ib.SimulationBuilder(seed=SEED)
-b._lib = type("L", (), {})()
-for name in dir(lib):
-    pass
-import incerto_b200.simulation as S
-class Proxy:
-    def __getattr__(self, k):
-        f = getattr(lib, k)
-        if k == "incerto_builder_add_entity_spawner": return Timed(f, "add")
-        if k == "incerto_builder_build": return Timed(f, "build")
-        return f
-b._lib = Proxy()
-pos = b.component("GridPosition2D", F.I16, lanes=2)
-cell = b.component("ForestCell.state", F.U8)
-b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
-b.add_entity_spawner(lambda s: s.spawn_batch(n, {pos: host_pos, cell: host_state}))
-b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.001))
-t0 = time.perf_counter()
-sim = b.build()
-tot = time.perf_counter() - t0
-print("build(): total %.1f ms = python %.1f + add_entity_spawner %.1f + incerto_builder_build %.1f" %
-      (tot * 1e3, (tot - acc["add"] - acc["build"]) * 1e3, acc["add"] * 1e3, acc["build"] * 1e3))

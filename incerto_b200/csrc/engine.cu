@@ -911,6 +911,7 @@ static int32_t do_run(Sim& s, uint64_t num_steps)
         if (op.prepare) INC_TRY(op.prepare(s, num_steps));
     INC_CUDA(cudaEventRecord(s.ev_begin, s.stream));
     INC_TRY(do_run_enqueue(s, num_steps));
+    INC_TRY(forest_finalize(s)); // the last step's FireStats record (every earlier one was written by its successor)
     INC_CUDA(cudaEventRecord(s.ev_end, s.stream));
     s.run_pending = true;
     series_after_run(s);
@@ -1287,6 +1288,7 @@ int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps)
         if (rc == INCERTO_OK) rc = do_run_enqueue(S, 1);
         fail(cudaEventRecord(ev[2 * i + 1], S.stream));
     }
+    if (rc == INCERTO_OK) rc = forest_finalize(S); // not inside any step's event pair: see forest_finalize
     fail(cudaStreamSynchronize(S.stream));
     double total = 0.0;
     for (uint64_t i = 0; i < num_steps && rc == INCERTO_OK; ++i)

@@ -53,6 +53,7 @@ void launch_iota_u32(uint32_t* p, uint64_t n, cudaStream_t st);
 void launch_flush(uint8_t* p, size_t bytes, uint32_t value, cudaStream_t st);
 // step counter kept on the device so that captured step programs need no new arguments
 void launch_step_increment(uint32_t* d_step, cudaStream_t st);
+void launch_set_u32(uint32_t* p, uint32_t value, cudaStream_t st);
 
 // dst row i = src row perm[i] (row reordering of a column)
 void launch_gather_rows(const void* src, void* dst, uint32_t row_bytes, const uint32_t* perm, uint64_t n, cudaStream_t st);
@@ -100,11 +101,14 @@ struct ForestArgs
     uint64_t thr_regrow_l2;     // floor(256 * p * 2^32), used when regrow_two_level
     uint32_t regrow_two_level;  // p * 256 <= 1
     uint32_t burn_duration;
-    uint32_t bump_step;         // this launch ends the step: StepNumber += 1 on the device
     PhiloxKey key_spread, key_regrow;
+    // StepNumber of the launch = (d_step ? *d_step : 0) + step_base: by value for single launches, device counter +
+    // offset inside a captured graph of steps (which then replays without new arguments)
     const uint32_t* d_step;
+    uint32_t step_base;
     // fused FireStats (forest_fire.rs:104-134): per-step record + series ring
-    uint64_t* stats_run;      // running totals (healthy, burning, empty) of this slab + owned overlays
+    uint64_t* stats_run;      // 12 u64: totals (healthy, burning, empty), last published step, two delta slots of
+                              // this slab + owned overlays (layout: kernels_forest.cu, forest_publish)
     uint32_t* error;          // device error flag
     uint32_t* ticket;
     uint64_t* stats_out;      // 5 u64: healthy, burning, burned, empty, total (state after this step)
@@ -130,6 +134,8 @@ struct ForestPeer
     uint32_t stamp = 0;
 };
 cudaError_t launch_forest_step(const ForestArgs& a, cudaStream_t st);
+// put step (d_step ? *d_step : 0) + step_base on record (idempotent) and add `bump` to the device StepNumber
+cudaError_t launch_forest_publish(const ForestArgs& a, uint32_t bump, cudaStream_t st);
 cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
                                   cudaStream_t st, const ForestPeer* peer = nullptr);
 int forest_step_grid_blocks(int32_t slab_w, int32_t H);

@@ -200,7 +200,60 @@ __device__ __forceinline__ bool overlay_marked(const ForestConst& c, const NearO
 //    event word per column and handled afterwards by a single rolled loop that patches single bytes of
 //    the freshly written buffer;
 //  * FireStats are kept incrementally: only state transitions are counted (one warp-aggregated atomic
-//    when a warp saw any), the last block to arrive publishes the running totals.
+//    when a warp saw any) into the step's delta slot; see forest_publish for who puts the step on record.
+// FireStats bookkeeping (forest_fire.rs:104-134, sampled every step by the fused series, time_series.rs:68-87).
+// A step only adds the deltas of its state transitions to one of two delta slots (fire-and-forget reductions, no
+// fence, no grid-wide ticket on the step's critical path).  The totals are brought up to date — and the record +
+// series slot of that step written — by ONE thread afterwards: the first thread of the next step's grid, which runs
+// while that grid's loads are in flight, or forest_publish_kernel after the last step of a run.
+// stats_run layout (u64): [0..2] totals healthy / burning / empty, [3] last published step,
+//                         [4..6] deltas of even steps, [8..10] deltas of odd steps.
+__device__ __forceinline__ void forest_publish(const ForestArgs& a, uint32_t slab_w, uint32_t p)
+{
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(a.stats_run);
+    if (p == 0 || __ldcg(st + 3) >= p) return; // nothing ran yet, or that step is already on record
+    unsigned long long* d = st + 4 + 4 * (p & 1u);
+    const uint64_t healthy = __ldcg(st + 0) + __ldcg(d + 0); // deltas are two's complement: wrapping adds
+    const uint64_t burning = __ldcg(st + 1) + __ldcg(d + 1);
+    const uint64_t empty = __ldcg(st + 2) + __ldcg(d + 2);
+    st[0] = healthy;
+    st[1] = burning;
+    st[2] = empty;
+    st[3] = p;
+    d[0] = d[1] = d[2] = 0ull; // the slot is used again two steps later
+    const uint64_t total = static_cast<uint64_t>(slab_w) * a.H + a.ov_owned;
+    const uint64_t burned = total - healthy - burning - empty;
+    a.stats_out[0] = healthy;
+    a.stats_out[1] = burning;
+    a.stats_out[2] = burned;
+    a.stats_out[3] = empty;
+    a.stats_out[4] = total;
+    if (a.series_values && a.series_interval && (p % a.series_interval) == 0)
+    {
+        // slot = number of sampling instants before this one (time_series.rs:68-87)
+        const uint64_t slot = p / a.series_interval - 1;
+        if (slot < a.series_capacity)
+        {
+            uint64_t* rec = reinterpret_cast<uint64_t*>(a.series_values) + slot * 5;
+            rec[0] = healthy;
+            rec[1] = burning;
+            rec[2] = burned;
+            rec[3] = empty;
+            rec[4] = total;
+            a.series_counts[slot] = total;
+        }
+    }
+}
+
+// After the last step of a run (and at the end of every captured graph of steps): put that step on record and,
+// for a graph, advance the device-side StepNumber (src/plugins/step_number.rs:20-23) by the steps it held.
+__global__ void forest_publish_kernel(ForestArgs a, uint32_t slab_w, uint32_t bump)
+{
+    const uint32_t p = (a.d_step ? *a.d_step : 0u) + a.step_base;
+    forest_publish(a, slab_w, p);
+    if (bump && a.d_step) *const_cast<uint32_t*>(a.d_step) += bump;
+}
+
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const __grid_constant__ ForestConst c)
 {
@@ -282,7 +335,10 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         for (int j = 1; j <= kColsPerThread; ++j)
             edge |= ((*reinterpret_cast<const uint32_t*>(p0 + static_cast<size_t>(j) * c.pitch + d) & m) ? 1u : 0u) << (j - 1);
     }
-    const uint32_t step = *a.d_step;
+    // StepNumber of this launch: by value, or (captured graphs) the device counter + the launch's offset in the graph
+    const uint32_t step = (a.d_step ? *a.d_step : 0u) + a.step_base;
+    // the previous step's FireStats go on record now, off every critical path (see forest_publish)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) forest_publish(a, c.slab_w, step - 1);
 
     // ---- overlays that can touch this CTA's tile (usually none): one bit per tile, prepared by the host.
     // The staging into shared memory (two barriers) only happens in the CTAs that have one nearby.
@@ -569,59 +625,26 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     __threadfence_block();
     if (atomicAdd(&s_done, 1u) != kTY - 1) return;
     {
-        unsigned long long* run = reinterpret_cast<unsigned long long*>(a.stats_run);
+        // the block's deltas go to this step's delta slot: reductions nobody waits for (the kernel boundary orders
+        // them before the thread that publishes the step)
+        unsigned long long* d = reinterpret_cast<unsigned long long*>(a.stats_run) + 4 + 4 * (step & 1u);
         const int32_t h = atomicAdd(&s_delta[0], 0), b = atomicAdd(&s_delta[1], 0), e = atomicAdd(&s_delta[2], 0);
-        if (h) atomicAdd(run + 0, static_cast<unsigned long long>(static_cast<long long>(h)));
-        if (b) atomicAdd(run + 1, static_cast<unsigned long long>(static_cast<long long>(b)));
-        if (e) atomicAdd(run + 2, static_cast<unsigned long long>(static_cast<long long>(e)));
-        // the totals are updated before this block is counted; with the fused halo transport so are the block's
-        // cells and overlay states, which a neighbour may pull as soon as the last block has stamped
-        const bool pulled = (c.peer.mail_lo || c.peer.mail_hi) && (by == 0 || by == gridDim.y - 1 || any_near);
-        if ((h | b | e) || pulled) __threadfence();
+        if (h) atomicAdd(d + 0, static_cast<unsigned long long>(static_cast<long long>(h)));
+        if (b) atomicAdd(d + 1, static_cast<unsigned long long>(static_cast<long long>(b)));
+        if (e) atomicAdd(d + 2, static_cast<unsigned long long>(static_cast<long long>(e)));
     }
+    if (!(c.peer.mail_lo || c.peer.mail_hi)) return;
+    // fused halo transport only: the last block to arrive publishes the step's stamp in the neighbours' mailboxes.
+    // The blocks that wrote a boundary column or an overlay state fence them (a neighbour may pull them as soon as
+    // the stamp is out) before they take the ticket.
+    if (by == 0 || by == gridDim.y - 1 || any_near) __threadfence(); // the blocks whose stores a neighbour pulls
     const uint32_t nblocks = gridDim.x * gridDim.y;
     const uint32_t t = atomicAdd(a.ticket, 1u);
     if (t != nblocks - 1) return;
     *a.ticket = 0u; // ready for the next launch
-    __threadfence();
-    if (c.peer.mail_lo || c.peer.mail_hi)
-    {
-        // every block has arrived (each fenced its stores before taking the ticket): publish the step's stamp
-        __threadfence_system();
-        if (c.peer.mail_lo) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_lo) = c.peer.stamp;
-        if (c.peer.mail_hi) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_hi) = c.peer.stamp;
-    }
-
-    // ================= last block: publish the step's FireStats =================
-    unsigned long long* run = reinterpret_cast<unsigned long long*>(a.stats_run);
-    const uint64_t healthy = atomicAdd(run + 0, 0ull);
-    const uint64_t burning = atomicAdd(run + 1, 0ull);
-    const uint64_t empty = atomicAdd(run + 2, 0ull);
-    const uint64_t total = static_cast<uint64_t>(c.slab_w) * a.H + a.ov_owned;
-    const uint64_t burned = total - healthy - burning - empty;
-    a.stats_out[0] = healthy;
-    a.stats_out[1] = burning;
-    a.stats_out[2] = burned;
-    a.stats_out[3] = empty;
-    a.stats_out[4] = total;
-    if (a.series_values && a.series_interval && (step % a.series_interval) == 0)
-    {
-        // slot = number of sampling instants before this one (time_series.rs:68-87)
-        const uint64_t slot = step / a.series_interval - 1;
-        if (slot < a.series_capacity)
-        {
-            uint64_t* rec = reinterpret_cast<uint64_t*>(a.series_values) + slot * 5;
-            rec[0] = healthy;
-            rec[1] = burning;
-            rec[2] = burned;
-            rec[3] = empty;
-            rec[4] = total;
-            a.series_counts[slot] = total;
-        }
-    }
-    // StepNumber += 1 (src/plugins/step_number.rs:20-23): the device-side counter
-    // lets a captured step program replay without new arguments
-    if (a.bump_step) *const_cast<uint32_t*>(a.d_step) = step + 1;
+    __threadfence_system();
+    if (c.peer.mail_lo) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_lo) = c.peer.stamp;
+    if (c.peer.mail_hi) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_hi) = c.peer.stamp;
 }
 
 __global__ void forest_spawn_kernel(uint8_t* cells, int32_t H, uint32_t pitch, int32_t x_begin, uint32_t slab_w,
@@ -707,6 +730,12 @@ cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, con
         forest_step_kernel<true><<<grid, block, 0, st>>>(c);
     else
         forest_step_kernel<false><<<grid, block, 0, st>>>(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forest_publish(const ForestArgs& a, uint32_t bump, cudaStream_t st)
+{
+    forest_publish_kernel<<<1, 1, 0, st>>>(a, static_cast<uint32_t>(a.x_end - a.x_begin), bump);
     return cudaGetLastError();
 }
 

@@ -434,6 +434,7 @@ __global__ void flush_kernel(uint4* p, size_t nvec, uint32_t value)
 }
 
 __global__ void step_increment_kernel(uint32_t* d_step) { *d_step += 1; }
+__global__ void set_u32_kernel(uint32_t* p, uint32_t v) { *p = v; }
 
 // ------------------------------------------------------------------ compaction
 // Pass 1: live rows per 1024-row block (ballot + popc). Pass 2: exclusive scan
@@ -670,6 +671,7 @@ void launch_flush(uint8_t* p, size_t bytes, uint32_t value, cudaStream_t st)
 }
 
 void launch_step_increment(uint32_t* d_step, cudaStream_t st) { step_increment_kernel<<<1, 1, 0, st>>>(d_step); }
+void launch_set_u32(uint32_t* p, uint32_t value, cudaStream_t st) { set_u32_kernel<<<1, 1, 0, st>>>(p, value); }
 
 namespace
 {

@@ -48,8 +48,8 @@ static int32_t forest_alloc(Sim& s, ForestModule& fm)
         INC_CUDA(cudaMalloc(&fm.d_alloc[i], bytes + 2 * kLead));
         fm.d_slab[i] = fm.d_alloc[i] + kLead;
     }
-    INC_CUDA(cudaMalloc(&fm.d_stats_run, 8 * sizeof(uint64_t)));
-    INC_CUDA(cudaMemsetAsync(fm.d_stats_run, 0, 8 * sizeof(uint64_t), s.stream));
+    INC_CUDA(cudaMalloc(&fm.d_stats_run, 16 * sizeof(uint64_t)));
+    INC_CUDA(cudaMemsetAsync(fm.d_stats_run, 0, 16 * sizeof(uint64_t), s.stream));
     INC_CUDA(cudaMalloc(&fm.d_stats, 8 * sizeof(uint64_t)));
     const size_t nov = std::max<uint32_t>(fm.n_overlay, 1);
     INC_CUDA(cudaMalloc(&fm.d_ov_pos, nov * 2 * sizeof(int16_t)));
@@ -284,8 +284,10 @@ static int32_t forest_init_stats(Sim& s, ForestModule& fm, const std::vector<uin
             ++st[2];
         ++st[4];
     }
-    const uint64_t run[3] = {st[0], st[1], st[3]};
+    // totals, last published step (none), two empty delta slots (layout: kernels_forest.cu, forest_publish)
+    const uint64_t run[12] = {st[0], st[1], st[3], 0, 0, 0, 0, 0, 0, 0, 0, 0};
     INC_CUDA(cudaMemcpyAsync(fm.d_stats_run, run, sizeof(run), cudaMemcpyHostToDevice, s.stream));
+    fm.unpublished_step = 0;
     INC_CUDA(cudaMemcpyAsync(fm.d_stats, st, sizeof(st), cudaMemcpyHostToDevice, s.stream));
     INC_CUDA(cudaStreamSynchronize(s.stream));
     fm.stats_valid = true;
@@ -691,6 +693,7 @@ int32_t forest_reset_after_spawn(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
     forest_graph_free(fm); // the replica key is baked into the captured kernel parameters
+    fm.d_step_mirror = ~0ull; // reset rewrote the device StepNumber
     Table& t = s.tables[fm.table];
     bool device_spawned = false;
     for (auto& sp : s.spawns)
@@ -741,7 +744,9 @@ int32_t forest_halo_exchange(Sim& s)
     return comm_halo(s, send_lo, recv_lo, send_hi, recv_hi, bytes, fm.n_overlay ? 2 : 1);
 }
 
-static int32_t forest_launch_one(Sim& s)
+// One step.  `step` is the StepNumber of the launch when `graph_offset` < 0; inside a captured graph the kernel reads
+// the device counter and adds `graph_offset`.
+static int32_t forest_launch_one(Sim& s, uint64_t step, int graph_offset, ForestArgs* args_out = nullptr)
 {
     ForestModule& fm = s.mods->forest;
     const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
@@ -768,10 +773,10 @@ static int32_t forest_launch_one(Sim& s)
     a.regrow_two_level = (fm.p_regrow * 256.0 <= 1.0) ? 1u : 0u;
     a.thr_regrow_l2 = bernoulli_threshold(fm.p_regrow * 256.0);
     a.burn_duration = fm.burn_duration;
-    a.bump_step = 1;
     a.key_spread = make_key(s.seed, s.replica, TAG_FOREST_SPREAD);
     a.key_regrow = make_key(s.seed, s.replica, TAG_FOREST_REGROW);
-    a.d_step = s.mods->d_step;
+    a.d_step = graph_offset >= 0 ? s.mods->d_step : nullptr;
+    a.step_base = graph_offset >= 0 ? static_cast<uint32_t>(graph_offset) : static_cast<uint32_t>(step);
     a.stats_run = fm.d_stats_run;
     a.error = s.d_error;
     a.ticket = s.d_ticket;
@@ -811,6 +816,40 @@ static int32_t forest_launch_one(Sim& s)
         INC_CUDA(launch_forest_step_ex(a, ov_lo, ov_hi, fm.d_ov_owner, s.stream, fused ? &pr : nullptr));
     }
     fm.cur = 1 - fm.cur;
+    if (args_out) *args_out = a;
+    if (graph_offset < 0) fm.unpublished_step = step; // on record once the next step starts or forest_finalize ran
+    return INCERTO_OK;
+}
+
+// The FireStats record / series slot of a step are written by the first thread of the NEXT step's grid (off the
+// step's critical path; kernels_forest.cu, forest_publish).  After the last step of a run somebody has to do it:
+// called at the end of every run()/run_async() (inside the timed region) and at the end of run_cold().
+int32_t forest_finalize(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    if (!fm.active || !fm.unpublished_step || !fm.d_alloc[0]) return INCERTO_OK;
+    ForestArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.H = fm.H;
+    a.x_begin = fm.x_begin;
+    a.x_end = fm.x_end;
+    a.ov_owned = static_cast<uint32_t>(std::count(fm.h_ov_owner.begin(), fm.h_ov_owner.end(), uint8_t(0)));
+    a.stats_run = fm.d_stats_run;
+    a.stats_out = fm.d_stats;
+    a.step_base = static_cast<uint32_t>(fm.unpublished_step);
+    if (fm.series >= 0)
+    {
+        SeriesInst& se = s.series[fm.series];
+        a.series_values = se.d_values;
+        a.series_counts = se.d_counts;
+        a.series_interval = se.interval;
+        a.series_capacity = se.capacity;
+    }
+    {
+        KTimer kt(s, "forest_publish", 0.0);
+        INC_CUDA(launch_forest_publish(a, 0u, s.stream));
+    }
+    fm.unpublished_step = 0;
     return INCERTO_OK;
 }
 
@@ -837,7 +876,14 @@ static int32_t forest_graph_ensure(Sim& s)
     const int cur0 = fm.cur;
     INC_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
     int32_t st = INCERTO_OK;
-    for (uint32_t i = 0; i < kGraphSteps && st == INCERTO_OK; ++i) st = forest_launch_one(s);
+    ForestArgs last;
+    for (uint32_t i = 0; i < kGraphSteps && st == INCERTO_OK; ++i) st = forest_launch_one(s, 0, static_cast<int>(i), &last);
+    if (st == INCERTO_OK)
+    {
+        // the graph's last node puts its last step on record and advances the device StepNumber by the steps held
+        last.step_base = kGraphSteps - 1;
+        if (launch_forest_publish(last, kGraphSteps, s.stream) != cudaSuccess) st = INCERTO_ERR_CUDA;
+    }
     cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
     fm.cur = cur0; // nothing ran yet
     if (st != INCERTO_OK)
@@ -871,16 +917,25 @@ int32_t forest_prepare(Sim& s, uint64_t nsteps)
 int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps)
 {
     ForestModule& fm = s.mods->forest;
-    (void)first_step;
     uint32_t done = 0;
     if (forest_use_graph(s, nsteps))
     {
         INC_TRY(forest_graph_ensure(s));
         const double bytes = 2.0 * (fm.x_end - fm.x_begin) * fm.H;
+        // the captured steps read the device StepNumber: bring it to this run's first step (a graph leaves it right
+        // for the next graph; single launches pass their step by value and do not touch it)
+        if (fm.d_step_mirror != first_step)
+        {
+            launch_set_u32(s.mods->d_step, static_cast<uint32_t>(first_step), s.stream);
+            INC_CUDA(cudaGetLastError());
+            fm.d_step_mirror = first_step;
+        }
         while (nsteps - done >= kGraphSteps)
         {
             INC_CUDA(cudaGraphLaunch(fm.graph_exec, s.stream));
             done += kGraphSteps;
+            fm.d_step_mirror += kGraphSteps;
+            fm.unpublished_step = 0; // the graph's last node published
             s.launches += kGraphSteps;
             KernelStat& ks = kstat(s, "forest_step");
             ks.launches += kGraphSteps;
@@ -894,7 +949,7 @@ int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps)
             // the halo columns this step reads were stored by the neighbours after their previous step
             launch_forest_halo_wait(fm.d_mail, fm.peer_mail_lo ? fm.pushes : 0u, fm.peer_mail_hi ? fm.pushes : 0u, s.d_error, s.stream);
         }
-        INC_TRY(forest_launch_one(s));
+        INC_TRY(forest_launch_one(s, first_step + done, -1));
         INC_TRY(forest_halo_exchange(s));
     }
     fm.stats_valid = true;

@@ -46,6 +46,8 @@ struct ForestModule
     uint64_t* d_stats = nullptr; // 5 u64 of the last step
     int series = -1;             // index of the fused FireStats series, -1 if none
     bool stats_valid = false;
+    uint64_t unpublished_step = 0;   // last step whose FireStats record is not written yet (0: none); forest_finalize
+    uint64_t d_step_mirror = ~0ull;  // what the device StepNumber holds (only captured graphs of steps read it)
     // captured step program: `graph_steps` consecutive steps (even, so the ping-pong buffers line up)
     cudaGraphExec_t graph_exec = nullptr;
     uint32_t graph_steps = 0;
@@ -162,6 +164,7 @@ int32_t forest_read_cells(Sim& s, uint8_t* out_rows); // W*H + overlays, uid ord
 int32_t forest_stats_now(Sim& s, uint64_t out5[5]);
 void forest_free(Sim& s);
 int32_t forest_halo_exchange(Sim& s);
+int32_t forest_finalize(Sim& s);
 int32_t forest_peer_setup(Sim& s);
 int32_t forest_peer_quiesce(Sim& s);
 void forest_peer_free(Sim& s);

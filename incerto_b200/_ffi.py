@@ -181,6 +181,7 @@ SYMBOLS = [
     "incerto_sim_grid_neighbors_of", "incerto_sim_grid_is_empty", "incerto_sim_grid_num_entities",
     "incerto_sim_grid_position_of", "incerto_sim_grid_in_bounds", "incerto_sim_step_number",
     "incerto_sim_num_entities", "incerto_sim_read_component", "incerto_sim_read_marker", "incerto_sim_last_run_stats",
+    "incerto_sim_span_ms",
     "incerto_sim_set_profiling", "incerto_sim_kernel_stats", "incerto_sim_flush_l2", "incerto_sim_run_cold", "incerto_comm_unique_id",
     "incerto_sim_attach_comm", "incerto_sim_allreduce_u64", "incerto_sim_allreduce_f64", "incerto_sim_halo_export",
     "incerto_sim_halo_import", "incerto_partition_range",
@@ -251,6 +252,7 @@ def load() -> C.CDLL:
     lib.incerto_sim_kernel_stats.argtypes = [vp, C.POINTER(KernelStat), C.c_uint32, C.POINTER(C.c_uint32)]
     lib.incerto_sim_flush_l2.argtypes = [vp]
     lib.incerto_sim_run_cold.argtypes = [vp, C.c_uint64]
+    lib.incerto_sim_span_ms.argtypes = [vp, vp, C.POINTER(C.c_double)]
     lib.incerto_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     lib.incerto_sim_attach_comm.argtypes = [vp, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32]
     lib.incerto_sim_allreduce_u64.argtypes = [vp, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32]

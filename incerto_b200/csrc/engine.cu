@@ -1306,6 +1306,25 @@ int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps)
     return incerto_sim_synchronize(s); // resolves the per-kernel timers and checks the device error flag
 }
 
+// Device time from the start of `first`'s last run to the end of `last`'s last run (CUDA events on the two handles'
+// streams, same device): the span of several handles driven concurrently with run_async.  Both must be synchronised.
+int32_t incerto_sim_span_ms(incerto_sim* first, incerto_sim* last, double* ms_out)
+{
+    Sim* A = reinterpret_cast<Sim*>(first);
+    Sim* B = reinterpret_cast<Sim*>(last);
+    if (!A || !B || !ms_out || A->device != B->device) return INCERTO_ERR_INVALID_ARGUMENT;
+    if (A->run_pending || B->run_pending)
+    {
+        set_error("span_ms: synchronize both handles first");
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    INC_CUDA(cudaSetDevice(A->device));
+    float ms = 0.f;
+    INC_CUDA(cudaEventElapsedTime(&ms, A->ev_begin, B->ev_end));
+    *ms_out = ms;
+    return INCERTO_OK;
+}
+
 int32_t incerto_sim_synchronize(incerto_sim* s)
 {
     INC_SIM(s);

@@ -144,15 +144,15 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
             uint32_t x = r.p[k] & 0xffffu, y = r.p[k] >> 16;
             if (a.do_move)
             {
-                // :121 stay put; :125 x axis else y axis; :128/:147 negative else positive direction; saturating
-                if (w[k] & 0x80000000u)
-                {
-                    const bool neg = !(w[k] & 0x20000000u);
-                    if (!(w[k] & 0x40000000u))
-                        x = neg ? (x > 0 ? x - 1 : x) : (x < G - 1 ? x + 1 : x);
-                    else
-                        y = neg ? (y > 0 ? y - 1 : y) : (y < G - 1 ? y + 1 : y);
-                }
+                // :121 stay put (bit 31 clear); :125 x axis (bit 30 clear) else y axis; :128/:147 negative (bit 29 clear)
+                // else positive direction; saturating at 0 and G-1.  Branch-free: a signed step per axis, masked by
+                // "moves along this axis", then clamp(v + step, 0, G-1) as one min-with-relu.
+                const uint32_t wk = w[k], wk1 = wk << 1;
+                const int32_t sgn = static_cast<int32_t>((wk >> 28) & 2u) - 1;                 // +1 / -1
+                const int32_t mx = static_cast<int32_t>(wk & ~wk1) >> 31;                      // all ones: moves along x
+                const int32_t my = static_cast<int32_t>(wk & wk1) >> 31;                       // all ones: moves along y
+                x = static_cast<uint32_t>(__vimin_s32_relu(static_cast<int32_t>(x) + (sgn & mx), static_cast<int32_t>(G) - 1));
+                y = static_cast<uint32_t>(__vimin_s32_relu(static_cast<int32_t>(y) + (sgn & my), static_cast<int32_t>(G) - 1));
                 r.p[k] = x | (y << 16);
             }
             if (a.do_infect && (fl & a.bit_infected))

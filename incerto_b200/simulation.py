@@ -685,6 +685,13 @@ class Simulation:
         return [dict(name=arr[i].name.decode(), launches=arr[i].launches, device_ms=arr[i].device_ms,
                      algorithmic_bytes=arr[i].algorithmic_bytes) for i in range(min(n.value, 64))]
 
+    def span_ms(self, last: "Simulation") -> float:
+        """Device time from the start of this handle's last run to the end of `last`'s (handles driven concurrently
+        with run_async on one GPU; both synchronised)."""
+        out = C.c_double(0.0)
+        _check(self._lib.incerto_sim_span_ms(self._h, last._h, C.byref(out)))
+        return out.value
+
     def flush_l2(self) -> None:
         _check(self._lib.incerto_sim_flush_l2(self._h))
 

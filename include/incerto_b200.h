@@ -490,6 +490,10 @@ int32_t incerto_sim_read_marker(incerto_sim* s, incerto_component marker, incert
 /* Device time (ms, CUDA events on the engine's stream) and kernel launches of
  * the last incerto_sim_run / run_async+synchronize. */
 int32_t incerto_sim_last_run_stats(incerto_sim* s, double* device_ms, uint64_t* kernel_launches);
+/* Independent replicas can run concurrently on one GPU: one handle (one stream) each, incerto_sim_run_async on all of
+ * them, then incerto_sim_synchronize.  This returns the device time from the start of `first`'s last run to the end of
+ * `last`'s last run (same device, both synchronised). */
+int32_t incerto_sim_span_ms(incerto_sim* first, incerto_sim* last, double* ms_out);
 /* Per-kernel accumulated device time since build: writes up to `capacity`
  * entries; names are static strings. */
 typedef struct incerto_kernel_stat

@@ -59,6 +59,7 @@ extern "C" {
     pub fn incerto_sim_kernel_stats(s: *mut incerto_sim, out: *mut incerto_kernel_stat, capacity: u32, n_out: *mut u32) -> i32;
     pub fn incerto_sim_flush_l2(s: *mut incerto_sim) -> i32;
     pub fn incerto_sim_run_cold(s: *mut incerto_sim, num_steps: u64) -> i32;
+    pub fn incerto_sim_span_ms(first: *mut incerto_sim, last: *mut incerto_sim, ms_out: *mut f64) -> i32;
     pub fn incerto_comm_unique_id(out: *mut u8) -> i32;
     pub fn incerto_sim_attach_comm(s: *mut incerto_sim, unique_id: *const u8, rank: u32, world: u32) -> i32;
     pub fn incerto_sim_halo_export(s: *mut incerto_sim, side: u32, out: *mut c_void, capacity: usize, n_out: *mut usize) -> i32;

@@ -119,8 +119,9 @@ struct ForestArgs
 // Halo transport fused into the step kernel (row partition, neighbours' slabs mapped through CUDA IPC).  A stamp k in
 // my mailbox says "that neighbour finished step k: the buffer that step wrote is complete".  The CTAs that read a halo
 // column wait for the stamp of the previous step and then PULL the neighbour's boundary column over NVLink into their
-// own halo column (nothing on the writer's side but one system-scope fence and the stamp, issued by the last block);
-// they are scheduled first, so that the wait and the NVLink round trip overlap with the rest of the grid.  The
+// own halo column (nothing on the writer's side but one system-scope fence and the stamp, issued by the last of the
+// boundary CTAs: only they write what a neighbour pulls); they are scheduled first, so that the wait, the NVLink round
+// trip and the stamp all happen while the rest of the grid works.  The
 // neighbour cannot overwrite what is being pulled: the warps that write its boundary column are the ones that wait
 // for MY stamp of this step.
 struct ForestPeer

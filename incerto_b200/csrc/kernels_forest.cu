@@ -634,11 +634,14 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         if (e) atomicAdd(d + 2, static_cast<unsigned long long>(static_cast<long long>(e)));
     }
     if (!(c.peer.mail_lo || c.peer.mail_hi)) return;
-    // fused halo transport only: the last block to arrive publishes the step's stamp in the neighbours' mailboxes.
-    // The blocks that wrote a boundary column or an overlay state fence them (a neighbour may pull them as soon as
-    // the stamp is out) before they take the ticket.
-    if (by == 0 || by == gridDim.y - 1 || any_near) __threadfence(); // the blocks whose stores a neighbour pulls
-    const uint32_t nblocks = gridDim.x * gridDim.y;
+    // fused halo transport only.  What a neighbour pulls - the two boundary columns and the states of overlay entities
+    // sitting in them - is written by the CTAs of the two boundary column groups alone, and those are the CTAs that
+    // read the neighbours' columns.  So only they take the ticket: the last of them publishes this step's stamp in the
+    // neighbours' mailboxes.  They are scheduled first, hence the stamp leaves long before the grid ends and neither
+    // the fence nor the stamp sits on this kernel's tail.
+    if (by != 0 && by != gridDim.y - 1) return;
+    __threadfence(); // this block's cells and overlay states, before it is counted
+    const uint32_t nblocks = gridDim.y > 1 ? 2 * gridDim.x : gridDim.x;
     const uint32_t t = atomicAdd(a.ticket, 1u);
     if (t != nblocks - 1) return;
     *a.ticket = 0u; // ready for the next launch

@@ -352,7 +352,10 @@ int32_t forest_spawn_device(Sim& s, const HostSpawn& sp)
 template <class Fn>
 static uint32_t host_parallel_or(uint64_t n, Fn fn)
 {
-    const unsigned hw = std::thread::hardware_concurrency();
+    // one process per GPU is the rule on a multi-GPU box: share the host cores with the other local ranks
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE"))
+        if (std::atoi(lw) > 1) hw /= static_cast<unsigned>(std::atoi(lw));
     const uint64_t nt = std::min<uint64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), n / (1u << 20));
     if (nt <= 1) return fn(0, n);
     std::vector<uint32_t> res(nt, 0u);

@@ -911,9 +911,25 @@ static int32_t forest_graph_ensure(Sim& s)
 
 static bool forest_use_graph(const Sim& s, uint64_t nsteps) { return s.part_world == 1 && !s.profiling && nsteps >= 2 * kGraphSteps; }
 
+static int32_t forest_sync_device_step(Sim& s, uint64_t first_step)
+{
+    // the captured steps read the device StepNumber: bring it to this run's first step (a graph leaves it right for
+    // the next graph; single launches pass their step by value and do not touch it)
+    ForestModule& fm = s.mods->forest;
+    if (fm.d_step_mirror == first_step) return INCERTO_OK;
+    launch_set_u32(s.mods->d_step, static_cast<uint32_t>(first_step), s.stream);
+    INC_CUDA(cudaGetLastError());
+    fm.d_step_mirror = first_step;
+    return INCERTO_OK;
+}
+
 int32_t forest_prepare(Sim& s, uint64_t nsteps)
 {
-    if (forest_use_graph(s, nsteps)) INC_TRY(forest_graph_ensure(s));
+    if (forest_use_graph(s, nsteps))
+    {
+        INC_TRY(forest_graph_ensure(s));
+        INC_TRY(forest_sync_device_step(s, s.step)); // before the run's first event (first use loads the kernel)
+    }
     return INCERTO_OK;
 }
 
@@ -925,14 +941,7 @@ int32_t forest_step(Sim& s, uint64_t first_step, uint32_t nsteps)
     {
         INC_TRY(forest_graph_ensure(s));
         const double bytes = 2.0 * (fm.x_end - fm.x_begin) * fm.H;
-        // the captured steps read the device StepNumber: bring it to this run's first step (a graph leaves it right
-        // for the next graph; single launches pass their step by value and do not touch it)
-        if (fm.d_step_mirror != first_step)
-        {
-            launch_set_u32(s.mods->d_step, static_cast<uint32_t>(first_step), s.stream);
-            INC_CUDA(cudaGetLastError());
-            fm.d_step_mirror = first_step;
-        }
+        INC_TRY(forest_sync_device_step(s, first_step));
         while (nsteps - done >= kGraphSteps)
         {
             INC_CUDA(cudaGraphLaunch(fm.graph_exec, s.stream));

@@ -245,3 +245,38 @@ def test_host_spawn_is_verified(W, H, borrow):
     with pytest.raises(EngineError) as e:
         build(np.concatenate([xy, np.array([[W, 0]], np.int16)]), np.concatenate([st, np.array([3], np.uint8)]))
     assert e.value.code == F.ERR_OUT_OF_BOUNDS
+
+
+@pytest.mark.parametrize("interval", [1, 3, 16, 40])
+def test_fused_series_cadence_over_graph_and_single_launches(interval):
+    """The FireStats record of a step is written by the next step's grid (or by the publish kernel after the last step
+    of a run / of a captured graph of 16 steps): every mix of run lengths must give the series of one long run, sampled
+    when step % interval == 0 (time_series.rs:68-87), and sample_aggregate must see the state after the last step."""
+    W, H = 80, 70
+    runs = [1, 2, 33, 5, 64, 16, 1, 47, 3]          # singles, graphs of 16 + remainders, in every order
+    total = sum(runs)
+    sim, _, cell = build_device_forest(W, H, density=0.85, p_regrow=0.004, fires=5, series=interval)
+    o = ForestOracle(SEED, 0, W, H, density=0.85, p_regrow=0.004, fires=5).spawn()
+    want = []
+    done = 0
+    for n in runs:
+        sim.run(n)
+        for _ in range(n):
+            o.run(1)
+            done += 1
+            if done % interval == 0:
+                want.append(tuple(int(v) for v in o.stats()))
+        assert stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell))) == tuple(int(v) for v in o.stats())
+        assert sim.step_number() == done + 1
+    ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
+    assert ts.len() == total // interval
+    assert [stats_tuple(v) for v in ts.values()] == want
+    assert list(ts.time()) == [interval * (k + 1) for k in range(total // interval)]
+    assert np.array_equal(sim.read_component(cell), o.cells()[0])
+    # and again after a reset under another replica key (the publish state restarts with the spawn)
+    sim.reset(5)
+    o2 = ForestOracle(SEED, 5, W, H, density=0.85, p_regrow=0.004, fires=5).spawn().run(35)
+    sim.run(35)
+    assert stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell))) == tuple(int(v) for v in o2.stats())
+    ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
+    assert ts.len() == 35 // interval

@@ -15,6 +15,10 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 W, H, steps = 64 * world, 96, 80
+if "--narrow" in sys.argv:   # slabs narrower than one CTA column group: both boundaries live in the same CTAs
+    W, H, steps = 9 * world, 700, 60
+if "--two-groups" in sys.argv:   # exactly two column groups per slab
+    W, H, steps = 27 * world, 300, 60
 RESET = "--reset" in sys.argv
 CUT = "--cut" in sys.argv   # host-spawned grid with overlay entities on both sides of every slab boundary
 b = ib.SimulationBuilder(seed=SEED, device=local)

@@ -7,10 +7,12 @@ Workload (config.workload):
   N = 1  forest_fire 4096 x 4096, 1 replica (BASELINE.json configs[1]; examples/forest_fire.rs with the
          three systems + the FireStats aggregate series every step);
   N > 1  the row-split forest of configs[1]: 16384 cells per column, 2048 columns per GPU, one-column halo
-         exchange per step over NCCL (N = 8 is exactly 16384 x 16384) — weak scaling.
+         exchange per step fused into the step kernel (peer memory over NVLink; NCCL send/recv as fallback;
+         N = 8 is exactly 16384 x 16384) — weak scaling.
 A "step" is one simulation step of the whole grid.  `value` is cell-updates/s with the state resident in
 HBM, every timed step started with a cold L2 (a 512 MB buffer is overwritten in between, excluded from
-the timing), timed with CUDA events on the engine's stream, max over ranks.  `e2e` is the same metric
+the timing; with N > 1 an untimed all-reduce then lines the ranks up again), timed with a CUDA event pair
+around every step on the engine's stream (one incerto_sim_run_cold call), max over ranks.  `e2e` is the same metric
 through the C ABI with host buffers: spawn from host arrays (H2D), run, read the FireStats series back.
 """
 from __future__ import annotations

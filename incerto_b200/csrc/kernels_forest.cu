@@ -608,8 +608,8 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         }
     }
     // Completion without a trailing block barrier (warps finish at very different times because of the
-    // rare-event loops): every warp arrives on a shared counter; the last warp of the block pushes the
-    // block's deltas to the running totals and takes the grid ticket; the last block publishes.
+    // rare-event loops): every warp arrives on a shared counter; the last warp of the block sends the
+    // block's deltas to the step's delta slot (forest_publish explains who puts the step on record).
 #ifdef INCERTO_FOREST_TRACE
     if (lane == 0)
     {

@@ -90,3 +90,14 @@ def test_builder_calls_without_device(engine_lib):
         with pytest.raises(ib.EngineError) as e:
             b.build()
         assert e.value.code == F.ERR_NO_DEVICE
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/incerto-cuda-sys cannot be built here (no cargo); at least its hand-written extern block must name exactly
+    the functions of the header, and the safe façade must only call functions that block declares."""
+    sys_rs = open(os.path.join(ROOT, "rust", "incerto-cuda-sys", "src", "lib.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (incerto_[a-z0-9_]+)\s*\(", sys_rs)))
+    assert declared == _declared_symbols()
+    facade = open(os.path.join(ROOT, "rust", "incerto-cuda", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(incerto_[a-z0-9_]+)\s*\(", facade))
+    assert used and used <= set(declared), used - set(declared)

@@ -176,7 +176,7 @@ SYMBOLS = [
     "incerto_builder_add_systems", "incerto_builder_add_spatial_grid",
     "incerto_builder_record_aggregate_time_series", "incerto_builder_record_time_series", "incerto_builder_build",
     "incerto_sim_run", "incerto_sim_run_async", "incerto_sim_synchronize", "incerto_sim_destroy", "incerto_sim_reset",
-    "incerto_sim_count", "incerto_sim_sample_aggregate", "incerto_sim_sample", "incerto_sim_sample_single",
+    "incerto_sim_count", "incerto_sim_sample_aggregate", "incerto_sim_sample_aggregate_global", "incerto_sim_sample", "incerto_sim_sample_single",
     "incerto_sim_get_aggregate_time_series", "incerto_sim_get_time_series", "incerto_sim_grid_entities_at",
     "incerto_sim_grid_neighbors_of", "incerto_sim_grid_is_empty", "incerto_sim_grid_num_entities",
     "incerto_sim_grid_position_of", "incerto_sim_grid_in_bounds", "incerto_sim_step_number",
@@ -227,6 +227,7 @@ def load() -> C.CDLL:
     lib.incerto_sim_reset.argtypes = [vp, C.c_uint32]
     lib.incerto_sim_count.argtypes = [vp, C.POINTER(Filter), C.POINTER(C.c_uint64)]
     lib.incerto_sim_sample_aggregate.argtypes = [vp, C.POINTER(AggregateDesc), vp, C.c_size_t]
+    lib.incerto_sim_sample_aggregate_global.argtypes = [vp, C.POINTER(AggregateDesc), vp, C.c_size_t]
     lib.incerto_sim_sample.argtypes = [vp, component_t, component_t, vp, vp, C.c_size_t]
     lib.incerto_sim_sample_single.argtypes = [vp, component_t, vp, C.c_size_t]
     lib.incerto_sim_get_aggregate_time_series.argtypes = [vp, C.POINTER(AggregateDesc), C.POINTER(C.POINTER(C.c_uint64)),

@@ -136,6 +136,19 @@ int32_t comm_allreduce(Sim& s, void* d_buf, uint32_t n, int is_f64, uint32_t op)
     return INCERTO_OK;
 }
 
+// n 64-bit host values (u64 or f64) reduced over the communicator in place
+int32_t comm_allreduce_host(Sim& S, void* values, uint32_t n, int is_f64, uint32_t op)
+{
+    if (!values || !n) return INCERTO_ERR_INVALID_ARGUMENT;
+    INC_CUDA(cudaSetDevice(S.device));
+    INC_TRY(ensure_scratch(S, static_cast<size_t>(n) * 8));
+    INC_CUDA(cudaMemcpyAsync(S.d_scratch, values, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, S.stream));
+    INC_TRY(comm_allreduce(S, S.d_scratch, n, is_f64, op));
+    INC_CUDA(cudaMemcpyAsync(values, S.d_scratch, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, S.stream));
+    INC_CUDA(cudaStreamSynchronize(S.stream));
+    return INCERTO_OK;
+}
+
 // every rank contributes `bytes` bytes; d_recv holds world * bytes
 int32_t comm_allgather_bytes(Sim& s, const void* d_send, void* d_recv, size_t bytes)
 {
@@ -198,30 +211,18 @@ int32_t incerto_sim_attach_comm(incerto_sim* s, const uint8_t unique_id[128], ui
     return forest_peer_setup(*S);
 }
 
-static int32_t allreduce_host(Sim& S, void* values, uint32_t n, int is_f64, uint32_t op)
-{
-    if (!values || !n) return INCERTO_ERR_INVALID_ARGUMENT;
-    INC_CUDA(cudaSetDevice(S.device));
-    INC_TRY(ensure_scratch(S, static_cast<size_t>(n) * 8));
-    INC_CUDA(cudaMemcpyAsync(S.d_scratch, values, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, S.stream));
-    INC_TRY(comm_allreduce(S, S.d_scratch, n, is_f64, op));
-    INC_CUDA(cudaMemcpyAsync(values, S.d_scratch, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, S.stream));
-    INC_CUDA(cudaStreamSynchronize(S.stream));
-    return INCERTO_OK;
-}
-
 int32_t incerto_sim_allreduce_u64(incerto_sim* s, uint64_t* values, uint32_t n, uint32_t op)
 {
     Sim* S = reinterpret_cast<Sim*>(s);
     if (!S) return INCERTO_ERR_INVALID_ARGUMENT;
-    return allreduce_host(*S, values, n, 0, op);
+    return comm_allreduce_host(*S, values, n, 0, op);
 }
 
 int32_t incerto_sim_allreduce_f64(incerto_sim* s, double* values, uint32_t n, uint32_t op)
 {
     Sim* S = reinterpret_cast<Sim*>(s);
     if (!S) return INCERTO_ERR_INVALID_ARGUMENT;
-    return allreduce_host(*S, values, n, 1, op);
+    return comm_allreduce_host(*S, values, n, 1, op);
 }
 
 } // extern "C"

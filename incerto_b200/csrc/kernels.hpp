@@ -37,9 +37,12 @@ void launch_count_rows(const uint8_t* flags, uint8_t need_set, uint8_t need_clea
 // to 64 bit like ReduceRecord::min_bits) lands in state[0], an index-out-of-range
 // flag in state[3].  k comes from `arg` (mode 0) or is derived on the device from
 // d_rec->count: mode 1 = Median (count/2), mode 2 = Percentile<arg>.
+// `between_passes` (optional) runs after every histogram pass, before the digit is picked: the hook of the distributed
+// select, which sums the 256 bins at state + 4 over all ranks (d_rec->count is then the global count).
 void launch_radix_select(const void* col, int dtype, uint32_t stride, uint32_t lane, const uint8_t* flags,
                          uint8_t need_set, uint8_t need_clear, uint64_t n, const ReduceRecord* d_rec, uint32_t mode,
-                         uint64_t arg, uint64_t* state, cudaStream_t st);
+                         uint64_t arg, uint64_t* state, cudaStream_t st, int32_t (*between_passes)(void*) = nullptr,
+                         void* hook_ctx = nullptr);
 constexpr size_t kSelectStateWords = 4 + 256;
 
 void launch_add_const(void* col, int dtype, uint32_t stride, const uint8_t* flags, uint8_t need_set, uint64_t n,

@@ -589,7 +589,7 @@ void launch_count_rows(const uint8_t* flags, uint8_t need_set, uint8_t need_clea
 
 void launch_radix_select(const void* col, int dtype, uint32_t stride, uint32_t lane, const uint8_t* flags,
                          uint8_t need_set, uint8_t need_clear, uint64_t n, const ReduceRecord* d_rec, uint32_t mode,
-                         uint64_t arg, uint64_t* state, cudaStream_t st)
+                         uint64_t arg, uint64_t* state, cudaStream_t st, int32_t (*between_passes)(void*), void* hook_ctx)
 {
     size_t esize = 1;
     switch (dtype)
@@ -613,6 +613,7 @@ void launch_radix_select(const void* col, int dtype, uint32_t stride, uint32_t l
                                                              need_set, need_clear, n, state)
         INC_DISPATCH_DTYPE(dtype, INC_SEL, 0)
 #undef INC_SEL
+        if (between_passes && between_passes(hook_ctx) != 0) return;
         select_pick_kernel<<<1, 32, 0, st>>>(state);
     }
 #define INC_FIN(T, ...) select_finish_kernel<T><<<1, 32, 0, st>>>(state)

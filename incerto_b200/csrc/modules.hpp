@@ -206,6 +206,8 @@ int32_t comm_attach(Sim& s, const uint8_t id[128], uint32_t rank, uint32_t world
 void comm_free(Sim& s);
 int32_t comm_allreduce(Sim& s, void* d_buf, uint32_t n, int is_f64, uint32_t op);
 int32_t comm_allgather_bytes(Sim& s, const void* d_send, void* d_recv, size_t bytes);
+// n 64-bit host values (u64 or f64) reduced over the communicator in place; op 0 sum, 1 min, 2 max
+int32_t comm_allreduce_host(Sim& S, void* values, uint32_t n, int is_f64, uint32_t op);
 // send `bytes_lo` from d_send_lo to rank-1 and `bytes_hi` from d_send_hi to rank+1, receive likewise
 int32_t comm_halo(Sim& s, const void* const* d_send_lo, void* const* d_recv_lo, const void* const* d_send_hi,
                   void* const* d_recv_hi, const size_t* bytes, uint32_t n_msgs);

@@ -8,6 +8,7 @@
 //   TimeSeriesPlugin::{time_series_init,time_series_sample}                       src/plugins/time_series.rs:133-162
 //   SpatialGrid queries                                                           src/plugins/spatial_grid.rs:244-389
 #include <algorithm>
+#include <limits>
 #include <array>
 #include <cmath>
 #include <cstdlib>
@@ -119,8 +120,68 @@ static std::vector<int> agg_tables(Sim& s, const AggSpec& a)
 }
 
 // Launch the kernels of one aggregate over one table; the raw record lands at d_raw.
-static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw)
+// ---- aggregates over the entities of ALL ranks of the attached communicator (incerto_sim_sample_aggregate_global):
+// the per-rank raw record is combined over NCCL before it is finalised, and Median / Percentile run as a distributed
+// radix select (global count, the 256-bin histogram of every pass summed over the ranks).
+static int32_t global_combine_record(Sim& s, GenericRaw* d_raw, int dt)
 {
+    GenericRaw g;
+    INC_CUDA(cudaMemcpyAsync(&g, d_raw, sizeof(g), cudaMemcpyDeviceToHost, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    const bool flt = dtype_is_float(dt), sgn = dtype_is_signed(dt);
+    const uint64_t flip = (!flt && sgn) ? 0x8000000000000000ull : 0ull; // signed order -> unsigned order
+    if (g.rec.count == 0)
+    {
+        // identities, whatever the reduction kernel left behind for an empty selection
+        g.rec.sum_bits = 0;
+        if (flt)
+        {
+            const double inf = std::numeric_limits<double>::infinity(), ninf = -inf;
+            std::memcpy(&g.rec.min_bits, &inf, 8);
+            std::memcpy(&g.rec.max_bits, &ninf, 8);
+        }
+        else
+        {
+            g.rec.min_bits = ~0ull ^ flip;
+            g.rec.max_bits = 0ull ^ flip;
+        }
+    }
+    uint64_t cnt[2] = {g.rec.count, g.rec.nan_seen};
+    INC_TRY(comm_allreduce_host(s, &cnt[0], 1, 0, 0));
+    INC_TRY(comm_allreduce_host(s, &cnt[1], 1, 0, 2));
+    uint64_t mn = g.rec.min_bits ^ flip, mx = g.rec.max_bits ^ flip;
+    INC_TRY(comm_allreduce_host(s, &g.rec.sum_bits, 1, flt ? 1 : 0, 0));
+    INC_TRY(comm_allreduce_host(s, &mn, 1, flt ? 1 : 0, 1));
+    INC_TRY(comm_allreduce_host(s, &mx, 1, flt ? 1 : 0, 2));
+    g.rec.count = cnt[0];
+    g.rec.nan_seen = static_cast<uint32_t>(cnt[1]);
+    g.rec.min_bits = mn ^ flip;
+    g.rec.max_bits = mx ^ flip;
+    INC_CUDA(cudaMemcpyAsync(d_raw, &g, sizeof(g), cudaMemcpyHostToDevice, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    return INCERTO_OK;
+}
+
+struct SelectHook
+{
+    Sim* s;
+    uint64_t* state;
+    int32_t rc;
+};
+static int32_t select_allreduce_histogram(void* ctx)
+{
+    SelectHook* h = static_cast<SelectHook*>(ctx);
+    h->rc = comm_allreduce(*h->s, h->state + 4, 256, 0, 0);
+    return h->rc;
+}
+
+static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw, bool global = false)
+{
+    if (global && !is_generic_kind(a.kind) && a.kind != INCERTO_AGG_COIN_ODDS && a.kind != INCERTO_AGG_FIRE_STATS)
+    {
+        set_error("sample_aggregate_global: aggregate kind %u is not available across ranks", a.kind);
+        return INCERTO_ERR_UNSUPPORTED;
+    }
     Table& t = s.tables[ti];
     const ComponentInfo& ci = s.comps[a.component];
     FilterSpec f = a.filter;
@@ -139,6 +200,7 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
         }
         uint64_t st[5];
         INC_TRY(forest_stats_now(s, st));
+        if (global && s.part_world <= 1) INC_TRY(comm_allreduce_host(s, st, 5, 0, 0));
         INC_CUDA(cudaMemcpyAsync(d_raw, st, sizeof(st), cudaMemcpyHostToDevice, s.stream));
         INC_CUDA(cudaStreamSynchronize(s.stream));
         return INCERTO_OK;
@@ -155,6 +217,7 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
         g.rec.count = t.n;
         INC_CUDA(cudaMemcpyAsync(d_raw, &g, sizeof(g), cudaMemcpyHostToDevice, s.stream));
         INC_CUDA(cudaStreamSynchronize(s.stream));
+        if (global) INC_TRY(global_combine_record(s, reinterpret_cast<GenericRaw*>(d_raw), INCERTO_U64));
         return INCERTO_OK;
     }
     if (a.kind == INCERTO_AGG_PANDEMIC_STATS)
@@ -192,6 +255,17 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
         KTimer kt(s, "coin_odds", 2.0 * t.n * dtype_size(ci.dtype));
         launch_coin_odds(h->d, c->d, ci.dtype, flags, rf.need_set, rf.need_clear, t.n,
                          reinterpret_cast<double*>(d_raw), s.d_scratch, s.d_ticket, s.stream);
+        if (global)
+        {
+            // record = { f64 sum of heads/tosses, u64 count }
+            uint64_t rec[2];
+            INC_CUDA(cudaMemcpyAsync(rec, d_raw, 16, cudaMemcpyDeviceToHost, s.stream));
+            INC_CUDA(cudaStreamSynchronize(s.stream));
+            INC_TRY(comm_allreduce_host(s, &rec[0], 1, 1, 0));
+            INC_TRY(comm_allreduce_host(s, &rec[1], 1, 0, 0));
+            INC_CUDA(cudaMemcpyAsync(d_raw, rec, 16, cudaMemcpyHostToDevice, s.stream));
+            INC_CUDA(cudaStreamSynchronize(s.stream));
+        }
         return INCERTO_OK;
     }
     if (!is_generic_kind(a.kind))
@@ -216,6 +290,7 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
             launch_count_rows(t.d_flags, rf.need_set, rf.need_clear, t.n, &raw->rec.count, s.d_scratch, s.d_ticket,
                               s.stream);
         }
+        if (global) INC_TRY(global_combine_record(s, raw, INCERTO_U64));
         return INCERTO_OK;
     }
     Column* col = t.col(a.component);
@@ -224,12 +299,16 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
         launch_reduce_column(col->d, ci.dtype, ci.stride(), 0, flags, rf.need_set, rf.need_clear, t.n, &raw->rec,
                              s.d_scratch, s.d_ticket, s.stream);
     }
+    if (global) INC_TRY(global_combine_record(s, raw, ci.dtype));
     if (a.kind == INCERTO_AGG_MEDIAN || a.kind == INCERTO_AGG_PERCENTILE)
     {
         uint64_t* state = reinterpret_cast<uint64_t*>(s.d_scratch + 64 * kNumSMs * 8);
         KTimer kt(s, "radix_select", 1.0 * t.n * dtype_size(ci.dtype) * dtype_size(ci.dtype));
+        SelectHook hook{&s, state, INCERTO_OK};
         launch_radix_select(col->d, ci.dtype, ci.stride(), 0, flags, rf.need_set, rf.need_clear, t.n, &raw->rec,
-                            a.kind == INCERTO_AGG_MEDIAN ? 1u : 2u, a.percentile, state, s.stream);
+                            a.kind == INCERTO_AGG_MEDIAN ? 1u : 2u, a.percentile, state, s.stream,
+                            global ? select_allreduce_histogram : nullptr, &hook);
+        INC_TRY(hook.rc);
         INC_CUDA(cudaMemcpyAsync(&raw->sel_value, &state[0], 8, cudaMemcpyDeviceToDevice, s.stream));
         INC_CUDA(cudaMemcpyAsync(&raw->sel_error, &state[3], 8, cudaMemcpyDeviceToDevice, s.stream));
     }
@@ -898,7 +977,25 @@ int32_t incerto_sim_count(incerto_sim* s, const incerto_filter* filter, uint64_t
     return INCERTO_OK;
 }
 
+static int32_t sample_aggregate_impl(incerto_sim* s, const incerto_aggregate_desc* agg, void* out, size_t out_size, bool global);
+
 int32_t incerto_sim_sample_aggregate(incerto_sim* s, const incerto_aggregate_desc* agg, void* out, size_t out_size)
+{
+    return sample_aggregate_impl(s, agg, out, out_size, false);
+}
+
+int32_t incerto_sim_sample_aggregate_global(incerto_sim* s, const incerto_aggregate_desc* agg, void* out, size_t out_size)
+{
+    INC_SIM(s);
+    if (!S.comm)
+    {
+        set_error("sample_aggregate_global: no communicator attached (incerto_sim_attach_comm)");
+        return INCERTO_ERR_COMM;
+    }
+    return sample_aggregate_impl(s, agg, out, out_size, true);
+}
+
+static int32_t sample_aggregate_impl(incerto_sim* s, const incerto_aggregate_desc* agg, void* out, size_t out_size, bool global)
 {
     INC_SIM(s);
     AggSpec a;
@@ -912,6 +1009,12 @@ int32_t incerto_sim_sample_aggregate(incerto_sim* s, const incerto_aggregate_des
         return INCERTO_ERR_INVALID_ARGUMENT;
     }
     std::vector<int> tabs = agg_tables(S, a);
+    if (global && tabs.size() != 1)
+    {
+        // every rank must take part in the same collectives: one archetype table holding the component on each
+        set_error("sample_aggregate_global: the component must live in exactly one archetype table on every rank");
+        return INCERTO_ERR_UNSUPPORTED;
+    }
     if (tabs.empty()) return INCERTO_ERR_AGGREGATE_NO_ENTITIES;
     if (tabs.size() > 16) return INCERTO_ERR_UNSUPPORTED;
     const size_t rs = raw_size(a.kind);
@@ -921,7 +1024,7 @@ int32_t incerto_sim_sample_aggregate(incerto_sim* s, const incerto_aggregate_des
     std::vector<uint8_t> h(rs * tabs.size());
     for (size_t i = 0; i < tabs.size(); ++i)
     {
-        INC_TRY(aggregate_launch(S, a, tabs[i], d_raw + i * 64));
+        INC_TRY(aggregate_launch(S, a, tabs[i], d_raw + i * 64, global));
         INC_CUDA(cudaMemcpyAsync(h.data() + i * rs, d_raw + i * 64, rs, cudaMemcpyDeviceToHost, S.stream));
     }
     INC_CUDA(cudaStreamSynchronize(S.stream));

@@ -537,6 +537,13 @@ class Simulation:
         _check(self._lib.incerto_sim_sample_aggregate(self._h, C.byref(d), buf, 64))
         return agg._decode(bytes(buf))
 
+    def sample_aggregate_global(self, agg: Aggregate):
+        """The aggregate over the entities of all ranks of the attached communicator (collective call)."""
+        d, keep = agg._desc()
+        buf = (C.c_uint8 * 64)()
+        _check(self._lib.incerto_sim_sample_aggregate_global(self._h, C.byref(d), buf, 64))
+        return agg._decode(bytes(buf))
+
     def sample_aggregate_filtered(self, agg: Aggregate, *filters):              # :136-152
         return self.sample_aggregate(agg.filtered(*filters))
 

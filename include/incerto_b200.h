@@ -445,6 +445,12 @@ int32_t incerto_sim_count(incerto_sim* s, const incerto_filter* filter, uint64_t
 /* Simulation::sample_aggregate / sample_aggregate_filtered (:107-152). `out`
  * receives the kind's record (see incerto_aggregate_kind). */
 int32_t incerto_sim_sample_aggregate(incerto_sim* s, const incerto_aggregate_desc* agg, void* out, size_t out_size);
+/* The same aggregate over the entities of ALL ranks of the attached communicator (cross-replica statistics: every rank
+ * holds one replica, or one shard).  Collective: every rank calls it with the same aggregate.  Count / Sum / Minimum /
+ * Maximum / Mean combine the per-rank records over NCCL; Median / Percentile run as a distributed radix select (global
+ * count, the 256-bin histogram of every pass summed over the ranks), so the answer is the one a single process
+ * holding all the entities would give (src/util/aggregate.rs:107-155).  Also COIN_ODDS and FIRE_STATS. */
+int32_t incerto_sim_sample_aggregate_global(incerto_sim* s, const incerto_aggregate_desc* agg, void* out, size_t out_size);
 /* Simulation::sample::<C, Id, Out> (:43-65). `id_value`: one value of the
  * identifier's dtype; `out`: `lanes` values of the component's dtype. */
 int32_t incerto_sim_sample(incerto_sim* s, incerto_component component, incerto_component identifier,

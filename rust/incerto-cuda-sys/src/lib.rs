@@ -40,6 +40,7 @@ extern "C" {
     pub fn incerto_sim_reset(s: *mut incerto_sim, replica: u32) -> i32;
     pub fn incerto_sim_count(s: *mut incerto_sim, filter: *const incerto_filter, out: *mut u64) -> i32;
     pub fn incerto_sim_sample_aggregate(s: *mut incerto_sim, agg: *const incerto_aggregate_desc, out: *mut c_void, out_size: usize) -> i32;
+    pub fn incerto_sim_sample_aggregate_global(s: *mut incerto_sim, agg: *const incerto_aggregate_desc, out: *mut c_void, out_size: usize) -> i32;
     pub fn incerto_sim_sample(s: *mut incerto_sim, component: incerto_component, identifier: incerto_component, id_value: *const c_void, out: *mut c_void, out_size: usize) -> i32;
     pub fn incerto_sim_sample_single(s: *mut incerto_sim, component: incerto_component, out: *mut c_void, out_size: usize) -> i32;
     pub fn incerto_sim_get_aggregate_time_series(s: *mut incerto_sim, agg: *const incerto_aggregate_desc, time: *mut *const u64, values: *mut *const c_void, len: *mut u64, record_size: *mut u64, sample_interval: *mut u64) -> i32;

@@ -316,3 +316,16 @@ def test_per_entity_time_series():                    # record_time_series / get
     with pytest.raises(ib.SamplingError) as e:
         sim.get_time_series(V, Id, 9)
     assert e.value.kind == "EntityIdentifierNotFound"
+
+
+def test_global_aggregate_needs_a_communicator():
+    """incerto_sim_sample_aggregate_global is a collective over the attached communicator (checked against numpy on
+    several GPUs by tools/check_global_aggregates.py); without one it says so."""
+    b = ib.SimulationBuilder(seed=SEED)
+    v = b.component("v", F.I32)
+    b.add_entity_spawner(lambda s: s.spawn_batch(4, {v: np.array([3, 1, 4, 1], np.int32)}))
+    sim = b.build()
+    assert sim.sample_aggregate(ib.Median(v)) == 3
+    with pytest.raises(ib.EngineError) as e:
+        sim.sample_aggregate_global(ib.Median(v))
+    assert e.value.code == F.ERR_COMM

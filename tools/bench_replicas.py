@@ -110,6 +110,9 @@ def main():
         f64[0:1] = sim.allreduce_f64(f64[0:1].copy(), 0)
         f64[1:2] = sim.allreduce_f64(f64[1:2].copy(), 1)
         f64[2:3] = sim.allreduce_f64(f64[2:3].copy(), 2)
+        if workload == "traders":
+            # a quantile over the traders of the replicas resident right now (one per rank): distributed radix select
+            resident_median = sim.sample_aggregate_global(ib.Median(sims[0][1]["tc"].net_worth))
     if rank == 0:
         value = n * steps * replicas / (ms * 1e-3)
         out = {"workload": workload, "metric": "entity-updates/sec (device-timed)", "unit": unit, "value": value,
@@ -120,6 +123,8 @@ def main():
             out["survivors_all_replicas"], out["infected_all_replicas"] = int(u64[0]), int(u64[1])
         else:
             out["mean_net_worth"] = {"mean_over_replicas": f64[0] / replicas, "min": f64[1], "max": f64[2]}
+            if world > 1:
+                out["median_net_worth_over_the_resident_replicas"] = resident_median
         print(json.dumps(out), flush=True)
     for s_, *_ in sims:
         s_.destroy()

@@ -321,7 +321,7 @@ def test_per_entity_time_series():                    # record_time_series / get
 def test_global_aggregate_needs_a_communicator():
     """incerto_sim_sample_aggregate_global is a collective over the attached communicator (checked against numpy on
     several GPUs by tools/check_global_aggregates.py); without one it says so."""
-    b = ib.SimulationBuilder(seed=SEED)
+    b = ib.SimulationBuilder()
     v = b.component("v", F.I32)
     b.add_entity_spawner(lambda s: s.spawn_batch(4, {v: np.array([3, 1, 4, 1], np.int32)}))
     sim = b.build()

@@ -254,7 +254,11 @@ __global__ void forest_publish_kernel(ForestArgs a, uint32_t slab_w, uint32_t bu
     if (bump && a.d_step) *const_cast<uint32_t*>(a.d_step) += bump;
 }
 
-template <bool ALIGNED>
+// HOIST: the level-1 regrowth draws are computed before the cells are looked at, i.e. while the loads are in flight.
+// That shortens a grid of one or two waves, whose CTAs all start together and would sit idle until their loads
+// arrive (4096^2 cold: 19.2 -> 18.6 us); a long grid is bound by instruction issue in steady state and runs 4 %
+// slower that way (16384^2: 131 -> 136 us), so the launcher picks per grid size.
+template <bool ALIGNED, bool HOIST>
 __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const __grid_constant__ ForestConst c)
 {
     const ForestArgs& a = c.a;
@@ -337,6 +341,21 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     }
     // StepNumber of this launch: by value, or (captured graphs) the device counter + the launch's offset in the graph
     const uint32_t step = (a.d_step ? *a.d_step : 0u) + a.step_base;
+    // ---- level-1 regrowth draws (one Philox call per 16 cells, uid0 % 16 == 0): nothing here depends on the cells,
+    // so the four calls of the thread run while its loads are in flight.  Their multiply chains interleave; per
+    // column one word survives: bit 8b+4+k set = cell 4k+b passed level 1 (~1/256 of the cells; the empty ones
+    // among them take the level-2 draw in the rare-event loop).
+    uint32_t zmask[kColsPerThread];
+    if (HOIST && ALIGNED && a.do_regrow && c.regrow_two_level)
+    {
+#pragma unroll
+        for (int j = 1; j <= kColsPerThread; ++j)
+        {
+            const uint32_t uid0 = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + y0;
+            const uint4 l1 = philox4x32_10(uid0 >> 4, 0u, step, 0u, c.rk_regrow);
+            zmask[j - 1] = (zero_bytes(l1.x) >> 3) | (zero_bytes(l1.y) >> 2) | (zero_bytes(l1.z) >> 1) | zero_bytes(l1.w);
+        }
+    }
     // the previous step's FireStats go on record now, off every critical path (see forest_publish)
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) forest_publish(a, c.slab_w, step - 1);
 
@@ -446,8 +465,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         }
     }
 
-    // ---- regrowth (:354-365): only EMPTY cells draw.  The level-1 Philox calls of the thread's columns
-    // sit in one basic block so that their dependent multiply chains interleave.
+    // ---- regrowth (:354-365): only EMPTY cells draw
     if (a.do_regrow)
     {
 #pragma unroll
@@ -456,10 +474,13 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             const uint32_t e0 = v[j].x & 0x80808080u, e1 = v[j].y & 0x80808080u, e2 = v[j].z & 0x80808080u,
                            e3 = v[j].w & 0x80808080u;
             uint32_t evj;
-            if (ALIGNED && c.regrow_two_level)
+            if (HOIST && ALIGNED && c.regrow_two_level)
+                evj = ((e0 >> 3) | (e1 >> 2) | (e2 >> 1) | e3) & zmask[j - 1]; // level 1 was drawn in the shadow of the loads
+            else if (ALIGNED && c.regrow_two_level)
             {
                 // uid0 % 16 == 0: one level-1 call covers the 16 cells of this chunk; ~1/256 of the empty
-                // cells pass it and take the level-2 draw in the rare-event loop
+                // cells pass it and take the level-2 draw in the rare-event loop.  The calls of the thread's
+                // columns sit in one basic block so that their dependent multiply chains interleave.
                 const uint32_t uid0 = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + y0;
                 const uint4 l1 = philox4x32_10(uid0 >> 4, 0u, step, 0u, c.rk_regrow);
                 evj = ((zero_bytes(l1.x) & e0) >> 3) | ((zero_bytes(l1.y) & e1) >> 2) | ((zero_bytes(l1.z) & e2) >> 1) |
@@ -729,10 +750,13 @@ cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, con
     c.rk_regrow = make_round_keys(a.key_regrow);
     dim3 block(kTX, kTY);
     dim3 grid((c.chunks_per_col + kTX - 1) / kTX, (c.slab_w + kTY * kColsPerThread - 1) / (kTY * kColsPerThread));
-    if ((a.H % 16) == 0) // uid of a chunk's first cell is a multiple of 16: one level-1 call per chunk
-        forest_step_kernel<true><<<grid, block, 0, st>>>(c);
+    const bool hoist = static_cast<uint64_t>(grid.x) * grid.y <= 4ull * kNumSMs * kMinBlocks; // at most four waves
+    if ((a.H % 16) != 0) // uid of a chunk's first cell is not a multiple of 16: no shared level-1 call per chunk
+        forest_step_kernel<false, false><<<grid, block, 0, st>>>(c);
+    else if (hoist)
+        forest_step_kernel<true, true><<<grid, block, 0, st>>>(c);
     else
-        forest_step_kernel<false><<<grid, block, 0, st>>>(c);
+        forest_step_kernel<true, false><<<grid, block, 0, st>>>(c);
     return cudaGetLastError();
 }
 

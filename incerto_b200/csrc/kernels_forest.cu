@@ -44,11 +44,11 @@ constexpr int kTX = 32;  // chunks (16 cells) along y per CTA
 #endif
 constexpr int kTY = INCERTO_FOREST_TY;   // column groups (warps) per CTA
 #ifndef INCERTO_FOREST_COLS
-#define INCERTO_FOREST_COLS 4
+#define INCERTO_FOREST_COLS 6
 #endif
 constexpr int kColsPerThread = INCERTO_FOREST_COLS; // adjacent columns per thread
 #ifndef INCERTO_FOREST_MIN_BLOCKS
-#define INCERTO_FOREST_MIN_BLOCKS 10
+#define INCERTO_FOREST_MIN_BLOCKS 9
 #endif
 constexpr int kMinBlocks = INCERTO_FOREST_MIN_BLOCKS;
 
@@ -189,9 +189,12 @@ __device__ __forceinline__ bool overlay_marked(const ForestConst& c, const NearO
     return false;
 }
 
-// The vectorised body: each thread owns kColsPerThread (4) adjacent columns x 16 cells.  (Wider threads were tried:
-// 8 / 16 / 24 columns are slower - 135 / 159 / 198 us against 127 us at 16384^2 - the level-1 Philox call per 16
-// cells dominates the instruction count and does not amortise; profiles/r01_forest_variant_sweep2.txt.)
+// The vectorised body: each thread owns kColsPerThread (6) adjacent columns x 16 cells (eight 128-bit loads incl. the
+// W/E neighbour columns).  Width and registers have to be tuned together: with the register budget of the 4-column
+// kernel (<= 48) wider threads spill and lose (an early sweep: 8 / 16 / 24 columns 135 / 159 / 198 us against 127 us
+// at 16384^2); given 56-72 registers, 6 / 8 columns run 16384^2 in 120 / 118 us against 131 us for 4 columns (fewer
+// neighbour-column loads, event-queue and vote overhead per cell), while a 4096^2 step (18.5-18.8 us) prefers <= 6:
+// profiles/r01_forest_cols_sweep.txt.
 //  * streaming path, fully unrolled and register resident: 128-bit loads of the chunk and its W/E
 //    neighbours, a warp-uniform "is there any fire around" vote that skips progression/spread work for the
 //    (vast majority of) warps far from the front, the level-1 regrowth draw (one Philox call per 16 cells),

@@ -34,9 +34,8 @@ for rep in range(3):
         sim.run_cold(1)
     ms, _ = sim.last_run_stats()
     lib = F.load()
-    tile_rows, warps_per_cta, cols_per_warp = 512, 4, 4
-    n_tiles = ((H + tile_rows - 1) // tile_rows) * ((W + 15) // 16)
-    ctas = min(n_tiles, 148 * int(os.environ.get("INCERTO_B200_FOREST_CTAS_PER_SM", "9")))   # persistent grid
+    tile_rows, warps_per_cta, cols_per_thread = 512, 4, 6     # kTX * 16, kTY, kColsPerThread of kernels_forest.cu
+    ctas = ((H + tile_rows - 1) // tile_rows) * ((W + warps_per_cta * cols_per_thread - 1) // (warps_per_cta * cols_per_thread))
     nwarps = min(ctas * warps_per_cta, 1 << 18)
     buf = np.zeros(4 * nwarps, np.uint64)
     lib.incerto_debug_forest_trace.argtypes = [C.c_void_p, C.c_uint64]

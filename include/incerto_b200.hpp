@@ -166,6 +166,22 @@ class Simulation // src/simulation.rs:17-259
         if (h_) incerto_sim_destroy(h_);
     }
     void run(uint64_t num_steps) { check(incerto_sim_run(h_, num_steps)); } // :25-31
+    // engine additions with no reference counterpart: enqueue only / wait; several handles (one stream each) may be
+    // in flight on one GPU, span_ms gives the device time from the start of this handle's run to the end of `last`'s
+    void run_async(uint64_t num_steps) { check(incerto_sim_run_async(h_, num_steps)); }
+    void synchronize() { check(incerto_sim_synchronize(h_)); }
+    double span_ms(Simulation& last)
+    {
+        double ms = 0.0;
+        check(incerto_sim_span_ms(h_, last.h_, &ms));
+        return ms;
+    }
+    void reset(uint32_t replica) { check(incerto_sim_reset(h_, replica)); }
+    // one process per GPU: attach the NCCL communicator (id from incerto_comm_unique_id on rank 0, broadcast by the host)
+    void attach_comm(const uint8_t unique_id[128], uint32_t rank, uint32_t world)
+    {
+        check(incerto_sim_attach_comm(h_, unique_id, rank, world));
+    }
     uint64_t count(const Filter& f)                                          // :163-173
     {
         uint64_t out = 0;
@@ -179,6 +195,15 @@ class Simulation // src/simulation.rs:17-259
         Out out{};
         const incerto_aggregate_desc d = a.raw();
         check(incerto_sim_sample_aggregate(h_, &d, &out, sizeof(out)));
+        return out;
+    }
+    // the same aggregate over the entities of all ranks of the attached communicator (collective)
+    template <typename Out>
+    Out sample_aggregate_global(const Aggregate& a)
+    {
+        Out out{};
+        const incerto_aggregate_desc d = a.raw();
+        check(incerto_sim_sample_aggregate_global(h_, &d, &out, sizeof(out)));
         return out;
     }
     template <typename Out, typename Id>

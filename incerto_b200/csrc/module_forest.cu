@@ -579,6 +579,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     INC_TRY(forest_alloc(s, fm));
     for (int i = 0; i < 2; ++i) INC_CUDA(cudaMemsetAsync(fm.d_alloc[i], 0, fm.slab_bytes + 2 * kLead, s.stream));
     const int32_t lo = std::max(fm.x_begin - 1, 0), hi = std::min(fm.x_end + 1, fm.W);
+    stage_mark("forest adopt: alloc, memset");
     INC_CUDA(cudaMemcpy2DAsync(fm.d_slab[0] + static_cast<size_t>(lo - (fm.x_begin - 1)) * fm.pitch, fm.pitch,
                                dense + static_cast<size_t>(lo) * fm.H, fm.H, fm.H, hi - lo, cudaMemcpyHostToDevice,
                                s.stream));
@@ -588,7 +589,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
         checker.join();
         INC_TRY(verdict(verified));
     }
-    stage_mark("forest adopt: alloc, H2D");
+    stage_mark("forest adopt: H2D (+ verify)");
     fm.cur = 0;
     fm.h_ov_pos.resize(2 * static_cast<size_t>(fm.n_overlay));
     std::vector<uint8_t> ovst(std::max<uint32_t>(fm.n_overlay, 1), 0);

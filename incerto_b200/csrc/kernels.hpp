@@ -105,6 +105,7 @@ struct ForestArgs
     uint32_t regrow_two_level;  // p * 256 <= 1
     uint32_t burn_duration;
     PhiloxKey key_spread, key_regrow;
+    uint32_t l2_resident;       // hint: consecutive steps of a grid whose two buffers stay in the L2 (graph replay)
     // StepNumber of the launch = (d_step ? *d_step : 0) + step_base: by value for single launches, device counter +
     // offset inside a captured graph of steps (which then replays without new arguments)
     const uint32_t* d_step;

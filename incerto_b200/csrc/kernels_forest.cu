@@ -753,7 +753,9 @@ cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, con
     c.rk_regrow = make_round_keys(a.key_regrow);
     dim3 block(kTX, kTY);
     dim3 grid((c.chunks_per_col + kTX - 1) / kTX, (c.slab_w + kTY * kColsPerThread - 1) / (kTY * kColsPerThread));
-    const bool hoist = static_cast<uint64_t>(grid.x) * grid.y <= 4ull * kNumSMs * kMinBlocks; // at most four waves
+    // at most four waves, and the loads actually take long (steps that find their cells in the L2 have no shadow worth
+    // filling: 4096^2 graph replay 13.2 us with, 12.9 us without)
+    const bool hoist = static_cast<uint64_t>(grid.x) * grid.y <= 4ull * kNumSMs * kMinBlocks && !a.l2_resident;
     if ((a.H % 16) != 0) // uid of a chunk's first cell is not a multiple of 16: no shared level-1 call per chunk
         forest_step_kernel<false, false><<<grid, block, 0, st>>>(c);
     else if (hoist)

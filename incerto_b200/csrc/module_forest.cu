@@ -779,6 +779,7 @@ static int32_t forest_launch_one(Sim& s, uint64_t step, int graph_offset, Forest
     a.burn_duration = fm.burn_duration;
     a.key_spread = make_key(s.seed, s.replica, TAG_FOREST_SPREAD);
     a.key_regrow = make_key(s.seed, s.replica, TAG_FOREST_REGROW);
+    a.l2_resident = (graph_offset >= 0 && 2 * fm.slab_bytes <= (96u << 20)) ? 1u : 0u; // 126 MB of L2, some of it for the rest
     a.d_step = graph_offset >= 0 ? s.mods->d_step : nullptr;
     a.step_base = graph_offset >= 0 ? static_cast<uint32_t>(graph_offset) : static_cast<uint32_t>(step);
     a.stats_run = fm.d_stats_run;

@@ -142,8 +142,61 @@ def test_reset_and_replicas():
     assert sim.get_aggregate_time_series(ib.FireStatsOf(cell)).len() == 30
 
 
+@pytest.mark.parametrize("W,H,fires", [(30, 1100, 6), (56, 2048, 8), (24, 513, 5), (7, 1537, 8), (100, 1024, 6)])
+def test_parity_tall_grids_cross_the_warp_span(W, H, fires):
+    """Columns longer than one warp span (512 cells in y; blockIdx.x > 0): the fire front crosses span and CTA-tile
+    borders in y, so the neighbour-across-the-span loads of forest_step_kernel decide real ignitions
+    (forest_fire.rs:282-329).  States and the FireStats record after every step, the series at the end."""
+    steps = 160
+    sim, pos, cell = build_device_forest(W, H, density=0.9, p_regrow=0.002, fires=fires)
+    o = ForestOracle(SEED, 0, W, H, density=0.9, p_regrow=0.002, fires=fires).spawn()
+    assert np.array_equal(sim.read_component(cell), o.cells()[0])
+    crossed = False
+    for k in range(steps):
+        sim.run(1)
+        o.run(1)
+        st = sim.read_component(cell)
+        assert np.array_equal(st, o.cells()[0]), f"step {k + 1}"
+        assert stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell))) == tuple(int(x) for x in o.stats())
+        g = st[:W * H].reshape(W, H)
+        burning = (g > 0) & (g < 0x40)
+        for y in range(512, H, 512):        # something burns on both sides of a span border at the same time
+            crossed = crossed or bool(burning[:, y - 1].any() and burning[:, y].any())
+    assert crossed, "the fire never crossed a warp-span border: the case does not test what it is for"
+    assert np.array_equal(np.array([stats_tuple(v) for v in sim.get_aggregate_time_series(ib.FireStatsOf(cell)).values()],
+                                   dtype=np.uint64), o.series())
+
+
+def test_parity_tall_grid_graph_replay():
+    """The same tall shape through run(n) with n > 16 (captured graphs of 16 steps + remainder)."""
+    W, H = 40, 1300
+    sim, pos, cell = build_device_forest(W, H, density=0.9, p_regrow=0.002, fires=8)
+    o = ForestOracle(SEED, 0, W, H, density=0.9, p_regrow=0.002, fires=8).spawn()
+    for n in (50, 33, 120):
+        sim.run(n)
+        o.run(n)
+        assert np.array_equal(sim.read_component(cell), o.cells()[0])
+    assert np.array_equal(np.array([stats_tuple(v) for v in sim.get_aggregate_time_series(ib.FireStatsOf(cell)).values()],
+                                   dtype=np.uint64), o.series())
+
+
+def test_full_size_against_the_oracle():
+    """BASELINE config 1 (4096 x 4096, the bench.py configuration) x 3 steps: every cell and the FireStats series
+    against the oracle (about 25 s of CPU)."""
+    W = H = 4096
+    sim, pos, cell = build_device_forest(W, H, series=1)
+    o = ForestOracle(SEED, 0, W, H).spawn()
+    assert np.array_equal(sim.read_component(cell), o.cells()[0])
+    sim.run(3)
+    o.run(3)
+    assert np.array_equal(sim.read_component(cell), o.cells()[0])
+    assert np.array_equal(np.array([stats_tuple(v) for v in sim.get_aggregate_time_series(ib.FireStatsOf(cell)).values()],
+                                   dtype=np.uint64), o.series())
+
+
 def test_full_size_properties():
-    """BASELINE config 1 (4096 x 4096): size-independent invariants + a window checked against the oracle."""
+    """BASELINE config 1 (4096 x 4096): size-independent invariants over 40 steps (the oracle comparison at this size
+    is test_full_size_against_the_oracle)."""
     W = H = 4096
     sim, pos, cell = build_device_forest(W, H, series=1)
     fs0 = stats_tuple(sim.sample_aggregate(ib.FireStatsOf(cell)))

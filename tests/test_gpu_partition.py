@@ -105,3 +105,22 @@ def test_partition_equals_undivided_run():
         step_all(sims)
     whole.run(40)
     assert np.array_equal(gather_cells(sims, W, H, 5), whole.read_component(cell_w)[:W * H])
+
+
+@pytest.mark.parametrize("W,H,world", [(48, 1100, 2), (60, 1300, 3)])
+def test_partition_tall_slabs_match_oracle(W, H, world):
+    """Slabs whose columns span several warp spans in y (H > 512; the shape every rank of the 16384-cell-column bench
+    configuration has): states and summed FireStats against the oracle after every step."""
+    steps = 150
+    sims = [build_rank(W, H, r, world, density=0.9, p_regrow=0.002, fires=8) for r in range(world)]
+    o = ForestOracle(SEED, 0, W, H, density=0.9, p_regrow=0.002, fires=8).spawn()
+    for k in range(steps):
+        step_all(sims)
+        o.run(1)
+        assert np.array_equal(gather_cells(sims, W, H, 8), o.cells()[0][:W * H]), f"step {k + 1}"
+        tot = np.zeros(5, np.int64)
+        for s, cell in sims:
+            fs = s.sample_aggregate(ib.FireStatsOf(cell))
+            tot += np.array([fs.healthy_count, fs.burning_count, fs.burned_count, fs.empty_count, fs.total_cells])
+        assert tuple(tot) == tuple(int(x) for x in o.stats())
+    assert o.stats()[2] > 0.2 * W * H

@@ -1288,9 +1288,23 @@ int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps)
         if (rc == INCERTO_OK) rc = do_run_enqueue(S, 1);
         fail(cudaEventRecord(ev[2 * i + 1], S.stream));
     }
-    if (rc == INCERTO_OK) rc = forest_finalize(S); // not inside any step's event pair: see forest_finalize
+    // the record of the last step (every earlier one was published by its successor's grid, inside that step's event
+    // pair): timed by a pair of its own and charged to the run like the steps
+    cudaEvent_t ev_fin[2] = {nullptr, nullptr};
+    for (auto& e : ev_fin) fail(cudaEventCreate(&e));
+    fail(cudaEventRecord(ev_fin[0], S.stream));
+    if (rc == INCERTO_OK) rc = forest_finalize(S);
+    fail(cudaEventRecord(ev_fin[1], S.stream));
     fail(cudaStreamSynchronize(S.stream));
     double total = 0.0;
+    if (rc == INCERTO_OK)
+    {
+        float ms = 0.f;
+        fail(cudaEventElapsedTime(&ms, ev_fin[0], ev_fin[1]));
+        total += ms;
+    }
+    for (auto& e : ev_fin)
+        if (e) cudaEventDestroy(e);
     for (uint64_t i = 0; i < num_steps && rc == INCERTO_OK; ++i)
     {
         float ms = 0.f;

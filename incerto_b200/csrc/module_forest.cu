@@ -423,9 +423,22 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
         pieces.push_back(Piece{pcol->bytes(), ccol->bytes(), sp.n});
         total += sp.n;
     }
-    if (total != t.n_spawned || total < cells)
+    // A row-partitioned handle may be given just the rows it needs - the columns [lo, hi) of its slab plus one halo
+    // column on each interior side, still x-major, followed by ALL overlay entities - instead of the whole world:
+    // `row0` is the global row (uid) of the first dense row this handle was handed.
+    uint64_t row0 = 0, dense_rows = cells;
+    if (s.part_world > 1 && total < cells)
     {
-        set_error("forest: the spawned cells do not cover the %dx%d grid", fm.W, fm.H);
+        int32_t xb = 0, xe = 0;
+        incerto_partition_range(fm.W, s.part_rank, s.part_world, &xb, &xe);
+        const int32_t lo = std::max(xb - 1, 0), hi = std::min(xe + 1, fm.W);
+        row0 = static_cast<uint64_t>(lo) * fm.H;
+        dense_rows = static_cast<uint64_t>(hi - lo) * fm.H;
+    }
+    if (total != t.n_spawned || total < dense_rows)
+    {
+        set_error("forest: the spawned cells do not cover the %dx%d grid%s", fm.W, fm.H,
+                  s.part_world > 1 ? " (nor this rank's slab + halo columns)" : "");
         return INCERTO_ERR_UNSUPPORTED;
     }
     const bool wide = pc.dtype == INCERTO_I32;
@@ -449,17 +462,17 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     std::vector<int32_t> ov_x, ov_y;
     const uint8_t* dense_states = nullptr; // the states of the dense prefix, when one spawn call holds them all
     std::vector<uint8_t> st;               // otherwise (several pieces): gathered here
-    if (!pieces.empty() && pieces[0].n >= cells)
+    if (!pieces.empty() && pieces[0].n >= dense_rows)
         dense_states = pieces[0].st;
     else
-        st.resize(cells);
+        st.resize(dense_rows);
     std::vector<uint8_t> ov_states;
     // pass A (cheap): the rows after the dense prefix are overlay entities
     {
         uint64_t g = 0; // global row
         for (auto& pz : pieces)
         {
-            const uint64_t n_dense = g < cells ? std::min<uint64_t>(pz.n, cells - g) : 0;
+            const uint64_t n_dense = g < dense_rows ? std::min<uint64_t>(pz.n, dense_rows - g) : 0;
             for (uint64_t r = n_dense; r < pz.n; ++r)
             {
                 int32_t x, y;
@@ -484,7 +497,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
         uint32_t bad_state = 0;
         for (auto& pz : pieces)
         {
-            const uint64_t n_dense = g < cells ? std::min<uint64_t>(pz.n, cells - g) : 0;
+            const uint64_t n_dense = g < dense_rows ? std::min<uint64_t>(pz.n, dense_rows - g) : 0;
             if (n_dense)
             {
                 if (!dense_states) std::memcpy(st.data() + g, pz.st, n_dense);
@@ -494,7 +507,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
                     const int32_t* q = reinterpret_cast<const int32_t*>(pz.pos);
                     for (uint64_t r = 0; r < n_dense; ++r)
                     {
-                        const uint64_t gg = g + r;
+                        const uint64_t gg = row0 + g + r;
                         bad |= static_cast<uint32_t>(q[2 * r] != static_cast<int32_t>(gg / fm.H)) |
                                static_cast<uint32_t>(q[2 * r + 1] != static_cast<int32_t>(gg % fm.H));
                     }
@@ -508,7 +521,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
                         uint32_t b = 0;
                         while (r < r_end)
                         {
-                            const uint64_t gg = g + r;
+                            const uint64_t gg = row0 + g + r;
                             const uint32_t x = static_cast<uint32_t>(gg / fm.H), y = static_cast<uint32_t>(gg % fm.H);
                             const uint64_t run = std::min<uint64_t>(r_end - r, static_cast<uint64_t>(fm.H) - y);
                             b |= static_cast<uint32_t>(q[r] != ((x & 0xffffu) | (y << 16)));
@@ -569,7 +582,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     } joiner{checker};
     stage_mark("forest adopt: host checks");
     const uint8_t* dense = dense_states ? dense_states : st.data();
-    fm.n_overlay = static_cast<uint32_t>(total - cells);
+    fm.n_overlay = static_cast<uint32_t>(std::min<uint64_t>(total - dense_rows, 0xffffffffu));
     if (fm.n_overlay > 256)
     {
         set_error("forest: at most 256 overlay entities on top of the dense grid");
@@ -581,7 +594,7 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     const int32_t lo = std::max(fm.x_begin - 1, 0), hi = std::min(fm.x_end + 1, fm.W);
     stage_mark("forest adopt: alloc, memset");
     INC_CUDA(cudaMemcpy2DAsync(fm.d_slab[0] + static_cast<size_t>(lo - (fm.x_begin - 1)) * fm.pitch, fm.pitch,
-                               dense + static_cast<size_t>(lo) * fm.H, fm.H, fm.H, hi - lo, cudaMemcpyHostToDevice,
+                               dense + (static_cast<size_t>(lo) * fm.H - row0), fm.H, fm.H, hi - lo, cudaMemcpyHostToDevice,
                                s.stream));
     INC_CUDA(cudaStreamSynchronize(s.stream));
     if (checker.joinable())

@@ -124,3 +124,30 @@ def test_partition_tall_slabs_match_oracle(W, H, world):
             tot += np.array([fs.healthy_count, fs.burning_count, fs.burned_count, fs.empty_count, fs.total_cells])
         assert tuple(tot) == tuple(int(x) for x in o.stats())
     assert o.stats()[2] > 0.2 * W * H
+
+
+def test_partition_slab_local_host_spawn():
+    """A partitioned handle may be handed only the rows it needs (its slab + one halo column per interior side, then
+    all overlay entities) instead of the whole world: same result as the undivided run and as the oracle."""
+    W, H, world = 48, 600, 3
+    rng = np.random.default_rng(11)
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H), indexing="ij")
+    xy = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int32)
+    st = np.where(rng.random(W * H) < 0.9, HEALTHY, EMPTY).astype(np.uint8)
+    ov_xy = np.array([[15, 300], [16, 511], [16, 512], [40, 10], [0, 599]], np.int32)
+    ov_st = np.array([3, 3, 3, 3, 3], np.uint8)
+    sims = []
+    for r in range(world):
+        b, e = ib.partition_range(W, r, world)
+        lo, hi = max(b - 1, 0), min(e + 1, W)
+        sims.append(build_rank(W, H, r, world, host=(np.concatenate([xy[lo * H:hi * H], ov_xy]),
+                                                      np.concatenate([st[lo * H:hi * H], ov_st])), p_regrow=0.002))
+    o = ForestOracle(SEED, 0, W, H, p_regrow=0.002, fires=0).spawn_explicit(np.concatenate([xy, ov_xy]), np.concatenate([st, ov_st]))
+    for k in range(80):
+        step_all(sims)
+        o.run(1)
+        assert np.array_equal(gather_cells(sims, W, H, len(ov_st)), o.cells()[0][:W * H]), f"step {k + 1}"
+    # a slab that is too short is refused
+    with pytest.raises(ib.EngineError) as err:
+        build_rank(W, H, 1, world, host=(np.concatenate([xy[:5 * H], ov_xy]), np.concatenate([st[:5 * H], ov_st])))
+    assert err.value.code in (F.ERR_UNSUPPORTED, F.ERR_INVALID_ARGUMENT)

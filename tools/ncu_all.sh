@@ -17,17 +17,17 @@ for w in "$@"; do
     coin) pat='regex:coin_'; skip=24;;
     forestbench)
       # forest_step exactly as bench.py times it: every launch preceded by the (untimed) L2 flush
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain_forestbench.log 2>&1 &&
-      ncu --set full --clock-control none --import-source on -k regex:forest_step -s 3 -c 2 -f -o gpurun_out/r01_forestbench \
-          python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_forestbench.log 2>&1
+      python bench.py --steps 2 --warmup 3 --only-headline > gpurun_out/plain_forestbench.log 2>&1 &&
+      ncu --set full --clock-control none --import-source on -k regex:forest_step -s 3 -c 2 -f -o gpurun_out/r02_forestbench \
+          python bench.py --steps 2 --warmup 3 --only-headline > gpurun_out/ncu_forestbench.log 2>&1
       echo "forestbench rc=$?"; continue;;
     launches)
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 &&
-      ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv \
-          python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+      python bench.py --steps 2 --warmup 3 --only-headline > gpurun_out/plain_bench.log 2>&1 &&
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv \
+          python bench.py --steps 2 --warmup 3 --only-headline > gpurun_out/ncu_bench.log 2>&1
       echo "launches rc=$?"; continue;;
   esac
   python tools/prof_workload.py $name $extra > gpurun_out/plain_$w.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k "$pat" -s $skip -c 2 -f -o gpurun_out/r01_$w python tools/prof_workload.py $name $extra > gpurun_out/ncu_$w.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "$pat" -s $skip -c 2 -f -o gpurun_out/r02_$w python tools/prof_workload.py $name $extra > gpurun_out/ncu_$w.log 2>&1
   echo "$w rc=$?"
 done

@@ -9,13 +9,15 @@
 // because die/recover iterate the pre-flush With<Infected> set.
 //
 // Device layout: Position{x,y} packed as one u32 per person (x | y << 16), flags u8 (alive + marker bits).
-// Algorithmic bytes per person-update: 10 (position 4+4, flags 1+1); the per-cell infected lists
-// (head 4 B/cell stamped with the step, next 4 B/infected) are scratch traffic reported separately.
+// Algorithmic bytes per person-update: 10 (position 4+4, flags 1+1); the per-cell infected lists (a hashed head
+// table of ~n/4 slots stamped with the step - small enough to stay in the L2 -, next 4 B/infected, 1 bit/cell
+// "somebody infected stands here") are scratch traffic reported separately.
 //
 // Draw contract:
 //   spawn   person uid: r = philox(key[PSPW], (uid,0,0,0)); x = mulhi(r.x,G), y = mulhi(r.y,G), infected = r.z < thr(p0)
-//   move    word w = word (uid&3) of philox(key[PMOV], (uid>>2,0,step,0)); the three p = 1/2 draws of :121-148
-//           are bits 31, 30, 29 of w ("true" = bit clear, i.e. (w << k) < 2^31): stay, x-axis, negative direction
+//   move    nibble (uid&7) of word ((uid>>3)&3) of philox(key[PMOV], (uid>>5,0,step,0)): the three p = 1/2 draws of
+//           :121-148 are bits 3, 2, 1 of the nibble ("true" = bit clear): stay, x-axis, negative direction - one call
+//           serves 32 people, one word the eight consecutive rows a thread owns
 //   fate    two-level when 256*p <= 1 for both probabilities: L1 = philox(key[PFAT], (uid>>3,0,step,0)), byte
 //           2*(uid&7) (die) / 2*(uid&7)+1 (recover) must be zero; L2 = philox(key[PFAT], (uid,0,step,1)):
 //           die = L2.x < thr(256 p_die), recover = L2.y < thr(256 p_rec).  Otherwise L2 alone with thr(p).
@@ -88,9 +90,16 @@ __device__ __forceinline__ void load_rows(const PandemicArgs& a, uint64_t row0, 
     }
 }
 
+__device__ __forceinline__ uint32_t head_slot(const PandemicArgs& a, uint32_t cell)
+{
+    // exact table (one slot per cell) when the grid is small, else a multiplicative hash into ~n/4 slots: a slot's list
+    // may then hold infected people of several cells and the walker compares positions
+    return a.head_shift ? (cell * 0x9E3779B1u) >> a.head_shift : cell;
+}
+
 // people_move + building the per-cell lists of infected people for the interaction kernel.
-// One thread = 8 consecutive rows (two Philox calls when uid == row).  All memory operations of the tile are issued
-// before any result is consumed: the returning exchanges that link the infected into their cells overlap.
+// One thread = 8 consecutive rows = (uid == row) one word of a Philox call.  All memory operations of the tile are
+// issued before any result is consumed: the returning exchanges that link the infected into their cells overlap.
 __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
 {
     const uint64_t ntiles = (a.n + kRows - 1) / kRows;
@@ -103,34 +112,21 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
         const bool full = row0 + kRows <= a.n;
         Rows8 r;
         load_rows(a, row0, true, r);
-        uint32_t w[kRows];
+        uint32_t nib8 = 0; // nibble k: the draws of row k
         if (a.do_move)
         {
             if (a.uid == nullptr)
-            {
-                const uint4 r0 = philox4x32_10(static_cast<uint32_t>(2 * q), 0u, a.step, 0u, a.rk_move);
-                const uint4 r1 = philox4x32_10(static_cast<uint32_t>(2 * q + 1), 0u, a.step, 0u, a.rk_move);
-                w[0] = r0.x;
-                w[1] = r0.y;
-                w[2] = r0.z;
-                w[3] = r0.w;
-                w[4] = r1.x;
-                w[5] = r1.y;
-                w[6] = r1.z;
-                w[7] = r1.w;
-            }
+                nib8 = word_of(philox4x32_10(static_cast<uint32_t>(q >> 2), 0u, a.step, 0u, a.rk_move), static_cast<uint32_t>(q) & 3u);
             else
             {
 #pragma unroll
                 for (int k = 0; k < kRows; ++k)
-                {
-                    w[k] = 0;
                     if ((r.f >> (8 * k)) & 1ull)
                     {
                         const uint32_t u = a.uid[row0 + k];
-                        w[k] = word_of(philox4x32_10(u >> 2, 0u, a.step, 0u, a.rk_move), u & 3u);
+                        const uint32_t w = word_of(philox4x32_10(u >> 5, 0u, a.step, 0u, a.rk_move), (u >> 3) & 3u);
+                        nib8 |= ((w >> (4 * (u & 7u))) & 0xfu) << (4 * k);
                     }
-                }
             }
         }
         uint32_t old[kRows];
@@ -140,27 +136,25 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
         {
             const uint32_t fl = static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu;
             old[k] = 0;
-            if (!(fl & 1u)) continue; // despawned
-            uint32_t x = r.p[k] & 0xffffu, y = r.p[k] >> 16;
             if (a.do_move)
             {
-                // :121 stay put (bit 31 clear); :125 x axis (bit 30 clear) else y axis; :128/:147 negative (bit 29 clear)
-                // else positive direction; saturating at 0 and G-1.  Branch-free: a signed step per axis, masked by
-                // "moves along this axis", then clamp(v + step, 0, G-1) as one min-with-relu.
-                const uint32_t wk = w[k], wk1 = wk << 1;
-                const int32_t sgn = static_cast<int32_t>((wk >> 28) & 2u) - 1;                 // +1 / -1
-                const int32_t mx = static_cast<int32_t>(wk & ~wk1) >> 31;                      // all ones: moves along x
-                const int32_t my = static_cast<int32_t>(wk & wk1) >> 31;                       // all ones: moves along y
-                x = static_cast<uint32_t>(__vimin_s32_relu(static_cast<int32_t>(x) + (sgn & mx), static_cast<int32_t>(G) - 1));
-                y = static_cast<uint32_t>(__vimin_s32_relu(static_cast<int32_t>(y) + (sgn & my), static_cast<int32_t>(G) - 1));
-                r.p[k] = x | (y << 16);
+                // :121 stay put (bit 3 clear); :125 x axis (bit 2 clear) else y axis; :128/:147 negative (bit 1 clear)
+                // else positive direction; saturating at 0 and G-1 (the halves of the packed word never carry into
+                // each other because the move is refused at the walls)
+                const uint32_t nib = nib8 >> (4 * k);
+                const uint32_t sh = (nib & 4u) << 2;                  // 0: x, 16: y
+                const uint32_t coord = (r.p[k] >> sh) & 0xffffu;
+                const bool pos_dir = (nib & 2u) != 0;
+                const bool ok = (fl & 1u) && (nib & 8u) && (pos_dir ? coord + 1 < G : coord > 0);
+                const uint32_t one = 1u << sh;
+                r.p[k] += ok ? (pos_dir ? one : 0u - one) : 0u;
             }
-            if (a.do_infect && (fl & a.bit_infected))
+            if (a.do_infect && (fl & 1u) && (fl & a.bit_infected))
             {
                 // per-cell list of infected people (order irrelevant: the draws are keyed by the pair)
-                const uint32_t cell = x * G + y;
+                const uint32_t cell = (r.p[k] & 0xffffu) * G + (r.p[k] >> 16);
                 atomicOr(&a.cell_bits[cell >> 5], 1u << (cell & 31));
-                old[k] = atomicExch(&a.cell_head[cell], tag | static_cast<uint32_t>(row0 + k));
+                old[k] = atomicExch(&a.cell_head[head_slot(a, cell)], tag | static_cast<uint32_t>(row0 + k));
                 linked |= 1u << k;
             }
         }
@@ -204,12 +198,21 @@ __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, uint32_t& to
 __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArgs a)
 {
     __shared__ uint32_t s_queue[kThreads / 32][2][32 * kRows]; // item = row | flags << 24 (rows < 2^24)
+    __shared__ uint32_t s_qpos[kThreads / 32][32 * kRows];     // packed position of the rows in queue 1
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     const uint32_t G = a.grid_size;
     const uint32_t tag = (a.step & 0xffu) << 24;
     const bool fate = (a.do_die | a.do_recover) != 0;
+    // the other bitmap (the next step's) is cleared on the side: no memset between the steps
+    if (a.cell_bits_clear)
+    {
+        uint4* z = reinterpret_cast<uint4*>(a.cell_bits_clear);
+        const uint64_t gsize = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+        for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.bits_vec4; i += gsize)
+            z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     for (uint64_t base = warp0 * (32 * kRows); base < a.n; base += nwarps * (32 * kRows))
     {
         const uint64_t row0 = base + lane * kRows;
@@ -249,7 +252,11 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
         {
             const uint32_t item = static_cast<uint32_t>(row0 + k) | ((static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu) << 24);
             if ((sick >> k) & 1u) s_queue[warp][0][o_sick++] = item;
-            if ((hit >> k) & 1u) s_queue[warp][1][o_hit++] = item;
+            if ((hit >> k) & 1u)
+            {
+                s_qpos[warp][o_hit] = r.p[k];
+                s_queue[warp][1][o_hit++] = item;
+            }
         }
         __syncwarp();
         for (uint32_t j = lane; j < n_sick; j += 32)
@@ -280,18 +287,22 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
             const uint32_t item = s_queue[warp][1][j];
             const uint32_t row = item & 0x00ffffffu, fl = item >> 24;
             const uint32_t uid = a.uid ? a.uid[row] : row;
-            const uint32_t p = a.pos[row];
+            const uint32_t p = s_qpos[warp][j];
             const uint32_t cell = (p & 0xffffu) * G + (p >> 16);
-            const uint32_t h = a.cell_head[cell];
+            const uint32_t h = a.cell_head[head_slot(a, cell)];
             uint32_t cur = ((h & 0xff000000u) == tag) ? (h & 0x00ffffffu) : 0x00ffffffu;
             bool infected = false;
             // (the guard only bounds the walk should the list ever be corrupt: never hang the device)
             for (uint32_t guard = 0; cur != 0x00ffffffu && guard < 0x01000000u; ++guard)
             {
-                const uint32_t iuid = a.uid ? a.uid[cur] : cur;
-                const uint4 rr = philox4x32_10(uid, iuid, a.step, 0u, a.rk_infect);
-                infected = infected || bernoulli(rr.x, a.thr_infect); // :184-188; every pair draws
-                cur = a.next_infected[cur];
+                const uint32_t nxt = a.next_infected[cur];
+                if (!a.head_shift || a.pos[cur] == p) // a hashed slot also lists the infected of other cells
+                {
+                    const uint32_t iuid = a.uid ? a.uid[cur] : cur;
+                    const uint4 rr = philox4x32_10(uid, iuid, a.step, 0u, a.rk_infect);
+                    infected = infected || bernoulli(rr.x, a.thr_infect); // :184-188; every pair draws
+                }
+                cur = nxt;
             }
             if (infected) a.flags[row] = static_cast<uint8_t>(fl | a.bit_infected); // commands.entity(healthy).insert(Infected) (:187)
         }

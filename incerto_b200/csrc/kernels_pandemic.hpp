@@ -24,7 +24,10 @@ struct PandemicArgs
     PhiloxRoundKeys rk_spawn, rk_move, rk_fate, rk_infect;
     // scratch: per-cell lists of infected people
     uint32_t* cell_bits;     // 1 bit per cell: some infected person stands here this step
-    uint32_t* cell_head;     // (step & 0xff) << 24 | row of the list head
+    uint32_t* cell_bits_clear; // the next step's bitmap, zeroed by this step's interact kernel (bits_vec4 x 16 B)
+    uint64_t bits_vec4;
+    uint32_t* cell_head;     // (step & 0xff) << 24 | row of the list head; slot = cell, or hashed (head_shift)
+    uint32_t head_shift;     // 0: one slot per cell; else slot = (cell * 0x9E3779B1) >> head_shift
     uint32_t* next_infected; // per row: next infected row in the same cell, 0xffffff = end
 };
 

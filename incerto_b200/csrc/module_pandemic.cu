@@ -82,10 +82,31 @@ int32_t pandemic_bind(Sim& s)
     if (pm.do_infect)
     {
         const uint64_t cells = static_cast<uint64_t>(pm.grid_size) * pm.grid_size;
-        INC_CUDA(cudaMalloc(&pm.d_cell_bits, (cells / 32 + 1) * 4));
-        INC_CUDA(cudaMalloc(&pm.d_cell_head, cells * 4));
+        pm.bits_vec4 = cells / 128 + 1;
+        INC_CUDA(cudaMalloc(&pm.d_cell_bits, 2 * pm.bits_vec4 * 16));
+        INC_CUDA(cudaMemsetAsync(pm.d_cell_bits, 0, 2 * pm.bits_vec4 * 16, s.stream));
+        // list heads: one slot per cell while that stays small, else ~n/4 hashed slots (a power of two): with the
+        // reference's density (0.4 people per cell, ~10 % infected) the exact table would be 10 x the population's own
+        // bytes and every exchange a DRAM round trip; the hashed one stays in the L2
+        uint64_t want = 4096;
+        while (want < t.n / 4) want <<= 1;
+        if (const char* e = std::getenv("INCERTO_B200_PANDEMIC_EXACT_HEADS"))
+            if (e[0] == '1') want = cells;
+        if (want >= cells || want > (1ull << 31))
+        {
+            pm.head_slots = cells;
+            pm.head_shift = 0;
+        }
+        else
+        {
+            pm.head_slots = want;
+            uint32_t lg = 0;
+            while ((1ull << lg) < want) ++lg;
+            pm.head_shift = 32 - lg;
+        }
+        INC_CUDA(cudaMalloc(&pm.d_cell_head, pm.head_slots * 4));
         INC_CUDA(cudaMalloc(&pm.d_next, std::max<uint64_t>(t.n, 1) * 4));
-        INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, cells * 4, s.stream));
+        INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, pm.head_slots * 4, s.stream));
     }
     return pandemic_sort_rows(s);
 }
@@ -114,8 +135,8 @@ int32_t pandemic_reset(Sim& s)
     PandemicModule& pm = s.mods->pandemic;
     if (pm.d_cell_head)
     {
-        const uint64_t cells = static_cast<uint64_t>(pm.grid_size) * pm.grid_size;
-        INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, cells * 4, s.stream));
+        INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, pm.head_slots * 4, s.stream));
+        INC_CUDA(cudaMemsetAsync(pm.d_cell_bits, 0, 2 * pm.bits_vec4 * 16, s.stream));
     }
     return pandemic_sort_rows(s);
 }
@@ -152,8 +173,12 @@ static void pandemic_fill(Sim& s, PandemicModule& pm, PandemicArgs& a, Table& t,
     a.rk_move = make_round_keys(make_key(s.seed, s.replica, TAG_PANDEMIC_MOVE));
     a.rk_fate = make_round_keys(make_key(s.seed, s.replica, TAG_PANDEMIC_FATE));
     a.rk_infect = make_round_keys(make_key(s.seed, s.replica, TAG_PANDEMIC_INFECT));
-    a.cell_bits = pm.d_cell_bits;
+    // two bitmaps: this step's (clean: zeroed by the previous step's interact kernel) and the next step's
+    a.cell_bits = pm.d_cell_bits ? pm.d_cell_bits + (step & 1u) * pm.bits_vec4 * 4 : nullptr;
+    a.cell_bits_clear = pm.d_cell_bits ? pm.d_cell_bits + ((step + 1) & 1u) * pm.bits_vec4 * 4 : nullptr;
+    a.bits_vec4 = pm.bits_vec4;
     a.cell_head = pm.d_cell_head;
+    a.head_shift = pm.head_shift;
     a.next_infected = pm.d_next;
 }
 
@@ -163,7 +188,6 @@ int32_t pandemic_step(Sim& s, uint64_t first_step, uint32_t nsteps)
     if (pm.table < 0) return INCERTO_OK;
     Table& t = s.tables[pm.table];
     if (!t.n) return INCERTO_OK;
-    const uint64_t cells = static_cast<uint64_t>(pm.grid_size) * pm.grid_size;
     for (uint32_t i = 0; i < nsteps; ++i)
     {
         const uint64_t step = first_step + i;
@@ -171,8 +195,7 @@ int32_t pandemic_step(Sim& s, uint64_t first_step, uint32_t nsteps)
         pandemic_fill(s, pm, a, t, step);
         if (pm.do_infect)
         {
-            INC_CUDA(cudaMemsetAsync(pm.d_cell_bits, 0, (cells / 32 + 1) * 4, s.stream));
-            if ((step & 0xffu) == 0) INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, cells * 4, s.stream));
+            if ((step & 0xffu) == 0) INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, pm.head_slots * 4, s.stream));
         }
         if (pm.do_move || pm.do_infect)
         {

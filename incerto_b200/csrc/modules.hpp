@@ -83,6 +83,9 @@ struct PandemicModule
     uint32_t* d_cell_bits = nullptr;
     uint32_t* d_cell_head = nullptr;
     uint32_t* d_next = nullptr;
+    uint64_t bits_vec4 = 0;    // 16-byte units of ONE of the two cell bitmaps in d_cell_bits (step parity selects)
+    uint64_t head_slots = 0;   // entries of d_cell_head
+    uint32_t head_shift = 0;   // 0: exact (one slot per cell), else the hash shift
 };
 
 struct AirModule

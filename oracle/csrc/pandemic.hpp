@@ -68,9 +68,11 @@ struct PandemicSim
         for (uint32_t e = 0; e < x.size(); ++e)
         {
             if (!alive[e]) continue;
-            const uint32_t w = rng.block(e >> 2, 0, static_cast<uint32_t>(step), 0).w[e & 3];
-            // the three p = 1/2 draws share one word: draw k is true iff bit 31-k is clear
-            const bool stay = !(w & 0x80000000u), x_axis = !(w & 0x40000000u), negative = !(w & 0x20000000u);
+            // the three p = 1/2 draws of a person share one nibble (DESIGN.md §2 "nibbles"): nibble e & 7 of word
+            // (e >> 3) & 3 of the call (e >> 5); draw k is true iff bit 3-k of the nibble is clear
+            const uint32_t w = rng.block(e >> 5, 0, static_cast<uint32_t>(step), 0).w[(e >> 3) & 3];
+            const uint32_t nib = (w >> (4 * (e & 7))) & 0xfu;
+            const bool stay = !(nib & 8u), x_axis = !(nib & 4u), negative = !(nib & 2u);
             if (stay)
             {
                 // do nothing

@@ -61,8 +61,10 @@ pub fn forest_regrow(seed: u64, replica: u32, uid: u32, step: u32, p: f64) -> bo
 
 /// examples/pandemic.rs:121-148  the three p = 1/2 draws: (stay, x_axis, negative)
 pub fn pandemic_move(seed: u64, replica: u32, uid: u32, step: u32) -> (bool, bool, bool) {
-    let w = Stream::new(seed, replica, b"PMOV").block(uid >> 2, 0, step, 0)[(uid & 3) as usize];
-    (w & 0x8000_0000 == 0, w & 0x4000_0000 == 0, w & 0x2000_0000 == 0)
+    // one nibble per person: nibble uid & 7 of word (uid >> 3) & 3 of the call uid >> 5; draw k = bit 3-k clear
+    let w = Stream::new(seed, replica, b"PMOV").block(uid >> 5, 0, step, 0)[((uid >> 3) & 3) as usize];
+    let nib = (w >> (4 * (uid & 7))) & 0xf;
+    (nib & 8 == 0, nib & 4 == 0, nib & 2 == 0)
 }
 
 /// examples/pandemic.rs:184  infect draw for the pair (healthy h, infected i)

@@ -10,8 +10,8 @@ Headline (`metric`, `value`, `roofline`, `e2e` - unchanged since round 1):
          exchange per step fused into the step kernel (peer memory over NVLink; NCCL send/recv as fallback;
          N = 8 is exactly 16384 x 16384) - weak scaling.
 A "step" is one simulation step of the whole grid.  `value` is cell-updates/s with the state resident in
-HBM, every timed step started with a cold L2 (a 512 MB buffer is overwritten in between, excluded from
-the timing; with N > 1 an untimed all-reduce then lines the ranks up again), timed with a CUDA event pair
+HBM, every timed step started with a cold L2 (a 512 MB buffer is overwritten and half of it read back in between -
+the L2 then holds clean foreign lines -, excluded from the timing; with N > 1 an untimed all-reduce then lines the ranks up again), timed with a CUDA event pair
 around every step on the engine's stream (one incerto_sim_run_cold call), max over ranks.  `e2e` is the same metric
 through the C ABI with host buffers: spawn from host arrays (H2D), run, read the FireStats series back -
 best and median of 5 jobs with a phase breakdown; for N > 1 the job is the row-split grid, every rank spawning its
@@ -638,7 +638,7 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "systems": "fire_spread + burn_progression + regrowth + FireStats series/1",
-                   "l2": "flushed between timed steps (512 MB written, untimed)", "seed": hex(SEED),
+                   "l2": "flushed between timed steps (512 MB written, then 256 MB of it read back so that the L2 holds clean lines; untimed)", "seed": hex(SEED),
                    "parallelism": "1 GPU" if world == 1 else f"row partition x{world}, halo transport: {halo}"},
         "roofline": roofline,
         "value_l2_resident": value_warm,

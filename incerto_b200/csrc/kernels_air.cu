@@ -18,6 +18,15 @@
 // 255 steps), (3) the conflict count: exact lookups for the flagged neighbour cells only.  Two aircraft in
 // face-adjacent cells always flag each other (the bitmap has no false negatives), so both are in the table.
 //
+// Bitmap layout (round 2; ncu had the candidates kernel bound by its six scattered 4-byte probes per aircraft, one
+// L1 wavefront each): cells are blocked 4 x 4 x 16 (x, y, z) into 256-bit sectors, 2 x 2 sectors into a 128-byte
+// line (8 x 8 x 16 cells), and the LINE is what gets hashed.  An aircraft fetches its own sector with one 256-bit
+// load and answers +-z and, unless it sits on a sector face, +-x / +-y from registers; only the crossing
+// neighbours (on average one per aircraft) cost another probe, and that one mostly hits the line just fetched.
+// The exact table is allocated for the worst case (every aircraft flagged) but a step only uses a power-of-two
+// prefix of it sized, on the device, by the number of aircraft the candidates kernel flagged (a few per cent at the
+// reference density): the slots it touches stay in the L2 instead of being 134 MB of random DRAM accesses.
+//
 // Draw contract:
 //   spawn  aircraft uid: a = philox(key[ASPW], (uid,0,0,0)), b = philox(key[ASPW], (uid,0,0,1));
 //          x = mulhi(a.x,SIZE), y = mulhi(a.y,SIZE), z = mulhi(a.z,HEIGHT), type = mulhi(a.w,3), target = mulhi(b.x,HEIGHT)
@@ -35,16 +44,32 @@ constexpr int kThreads = 256;
 
 __device__ __forceinline__ int lane16(uint32_t w, int hi) { return static_cast<int16_t>(hi ? (w >> 16) : (w & 0xffffu)); }
 
-__device__ __forceinline__ uint32_t slot_of(const AirArgs& a, uint32_t key)
+// The part of the exact table this step uses: the smallest power of two >= 4 x the aircraft flagged by the
+// candidates kernel (counted in acc[4 + (step & 1)]), at least 1024 slots, at most the whole allocation.
+struct TableView
 {
-    return (key * 0x9E3779B1u) >> a.slot_shift;
+    uint32_t mask, shift;
+};
+__device__ __forceinline__ TableView table_view(const AirArgs& a)
+{
+    const unsigned long long nf = a.acc[4 + (a.step & 1u)];
+    const unsigned long long want = nf * 4ull > 1024ull ? nf * 4ull : 1024ull;
+    uint32_t bits = 64u - static_cast<uint32_t>(__clzll(static_cast<long long>(want - 1ull)));
+    const uint32_t max_bits = 32u - a.slot_shift;
+    bits = bits > max_bits ? max_bits : bits;
+    TableView v;
+    v.mask = (1u << bits) - 1u;
+    v.shift = 32u - bits;
+    return v;
 }
 
-__device__ __forceinline__ void index_insert(const AirArgs& a, uint32_t key)
+__device__ __forceinline__ uint32_t slot_of(const TableView& tv, uint32_t key) { return (key * 0x9E3779B1u) >> tv.shift; }
+
+__device__ __forceinline__ void index_insert(const AirArgs& a, const TableView& tv, uint32_t key)
 {
-    uint32_t h = slot_of(a, key);
+    uint32_t h = slot_of(tv, key);
     const unsigned long long fresh = (static_cast<unsigned long long>(a.tag) << 56) | (static_cast<unsigned long long>(key) << 24) | 1ull;
-    for (uint32_t guard = 0; guard <= a.slot_mask; )
+    for (uint32_t guard = 0; guard <= tv.mask; )
     {
         const unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&a.slots[h]);
         if (static_cast<uint32_t>(old >> 56) != a.tag)
@@ -57,20 +82,20 @@ __device__ __forceinline__ void index_insert(const AirArgs& a, uint32_t key)
             atomicAdd(&a.slots[h], 1ull);
             return;
         }
-        h = (h + 1) & a.slot_mask;
+        h = (h + 1) & tv.mask;
         ++guard;
     }
 }
 
-__device__ __forceinline__ uint32_t index_count(const AirArgs& a, uint32_t key)
+__device__ __forceinline__ uint32_t index_count(const AirArgs& a, const TableView& tv, uint32_t key)
 {
-    uint32_t h = slot_of(a, key);
-    for (uint32_t guard = 0; guard <= a.slot_mask; ++guard)
+    uint32_t h = slot_of(tv, key);
+    for (uint32_t guard = 0; guard <= tv.mask; ++guard)
     {
         const unsigned long long s = a.slots[h];
         if (static_cast<uint32_t>(s >> 56) != a.tag) return 0;
         if (static_cast<uint32_t>(s >> 24) == key) return static_cast<uint32_t>(s) & 0x00ffffffu;
-        h = (h + 1) & a.slot_mask;
+        h = (h + 1) & tv.mask;
     }
     return 0;
 }
@@ -98,26 +123,38 @@ __device__ __forceinline__ bool cell_of(const AirArgs& a, const uint2& p, int& g
     key = (static_cast<uint32_t>(gx) * a.ext[1] + static_cast<uint32_t>(gy)) * a.ext[2] + static_cast<uint32_t>(gz);
     return true;
 }
-// bit of a cell in the pre-filter: runs of 256 consecutive cell keys (the z column of ~25 adjacent y) share one
-// hashed 32-byte sector, so the own cell and its +-z / +-y neighbours are usually answered by one sector
-__device__ __forceinline__ uint32_t bit_of(const AirArgs& a, uint32_t key)
+// Bit of a cell in the pre-filter.  Sector = 4 x 4 x 16 cells (bit = (x & 3) * 64 + (y & 3) * 16 + (z & 15)), line =
+// 2 x 2 sectors = 8 x 8 x 16 cells, the line index is hashed into the table of 2^(filter_bits - 10) lines.
+__device__ __forceinline__ uint32_t bit_of(const AirArgs& a, int gx, int gy, int gz)
 {
-    return ((((key >> 8) * 0x85EBCA6Bu) >> a.bits_shift) << 8) | (key & 255u);
+    const uint32_t line = ((static_cast<uint32_t>(gx) >> 3) * a.lines_y + (static_cast<uint32_t>(gy) >> 3)) * a.lines_z +
+                          (static_cast<uint32_t>(gz) >> 4);
+    const uint32_t slot = (line * 0x85EBCA6Bu) >> a.bits_shift;
+    return (slot << 10) | ((static_cast<uint32_t>(gx) & 4u) << 7) | ((static_cast<uint32_t>(gy) & 4u) << 6) |
+           ((static_cast<uint32_t>(gx) & 3u) << 6) | ((static_cast<uint32_t>(gy) & 3u) << 4) | (static_cast<uint32_t>(gz) & 15u);
+}
+__device__ __forceinline__ uint32_t probe_bit(const AirArgs& a, int gx, int gy, int gz)
+{
+    const uint32_t h = bit_of(a, gx, gy, gz);
+    return (a.bits[h >> 5] >> (h & 31u)) & 1u;
+}
+__device__ __forceinline__ void ld_sector(const uint32_t* p, unsigned long long (&q)[4])
+{
+    // one 256-bit load: the four x-slices (64 bits = 4 y-columns of 16 z-bits) of a sector
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
 }
 
-// the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds, spatial_grid.rs:337-340),
-// in the fixed order -x +x -y +y -z +z
-__device__ __forceinline__ uint32_t neighbour_keys(const AirArgs& a, int gx, int gy, int gz, uint32_t key, uint32_t (&nk)[6])
+// validity of the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds,
+// spatial_grid.rs:337-340), in the fixed order -x +x -y +y -z +z
+__device__ __forceinline__ uint32_t neighbour_valid(const AirArgs& a, int gx, int gy, int gz)
 {
-    const uint32_t sx = static_cast<uint32_t>(a.ext[1]) * a.ext[2], sy = a.ext[2];
-    nk[0] = key - sx;
-    nk[1] = key + sx;
-    nk[2] = key - sy;
-    nk[3] = key + sy;
-    nk[4] = key - 1;
-    nk[5] = key + 1;
     return (gx > 0 ? 1u : 0u) | (gx < a.ext[0] - 1 ? 2u : 0u) | (gy > 0 ? 4u : 0u) | (gy < a.ext[1] - 1 ? 8u : 0u) |
            (gz > 0 ? 16u : 0u) | (gz < a.ext[2] - 1 ? 32u : 0u);
+}
+__device__ __forceinline__ uint32_t neighbour_key(const AirArgs& a, uint32_t key, int j)
+{
+    const uint32_t sx = static_cast<uint32_t>(a.ext[1]) * a.ext[2], sy = a.ext[2];
+    return j == 0 ? key - sx : (j == 1 ? key + sx : (j == 2 ? key - sy : (j == 3 ? key + sy : (j == 4 ? key - 1 : key + 1))));
 }
 
 // PreUpdate, pass 1: spatial_grid_update_system (spatial_grid.rs:434-443) - every aircraft sets the bit of its cell.
@@ -137,13 +174,44 @@ __global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
                 a.error[1] = static_cast<uint32_t>(i);
             continue;
         }
-        const uint32_t h = bit_of(a, key);
+        const uint32_t h = bit_of(a, gx, gy, gz);
         atomicOr(&a.bits[h >> 5], 1u << (h & 31));
     }
 }
 
-// PreUpdate, pass 2: aircraft with a possibly occupied neighbour cell enter the exact per-cell index.
-// One thread = 2 consecutive rows (one 128-bit position load, twelve independent bit probes in flight).
+// which of the six face-neighbour cells of (gx, gy, gz) show a set bit in the pre-filter
+__device__ __forceinline__ uint32_t probe_neighbours(const AirArgs& a, int gx, int gy, int gz)
+{
+    const uint32_t valid = neighbour_valid(a, gx, gy, gz);
+    const uint32_t h = bit_of(a, gx, gy, gz);
+    unsigned long long q[4];
+    ld_sector(a.bits + ((h >> 8) << 3), q);
+    const uint32_t xs = static_cast<uint32_t>(gx) & 3u, ys = static_cast<uint32_t>(gy) & 3u, zs = static_cast<uint32_t>(gz) & 15u;
+    // the neighbours that leave the sector: at most one per axis; their probes are issued before anything is consumed
+    const bool cx = xs == 0 ? (valid & 1u) != 0 : (xs == 3 ? (valid & 2u) != 0 : false);
+    const bool cy = ys == 0 ? (valid & 4u) != 0 : (ys == 3 ? (valid & 8u) != 0 : false);
+    const bool cz = zs == 0 ? (valid & 16u) != 0 : (zs == 15 ? (valid & 32u) != 0 : false);
+    uint32_t px = 0, py = 0, pz = 0;
+    if (cx) px = probe_bit(a, xs == 0 ? gx - 1 : gx + 1, gy, gz);
+    if (cy) py = probe_bit(a, gx, ys == 0 ? gy - 1 : gy + 1, gz);
+    if (cz) pz = probe_bit(a, gx, gy, zs == 0 ? gz - 1 : gz + 1);
+    const unsigned long long own = xs == 0 ? q[0] : (xs == 1 ? q[1] : (xs == 2 ? q[2] : q[3]));
+    const unsigned long long lo = xs == 1 ? q[0] : (xs == 2 ? q[1] : q[2]); // slice x-1 (xs > 0)
+    const unsigned long long hi = xs == 0 ? q[1] : (xs == 1 ? q[2] : q[3]); // slice x+1 (xs < 3)
+    const uint32_t sh = 16u * ys + zs;
+    uint32_t probe = 0;
+    probe |= (xs > 0 ? static_cast<uint32_t>(lo >> sh) & 1u : px) << 0;
+    probe |= (xs < 3 ? static_cast<uint32_t>(hi >> sh) & 1u : px) << 1;
+    probe |= (ys > 0 ? static_cast<uint32_t>(own >> ((sh - 16u) & 63u)) & 1u : py) << 2;
+    probe |= (ys < 3 ? static_cast<uint32_t>(own >> ((sh + 16u) & 63u)) & 1u : py) << 3;
+    probe |= (zs > 0 ? static_cast<uint32_t>(own >> ((sh - 1u) & 63u)) & 1u : pz) << 4;
+    probe |= (zs < 15 ? static_cast<uint32_t>(own >> ((sh + 1u) & 63u)) & 1u : pz) << 5;
+    return probe & valid;
+}
+
+// PreUpdate, pass 2: which aircraft have a possibly occupied neighbour cell?  One thread = 2 consecutive rows (one
+// 128-bit position load, two sector loads + the crossing probes in flight).  Also counts them (the exact table of
+// this step is sized from the count) and zeroes the next step's bitmap on the side.
 __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
 {
     const uint64_t npairs = (a.n + 1) >> 1;
@@ -160,6 +228,12 @@ __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
             a.acc[2] = 0;
         }
     }
+    if (a.bits_next)
+    {
+        uint4* z = reinterpret_cast<uint4*>(a.bits_next);
+        for (uint64_t i = first; i < a.bits_vec4; i += gstride) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint32_t flagged = 0;
     for (uint64_t q = first; q < npairs; q += gstride)
     {
         const uint64_t row0 = q * 2;
@@ -173,27 +247,77 @@ __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
         }
         else
             p[0] = p[1] = a.pos[row0];
-        uint32_t key[2] = {0, 0}, probe[2] = {0, 0};
+        uint32_t probe[2] = {0, 0};
 #pragma unroll
         for (int k = 0; k < 2; ++k)
         {
             int gx, gy, gz;
-            if ((k == 1 && !full) || (a.flags && !(a.flags[row0 + k] & 1u)) || !cell_of(a, p[k], gx, gy, gz, key[k])) continue;
-            uint32_t nk[6];
-            const uint32_t valid = neighbour_keys(a, gx, gy, gz, key[k], nk);
-#pragma unroll
-            for (int j = 0; j < 6; ++j)
-            {
-                const uint32_t h = bit_of(a, nk[j]);
-                if ((valid >> j) & 1u) probe[k] |= ((a.bits[h >> 5] >> (h & 31)) & 1u) << j;
-            }
+            uint32_t key;
+            if ((k == 1 && !full) || (a.flags && !(a.flags[row0 + k] & 1u)) || !cell_of(a, p[k], gx, gy, gz, key)) continue;
+            probe[k] = probe_neighbours(a, gx, gy, gz);
         }
-        if (probe[0]) index_insert(a, key[0]);
-        if (probe[1]) index_insert(a, key[1]);
+        flagged += (probe[0] ? 1u : 0u) + (probe[1] ? 1u : 0u);
         if (full)
             *reinterpret_cast<uint16_t*>(a.cand + row0) = static_cast<uint16_t>(probe[0] | (probe[1] << 8));
         else
             a.cand[row0] = static_cast<uint8_t>(probe[0]);
+    }
+    uint32_t v[1] = {flagged};
+    __shared__ uint32_t smem[32];
+    block_sum<uint32_t, 1>(v, smem);
+    if (threadIdx.x == 0 && v[0])
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.acc[4 + (a.step & 1u)]), static_cast<unsigned long long>(v[0]));
+}
+
+// PreUpdate, pass 3: the flagged aircraft enter the exact per-cell index.  A warp streams 256 candidate bytes (one
+// 64-bit load per lane), compacts the flagged rows into a shared-memory queue and deals them out one per lane, so the
+// insertions (a position load and a compare-and-swap each) run with full warps.
+__global__ void __launch_bounds__(kThreads) air_insert_kernel(AirArgs a)
+{
+    __shared__ uint32_t s_q[kThreads / 32][256];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    const TableView tv = table_view(a);
+    for (uint64_t base = warp0 * 256; base < a.n; base += nwarps * 256)
+    {
+        const uint64_t row0 = base + lane * 8;
+        unsigned long long c = 0;
+        if (row0 + 8 <= a.n)
+            c = *reinterpret_cast<const unsigned long long*>(a.cand + row0);
+        else
+            for (uint64_t k = 0; row0 + k < a.n; ++k) c |= static_cast<unsigned long long>(a.cand[row0 + k]) << (8 * k);
+        // 0x01 in every non-zero byte (the candidate masks use bits 0..5)
+        unsigned long long nz = c | (c >> 4);
+        nz |= nz >> 2;
+        nz |= nz >> 1;
+        nz &= 0x0101010101010101ull;
+        const uint32_t mine = __popcll(nz);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= static_cast<uint32_t>(o)) incl += up;
+        }
+        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        if (!total) continue;
+        uint32_t slot = incl - mine;
+        while (nz)
+        {
+            const uint32_t k = (__ffsll(static_cast<long long>(nz)) - 1) >> 3;
+            nz &= nz - 1;
+            s_q[warp][slot++] = static_cast<uint32_t>(row0 + k);
+        }
+        __syncwarp();
+        for (uint32_t j = lane; j < total; j += 32)
+        {
+            const uint32_t row = s_q[warp][j];
+            int gx, gy, gz;
+            uint32_t key;
+            if (cell_of(a, a.pos[row], gx, gy, gz, key)) index_insert(a, tv, key);
+        }
+        __syncwarp();
     }
 }
 
@@ -203,6 +327,13 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
     const uint64_t npairs = (a.n + 1) >> 1;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t conflicts = 0, indexed = 0;
+    TableView tv{0u, 0u};
+    if (a.do_check)
+    {
+        tv = table_view(a);
+        // the other parity's candidate counter is the next step's: leave it at zero
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.acc[4 + ((a.step + 1u) & 1u)] = 0;
+    }
     for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < npairs; q += gstride)
     {
         const uint64_t row0 = q * 2;
@@ -239,16 +370,11 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
                 {
                     indexed += 1;
                     uint32_t mask = (c2 >> (8 * k)) & 0xffu;
-                    if (mask)
+                    while (mask)
                     {
-                        uint32_t nk[6];
-                        neighbour_keys(a, gx, gy, gz, key, nk);
-                        while (mask)
-                        {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            conflicts += index_count(a, j == 0 ? nk[0] : (j == 1 ? nk[1] : (j == 2 ? nk[2] : (j == 3 ? nk[3] : (j == 4 ? nk[4] : nk[5])))));
-                        }
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        conflicts += index_count(a, tv, neighbour_key(a, key, j));
                     }
                 }
             }
@@ -275,7 +401,7 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
                 uint32_t key;
                 if (cell_of(a, p[k], gx, gy, gz, key))
                 {
-                    const uint32_t h = bit_of(a, key);
+                    const uint32_t h = bit_of(a, gx, gy, gz);
                     atomicOr(&a.bits_next[h >> 5], 1u << (h & 31));
                 }
                 else
@@ -319,7 +445,8 @@ void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out,
     air_spawn_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a, target_out, flags_out);
 }
 void launch_air_bits(const AirArgs& a, cudaStream_t st) { air_bits_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
-void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
+void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a); }
+void launch_air_insert(const AirArgs& a, cudaStream_t st) { air_insert_kernel<<<blocks_for((a.n + 7) / 8), kThreads, 0, st>>>(a); }
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
     air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);

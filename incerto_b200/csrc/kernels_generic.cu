@@ -433,6 +433,21 @@ __global__ void flush_kernel(uint4* p, size_t nvec, uint32_t value)
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += gstride) p[i] = v;
 }
 
+// second half of the flush: reading lines that are not in the L2 evicts (writes back) the dirty lines the first half
+// left behind, so the timed kernel starts with an L2 full of CLEAN foreign lines - a miss then costs a fetch, not a
+// write-back plus a fetch
+__global__ void flush_read_kernel(const uint4* p, size_t nvec, uint32_t* sink)
+{
+    const size_t gstride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    uint32_t acc = 0;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += gstride)
+    {
+        const uint4 v = ld_stream_v4(p + i);
+        acc |= v.x ^ v.y ^ v.z ^ v.w; // all four words hold the same value: always 0
+    }
+    if (acc) *sink = acc;
+}
+
 __global__ void step_increment_kernel(uint32_t* d_step) { *d_step += 1; }
 __global__ void set_u32_kernel(uint32_t* p, uint32_t v) { *p = v; }
 
@@ -669,6 +684,8 @@ void launch_iota_u32(uint32_t* p, uint64_t n, cudaStream_t st)
 void launch_flush(uint8_t* p, size_t bytes, uint32_t value, cudaStream_t st)
 {
     flush_kernel<<<kNumSMs * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(p), bytes / 16, value);
+    // the first half of the buffer was written first and has long left the L2: read it back
+    flush_read_kernel<<<kNumSMs * 8, 256, 0, st>>>(reinterpret_cast<const uint4*>(p), bytes / 32, reinterpret_cast<uint32_t*>(p));
 }
 
 void launch_step_increment(uint32_t* d_step, cudaStream_t st) { step_increment_kernel<<<1, 1, 0, st>>>(d_step); }

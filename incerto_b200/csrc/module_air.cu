@@ -181,7 +181,10 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.acc = am.d_acc;
     a.bits = am.d_bits;
     a.bits_next = am.do_check ? am.d_bits_next : nullptr;
-    a.bits_shift = 32 - (am.filter_bits - 8); // 256-bit sectors are hashed, the low 8 key bits index inside
+    a.bits_shift = 32 - (am.filter_bits - 10); // 1024-bit lines (8 x 8 x 16 cells) are hashed
+    a.lines_y = static_cast<uint32_t>(a.ext[1] + 7) >> 3;
+    a.lines_z = static_cast<uint32_t>(a.ext[2] + 15) >> 4;
+    a.bits_vec4 = (1ull << am.filter_bits) / 128;
     a.cand = am.d_cand;
     a.error = s.d_error;
 }
@@ -207,10 +210,14 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
                 KTimer kt(s, "air_bits", 8.0 * t.n);
                 launch_air_bits(a, s.stream);
             }
-            INC_CUDA(cudaMemsetAsync(am.d_bits_next, 0, (1ull << am.filter_bits) / 8, s.stream));
             {
+                // position r 8 B + candidate byte w; also zeroes the next step's bitmap (no memset between the steps)
                 KTimer kt(s, "air_candidates", 9.0 * t.n);
                 launch_air_candidates(a, s.stream);
+            }
+            {
+                KTimer kt(s, "air_insert", 1.0 * t.n);
+                launch_air_insert(a, s.stream);
             }
         }
         {

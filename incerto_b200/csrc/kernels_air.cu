@@ -23,6 +23,13 @@
 // line (8 x 8 x 16 cells), and the LINE is what gets hashed.  An aircraft fetches its own sector with one 256-bit
 // load and answers +-z and, unless it sits on a sector face, +-x / +-y from registers; only the crossing
 // neighbours (on average one per aircraft) cost another probe, and that one mostly hits the line just fetched.
+// Airspaces of at most 14 levels leave the top bits of every 16-bit z-column unused: two of the (2 x spare) spare
+// bits of a 32-bit word, chosen by a hash of the LINE id, are set together with the cell bit (same word, same
+// atomic) and required by every probe of that word - two different lines folded onto one hashed slot then only
+// produce a false positive when their signatures collide too (1 in C(2 spare, 2)): ~18 % of the aircraft flagged
+// by the plain bitmap at the reference density become the ~3 % that really have a face neighbour.
+// The flagged aircraft are appended to a compact list (row | neighbour mask << 32, one warp-aggregated atomic per
+// 64 rows); the insertions into the exact table and the exact look-ups run over that list with full warps.
 // The exact table is allocated for the worst case (every aircraft flagged) but a step only uses a power-of-two
 // prefix of it sized, on the device, by the number of aircraft the candidates kernel flagged (a few per cent at the
 // reference density): the slots it touches stay in the L2 instead of being 134 MB of random DRAM accesses.
@@ -133,15 +140,36 @@ __device__ __forceinline__ uint32_t bit_of(const AirArgs& a, int gx, int gy, int
     return (slot << 10) | ((static_cast<uint32_t>(gx) & 4u) << 7) | ((static_cast<uint32_t>(gy) & 4u) << 6) |
            ((static_cast<uint32_t>(gx) & 3u) << 6) | ((static_cast<uint32_t>(gy) & 3u) << 4) | (static_cast<uint32_t>(gz) & 15u);
 }
-__device__ __forceinline__ uint32_t probe_bit(const AirArgs& a, int gx, int gy, int gz)
-{
-    const uint32_t h = bit_of(a, gx, gy, gz);
-    return (a.bits[h >> 5] >> (h & 31u)) & 1u;
-}
 __device__ __forceinline__ void ld_sector(const uint32_t* p, unsigned long long (&q)[4])
 {
     // one 256-bit load: the four x-slices (64 bits = 4 y-columns of 16 z-bits) of a sector
     asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
+}
+
+// signature of a line: two of the spare bits of a 32-bit word (z-levels ext_z..15 of its two columns); 0 when the
+// airspace is too tall to leave any
+__device__ __forceinline__ uint32_t line_sig(const AirArgs& a, uint32_t line)
+{
+    if (a.sig_ns < 4u) return 0u;
+    const uint32_t spare = a.sig_ns >> 1, ez = 16u - spare;
+    const uint32_t h = line * 0x9E3779B1u;
+    const uint32_t i = __umulhi(h, a.sig_ns);
+    uint32_t j = i + 1u + __umulhi(h * 0x85EBCA6Bu + 0x7F4A7C15u, a.sig_ns - 1u);
+    j = j >= a.sig_ns ? j - a.sig_ns : j;
+    const uint32_t pi = i < spare ? ez + i : 16u + ez + (i - spare);
+    const uint32_t pj = j < spare ? ez + j : 16u + ez + (j - spare);
+    return (1u << pi) | (1u << pj);
+}
+__device__ __forceinline__ uint32_t line_of(const AirArgs& a, int gx, int gy, int gz)
+{
+    return ((static_cast<uint32_t>(gx) >> 3) * a.lines_y + (static_cast<uint32_t>(gy) >> 3)) * a.lines_z + (static_cast<uint32_t>(gz) >> 4);
+}
+
+// the word that holds a cell's bit | what must be set in it for "somebody may be there"
+__device__ __forceinline__ uint32_t need_of(const AirArgs& a, int gx, int gy, int gz, uint32_t& h)
+{
+    h = bit_of(a, gx, gy, gz);
+    return (1u << (h & 31u)) | line_sig(a, line_of(a, gx, gy, gz));
 }
 
 // validity of the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds,
@@ -174,12 +202,13 @@ __global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
                 a.error[1] = static_cast<uint32_t>(i);
             continue;
         }
-        const uint32_t h = bit_of(a, gx, gy, gz);
-        atomicOr(&a.bits[h >> 5], 1u << (h & 31));
+        uint32_t h;
+        const uint32_t need = need_of(a, gx, gy, gz, h);
+        atomicOr(&a.bits[h >> 5], need);
     }
 }
 
-// which of the six face-neighbour cells of (gx, gy, gz) show a set bit in the pre-filter
+// which of the six face-neighbour cells of (gx, gy, gz) may be occupied according to the pre-filter
 __device__ __forceinline__ uint32_t probe_neighbours(const AirArgs& a, int gx, int gy, int gz)
 {
     const uint32_t valid = neighbour_valid(a, gx, gy, gz);
@@ -191,21 +220,44 @@ __device__ __forceinline__ uint32_t probe_neighbours(const AirArgs& a, int gx, i
     const bool cx = xs == 0 ? (valid & 1u) != 0 : (xs == 3 ? (valid & 2u) != 0 : false);
     const bool cy = ys == 0 ? (valid & 4u) != 0 : (ys == 3 ? (valid & 8u) != 0 : false);
     const bool cz = zs == 0 ? (valid & 16u) != 0 : (zs == 15 ? (valid & 32u) != 0 : false);
-    uint32_t px = 0, py = 0, pz = 0;
-    if (cx) px = probe_bit(a, xs == 0 ? gx - 1 : gx + 1, gy, gz);
-    if (cy) py = probe_bit(a, gx, ys == 0 ? gy - 1 : gy + 1, gz);
-    if (cz) pz = probe_bit(a, gx, gy, zs == 0 ? gz - 1 : gz + 1);
+    uint32_t wx = 0, wy = 0, wz = 0, nx = 1, ny = 1, nz = 1; // word fetched | bits needed in it (need != 0: no hit by default)
+    if (cx)
+    {
+        uint32_t hh;
+        nx = need_of(a, xs == 0 ? gx - 1 : gx + 1, gy, gz, hh);
+        wx = a.bits[hh >> 5];
+    }
+    if (cy)
+    {
+        uint32_t hh;
+        ny = need_of(a, gx, ys == 0 ? gy - 1 : gy + 1, gz, hh);
+        wy = a.bits[hh >> 5];
+    }
+    if (cz)
+    {
+        uint32_t hh;
+        nz = need_of(a, gx, gy, zs == 0 ? gz - 1 : gz + 1, hh);
+        wz = a.bits[hh >> 5];
+    }
+    const uint32_t px = (wx & nx) == nx, py = (wy & ny) == ny, pz = (wz & nz) == nz;
+    // inside the sector: the same line, hence the same signature
+    const uint32_t sig = line_sig(a, line_of(a, gx, gy, gz));
     const unsigned long long own = xs == 0 ? q[0] : (xs == 1 ? q[1] : (xs == 2 ? q[2] : q[3]));
     const unsigned long long lo = xs == 1 ? q[0] : (xs == 2 ? q[1] : q[2]); // slice x-1 (xs > 0)
     const unsigned long long hi = xs == 0 ? q[1] : (xs == 1 ? q[2] : q[3]); // slice x+1 (xs < 3)
-    const uint32_t sh = 16u * ys + zs;
+    // (slice, column y', level z') -> the 32-bit word of that column pair must hold the cell bit and the signature
+    auto hit = [&](unsigned long long slice, uint32_t yy, uint32_t zz) -> uint32_t {
+        const uint32_t w = static_cast<uint32_t>(slice >> (32u * (yy >> 1)));
+        const uint32_t need = (1u << (16u * (yy & 1u) + zz)) | sig;
+        return (w & need) == need ? 1u : 0u;
+    };
     uint32_t probe = 0;
-    probe |= (xs > 0 ? static_cast<uint32_t>(lo >> sh) & 1u : px) << 0;
-    probe |= (xs < 3 ? static_cast<uint32_t>(hi >> sh) & 1u : px) << 1;
-    probe |= (ys > 0 ? static_cast<uint32_t>(own >> ((sh - 16u) & 63u)) & 1u : py) << 2;
-    probe |= (ys < 3 ? static_cast<uint32_t>(own >> ((sh + 16u) & 63u)) & 1u : py) << 3;
-    probe |= (zs > 0 ? static_cast<uint32_t>(own >> ((sh - 1u) & 63u)) & 1u : pz) << 4;
-    probe |= (zs < 15 ? static_cast<uint32_t>(own >> ((sh + 1u) & 63u)) & 1u : pz) << 5;
+    probe |= (xs > 0 ? hit(lo, ys, zs) : px) << 0;
+    probe |= (xs < 3 ? hit(hi, ys, zs) : px) << 1;
+    probe |= (ys > 0 ? hit(own, (ys - 1u) & 3u, zs) : py) << 2;
+    probe |= (ys < 3 ? hit(own, (ys + 1u) & 3u, zs) : py) << 3;
+    probe |= (zs > 0 ? hit(own, ys, (zs - 1u) & 15u) : pz) << 4;
+    probe |= (zs < 15 ? hit(own, ys, (zs + 1u) & 15u) : pz) << 5;
     return probe & valid;
 }
 
@@ -233,66 +285,40 @@ __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
         uint4* z = reinterpret_cast<uint4*>(a.bits_next);
         for (uint64_t i = first; i < a.bits_vec4; i += gstride) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    uint32_t flagged = 0;
-    for (uint64_t q = first; q < npairs; q += gstride)
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(&a.acc[4 + (a.step & 1u)]);
+    // every warp runs the same number of iterations (the shuffles below need all lanes)
+    const uint64_t iters = (npairs + gstride - 1) / gstride;
+    for (uint64_t it = 0; it < iters; ++it)
     {
+        const uint64_t q = first + it * gstride;
+        uint32_t probe[2] = {0, 0}, keys[2] = {0, 0};
         const uint64_t row0 = q * 2;
-        const bool full = row0 + 2 <= a.n;
-        uint2 p[2];
-        if (full)
+        if (q < npairs)
         {
-            const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
-            p[0] = make_uint2(v.x, v.y);
-            p[1] = make_uint2(v.z, v.w);
-        }
-        else
-            p[0] = p[1] = a.pos[row0];
-        uint32_t probe[2] = {0, 0};
+            const bool full = row0 + 2 <= a.n;
+            uint2 p[2];
+            if (full)
+            {
+                const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
+                p[0] = make_uint2(v.x, v.y);
+                p[1] = make_uint2(v.z, v.w);
+            }
+            else
+                p[0] = p[1] = a.pos[row0];
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-        {
-            int gx, gy, gz;
-            uint32_t key;
-            if ((k == 1 && !full) || (a.flags && !(a.flags[row0 + k] & 1u)) || !cell_of(a, p[k], gx, gy, gz, key)) continue;
-            probe[k] = probe_neighbours(a, gx, gy, gz);
+            for (int k = 0; k < 2; ++k)
+            {
+                int gx, gy, gz;
+                uint32_t key;
+                if ((k == 1 && !full) || (a.flags && !(a.flags[row0 + k] & 1u)) || !cell_of(a, p[k], gx, gy, gz, key)) continue;
+                probe[k] = probe_neighbours(a, gx, gy, gz);
+                keys[k] = key;
+            }
         }
-        flagged += (probe[0] ? 1u : 0u) + (probe[1] ? 1u : 0u);
-        if (full)
-            *reinterpret_cast<uint16_t*>(a.cand + row0) = static_cast<uint16_t>(probe[0] | (probe[1] << 8));
-        else
-            a.cand[row0] = static_cast<uint8_t>(probe[0]);
-    }
-    uint32_t v[1] = {flagged};
-    __shared__ uint32_t smem[32];
-    block_sum<uint32_t, 1>(v, smem);
-    if (threadIdx.x == 0 && v[0])
-        atomicAdd(reinterpret_cast<unsigned long long*>(&a.acc[4 + (a.step & 1u)]), static_cast<unsigned long long>(v[0]));
-}
-
-// PreUpdate, pass 3: the flagged aircraft enter the exact per-cell index.  A warp streams 256 candidate bytes (one
-// 64-bit load per lane), compacts the flagged rows into a shared-memory queue and deals them out one per lane, so the
-// insertions (a position load and a compare-and-swap each) run with full warps.
-__global__ void __launch_bounds__(kThreads) air_insert_kernel(AirArgs a)
-{
-    __shared__ uint32_t s_q[kThreads / 32][256];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-    const TableView tv = table_view(a);
-    for (uint64_t base = warp0 * 256; base < a.n; base += nwarps * 256)
-    {
-        const uint64_t row0 = base + lane * 8;
-        unsigned long long c = 0;
-        if (row0 + 8 <= a.n)
-            c = *reinterpret_cast<const unsigned long long*>(a.cand + row0);
-        else
-            for (uint64_t k = 0; row0 + k < a.n; ++k) c |= static_cast<unsigned long long>(a.cand[row0 + k]) << (8 * k);
-        // 0x01 in every non-zero byte (the candidate masks use bits 0..5)
-        unsigned long long nz = c | (c >> 4);
-        nz |= nz >> 2;
-        nz |= nz >> 1;
-        nz &= 0x0101010101010101ull;
-        const uint32_t mine = __popcll(nz);
+        // append the flagged aircraft (cell key | neighbour mask << 32) to the step's list: one atomic per warp iteration that saw any
+        const uint32_t mine = (probe[0] ? 1u : 0u) + (probe[1] ? 1u : 0u);
+        if (!__any_sync(kFullMask, mine != 0)) continue;
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
@@ -301,23 +327,24 @@ __global__ void __launch_bounds__(kThreads) air_insert_kernel(AirArgs a)
             if (lane >= static_cast<uint32_t>(o)) incl += up;
         }
         const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-        if (!total) continue;
-        uint32_t slot = incl - mine;
-        while (nz)
-        {
-            const uint32_t k = (__ffsll(static_cast<long long>(nz)) - 1) >> 3;
-            nz &= nz - 1;
-            s_q[warp][slot++] = static_cast<uint32_t>(row0 + k);
-        }
-        __syncwarp();
-        for (uint32_t j = lane; j < total; j += 32)
-        {
-            const uint32_t row = s_q[warp][j];
-            int gx, gy, gz;
-            uint32_t key;
-            if (cell_of(a, a.pos[row], gx, gy, gz, key)) index_insert(a, tv, key);
-        }
-        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, static_cast<unsigned long long>(total));
+        base = __shfl_sync(kFullMask, base, 0);
+        unsigned long long slot = base + (incl - mine);
+        if (probe[0]) a.list[slot++] = static_cast<unsigned long long>(keys[0]) | (static_cast<unsigned long long>(probe[0]) << 32);
+        if (probe[1]) a.list[slot] = static_cast<unsigned long long>(keys[1]) | (static_cast<unsigned long long>(probe[1]) << 32);
+    }
+}
+
+// PreUpdate, pass 3: the flagged aircraft enter the exact per-cell index (one list entry per thread: full warps).
+__global__ void __launch_bounds__(kThreads) air_insert_kernel(AirArgs a)
+{
+    const TableView tv = table_view(a);
+    const unsigned long long nf = a.acc[4 + (a.step & 1u)];
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nf; i += gstride)
+    {
+        index_insert(a, tv, static_cast<uint32_t>(a.list[i]));
     }
 }
 
@@ -327,11 +354,25 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
     const uint64_t npairs = (a.n + 1) >> 1;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t conflicts = 0, indexed = 0;
-    TableView tv{0u, 0u};
     if (a.do_check)
     {
-        tv = table_view(a);
-        // the other parity's candidate counter is the next step's: leave it at zero
+        // check_conflicts (:124-162): exact look-ups for the neighbour cells the pre-filter flagged, one list entry per
+        // thread (the list holds cell keys: nothing here reads the positions this kernel is about to move)
+        const TableView tv = table_view(a);
+        const unsigned long long nf = a.acc[4 + (a.step & 1u)];
+        for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nf; i += gstride)
+        {
+            const unsigned long long e = a.list[i];
+            const uint32_t key = static_cast<uint32_t>(e);
+            uint32_t mask = static_cast<uint32_t>(e >> 32);
+            while (mask)
+            {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                conflicts += index_count(a, tv, neighbour_key(a, key, j));
+            }
+        }
+        // the other parity's counter is the next step's: leave it at zero
         if (blockIdx.x == 0 && threadIdx.x == 0) a.acc[4 + ((a.step + 1u) & 1u)] = 0;
     }
     for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < npairs; q += gstride)
@@ -339,21 +380,19 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
         const uint64_t row0 = q * 2;
         const bool full = row0 + 2 <= a.n;
         uint2 p[2];
-        uint32_t t2, c2 = 0;
+        uint32_t t2;
         if (full)
         {
             const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
             p[0] = make_uint2(v.x, v.y);
             p[1] = make_uint2(v.z, v.w);
             t2 = *reinterpret_cast<const uint32_t*>(a.target + row0);
-            if (a.do_check) c2 = *reinterpret_cast<const uint16_t*>(a.cand + row0);
         }
         else
         {
             p[0] = a.pos[row0];
             p[1] = p[0];
             t2 = static_cast<uint16_t>(a.target[row0]);
-            if (a.do_check) c2 = a.cand[row0];
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k)
@@ -366,17 +405,7 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
             {
                 int gx, gy, gz;
                 uint32_t key;
-                if (cell_of(a, p[k], gx, gy, gz, key)) // aircraft outside the bounds were reported by the bits kernel
-                {
-                    indexed += 1;
-                    uint32_t mask = (c2 >> (8 * k)) & 0xffu;
-                    while (mask)
-                    {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        conflicts += index_count(a, tv, neighbour_key(a, key, j));
-                    }
-                }
+                if (cell_of(a, p[k], gx, gy, gz, key)) indexed += 1; // aircraft outside the bounds were reported by the bits kernel
             }
             if (a.do_move)
             {
@@ -401,8 +430,9 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
                 uint32_t key;
                 if (cell_of(a, p[k], gx, gy, gz, key))
                 {
-                    const uint32_t h = bit_of(a, gx, gy, gz);
-                    atomicOr(&a.bits_next[h >> 5], 1u << (h & 31));
+                    uint32_t h;
+                    const uint32_t need = need_of(a, gx, gy, gz, h);
+                    atomicOr(&a.bits_next[h >> 5], need);
                 }
                 else
                     atomicMax(reinterpret_cast<unsigned long long*>(&a.acc[2]), static_cast<unsigned long long>(row + 1));
@@ -446,7 +476,7 @@ void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out,
 }
 void launch_air_bits(const AirArgs& a, cudaStream_t st) { air_bits_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
 void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a); }
-void launch_air_insert(const AirArgs& a, cudaStream_t st) { air_insert_kernel<<<blocks_for((a.n + 7) / 8), kThreads, 0, st>>>(a); }
+void launch_air_insert(const AirArgs& a, cudaStream_t st) { air_insert_kernel<<<kNumSMs * 4, kThreads, 0, st>>>(a); }
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
     air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);

@@ -17,10 +17,14 @@ namespace
 __device__ __forceinline__ bool cell_key(const GridDesc& g, const int16_t* __restrict__ pos, uint32_t stride,
                                          uint64_t row, uint32_t& key)
 {
-    const int x = pos[row * stride + 0] - g.bmin[0];
-    const int y = pos[row * stride + 1] - g.bmin[1];
-    const int z = g.dim == 3 ? pos[row * stride + 2] - g.bmin[2] : 0;
-    if (x < 0 || x >= g.ext[0] || y < 0 || y >= g.ext[1] || z < 0 || z >= g.ext[2]) return false;
+    int x = pos[row * stride + 0] - g.bmin[0];
+    int y = pos[row * stride + 1] - g.bmin[1];
+    int z = g.dim == 3 ? pos[row * stride + 2] - g.bmin[2] : 0;
+    if (x < 0 || y < 0 || z < 0) return false;
+    x >>= g.shift;
+    y >>= g.shift;
+    z >>= g.shift;
+    if (x >= g.ext[0] || y >= g.ext[1] || z >= g.ext[2]) return false;
     key = (static_cast<uint32_t>(x) * g.ext[1] + static_cast<uint32_t>(y)) * g.ext[2] + static_cast<uint32_t>(z);
     return true;
 }

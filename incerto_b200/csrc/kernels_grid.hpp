@@ -13,7 +13,8 @@ struct GridDesc
 {
     uint32_t dim;    // 2 or 3
     int32_t bmin[3]; // inclusive lower bound (GridBounds::min, spatial_grid.rs:45-53)
-    int32_t ext[3];  // max - min + 1 per axis (1 for the unused z of a 2-D grid)
+    int32_t ext[3];  // max - min + 1 per axis (1 for the unused z of a 2-D grid), in units of 2^shift cells
+    uint32_t shift = 0; // cells are blocked 2^shift per axis before linearising (row sorts by tile; 0 for real grids)
 };
 
 // key = ((x - minx) * ext_y + (y - miny)) * ext_z + (z - minz)

@@ -23,11 +23,6 @@
 // line (8 x 8 x 16 cells), and the LINE is what gets hashed.  An aircraft fetches its own sector with one 256-bit
 // load and answers +-z and, unless it sits on a sector face, +-x / +-y from registers; only the crossing
 // neighbours (on average one per aircraft) cost another probe, and that one mostly hits the line just fetched.
-// Airspaces of at most 14 levels leave the top bits of every 16-bit z-column unused: two of the (2 x spare) spare
-// bits of a 32-bit word, chosen by a hash of the LINE id, are set together with the cell bit (same word, same
-// atomic) and required by every probe of that word - two different lines folded onto one hashed slot then only
-// produce a false positive when their signatures collide too (1 in C(2 spare, 2)): ~18 % of the aircraft flagged
-// by the plain bitmap at the reference density become the ~3 % that really have a face neighbour.
 // The flagged aircraft are appended to a compact list (row | neighbour mask << 32, one warp-aggregated atomic per
 // 64 rows); the insertions into the exact table and the exact look-ups run over that list with full warps.
 // The exact table is allocated for the worst case (every aircraft flagged) but a step only uses a power-of-two
@@ -146,30 +141,10 @@ __device__ __forceinline__ void ld_sector(const uint32_t* p, unsigned long long 
     asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
 }
 
-// signature of a line: two of the spare bits of a 32-bit word (z-levels ext_z..15 of its two columns); 0 when the
-// airspace is too tall to leave any
-__device__ __forceinline__ uint32_t line_sig(const AirArgs& a, uint32_t line)
+__device__ __forceinline__ uint32_t probe_bit(const AirArgs& a, int gx, int gy, int gz)
 {
-    if (a.sig_ns < 4u) return 0u;
-    const uint32_t spare = a.sig_ns >> 1, ez = 16u - spare;
-    const uint32_t h = line * 0x9E3779B1u;
-    const uint32_t i = __umulhi(h, a.sig_ns);
-    uint32_t j = i + 1u + __umulhi(h * 0x85EBCA6Bu + 0x7F4A7C15u, a.sig_ns - 1u);
-    j = j >= a.sig_ns ? j - a.sig_ns : j;
-    const uint32_t pi = i < spare ? ez + i : 16u + ez + (i - spare);
-    const uint32_t pj = j < spare ? ez + j : 16u + ez + (j - spare);
-    return (1u << pi) | (1u << pj);
-}
-__device__ __forceinline__ uint32_t line_of(const AirArgs& a, int gx, int gy, int gz)
-{
-    return ((static_cast<uint32_t>(gx) >> 3) * a.lines_y + (static_cast<uint32_t>(gy) >> 3)) * a.lines_z + (static_cast<uint32_t>(gz) >> 4);
-}
-
-// the word that holds a cell's bit | what must be set in it for "somebody may be there"
-__device__ __forceinline__ uint32_t need_of(const AirArgs& a, int gx, int gy, int gz, uint32_t& h)
-{
-    h = bit_of(a, gx, gy, gz);
-    return (1u << (h & 31u)) | line_sig(a, line_of(a, gx, gy, gz));
+    const uint32_t h = bit_of(a, gx, gy, gz);
+    return (a.bits[h >> 5] >> (h & 31u)) & 1u;
 }
 
 // validity of the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds,
@@ -202,62 +177,61 @@ __global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
                 a.error[1] = static_cast<uint32_t>(i);
             continue;
         }
-        uint32_t h;
-        const uint32_t need = need_of(a, gx, gy, gz, h);
-        atomicOr(&a.bits[h >> 5], need);
+        const uint32_t h = bit_of(a, gx, gy, gz);
+        atomicOr(&a.bits[h >> 5], 1u << (h & 31u));
     }
 }
 
-// which of the six face-neighbour cells of (gx, gy, gz) may be occupied according to the pre-filter
+// which of the six face-neighbour cells of (gx, gy, gz) show a set bit in the pre-filter
 __device__ __forceinline__ uint32_t probe_neighbours(const AirArgs& a, int gx, int gy, int gz)
 {
     const uint32_t valid = neighbour_valid(a, gx, gy, gz);
-    const uint32_t h = bit_of(a, gx, gy, gz);
+    const uint32_t line = ((static_cast<uint32_t>(gx) >> 3) * a.lines_y + (static_cast<uint32_t>(gy) >> 3)) * a.lines_z +
+                          (static_cast<uint32_t>(gz) >> 4);
+    // position inside the line: sector (bits 9, 8), x-slice (7, 6), y-column (5, 4), level (3..0)
+    const uint32_t low = ((static_cast<uint32_t>(gx) & 4u) << 7) | ((static_cast<uint32_t>(gy) & 4u) << 6) |
+                         ((static_cast<uint32_t>(gx) & 3u) << 6) | ((static_cast<uint32_t>(gy) & 3u) << 4) | (static_cast<uint32_t>(gz) & 15u);
+    const uint32_t h = (((line * 0x85EBCA6Bu) >> a.bits_shift) << 10) | low;
     unsigned long long q[4];
     ld_sector(a.bits + ((h >> 8) << 3), q);
     const uint32_t xs = static_cast<uint32_t>(gx) & 3u, ys = static_cast<uint32_t>(gy) & 3u, zs = static_cast<uint32_t>(gz) & 15u;
-    // the neighbours that leave the sector: at most one per axis; their probes are issued before anything is consumed
+    // the neighbours that leave the sector: at most one per axis; their probes are issued before anything is consumed.
+    // A crossing neighbour has the mirrored coordinate inside its sector (x-slice 0 <-> 3: flip bits 7, 6; ...) in the
+    // adjacent sector of the line (flip the sector bit) or, on a line face, in the adjacent line.
     const bool cx = xs == 0 ? (valid & 1u) != 0 : (xs == 3 ? (valid & 2u) != 0 : false);
     const bool cy = ys == 0 ? (valid & 4u) != 0 : (ys == 3 ? (valid & 8u) != 0 : false);
     const bool cz = zs == 0 ? (valid & 16u) != 0 : (zs == 15 ? (valid & 32u) != 0 : false);
-    uint32_t wx = 0, wy = 0, wz = 0, nx = 1, ny = 1, nz = 1; // word fetched | bits needed in it (need != 0: no hit by default)
+    auto cross = [&](uint32_t line_n, uint32_t flip) -> uint32_t {
+        const uint32_t hh = (((line_n * 0x85EBCA6Bu) >> a.bits_shift) << 10) | (low ^ flip);
+        return (a.bits[hh >> 5] >> (hh & 31u)) & 1u;
+    };
+    uint32_t px = 0, py = 0, pz = 0;
     if (cx)
     {
-        uint32_t hh;
-        nx = need_of(a, xs == 0 ? gx - 1 : gx + 1, gy, gz, hh);
-        wx = a.bits[hh >> 5];
+        const uint32_t g7 = static_cast<uint32_t>(gx) & 7u, step_l = a.lines_y * a.lines_z;
+        px = cross(xs == 0 ? (g7 == 0 ? line - step_l : line) : (g7 == 7 ? line + step_l : line), 0x2c0u);
     }
     if (cy)
     {
-        uint32_t hh;
-        ny = need_of(a, gx, ys == 0 ? gy - 1 : gy + 1, gz, hh);
-        wy = a.bits[hh >> 5];
+        const uint32_t g7 = static_cast<uint32_t>(gy) & 7u;
+        py = cross(ys == 0 ? (g7 == 0 ? line - a.lines_z : line) : (g7 == 7 ? line + a.lines_z : line), 0x130u);
     }
-    if (cz)
-    {
-        uint32_t hh;
-        nz = need_of(a, gx, gy, zs == 0 ? gz - 1 : gz + 1, hh);
-        wz = a.bits[hh >> 5];
-    }
-    const uint32_t px = (wx & nx) == nx, py = (wy & ny) == ny, pz = (wz & nz) == nz;
-    // inside the sector: the same line, hence the same signature
-    const uint32_t sig = line_sig(a, line_of(a, gx, gy, gz));
+    if (cz) pz = cross(zs == 0 ? line - 1u : line + 1u, 0x00fu);
+    // inside the sector: the own x-slice (64 bits = 4 y-columns of 16 levels) shifted so that the own bit lands on
+    // bit 0 (`up`: +z is bit 1, +y bit 16) and on bit 63 (`dn`: -z is bit 62, -y bit 47); the x neighbours sit at the
+    // own bit position of the adjacent slices
     const unsigned long long own = xs == 0 ? q[0] : (xs == 1 ? q[1] : (xs == 2 ? q[2] : q[3]));
     const unsigned long long lo = xs == 1 ? q[0] : (xs == 2 ? q[1] : q[2]); // slice x-1 (xs > 0)
     const unsigned long long hi = xs == 0 ? q[1] : (xs == 1 ? q[2] : q[3]); // slice x+1 (xs < 3)
-    // (slice, column y', level z') -> the 32-bit word of that column pair must hold the cell bit and the signature
-    auto hit = [&](unsigned long long slice, uint32_t yy, uint32_t zz) -> uint32_t {
-        const uint32_t w = static_cast<uint32_t>(slice >> (32u * (yy >> 1)));
-        const uint32_t need = (1u << (16u * (yy & 1u) + zz)) | sig;
-        return (w & need) == need ? 1u : 0u;
-    };
+    const uint32_t sh = 16u * ys + zs;
+    const unsigned long long up = own >> sh, dn = own << (63u - sh);
     uint32_t probe = 0;
-    probe |= (xs > 0 ? hit(lo, ys, zs) : px) << 0;
-    probe |= (xs < 3 ? hit(hi, ys, zs) : px) << 1;
-    probe |= (ys > 0 ? hit(own, (ys - 1u) & 3u, zs) : py) << 2;
-    probe |= (ys < 3 ? hit(own, (ys + 1u) & 3u, zs) : py) << 3;
-    probe |= (zs > 0 ? hit(own, ys, (zs - 1u) & 15u) : pz) << 4;
-    probe |= (zs < 15 ? hit(own, ys, (zs + 1u) & 15u) : pz) << 5;
+    probe |= (xs > 0 ? static_cast<uint32_t>(lo >> sh) & 1u : px) << 0;
+    probe |= (xs < 3 ? static_cast<uint32_t>(hi >> sh) & 1u : px) << 1;
+    probe |= (ys > 0 ? static_cast<uint32_t>(dn >> 47) & 1u : py) << 2;
+    probe |= (ys < 3 ? static_cast<uint32_t>(up >> 16) & 1u : py) << 3;
+    probe |= (zs > 0 ? static_cast<uint32_t>(dn >> 62) & 1u : pz) << 4;
+    probe |= (zs < 15 ? static_cast<uint32_t>(up >> 1) & 1u : pz) << 5;
     return probe & valid;
 }
 
@@ -430,9 +404,8 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
                 uint32_t key;
                 if (cell_of(a, p[k], gx, gy, gz, key))
                 {
-                    uint32_t h;
-                    const uint32_t need = need_of(a, gx, gy, gz, h);
-                    atomicOr(&a.bits_next[h >> 5], need);
+                    const uint32_t h = bit_of(a, gx, gy, gz);
+                    atomicOr(&a.bits_next[h >> 5], 1u << (h & 31u));
                 }
                 else
                     atomicMax(reinterpret_cast<unsigned long long*>(&a.acc[2]), static_cast<unsigned long long>(row + 1));
@@ -476,7 +449,7 @@ void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out,
 }
 void launch_air_bits(const AirArgs& a, cudaStream_t st) { air_bits_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
 void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a); }
-void launch_air_insert(const AirArgs& a, cudaStream_t st) { air_insert_kernel<<<kNumSMs * 4, kThreads, 0, st>>>(a); }
+void launch_air_insert(const AirArgs& a, cudaStream_t st) { air_insert_kernel<<<kNumSMs * 8, kThreads, 0, st>>>(a); }
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
     air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);

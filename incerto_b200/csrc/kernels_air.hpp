@@ -37,7 +37,6 @@ struct AirArgs
     uint32_t lines_y, lines_z; // lines (8 x 8 x 16 cells) along y and z
     uint64_t bits_vec4;  // 16-byte units of one bitmap
     unsigned long long* list; // this step's flagged aircraft: cell key | mask of the neighbour cells (-x +x -y +y -z +z) that may be occupied << 32
-    uint32_t sig_ns;     // 2 x spare z-bits per 16-bit column (signature positions per word); < 4: no signatures
     uint32_t* error;
 };
 

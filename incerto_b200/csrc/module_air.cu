@@ -189,11 +189,6 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.lines_z = static_cast<uint32_t>(a.ext[2] + 15) >> 4;
     a.bits_vec4 = (1ull << am.filter_bits) / 128;
     a.list = am.d_list;
-    {
-        // spare z-bits of a 16-bit column carry the line signatures (kernels_air.cu)
-        const uint32_t spare = (a.lines_z == 1 && a.ext[2] < 16) ? static_cast<uint32_t>(16 - a.ext[2]) : 0u;
-        a.sig_ns = 2 * spare;
-    }
     a.error = s.d_error;
 }
 

@@ -110,21 +110,18 @@ int32_t air_bind(Sim& s)
     return air_sort_rows(s);
 }
 
-// rows in tile order (8 x 8 columns = the (x, y) footprint of one bitmap line): the aircraft of a warp then touch a
-// handful of lines instead of one each.  Aircraft drift one cell per step at most, so the order set up at spawn holds
-// for the example's 50 steps and decays gracefully after.
+// rows in (x, y) column order: neighbouring aircraft then probe neighbouring sectors of the pre-filter
 static int32_t air_sort_rows(Sim& s)
 {
     AirModule& am = s.mods->air;
     if (am.table < 0 || am.grid < 0 || !am.do_check) return INCERTO_OK;
     const GridInst& gi = s.grids[am.grid];
     GridDesc g;
-    g.dim = 2; // z (lane 2) is ignored: one sort bin per tile of columns
-    g.shift = 3;
+    g.dim = 2; // z (lane 2) is ignored: one sort bin per column
     for (int d = 0; d < 3; ++d)
     {
         g.bmin[d] = d < 2 ? gi.bmin[d] : 0;
-        g.ext[d] = d < 2 ? ((gi.bmax[d] - gi.bmin[d] + 1) + 7) >> 3 : 1;
+        g.ext[d] = d < 2 ? gi.bmax[d] - gi.bmin[d] + 1 : 1;
     }
     return table_sort_by_cell(s, am.table, am.comp_pos, g, {});
 }
@@ -184,7 +181,7 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.acc = am.d_acc;
     a.bits = am.d_bits;
     a.bits_next = am.do_check ? am.d_bits_next : nullptr;
-    a.bits_shift = 32 - (am.filter_bits - 10); // 1024-bit lines (8 x 8 x 16 cells) are hashed
+    a.bits_shift = 32 - (am.filter_bits - 8); // 256-bit sectors are hashed, the low 8 key bits index inside
     a.lines_y = static_cast<uint32_t>(a.ext[1] + 7) >> 3;
     a.lines_z = static_cast<uint32_t>(a.ext[2] + 15) >> 4;
     a.bits_vec4 = (1ull << am.filter_bits) / 128;

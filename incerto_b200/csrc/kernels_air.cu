@@ -18,15 +18,6 @@
 // 255 steps), (3) the conflict count: exact lookups for the flagged neighbour cells only.  Two aircraft in
 // face-adjacent cells always flag each other (the bitmap has no false negatives), so both are in the table.
 //
-// Round 2 measured and dropped a blocked bitmap (4 x 4 x 16-cell sectors fetched with one 256-bit load, crossing
-// neighbours probed separately): fewer loads, but 1.7 x the instructions and a third more false positives (the five
-// unused z-levels of every 16-bit column) - 80 us against the 83 us of this layout (profiles/experiments/).
-// The flagged aircraft are appended to a compact list (row | neighbour mask << 32, one warp-aggregated atomic per
-// 64 rows); the insertions into the exact table and the exact look-ups run over that list with full warps.
-// The exact table is allocated for the worst case (every aircraft flagged) but a step only uses a power-of-two
-// prefix of it sized, on the device, by the number of aircraft the candidates kernel flagged (a few per cent at the
-// reference density): the slots it touches stay in the L2 instead of being 134 MB of random DRAM accesses.
-//
 // Draw contract:
 //   spawn  aircraft uid: a = philox(key[ASPW], (uid,0,0,0)), b = philox(key[ASPW], (uid,0,0,1));
 //          x = mulhi(a.x,SIZE), y = mulhi(a.y,SIZE), z = mulhi(a.z,HEIGHT), type = mulhi(a.w,3), target = mulhi(b.x,HEIGHT)
@@ -41,36 +32,19 @@ namespace
 {
 
 constexpr int kThreads = 256;
-constexpr uint32_t kStage = 2048; // staged list entries per block (16 KB)
 
 __device__ __forceinline__ int lane16(uint32_t w, int hi) { return static_cast<int16_t>(hi ? (w >> 16) : (w & 0xffffu)); }
 
-// The part of the exact table this step uses: the smallest power of two >= 4 x the aircraft flagged by the
-// candidates kernel (counted in acc[4 + (step & 1)]), at least 1024 slots, at most the whole allocation.
-struct TableView
+__device__ __forceinline__ uint32_t slot_of(const AirArgs& a, uint32_t key)
 {
-    uint32_t mask, shift;
-};
-__device__ __forceinline__ TableView table_view(const AirArgs& a)
-{
-    const unsigned long long nf = a.acc[4 + (a.step & 1u)];
-    const unsigned long long want = nf * 4ull > 1024ull ? nf * 4ull : 1024ull;
-    uint32_t bits = 64u - static_cast<uint32_t>(__clzll(static_cast<long long>(want - 1ull)));
-    const uint32_t max_bits = 32u - a.slot_shift;
-    bits = bits > max_bits ? max_bits : bits;
-    TableView v;
-    v.mask = (1u << bits) - 1u;
-    v.shift = 32u - bits;
-    return v;
+    return (key * 0x9E3779B1u) >> a.slot_shift;
 }
 
-__device__ __forceinline__ uint32_t slot_of(const TableView& tv, uint32_t key) { return (key * 0x9E3779B1u) >> tv.shift; }
-
-__device__ __forceinline__ void index_insert(const AirArgs& a, const TableView& tv, uint32_t key)
+__device__ __forceinline__ void index_insert(const AirArgs& a, uint32_t key)
 {
-    uint32_t h = slot_of(tv, key);
+    uint32_t h = slot_of(a, key);
     const unsigned long long fresh = (static_cast<unsigned long long>(a.tag) << 56) | (static_cast<unsigned long long>(key) << 24) | 1ull;
-    for (uint32_t guard = 0; guard <= tv.mask; )
+    for (uint32_t guard = 0; guard <= a.slot_mask; )
     {
         const unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&a.slots[h]);
         if (static_cast<uint32_t>(old >> 56) != a.tag)
@@ -83,20 +57,20 @@ __device__ __forceinline__ void index_insert(const AirArgs& a, const TableView& 
             atomicAdd(&a.slots[h], 1ull);
             return;
         }
-        h = (h + 1) & tv.mask;
+        h = (h + 1) & a.slot_mask;
         ++guard;
     }
 }
 
-__device__ __forceinline__ uint32_t index_count(const AirArgs& a, const TableView& tv, uint32_t key)
+__device__ __forceinline__ uint32_t index_count(const AirArgs& a, uint32_t key)
 {
-    uint32_t h = slot_of(tv, key);
-    for (uint32_t guard = 0; guard <= tv.mask; ++guard)
+    uint32_t h = slot_of(a, key);
+    for (uint32_t guard = 0; guard <= a.slot_mask; ++guard)
     {
         const unsigned long long s = a.slots[h];
         if (static_cast<uint32_t>(s >> 56) != a.tag) return 0;
         if (static_cast<uint32_t>(s >> 24) == key) return static_cast<uint32_t>(s) & 0x00ffffffu;
-        h = (h + 1) & tv.mask;
+        h = (h + 1) & a.slot_mask;
     }
     return 0;
 }
@@ -131,17 +105,19 @@ __device__ __forceinline__ uint32_t bit_of(const AirArgs& a, uint32_t key)
     return ((((key >> 8) * 0x85EBCA6Bu) >> a.bits_shift) << 8) | (key & 255u);
 }
 
-// validity of the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds,
-// spatial_grid.rs:337-340), in the fixed order -x +x -y +y -z +z
-__device__ __forceinline__ uint32_t neighbour_valid(const AirArgs& a, int gx, int gy, int gz)
-{
-    return (gx > 0 ? 1u : 0u) | (gx < a.ext[0] - 1 ? 2u : 0u) | (gy > 0 ? 4u : 0u) | (gy < a.ext[1] - 1 ? 8u : 0u) |
-           (gz > 0 ? 16u : 0u) | (gz < a.ext[2] - 1 ? 32u : 0u);
-}
-__device__ __forceinline__ uint32_t neighbour_key(const AirArgs& a, uint32_t key, int j)
+// the six face-neighbour cells inside the grid bounds (neighbors_of filters by bounds, spatial_grid.rs:337-340),
+// in the fixed order -x +x -y +y -z +z
+__device__ __forceinline__ uint32_t neighbour_keys(const AirArgs& a, int gx, int gy, int gz, uint32_t key, uint32_t (&nk)[6])
 {
     const uint32_t sx = static_cast<uint32_t>(a.ext[1]) * a.ext[2], sy = a.ext[2];
-    return j == 0 ? key - sx : (j == 1 ? key + sx : (j == 2 ? key - sy : (j == 3 ? key + sy : (j == 4 ? key - 1 : key + 1))));
+    nk[0] = key - sx;
+    nk[1] = key + sx;
+    nk[2] = key - sy;
+    nk[3] = key + sy;
+    nk[4] = key - 1;
+    nk[5] = key + 1;
+    return (gx > 0 ? 1u : 0u) | (gx < a.ext[0] - 1 ? 2u : 0u) | (gy > 0 ? 4u : 0u) | (gy < a.ext[1] - 1 ? 8u : 0u) |
+           (gz > 0 ? 16u : 0u) | (gz < a.ext[2] - 1 ? 32u : 0u);
 }
 
 // PreUpdate, pass 1: spatial_grid_update_system (spatial_grid.rs:434-443) - every aircraft sets the bit of its cell.
@@ -162,27 +138,12 @@ __global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
             continue;
         }
         const uint32_t h = bit_of(a, key);
-        atomicOr(&a.bits[h >> 5], 1u << (h & 31u));
+        atomicOr(&a.bits[h >> 5], 1u << (h & 31));
     }
 }
 
-// which of the six face-neighbour cells show a set bit in the pre-filter (six independent probes in flight)
-__device__ __forceinline__ uint32_t probe_neighbours(const AirArgs& a, int gx, int gy, int gz, uint32_t key)
-{
-    const uint32_t valid = neighbour_valid(a, gx, gy, gz);
-    uint32_t probe = 0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-    {
-        const uint32_t h = bit_of(a, neighbour_key(a, key, j));
-        if ((valid >> j) & 1u) probe |= ((a.bits[h >> 5] >> (h & 31u)) & 1u) << j;
-    }
-    return probe;
-}
-
-// PreUpdate, pass 2: which aircraft have a possibly occupied neighbour cell?  One thread = 2 consecutive rows (one
-// 128-bit position load, two sector loads + the crossing probes in flight).  Also counts them (the exact table of
-// this step is sized from the count) and zeroes the next step's bitmap on the side.
+// PreUpdate, pass 2: aircraft with a possibly occupied neighbour cell enter the exact per-cell index.
+// One thread = 2 consecutive rows (one 128-bit position load, twelve independent bit probes in flight).
 __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
 {
     const uint64_t npairs = (a.n + 1) >> 1;
@@ -199,82 +160,40 @@ __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
             a.acc[2] = 0;
         }
     }
-    if (a.bits_next)
+    for (uint64_t q = first; q < npairs; q += gstride)
     {
-        uint4* z = reinterpret_cast<uint4*>(a.bits_next);
-        for (uint64_t i = first; i < a.bits_vec4; i += gstride) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    // flagged aircraft (cell key | neighbour mask << 32) are staged per block and appended to the step's list with
-    // one atomic per block: every warp hammering one counter showed up as a quarter of this kernel's stall samples
-    __shared__ unsigned long long s_list[kStage];
-    __shared__ uint32_t s_n;
-    __shared__ unsigned long long s_base;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    unsigned long long* counter = reinterpret_cast<unsigned long long*>(&a.acc[4 + (a.step & 1u)]);
-    auto flush = [&]() {
-        // all threads of the block
-        __syncthreads();
-        const uint32_t n = s_n < kStage ? s_n : kStage;
-        if (threadIdx.x == 0) s_base = n ? atomicAdd(counter, static_cast<unsigned long long>(n)) : 0ull;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a.list[s_base + i] = s_list[i];
-        __syncthreads();
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-    };
-    // every thread of the block runs the same number of iterations (the block-wide flush needs all of them)
-    const uint64_t iters = (npairs + gstride - 1) / gstride;
-    for (uint64_t it = 0; it < iters; ++it)
-    {
-        // room for this iteration's worst case (2 entries per thread)?
-        if (s_n + 2 * kThreads > kStage) flush();
-        const uint64_t q = first + it * gstride;
-        uint32_t probe[2] = {0, 0}, keys[2] = {0, 0};
         const uint64_t row0 = q * 2;
-        if (q < npairs)
+        const bool full = row0 + 2 <= a.n;
+        uint2 p[2];
+        if (full)
         {
-            const bool full = row0 + 2 <= a.n;
-            uint2 p[2];
-            if (full)
-            {
-                const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
-                p[0] = make_uint2(v.x, v.y);
-                p[1] = make_uint2(v.z, v.w);
-            }
-            else
-                p[0] = p[1] = a.pos[row0];
+            const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
+            p[0] = make_uint2(v.x, v.y);
+            p[1] = make_uint2(v.z, v.w);
+        }
+        else
+            p[0] = p[1] = a.pos[row0];
+        uint32_t key[2] = {0, 0}, probe[2] = {0, 0};
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < 2; ++k)
+        {
+            int gx, gy, gz;
+            if ((k == 1 && !full) || (a.flags && !(a.flags[row0 + k] & 1u)) || !cell_of(a, p[k], gx, gy, gz, key[k])) continue;
+            uint32_t nk[6];
+            const uint32_t valid = neighbour_keys(a, gx, gy, gz, key[k], nk);
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
             {
-                int gx, gy, gz;
-                uint32_t key;
-                if ((k == 1 && !full) || (a.flags && !(a.flags[row0 + k] & 1u)) || !cell_of(a, p[k], gx, gy, gz, key)) continue;
-                probe[k] = probe_neighbours(a, gx, gy, gz, key);
-                keys[k] = key;
+                const uint32_t h = bit_of(a, nk[j]);
+                if ((valid >> j) & 1u) probe[k] |= ((a.bits[h >> 5] >> (h & 31)) & 1u) << j;
             }
         }
-        const uint32_t mine = (probe[0] ? 1u : 0u) + (probe[1] ? 1u : 0u);
-        if (mine)
-        {
-            uint32_t slot = atomicAdd(&s_n, mine);
-            if (probe[0]) s_list[slot++] = static_cast<unsigned long long>(keys[0]) | (static_cast<unsigned long long>(probe[0]) << 32);
-            if (probe[1]) s_list[slot] = static_cast<unsigned long long>(keys[1]) | (static_cast<unsigned long long>(probe[1]) << 32);
-        }
-        __syncthreads(); // s_n is read by everybody at the top of the next iteration
-    }
-    flush();
-}
-
-// PreUpdate, pass 3: the flagged aircraft enter the exact per-cell index (one list entry per thread: full warps).
-__global__ void __launch_bounds__(kThreads) air_insert_kernel(AirArgs a)
-{
-    const TableView tv = table_view(a);
-    const unsigned long long nf = a.acc[4 + (a.step & 1u)];
-    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nf; i += gstride)
-    {
-        index_insert(a, tv, static_cast<uint32_t>(a.list[i]));
+        if (probe[0]) index_insert(a, key[0]);
+        if (probe[1]) index_insert(a, key[1]);
+        if (full)
+            *reinterpret_cast<uint16_t*>(a.cand + row0) = static_cast<uint16_t>(probe[0] | (probe[1] << 8));
+        else
+            a.cand[row0] = static_cast<uint8_t>(probe[0]);
     }
 }
 
@@ -284,45 +203,26 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
     const uint64_t npairs = (a.n + 1) >> 1;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t conflicts = 0, indexed = 0;
-    if (a.do_check)
-    {
-        // check_conflicts (:124-162): exact look-ups for the neighbour cells the pre-filter flagged, one list entry per
-        // thread (the list holds cell keys: nothing here reads the positions this kernel is about to move)
-        const TableView tv = table_view(a);
-        const unsigned long long nf = a.acc[4 + (a.step & 1u)];
-        for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nf; i += gstride)
-        {
-            const unsigned long long e = a.list[i];
-            const uint32_t key = static_cast<uint32_t>(e);
-            uint32_t mask = static_cast<uint32_t>(e >> 32);
-            while (mask)
-            {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                conflicts += index_count(a, tv, neighbour_key(a, key, j));
-            }
-        }
-        // the other parity's counter is the next step's: leave it at zero
-        if (blockIdx.x == 0 && threadIdx.x == 0) a.acc[4 + ((a.step + 1u) & 1u)] = 0;
-    }
     for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < npairs; q += gstride)
     {
         const uint64_t row0 = q * 2;
         const bool full = row0 + 2 <= a.n;
         uint2 p[2];
-        uint32_t t2;
+        uint32_t t2, c2 = 0;
         if (full)
         {
             const uint4 v = *reinterpret_cast<const uint4*>(a.pos + row0);
             p[0] = make_uint2(v.x, v.y);
             p[1] = make_uint2(v.z, v.w);
             t2 = *reinterpret_cast<const uint32_t*>(a.target + row0);
+            if (a.do_check) c2 = *reinterpret_cast<const uint16_t*>(a.cand + row0);
         }
         else
         {
             p[0] = a.pos[row0];
             p[1] = p[0];
             t2 = static_cast<uint16_t>(a.target[row0]);
+            if (a.do_check) c2 = a.cand[row0];
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k)
@@ -335,7 +235,22 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
             {
                 int gx, gy, gz;
                 uint32_t key;
-                if (cell_of(a, p[k], gx, gy, gz, key)) indexed += 1; // aircraft outside the bounds were reported by the bits kernel
+                if (cell_of(a, p[k], gx, gy, gz, key)) // aircraft outside the bounds were reported by the bits kernel
+                {
+                    indexed += 1;
+                    uint32_t mask = (c2 >> (8 * k)) & 0xffu;
+                    if (mask)
+                    {
+                        uint32_t nk[6];
+                        neighbour_keys(a, gx, gy, gz, key, nk);
+                        while (mask)
+                        {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            conflicts += index_count(a, j == 0 ? nk[0] : (j == 1 ? nk[1] : (j == 2 ? nk[2] : (j == 3 ? nk[3] : (j == 4 ? nk[4] : nk[5])))));
+                        }
+                    }
+                }
             }
             if (a.do_move)
             {
@@ -361,7 +276,7 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
                 if (cell_of(a, p[k], gx, gy, gz, key))
                 {
                     const uint32_t h = bit_of(a, key);
-                    atomicOr(&a.bits_next[h >> 5], 1u << (h & 31u));
+                    atomicOr(&a.bits_next[h >> 5], 1u << (h & 31));
                 }
                 else
                     atomicMax(reinterpret_cast<unsigned long long*>(&a.acc[2]), static_cast<unsigned long long>(row + 1));
@@ -404,8 +319,7 @@ void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out,
     air_spawn_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a, target_out, flags_out);
 }
 void launch_air_bits(const AirArgs& a, cudaStream_t st) { air_bits_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
-void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a); }
-void launch_air_insert(const AirArgs& a, cudaStream_t st) { air_insert_kernel<<<kNumSMs * 8, kThreads, 0, st>>>(a); }
+void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
     air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);

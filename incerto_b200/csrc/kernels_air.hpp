@@ -27,23 +27,19 @@ struct AirArgs
     uint32_t slot_mask; // slots - 1 (power of two)
     uint32_t slot_shift; // 32 - log2(slots)
     uint32_t tag;       // 1..255, changes every step; slots with another tag are empty
-    uint64_t* acc;      // [0] conflicts of this step (each pair counted twice), [1] aircraft indexed, [2] row + 1 of an aircraft
-                        // that left the bounds, [4 + (step & 1)] aircraft flagged by this step's candidates kernel
+    uint64_t* acc;      // [0] conflicts of this step (each pair counted twice), [1] aircraft indexed, [2] row + 1 of an aircraft that left the bounds
     // occupancy pre-filter: one bit per hashed cell (no false negatives); only aircraft that see a set bit
     // in one of their six face-neighbour cells enter the exact index above
     uint32_t* bits;
     uint32_t* bits_next; // bitmap of the next step, filled by the step kernel from the moved positions (nullptr: not wanted)
-    uint32_t bits_shift; // 32 - log2(number of 1024-bit lines)
-    uint32_t lines_y, lines_z; // lines (8 x 8 x 16 cells) along y and z
-    uint64_t bits_vec4;  // 16-byte units of one bitmap
-    unsigned long long* list; // this step's flagged aircraft: cell key | mask of the neighbour cells (-x +x -y +y -z +z) that may be occupied << 32
+    uint32_t bits_shift; // 32 - log2(number of bits)
+    uint8_t* cand;       // per row: which of the six neighbour cells (-x +x -y +y -z +z) showed a set bit
     uint32_t* error;
 };
 
 void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out, cudaStream_t st);
 void launch_air_bits(const AirArgs& a, cudaStream_t st);
 void launch_air_candidates(const AirArgs& a, cudaStream_t st);
-void launch_air_insert(const AirArgs& a, cudaStream_t st);
 void launch_air_step(const AirArgs& a, cudaStream_t st);
 
 } // namespace incerto

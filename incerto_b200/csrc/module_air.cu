@@ -105,7 +105,7 @@ int32_t air_bind(Sim& s)
         am.filter_bits = fb;
         INC_CUDA(cudaMalloc(&am.d_bits, (1ull << fb) / 8));
         INC_CUDA(cudaMalloc(&am.d_bits_next, (1ull << fb) / 8));
-        INC_CUDA(cudaMalloc(&am.d_list, std::max<uint64_t>(t.n, 2) * 8));
+        INC_CUDA(cudaMalloc(&am.d_cand, std::max<uint64_t>(t.n, 2)));
     }
     return air_sort_rows(s);
 }
@@ -143,9 +143,9 @@ void air_free(Sim& s)
     cudaFree(am.d_bits);
     cudaFree(am.d_bits_next);
     am.d_bits_next = nullptr;
-    cudaFree(am.d_list);
+    cudaFree(am.d_cand);
     am.d_bits = nullptr;
-    am.d_list = nullptr;
+    am.d_cand = nullptr;
     am.d_slots = nullptr;
     am.d_acc = nullptr;
 }
@@ -182,10 +182,7 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.bits = am.d_bits;
     a.bits_next = am.do_check ? am.d_bits_next : nullptr;
     a.bits_shift = 32 - (am.filter_bits - 8); // 256-bit sectors are hashed, the low 8 key bits index inside
-    a.lines_y = static_cast<uint32_t>(a.ext[1] + 7) >> 3;
-    a.lines_z = static_cast<uint32_t>(a.ext[2] + 15) >> 4;
-    a.bits_vec4 = (1ull << am.filter_bits) / 128;
-    a.list = am.d_list;
+    a.cand = am.d_cand;
     a.error = s.d_error;
 }
 
@@ -210,18 +207,14 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
                 KTimer kt(s, "air_bits", 8.0 * t.n);
                 launch_air_bits(a, s.stream);
             }
+            INC_CUDA(cudaMemsetAsync(am.d_bits_next, 0, (1ull << am.filter_bits) / 8, s.stream));
             {
-                // position r 8 B (+ the list of flagged aircraft); also zeroes the next step's bitmap
-                KTimer kt(s, "air_candidates", 8.0 * t.n);
+                KTimer kt(s, "air_candidates", 9.0 * t.n);
                 launch_air_candidates(a, s.stream);
-            }
-            {
-                KTimer kt(s, "air_insert", 0.0);
-                launch_air_insert(a, s.stream);
             }
         }
         {
-            KTimer kt(s, "air_step", (am.do_move ? 18.0 : 8.0) * t.n);
+            KTimer kt(s, "air_step", (am.do_move ? 18.0 : 8.0) * t.n + (am.do_check ? 1.0 : 0.0) * t.n);
             launch_air_step(a, s.stream);
         }
         INC_CUDA(cudaGetLastError());

@@ -103,7 +103,7 @@ struct AirModule
     uint32_t* d_bits_next = nullptr;      // the same for the next step, filled by the step kernel
     bool bits_ready = false;              // d_bits already describes the current positions
     uint32_t filter_bits = 0;
-    unsigned long long* d_list = nullptr; // this step's flagged aircraft (cell key | neighbour mask << 32), capacity n
+    uint8_t* d_cand = nullptr;            // per row: neighbour cells that showed a set bit
     uint64_t* d_acc = nullptr;            // [0] conflicts of the last step (pairs counted twice), [1] aircraft indexed
 };
 

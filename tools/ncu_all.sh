@@ -6,11 +6,10 @@ set -u
 mkdir -p gpurun_out
 for w in "$@"; do
   extra=""
-  cnt=2
   name=$w
   case $w in
     spatial) pat='regex:spatial_(prepare|interact)'; skip=24;;
-    air) pat='regex:air_(candidates|insert|step)'; skip=36; cnt=3;;
+    air) pat='regex:air_(candidates|step)'; skip=24;;
     traders) pat='regex:traders_step'; skip=12;;
     pandemic) pat='regex:pandemic_(move|interact)'; skip=24;;
     forest) pat='regex:forest_step'; skip=12;;
@@ -29,6 +28,6 @@ for w in "$@"; do
       echo "launches rc=$?"; continue;;
   esac
   python tools/prof_workload.py $name $extra > gpurun_out/plain_$w.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k "$pat" -s $skip -c $cnt -f -o gpurun_out/r02_$w python tools/prof_workload.py $name $extra > gpurun_out/ncu_$w.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "$pat" -s $skip -c 2 -f -o gpurun_out/r02_$w python tools/prof_workload.py $name $extra > gpurun_out/ncu_$w.log 2>&1
   echo "$w rc=$?"
 done

@@ -63,21 +63,24 @@ def _deps_mtime() -> float:
 
 def build(verbose: bool = False, force: bool = False, extra_flags: list[str] | None = None,
           variant: str | None = None) -> str:
-    """`variant` builds a tuning variant into lib/libincerto_b200.<variant>.so (selected with INCERTO_B200_LIB)."""
-    global OBJDIR, LIB
-    if variant:
-        OBJDIR = os.path.join(HERE, "build", variant)
-        LIB = os.path.join(LIBDIR, f"libincerto_b200.{variant}.so")
+    """`variant` builds a tuning variant into lib/libincerto_b200.<variant>.so (selected with INCERTO_B200_LIB).
+    Objects are cached per flag set: `extra_flags` without a `variant` get an object directory (and a library) named
+    after a hash of the flags, so a sweep can never relink stale objects into the default library."""
+    flags = NVCC_FLAGS + (extra_flags or [])
+    if extra_flags and not variant:
+        import hashlib
+        variant = "f" + hashlib.sha1(" ".join(extra_flags).encode()).hexdigest()[:10]
+    objdir = os.path.join(HERE, "build", variant) if variant else OBJDIR
+    lib = os.path.join(LIBDIR, f"libincerto_b200.{variant}.so") if variant else LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     hdr_m = _deps_mtime()
-    flags = NVCC_FLAGS + (extra_flags or [])
     jobs = []
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
             jobs.append([nvcc, *flags, "-c", s, "-o", o])
@@ -94,10 +97,10 @@ def build(verbose: bool = False, force: bool = False, extra_flags: list[str] | N
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
-    if jobs or not os.path.exists(LIB):
+    if jobs or not os.path.exists(lib):
         # libcudart is linked statically (nvcc default); NCCL is dlopen-ed at attach time
-        run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"])
-    return LIB
+        run([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"])
+    return lib
 
 
 if __name__ == "__main__":

@@ -8,6 +8,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstring>
+#include <vector>
+
 #include "modules.hpp"
 
 namespace incerto
@@ -84,6 +87,18 @@ struct Comm
     uint32_t rank = 0, world = 1;
 };
 
+// Communicators are cached per unique id for the life of the process: creating and destroying an NCCL communicator
+// costs ~0.5 s each, which a host that builds one simulation after another (bench.py's end-to-end jobs, replicas
+// through fresh handles) must not pay per handle.  Handles that attach with the same id share the communicator; they
+// are used from one thread, one collective at a time (the handle contract, incerto_b200.h).
+struct CachedComm
+{
+    uint8_t id[128];
+    int device;
+    Comm comm;
+};
+static std::vector<CachedComm*> g_comm_cache;
+
 int32_t comm_unique_id(uint8_t out[128])
 {
     INC_TRY(nccl_load());
@@ -99,29 +114,38 @@ int32_t comm_attach(Sim& s, const uint8_t idb[128], uint32_t rank, uint32_t worl
     INC_TRY(nccl_load());
     if (s.comm) comm_free(s);
     INC_CUDA(cudaSetDevice(s.device));
+    for (CachedComm* cc : g_comm_cache)
+        if (std::memcmp(cc->id, idb, 128) == 0 && cc->device == s.device)
+        {
+            if (cc->comm.rank != rank || cc->comm.world != world)
+            {
+                set_error("attach_comm: this unique id is already bound to rank %u of %u in this process", cc->comm.rank, cc->comm.world);
+                return INCERTO_ERR_INVALID_ARGUMENT;
+            }
+            s.comm = &cc->comm;
+            return INCERTO_OK;
+        }
     ncclUniqueId id;
     std::memcpy(&id, idb, 128);
-    Comm* c = new Comm;
-    c->rank = rank;
-    c->world = world;
-    ncclResult_t r = g_nccl.CommInitRank(&c->comm, static_cast<int>(world), id, static_cast<int>(rank));
+    CachedComm* cc = new CachedComm;
+    std::memcpy(cc->id, idb, 128);
+    cc->device = s.device;
+    cc->comm.rank = rank;
+    cc->comm.world = world;
+    ncclResult_t r = g_nccl.CommInitRank(&cc->comm.comm, static_cast<int>(world), id, static_cast<int>(rank));
     if (r != ncclSuccess)
     {
         set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
-        delete c;
+        delete cc;
         return INCERTO_ERR_COMM;
     }
-    s.comm = c;
+    g_comm_cache.push_back(cc);
+    s.comm = &cc->comm;
     return INCERTO_OK;
 }
 
-void comm_free(Sim& s)
-{
-    if (!s.comm) return;
-    if (s.comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm->comm);
-    delete s.comm;
-    s.comm = nullptr;
-}
+// the handle lets go of the (cached, shared) communicator; the communicator itself lives until the process ends
+void comm_free(Sim& s) { s.comm = nullptr; }
 
 int32_t comm_allreduce(Sim& s, void* d_buf, uint32_t n, int is_f64, uint32_t op)
 {
@@ -171,20 +195,38 @@ int32_t comm_halo(Sim& s, const void* const* d_send_lo, void* const* d_recv_lo, 
     }
     Comm& c = *s.comm;
     INC_NCCL(g_nccl.GroupStart());
-    for (uint32_t m = 0; m < n_msgs; ++m)
+    // inside the group an error must not return early: the group would stay open and swallow every later NCCL call
+    // of this thread.  Remember the first failure, stop queueing, always close the group.
+    ncclResult_t first = ncclSuccess;
+    const char* where = "";
+    auto q = [&](ncclResult_t r, const char* what) {
+        if (r != ncclSuccess && first == ncclSuccess)
+        {
+            first = r;
+            where = what;
+        }
+        return first == ncclSuccess;
+    };
+    for (uint32_t m = 0; m < n_msgs && first == ncclSuccess; ++m)
     {
         if (c.rank > 0)
         {
-            INC_NCCL(g_nccl.Send(d_send_lo[m], bytes[m], ncclUint8, static_cast<int>(c.rank) - 1, c.comm, s.stream));
-            INC_NCCL(g_nccl.Recv(d_recv_lo[m], bytes[m], ncclUint8, static_cast<int>(c.rank) - 1, c.comm, s.stream));
+            if (!q(g_nccl.Send(d_send_lo[m], bytes[m], ncclUint8, static_cast<int>(c.rank) - 1, c.comm, s.stream), "ncclSend(lower)")) break;
+            if (!q(g_nccl.Recv(d_recv_lo[m], bytes[m], ncclUint8, static_cast<int>(c.rank) - 1, c.comm, s.stream), "ncclRecv(lower)")) break;
         }
         if (c.rank + 1 < c.world)
         {
-            INC_NCCL(g_nccl.Send(d_send_hi[m], bytes[m], ncclUint8, static_cast<int>(c.rank) + 1, c.comm, s.stream));
-            INC_NCCL(g_nccl.Recv(d_recv_hi[m], bytes[m], ncclUint8, static_cast<int>(c.rank) + 1, c.comm, s.stream));
+            if (!q(g_nccl.Send(d_send_hi[m], bytes[m], ncclUint8, static_cast<int>(c.rank) + 1, c.comm, s.stream), "ncclSend(upper)")) break;
+            if (!q(g_nccl.Recv(d_recv_hi[m], bytes[m], ncclUint8, static_cast<int>(c.rank) + 1, c.comm, s.stream), "ncclRecv(upper)")) break;
         }
     }
-    INC_NCCL(g_nccl.GroupEnd());
+    const ncclResult_t end = g_nccl.GroupEnd();
+    if (first != ncclSuccess)
+    {
+        set_error("NCCL error %d (%s) in %s", static_cast<int>(first), g_nccl.GetErrorString(first), where);
+        return INCERTO_ERR_COMM;
+    }
+    INC_NCCL(end);
     return INCERTO_OK;
 }
 

@@ -138,23 +138,24 @@ KernelStat& kstat(Sim& s, const char* name)
     return s.kstats.back();
 }
 
-struct PendingTimer
+// Profiling timers wait in the handle that launched them (Sim::pending_timers) until that handle synchronises: two
+// handles driven from one thread (replicas in flight) never see each other's events.
+KTimer::KTimer(Sim& s_, const char* name, double bytes) : s(s_)
 {
-    cudaEvent_t a, b;
-    size_t stat;
-};
-static thread_local std::vector<PendingTimer> g_pending; // resolved at synchronize
-
-KTimer::KTimer(Sim& s_, const char* name, double bytes) : s(s_), st(kstat(s_, name))
-{
+    KernelStat& st = kstat(s_, name);
+    stat = static_cast<size_t>(&st - s.kstats.data()); // an index: kstats may grow while this timer is alive
     st.launches += 1;
     st.algorithmic_bytes += bytes;
     s.launches += 1;
     if (s.profiling)
     {
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
-        cudaEventRecord(a, s.stream);
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess || cudaEventRecord(a, s.stream) != cudaSuccess)
+        {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+            a = b = nullptr;
+            cudaGetLastError();
+        }
     }
 }
 KTimer::~KTimer()
@@ -162,25 +163,23 @@ KTimer::~KTimer()
     if (a)
     {
         cudaEventRecord(b, s.stream);
-        PendingTimer p;
-        p.a = a;
-        p.b = b;
-        p.stat = static_cast<size_t>(&st - s.kstats.data());
-        g_pending.push_back(p);
+        s.pending_timers.push_back(PendingTimer{a, b, stat});
     }
 }
 
 static void resolve_timers(Sim& s)
 {
-    for (auto& p : g_pending)
+    for (auto& p : s.pending_timers)
     {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess && p.stat < s.kstats.size())
             s.kstats[p.stat].device_ms += ms;
+        else
+            cudaGetLastError();
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
     }
-    g_pending.clear();
+    s.pending_timers.clear();
 }
 
 int32_t live_rows_by_uid(Sim& s, Table& t, std::vector<uint32_t>& rows, std::vector<uint32_t>& uids)
@@ -901,8 +900,22 @@ int32_t grids_rebuild_for_step(Sim& s, uint64_t step, bool last_of_run);
 
 static int32_t do_run_enqueue(Sim& s, uint64_t num_steps);
 
+// StepNumber and the Philox counter word that carries it are 32 bit on the device: a run that would take the step
+// counter past 2^32 - 1 is refused instead of silently repeating its draws
+static int32_t check_step_range(const Sim& s, uint64_t num_steps)
+{
+    if (num_steps > 0xffffffffull || s.step + num_steps > 0xffffffffull)
+    {
+        set_error("run: StepNumber would exceed 2^32 - 1 (step %llu + %llu); the draw counter is 32 bit",
+                  static_cast<unsigned long long>(s.step), static_cast<unsigned long long>(num_steps));
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    return INCERTO_OK;
+}
+
 static int32_t do_run(Sim& s, uint64_t num_steps)
 {
+    INC_TRY(check_step_range(s, num_steps));
     INC_CUDA(cudaSetDevice(s.device));
     if (s.run_pending) INC_TRY(incerto_sim_synchronize(reinterpret_cast<incerto_sim*>(&s)));
     s.last_launches = s.launches;
@@ -1256,6 +1269,7 @@ int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps)
     INC_SIM(s);
     INC_CUDA(cudaSetDevice(S.device));
     if (num_steps == 0 || num_steps > 65536) return INCERTO_ERR_INVALID_ARGUMENT;
+    INC_TRY(check_step_range(S, num_steps));
     if (S.run_pending) INC_TRY(incerto_sim_synchronize(s));
     INC_TRY(incerto_sim_flush_l2(s)); // allocates the flush buffer on first use
     std::vector<cudaEvent_t> ev(2 * num_steps, nullptr);

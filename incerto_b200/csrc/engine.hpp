@@ -210,6 +210,12 @@ struct KernelStat
 
 struct Comm; // NCCL, comm.cpp
 
+struct PendingTimer
+{
+    cudaEvent_t a, b;
+    size_t stat;
+};
+
 struct Sim
 {
     int device = 0;
@@ -242,6 +248,7 @@ struct Sim
     uint64_t last_launches = 0, launches = 0;
     bool profiling = false;
     std::vector<KernelStat> kstats;
+    std::vector<PendingTimer> pending_timers; // profiling event pairs of this handle, resolved when it synchronises
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
 
     // workload state owned by modules (forest, pandemic, ...), see workloads.hpp
@@ -282,7 +289,7 @@ void stage_mark(const char* what);
 struct KTimer
 {
     Sim& s;
-    KernelStat& st;
+    size_t stat = 0; // index into s.kstats
     cudaEvent_t a = nullptr, b = nullptr;
     KTimer(Sim& s_, const char* name, double bytes);
     ~KTimer();

@@ -43,6 +43,18 @@ void launch_radix_select(const void* col, int dtype, uint32_t stride, uint32_t l
                          uint8_t need_set, uint8_t need_clear, uint64_t n, const ReduceRecord* d_rec, uint32_t mode,
                          uint64_t arg, uint64_t* state, cudaStream_t st, int32_t (*between_passes)(void*) = nullptr,
                          void* hook_ctx = nullptr);
+// the same over several columns of one dtype (entities of several archetype tables): every pass accumulates the
+// digit histogram of all sources before the digit is picked; `d_rec` holds the combined count
+struct SelectSource
+{
+    const void* col;
+    uint32_t stride;
+    const uint8_t* flags;
+    uint8_t need_set, need_clear;
+    uint64_t n;
+};
+void launch_radix_select_multi(const SelectSource* srcs, size_t n_srcs, int dtype, const ReduceRecord* d_rec, uint32_t mode,
+                               uint64_t arg, uint64_t* state, cudaStream_t st);
 constexpr size_t kSelectStateWords = 4 + 256;
 
 void launch_add_const(void* col, int dtype, uint32_t stride, const uint8_t* flags, uint8_t need_set, uint64_t n,

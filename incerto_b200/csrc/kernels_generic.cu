@@ -636,6 +636,43 @@ void launch_radix_select(const void* col, int dtype, uint32_t stride, uint32_t l
 #undef INC_FIN
 }
 
+void launch_radix_select_multi(const SelectSource* srcs, size_t n_srcs, int dtype, const ReduceRecord* d_rec, uint32_t mode,
+                               uint64_t arg, uint64_t* state, cudaStream_t st)
+{
+    size_t esize = 1;
+    switch (dtype)
+    {
+    case INCERTO_U16:
+    case INCERTO_I16: esize = 2; break;
+    case INCERTO_U32:
+    case INCERTO_I32:
+    case INCERTO_F32: esize = 4; break;
+    case INCERTO_U64:
+    case INCERTO_I64:
+    case INCERTO_F64: esize = 8; break;
+    default: break;
+    }
+    select_init_kernel<<<1, 256, 0, st>>>(state, d_rec, mode, arg, static_cast<uint32_t>(esize * 8 - 8));
+    for (size_t pass = 0; pass < esize; ++pass)
+    {
+        for (size_t k = 0; k < n_srcs; ++k)
+        {
+            const SelectSource& q = srcs[k];
+            if (!q.n) continue;
+            const int blocks = blocks_for(q.n, kReduceThreads, 4);
+#define INC_SELM(T, ...)                                                                                  \
+    select_hist_kernel<T><<<blocks, kReduceThreads, 0, st>>>(static_cast<const T*>(q.col), q.stride, 0u, q.flags, \
+                                                             q.need_set, q.need_clear, q.n, state)
+            INC_DISPATCH_DTYPE(dtype, INC_SELM, 0)
+#undef INC_SELM
+        }
+        select_pick_kernel<<<1, 32, 0, st>>>(state);
+    }
+#define INC_FINM(T, ...) select_finish_kernel<T><<<1, 32, 0, st>>>(state)
+    INC_DISPATCH_DTYPE(dtype, INC_FINM, 0)
+#undef INC_FINM
+}
+
 void launch_add_const(void* col, int dtype, uint32_t stride, const uint8_t* flags, uint8_t need_set, uint64_t n,
                       int64_t amount, cudaStream_t st)
 {

@@ -687,21 +687,25 @@ static int32_t series_materialize(Sim& s, SeriesInst& se)
         INC_CUDA(cudaStreamSynchronize(s.stream));
         if (s.comm && se.agg.kind == INCERTO_AGG_FIRE_STATS && s.part_world > 1)
         {
-            // row-partitioned forest: every rank holds partial counts
+            // row-partitioned forest: every rank holds partial counts.  COLLECTIVE: every rank of the communicator must
+            // read the series the same number of times between runs (documented at incerto_sim_get_aggregate_time_series)
             uint64_t* d = nullptr;
             const size_t words = raw.size() / 8 + counts.size();
             INC_CUDA(cudaMalloc(&d, words * 8));
             INC_CUDA(cudaMemcpyAsync(d, raw.data(), raw.size(), cudaMemcpyHostToDevice, s.stream));
             INC_CUDA(cudaMemcpyAsync(d + raw.size() / 8, counts.data(), counts.size() * 8, cudaMemcpyHostToDevice, s.stream));
             int32_t st = comm_allreduce(s, d, static_cast<uint32_t>(words), 0, 0);
+            cudaError_t ce = cudaSuccess;
             if (st == INCERTO_OK)
             {
-                cudaMemcpyAsync(raw.data(), d, raw.size(), cudaMemcpyDeviceToHost, s.stream);
-                cudaMemcpyAsync(counts.data(), d + raw.size() / 8, counts.size() * 8, cudaMemcpyDeviceToHost, s.stream);
-                cudaStreamSynchronize(s.stream);
+                ce = cudaMemcpyAsync(raw.data(), d, raw.size(), cudaMemcpyDeviceToHost, s.stream);
+                if (ce == cudaSuccess)
+                    ce = cudaMemcpyAsync(counts.data(), d + raw.size() / 8, counts.size() * 8, cudaMemcpyDeviceToHost, s.stream);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(s.stream);
             }
             cudaFree(d);
             INC_TRY(st);
+            INC_CUDA(ce);
         }
         std::vector<uint8_t> rec(fs ? fs : 8);
         for (uint64_t k = 0; k < se.n_slots; ++k)
@@ -744,8 +748,13 @@ int32_t grids_allocate(Sim& s)
         }
         if (!g.bounded)
         {
-            set_error("spatial grid without bounds is not supported by the dense cell table");
-            return INCERTO_ERR_UNSUPPORTED;
+            // add_spatial_grid(None) (simulation_builder.rs:114-121; in_bounds is "always true if no bounds are set",
+            // spatial_grid.rs:265-270): the index is built on demand over the bounding box of the positions the last
+            // PreUpdate saw (grid_ensure_built); no position is ever refused
+            g.lazy = true;
+            g.n_cells = 1;
+            g.cap_rows = s.tables[g.table].n;
+            continue;
         }
         uint64_t cells = 1;
         for (uint32_t d = 0; d < g.dim; ++d) cells *= static_cast<uint64_t>(g.bmax[d] - g.bmin[d] + 1);
@@ -816,10 +825,55 @@ static int32_t grid_rebuild(Sim& s, GridInst& g, uint64_t step, bool last_of_run
 static int32_t grid_ensure_built(Sim& s, GridInst& g)
 {
     if (!g.lazy || !g.snap_valid || g.snap_built) return INCERTO_OK;
-    INC_TRY(grid_alloc_dense(g));
     FilterSpec f;
     f.with.push_back(g.component);
     RowFilter rf = row_filter(s, s.tables[g.table], f);
+    if (!g.bounded)
+    {
+        // the table covers the bounding box of the snapshot (the reference's HashMap has no extent at all)
+        const uint32_t stride = s.comps[g.position].stride();
+        std::vector<int16_t> pos(g.snap_n * stride);
+        std::vector<uint8_t> fl(g.snap_n);
+        INC_CUDA(cudaMemcpyAsync(pos.data(), g.d_snap_pos, pos.size() * 2, cudaMemcpyDeviceToHost, s.stream));
+        INC_CUDA(cudaMemcpyAsync(fl.data(), g.d_snap_flags, fl.size(), cudaMemcpyDeviceToHost, s.stream));
+        INC_CUDA(cudaStreamSynchronize(s.stream));
+        int32_t lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        bool any = false;
+        for (uint64_t r = 0; r < g.snap_n; ++r)
+        {
+            if ((fl[r] & rf.need_set) != rf.need_set || !(fl[r] & 1u)) continue;
+            for (uint32_t d = 0; d < g.dim; ++d)
+            {
+                const int32_t v = pos[r * stride + d]; // lanes are read as i16, as the index kernels read them
+                lo[d] = any ? std::min(lo[d], v) : v;
+                hi[d] = any ? std::max(hi[d], v) : v;
+            }
+            any = true;
+        }
+        uint64_t cells = 1;
+        for (uint32_t d = 0; d < g.dim; ++d) cells *= static_cast<uint64_t>(hi[d] - lo[d] + 1);
+        if (cells > (1ull << 28))
+        {
+            set_error("unbounded spatial grid: the entities span %llu cells, more than the on-demand index holds (2^28)",
+                      static_cast<unsigned long long>(cells));
+            return INCERTO_ERR_UNSUPPORTED;
+        }
+        if (cells != g.n_cells || !g.d_cell_start)
+        {
+            cudaFree(g.d_cell_start);
+            cudaFree(g.d_cursor);
+            cudaFree(g.d_sorted_rows);
+            g.d_cell_start = g.d_cursor = g.d_sorted_rows = nullptr;
+            g.n_cells = cells;
+        }
+        for (uint32_t d = 0; d < 3; ++d)
+        {
+            g.bmin[d] = d < g.dim ? lo[d] : 0;
+            g.bmax[d] = d < g.dim ? hi[d] : 0;
+        }
+        g.cap_rows = std::max<uint64_t>(g.cap_rows, g.snap_n);
+    }
+    INC_TRY(grid_alloc_dense(g));
     INC_TRY(ensure_scratch(s, scan_scratch_bytes(g.n_cells) + 256));
     KTimer kt(s, "grid_build", 16.0 * g.snap_n + 12.0 * g.n_cells);
     launch_grid_build(grid_desc(g), static_cast<const int16_t*>(g.d_snap_pos), s.comps[g.position].stride(),
@@ -1029,6 +1083,44 @@ static int32_t sample_aggregate_impl(incerto_sim* s, const incerto_aggregate_des
     }
     INC_CUDA(cudaStreamSynchronize(S.stream));
     INC_TRY(incerto_sim_synchronize(s));
+    if ((a.kind == INCERTO_AGG_MEDIAN || a.kind == INCERTO_AGG_PERCENTILE) && tabs.size() > 1)
+    {
+        // the query of the reference spans archetypes (simulation.rs:107-121): one selection over the columns of all
+        // tables.  The per-table records above give the combined count (which fixes the index) and the NaN flag.
+        GenericRaw tot;
+        std::memset(&tot, 0, sizeof(tot));
+        for (size_t i = 0; i < tabs.size(); ++i)
+        {
+            GenericRaw g;
+            std::memcpy(&g, h.data() + i * rs, sizeof(g));
+            tot.rec.count += g.rec.count;
+            tot.rec.nan_seen |= g.rec.nan_seen;
+        }
+        if (tot.rec.count == 0) return INCERTO_ERR_AGGREGATE_NO_ENTITIES;
+        const ComponentInfo& ci = S.comps[a.component];
+        std::vector<SelectSource> srcs;
+        for (int ti : tabs)
+        {
+            Table& t = S.tables[ti];
+            RowFilter rf = row_filter(S, t, a.filter);
+            if (rf.impossible || !t.n) continue;
+            srcs.push_back(SelectSource{t.col(a.component)->d, ci.stride(), rf.trivial ? nullptr : t.d_flags, rf.need_set,
+                                        rf.need_clear, t.n});
+        }
+        GenericRaw* d_tot = reinterpret_cast<GenericRaw*>(d_raw);
+        INC_CUDA(cudaMemcpyAsync(d_tot, &tot, sizeof(tot), cudaMemcpyHostToDevice, S.stream));
+        uint64_t* state = reinterpret_cast<uint64_t*>(S.d_scratch + 64 * kNumSMs * 8);
+        {
+            KTimer kt(S, "radix_select", 1.0 * tot.rec.count * dtype_size(ci.dtype) * dtype_size(ci.dtype));
+            launch_radix_select_multi(srcs.data(), srcs.size(), ci.dtype, &d_tot->rec, a.kind == INCERTO_AGG_MEDIAN ? 1u : 2u,
+                                      a.percentile, state, S.stream);
+        }
+        INC_CUDA(cudaMemcpyAsync(&tot.sel_value, &state[0], 8, cudaMemcpyDeviceToHost, S.stream));
+        INC_CUDA(cudaMemcpyAsync(&tot.sel_error, &state[3], 8, cudaMemcpyDeviceToHost, S.stream));
+        INC_CUDA(cudaStreamSynchronize(S.stream));
+        INC_TRY(incerto_sim_synchronize(s));
+        return aggregate_finalize(S, a, reinterpret_cast<const uint8_t*>(&tot), 1, out, nullptr);
+    }
     return aggregate_finalize(S, a, h.data(), tabs.size(), out, nullptr);
 }
 
@@ -1417,6 +1509,9 @@ static int32_t grid_cell_uids(Sim& S, GridInst& g, const int32_t* pos, std::vect
     }
     INC_TRY(grid_ensure_built(S, g));
     if (g.table < 0 || !g.d_cell_start || g.built_step == ~0ull) return INCERTO_OK;
+    if (!g.bounded) // the on-demand table of an unbounded grid covers the entities' bounding box: nobody lives outside it
+        for (uint32_t k = 0; k < g.dim; ++k)
+            if (pos[k] < g.bmin[k] || pos[k] > g.bmax[k]) return INCERTO_OK;
     GridDesc d = grid_desc(g);
     const uint64_t key = grid_cell_key(d, pos[0], pos[1], g.dim == 3 ? pos[2] : 0);
     uint32_t se[2];

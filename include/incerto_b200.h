@@ -370,8 +370,10 @@ typedef struct incerto_spawn_stocks_params
  * {min x,y[,z], max x,y[,z]} inclusive (GridBounds, spatial_grid.rs:45-53) or
  * NULL.  On the device the HashMap of the reference becomes a counting sort by
  * cell key rebuilt at the start of every step (the PreUpdate maintenance of
- * spatial_grid.rs:410-455 observed at step granularity). Unbounded grids
- * (bounds == NULL) are not supported by the dense cell table. */
+ * spatial_grid.rs:410-455 observed at step granularity).  Unbounded grids
+ * (bounds == NULL, simulation_builder.rs:114-121) accept every position; their index is built on demand, when the
+ * host queries it, over the bounding box of the entities the last PreUpdate saw (at most 2^28 cells).  The example
+ * systems that iterate a grid on the device (forest_fire, air_traffic_3d) need bounds. */
 typedef int32_t incerto_grid;
 int32_t incerto_builder_add_spatial_grid(incerto_builder* b, uint32_t dim, const int32_t* bounds,
                                          incerto_component position, incerto_component component,
@@ -459,7 +461,10 @@ int32_t incerto_sim_sample(incerto_sim* s, incerto_component component, incerto_
 int32_t incerto_sim_sample_single(incerto_sim* s, incerto_component component, void* out, size_t out_size);
 
 /* Simulation::get_aggregate_time_series{,_filtered} (:226-258).  *values is an
- * array of *len records of *record_size bytes, *time the step stamps. */
+ * array of *len records of *record_size bytes, *time the step stamps.
+ * COLLECTIVE for the FireStats series of a row-partitioned forest with a communicator attached: the per-rank partial
+ * records are all-reduced when the series is first read after a run (then cached until the next run), so every rank
+ * of the communicator must read it - the same number of times between runs - or none may. */
 int32_t incerto_sim_get_aggregate_time_series(incerto_sim* s, const incerto_aggregate_desc* agg,
                                               const uint64_t** time, const void** values, uint64_t* len,
                                               uint64_t* record_size, uint64_t* sample_interval);
@@ -524,7 +529,10 @@ int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps);
 /* Attach an NCCL communicator (one process per GPU).  `unique_id` is the
  * 128-byte ncclUniqueId created on rank 0 (incerto_comm_unique_id) and
  * distributed by the host (torch.distributed in this repo).  Used for the
- * forest-fire halo exchange and for cross-replica aggregate reductions. */
+ * forest-fire halo exchange and for cross-replica aggregate reductions.
+ * Communicators are cached per (unique id, device) for the life of the process: handles that attach with the same id
+ * share one ncclComm (created by the first attach, ~0.5 s), so building simulation after simulation does not pay for
+ * communicator setup again.  The handles sharing it are driven from one thread, one collective at a time. */
 int32_t incerto_comm_unique_id(uint8_t out[128]);
 int32_t incerto_sim_attach_comm(incerto_sim* s, const uint8_t unique_id[128], uint32_t rank, uint32_t world);
 /* Manual halo transport for the row-partitioned forest (any host transport instead of NCCL; also how

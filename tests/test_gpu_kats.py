@@ -329,3 +329,85 @@ def test_global_aggregate_needs_a_communicator():
     with pytest.raises(ib.EngineError) as e:
         sim.sample_aggregate_global(ib.Median(v))
     assert e.value.code == F.ERR_COMM
+
+
+def test_unbounded_spatial_grid_matches_oracle(oracle_lib):
+    """add_spatial_grid(None) (simulation_builder.rs:114-121): no position is out of bounds (spatial_grid.rs:265-270,
+    negative coordinates included), neighbour queries are not filtered by bounds; the device index is built on demand
+    over the bounding box of the entities."""
+    import ctypes as C
+    rng = np.random.default_rng(6)
+    n = 5000
+    pos = rng.integers(-40, 41, (n, 2)).astype(np.int16)
+    pos[0] = (-300, 250)                               # an outlier widens the bounding box
+    b = ib.SimulationBuilder()
+    Pos = b.component("GridPosition2D", F.I16, lanes=2)
+    Val = b.component("Val", F.U32)
+    b.add_spatial_grid_2d(Pos, Val, bounds=None)
+    g = b.last_grid
+    b.add_entity_spawner(lambda s: s.spawn_batch(n, {Pos: pos, Val: np.arange(n)}))
+    sim = b.build()
+    sim.run(1)
+    og = oracle_lib.oracle_grid_new(2, 0, None)
+    for e in range(n):
+        oracle_lib.oracle_grid_insert(og, e, (C.c_int32 * 2)(int(pos[e, 0]), int(pos[e, 1])))
+    assert sim.grid_num_entities(g) == oracle_lib.oracle_grid_num_entities(og) == n
+    out = (C.c_uint32 * n)()
+    for (x, y) in [(0, 0), (-40, -40), (40, 40), (-300, 250), (-301, 250), (41, 0), (5000, 5000), (-7, 13)]:
+        q = (C.c_int32 * 2)(x, y)
+        assert sim.grid_in_bounds(g, (x, y))
+        for mode, fn in ((0, lambda: sim.grid_entities_at(g, (x, y))), (1, lambda: sim.grid_neighbors_of(g, (x, y))),
+                         (2, lambda: sim.grid_neighbors_of(g, (x, y), orthogonal=True))):
+            k = oracle_lib.oracle_grid_query(og, mode, q, out, n)
+            assert fn() == sorted(out[i] for i in range(k)), (x, y, mode)
+    oracle_lib.oracle_grid_free(og)
+
+
+def test_run_refuses_to_wrap_the_32_bit_step_counter():
+    """StepNumber and the Philox counter word are 32 bit on the device: a run past 2^32 - 1 is an error, not a
+    silent repeat of the draws."""
+    b = ib.SimulationBuilder()
+    c = b.component("Counter", F.I32)
+    b.add_entity_spawner(lambda s: s.spawn({c: 0}))
+    b.add_systems(ib.AddConst(c, 1))
+    sim = b.build()
+    sim.run(3)
+    with pytest.raises(ib.EngineError) as e:
+        sim.run(1 << 32)
+    assert e.value.code == F.ERR_INVALID_ARGUMENT
+    sim.run(2)
+    assert sim.sample_single(c) == 5
+
+
+@pytest.mark.parametrize("dt,npdt", [(F.F64, np.float64), (F.I32, np.int32), (F.U16, np.uint16)])
+def test_median_and_percentile_across_archetype_tables(dt, npdt):
+    """sample_aggregate queries every entity that has the component, whatever else it carries (simulation.rs:107-121):
+    Median / Percentile over a component living in three archetype tables = one selection over all of them
+    (aggregate.rs:107-155: sorted[len / 2], sorted[floor(P / 100 * len)])."""
+    rng = np.random.default_rng(12)
+    sizes = (4001, 1, 2500)
+    if npdt is np.float64:
+        vals = [rng.normal(size=n).astype(npdt) for n in sizes]
+    else:
+        vals = [rng.integers(0, 30000, n).astype(npdt) for n in sizes]
+    b = ib.SimulationBuilder()
+    Val = b.component("Val", dt)
+    A, B = b.component("ExtraA", F.U32), b.component("ExtraB", F.F64)
+    Tag = b.component("Tag")
+    tags = [(rng.random(n) < 0.5).astype(np.uint8) for n in sizes]
+    b.add_entity_spawner(lambda s: s.spawn_batch(sizes[0], {Val: vals[0], Tag: tags[0]}))
+    b.add_entity_spawner(lambda s: s.spawn_batch(sizes[1], {Val: vals[1], A: np.zeros(sizes[1], np.uint32), Tag: tags[1]}))
+    b.add_entity_spawner(lambda s: s.spawn_batch(sizes[2], {Val: vals[2], A: np.zeros(sizes[2], np.uint32),
+                                                            B: np.zeros(sizes[2]), Tag: tags[2]}))
+    sim = b.build()
+    allv = np.sort(np.concatenate(vals))
+    assert sim.sample_aggregate(ib.Count(Val)) == len(allv)
+    assert sim.sample_aggregate(ib.Median(Val)) == allv[len(allv) // 2]
+    for p in (0, 1, 29, 50, 57, 99):
+        assert sim.sample_aggregate(ib.Percentile(Val, p)) == allv[int(np.floor(p / 100.0 * len(allv)))]
+    with pytest.raises(ib.EngineError) as e:
+        sim.sample_aggregate(ib.Percentile(Val, 100))
+    assert e.value.code == F.ERR_PERCENTILE_RANGE
+    sel = np.sort(np.concatenate([v[t.astype(bool)] for v, t in zip(vals, tags)]))
+    assert sim.sample_aggregate_filtered(ib.Median(Val), ib.With(Tag)) == sel[len(sel) // 2]
+    assert sim.sample_aggregate(ib.Minimum(Val)) == allv[0] and sim.sample_aggregate(ib.Maximum(Val)) == allv[-1]

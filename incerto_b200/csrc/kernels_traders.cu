@@ -36,19 +36,32 @@ __device__ __forceinline__ uint32_t byte_of(const uint4& v, uint32_t b)
     return (w >> (8 * (b & 3))) & 0xffu;
 }
 
-// 0xff in every byte of w that is < t (t <= 256)
-__device__ __forceinline__ uint32_t bytes_below(uint32_t w, uint32_t t)
+// Level-1 byte tests, SWAR (the emulated __vcmpltu4 of round 1 cost as many instructions as the Philox call that
+// produced the word): 0x80 in every byte of x that is < t, for a threshold t in 1..=256 fixed per launch.
+//   t <= 128:  byte < t  <=>  high bit clear  and  (low 7 bits + 128 - t) does not reach the high bit
+//   t <  256:  byte < t  <=>  high bit clear  or   (low 7 bits + 256 - t) does not reach the high bit
+struct ByteLess
 {
-    if (t >= 256u) return 0xffffffffu;
-    return __vcmpltu4(w, t * 0x01010101u);
-}
-
-// bit k of the result: byte k of w is < t
-__device__ __forceinline__ uint32_t bytes_below_bits(uint32_t w, uint32_t t)
-{
-    const uint32_t m = bytes_below(w, t) & 0x08040201u;
-    return (m * 0x01010101u) >> 24; // the four selected bits land in the top byte without carries
-}
+    uint32_t addc, mode; // mode 0: t <= 128, 1: 128 < t < 256, 2: t >= 256 (always true)
+    __device__ __forceinline__ explicit ByteLess(uint32_t t)
+    {
+        mode = t >= 256u ? 2u : (t > 128u ? 1u : 0u);
+        addc = (mode == 1u ? 256u - t : 128u - (t > 128u ? 128u : t)) * 0x01010101u;
+    }
+    __device__ __forceinline__ uint32_t mask80(uint32_t x) const
+    {
+        if (mode == 2u) return 0x80808080u;
+        const uint32_t y = (x & 0x7f7f7f7fu) + addc;
+        return (mode == 0u ? (~x & ~y) : (~x | ~y)) & 0x80808080u;
+    }
+    // bit k of the result: byte k of x is below the threshold (the multiply gathers bits 0, 8, 16, 24 into 24..27)
+    __device__ __forceinline__ uint32_t bits4(uint32_t x) const { return ((mask80(x) >> 7) * 0x01020408u) >> 24; }
+    // the sixteen bytes of a Philox call
+    __device__ __forceinline__ uint32_t bits16(const uint4& v) const
+    {
+        return bits4(v.x) | (bits4(v.y) << 4) | (bits4(v.z) << 8) | (bits4(v.w) << 12);
+    }
+};
 // bit k of the result: nibble k of w is non-zero
 __device__ __forceinline__ uint32_t nibbles_nonzero_bits(uint32_t w)
 {
@@ -58,23 +71,6 @@ __device__ __forceinline__ uint32_t nibbles_nonzero_bits(uint32_t w)
     return (y | (y >> 12)) & 0xffu;
 }
 
-template <int NW>
-__device__ __forceinline__ uint32_t nibble_at(const uint32_t (&pw)[NW], uint32_t s)
-{
-    uint32_t w = 0;
-#pragma unroll
-    for (int k = 0; k < NW; ++k)
-        if (static_cast<uint32_t>(k) == (s >> 3)) w = pw[k];
-    return (w >> (4 * (s & 7u))) & 0xfu;
-}
-template <int NW>
-__device__ __forceinline__ void nibble_set(uint32_t (&pw)[NW], uint32_t s, uint32_t v)
-{
-    const uint32_t sh = 4 * (s & 7u);
-#pragma unroll
-    for (int k = 0; k < NW; ++k)
-        if (static_cast<uint32_t>(k) == (s >> 3)) pw[k] = (pw[k] & ~(0xfu << sh)) | (v << sh);
-}
 // lowest set bit of a multi-word mask, cleared on return; -1 when empty
 template <int NC>
 __device__ __forceinline__ int pop_lowest(unsigned long long (&m)[NC])
@@ -89,18 +85,36 @@ __device__ __forceinline__ int pop_lowest(unsigned long long (&m)[NC])
         }
     return s;
 }
+template <int NC>
+__device__ __forceinline__ void mask_set(unsigned long long (&m)[NC], uint32_t s, bool on)
+{
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if (static_cast<uint32_t>(c) == (s >> 6))
+        {
+            const unsigned long long bit = 1ull << (s & 63u);
+            m[c] = on ? (m[c] | bit) : (m[c] & ~bit);
+        }
+}
+template <int NC>
+__device__ __forceinline__ uint32_t mask16(const unsigned long long (&m)[NC], int b)
+{
+    return static_cast<uint32_t>(m[b >> 2] >> (16 * (b & 3))) & 0xffffu;
+}
 
-// One thread = one trader.  The level-1 draws of all stocks are taken first (one Philox call per 16 stocks,
-// no divergence) and reduced to candidate bit masks; the rare level-2 events are then handled by a short loop
-// in ascending StockId order, so that a warp executes the expensive path max-events-per-lane times instead of
-// once per stock position.
+// One thread = one trader.  The trader's portfolio words live in shared memory (column `threadIdx.x`, conflict free:
+// the rare-event paths index them by stock; in registers that was a 14-way select per access and 28 registers), next
+// to a 1-bit-per-stock ownership mask in registers that buy, sell and net worth share.  The level-1 draws of all
+// stocks are taken first (one Philox call per 16 stocks, no divergence) and reduced to candidate bit masks; the rare
+// level-2 events are then handled by a short loop in ascending StockId order.
 template <int NW>
 __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
 {
     constexpr int NB = (NW + 1) / 2;  // 16-stock blocks
-    constexpr int NC = (NW + 7) / 8;  // 64-stock candidate words
+    constexpr int NC = (NW + 7) / 8;  // 64-stock mask words
     __shared__ double s_price[kTradersMaxStocks];
     __shared__ uint32_t s_listed[kTradersMaxStocks / 32]; // bit s: stock s exists and is not delisted
+    __shared__ uint32_t s_pw[NW][kThreads];
     for (uint32_t i = threadIdx.x; i < kTradersMaxStocks / 32; i += blockDim.x) s_listed[i] = 0;
     __syncthreads();
     for (uint32_t s = threadIdx.x; s < a.num_stocks; s += blockDim.x)
@@ -110,20 +124,26 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
         if ((fl & 1u) && !(fl & a.bit_delisted)) atomicOr(&s_listed[s >> 5], 1u << (s & 31));
     }
     __syncthreads();
+    const ByteLess buy_lt(a.buy_t1), sell_lt(a.sell_t1);
     const uint32_t nw_used = (a.num_stocks + 7) >> 3;
     const uint32_t nblk = (a.num_stocks + 15) >> 4;
+    const uint32_t tid = threadIdx.x;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     for (uint64_t row = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < a.n; row += gstride)
     {
         if (a.trader_flags && !(a.trader_flags[row] & 1u)) continue;
         const uint32_t uid = a.trader_uid ? a.trader_uid[row] : static_cast<uint32_t>(row);
-        uint32_t pw[NW], pw0[NW];
+        unsigned long long owned[NC]; // bit s: the trader holds shares of stock s
+#pragma unroll
+        for (int c = 0; c < NC; ++c) owned[c] = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
-            pw[w] = (static_cast<uint32_t>(w) < nw_used) ? a.portfolio[static_cast<uint64_t>(w) * a.n_cap + row] : 0u;
-            pw0[w] = pw[w];
+            const uint32_t v = (static_cast<uint32_t>(w) < nw_used) ? a.portfolio[static_cast<uint64_t>(w) * a.n_cap + row] : 0u;
+            s_pw[w][tid] = v;
+            owned[w >> 3] |= static_cast<unsigned long long>(nibbles_nonzero_bits(v)) << (8 * (w & 7));
         }
+        uint32_t dirty = 0; // bit w: portfolio word w changed
         double cash = a.cash[row];
 
         if (a.do_buy)
@@ -135,13 +155,10 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
 #pragma unroll
             for (int b = 0; b < NB; ++b)
             {
-                if (static_cast<uint32_t>(b) >= nblk) break;
-                const uint4 l1 = philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_buy);
-                const uint32_t hit = bytes_below_bits(l1.x, a.buy_t1) | (bytes_below_bits(l1.y, a.buy_t1) << 4) |
-                                     (bytes_below_bits(l1.z, a.buy_t1) << 8) | (bytes_below_bits(l1.w, a.buy_t1) << 12);
+                if (static_cast<uint32_t>(b) >= nblk) continue; // (no break: the loop stays fully unrolled, the masks in registers)
+                const uint32_t hit = buy_lt.bits16(philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_buy));
                 const uint32_t listed = (s_listed[b >> 1] >> (16 * (b & 1))) & 0xffffu;
-                const uint32_t owned = nibbles_nonzero_bits(pw[2 * b]) | ((2 * b + 1 < NW ? nibbles_nonzero_bits(pw[2 * b + 1]) : 0u) << 8);
-                cand[b >> 2] |= static_cast<unsigned long long>(hit & listed & ~owned) << (16 * (b & 3));
+                cand[b >> 2] |= static_cast<unsigned long long>(hit & listed & ~mask16<NC>(owned, b)) << (16 * (b & 3));
             }
             for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))
             {
@@ -150,56 +167,55 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
                 const uint32_t num_shares = a.shares_min + uniform_below(l2.y, a.shares_range);
                 const double amount = dm_mul(static_cast<double>(num_shares), s_price[s]);
                 if (amount > cash) continue; // :184-188
-                nibble_set<NW>(pw, static_cast<uint32_t>(s), num_shares);
+                s_pw[s >> 3][tid] |= num_shares << (4 * (s & 7)); // the nibble was empty: not owned
+                dirty |= 1u << (s >> 3);
+                mask_set<NC>(owned, static_cast<uint32_t>(s), num_shares != 0);
                 cash = dm_sub(cash, amount);
             }
         }
 
-        double value = 0.0;
         if (a.do_sell)
         {
-            // candidates: owned and level-1 byte below T1 (:216-223)
+            // candidates: owned and level-1 byte below T1 (:216-223); blocks without an owned stock draw nothing
             unsigned long long cand[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) cand[c] = 0;
 #pragma unroll
             for (int b = 0; b < NB; ++b)
             {
-                const uint32_t owned = nibbles_nonzero_bits(pw[2 * b]) | ((2 * b + 1 < NW ? nibbles_nonzero_bits(pw[2 * b + 1]) : 0u) << 8);
-                if (!owned) continue;
-                const uint4 l1 = philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_sell);
-                const uint32_t hit = bytes_below_bits(l1.x, a.sell_t1) | (bytes_below_bits(l1.y, a.sell_t1) << 4) |
-                                     (bytes_below_bits(l1.z, a.sell_t1) << 8) | (bytes_below_bits(l1.w, a.sell_t1) << 12);
-                cand[b >> 2] |= static_cast<unsigned long long>(hit & owned) << (16 * (b & 3));
+                const uint32_t own16 = mask16<NC>(owned, b);
+                if (!own16) continue;
+                const uint32_t hit = sell_lt.bits16(philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_sell));
+                cand[b >> 2] |= static_cast<unsigned long long>(hit & own16) << (16 * (b & 3));
             }
             for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))
             {
                 if (!bernoulli(philox4x32_10(uid, static_cast<uint32_t>(s), a.step, 1u, a.rk_sell).x, a.sell_thr2)) continue;
-                const uint32_t n_sh = nibble_at<NW>(pw, static_cast<uint32_t>(s));
-                cash = dm_add(cash, dm_mul(static_cast<double>(n_sh), s_price[s])); // :229-233, ascending StockId
-                nibble_set<NW>(pw, static_cast<uint32_t>(s), 0u);
+                const uint32_t sh = 4 * (s & 7);
+                const uint32_t wv = s_pw[s >> 3][tid];
+                cash = dm_add(cash, dm_mul(static_cast<double>((wv >> sh) & 0xfu), s_price[s])); // :229-233, ascending StockId
+                s_pw[s >> 3][tid] = wv & ~(0xfu << sh);
+                dirty |= 1u << (s >> 3);
+                mask_set<NC>(owned, static_cast<uint32_t>(s), false);
             }
         }
+        double value = 0.0;
         if (a.do_net_worth)
         {
             // :250-261 portfolio value summed in ascending StockId order
+            unsigned long long rest[NC];
 #pragma unroll
-            for (int w = 0; w < NW; ++w)
+            for (int c = 0; c < NC; ++c) rest[c] = owned[c];
+            for (int s = pop_lowest<NC>(rest); s >= 0; s = pop_lowest<NC>(rest))
             {
-                uint32_t rest = pw[w];
-                while (rest)
-                {
-                    const uint32_t k = (__ffs(rest) - 1) >> 2;
-                    const uint32_t n_sh = (rest >> (4 * k)) & 0xfu;
-                    rest &= ~(0xfu << (4 * k));
-                    value = dm_add(value, dm_mul(static_cast<double>(n_sh), s_price[8 * w + k]));
-                }
+                const uint32_t n_sh = (s_pw[s >> 3][tid] >> (4 * (s & 7))) & 0xfu;
+                value = dm_add(value, dm_mul(static_cast<double>(n_sh), s_price[s]));
             }
         }
 
 #pragma unroll
         for (int w = 0; w < NW; ++w)
-            if (pw[w] != pw0[w]) a.portfolio[static_cast<uint64_t>(w) * a.n_cap + row] = pw[w];
+            if ((dirty >> w) & 1u) a.portfolio[static_cast<uint64_t>(w) * a.n_cap + row] = s_pw[w][tid];
         if (a.do_buy || a.do_sell) a.cash[row] = cash;
         if (a.do_net_worth) a.net_worth[row] = dm_add(cash, value); // :261
     }

@@ -9,6 +9,9 @@ print(f"headline: {d['config']['workload']}: {d['ms_per_step'] * 1e3:.2f} us/ste
 for k in ("same_slab_1gpu_us", "same_slab_1gpu_l2_resident_us", "fixed_cost_us", "fixed_cost_l2_resident_us", "partition_parity", "replica_parity"):
     if k in d:
         print(f"  {k}: {d[k]}")
+if "replica_stream" in d:
+    q = d["replica_stream"]
+    print(f"replica_stream: {q['replicas_in_flight']} x 4096^2 in flight: {q['us_per_replica_step']:.2f} us per replica-step, {q['achieved_GBps']:.0f} GB/s, frac {q['frac']:.3f}")
 if "e2e" in d:
     e = d["e2e"]
     print(f"e2e: best {e['value'] / 1e9:.1f} G/s ({e['seconds'] * 1e3:.2f} ms), median {e['median'] / 1e9:.1f} G/s; {e['breakdown_best_job_ms']}")

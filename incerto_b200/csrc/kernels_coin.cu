@@ -151,10 +151,8 @@ __global__ void __launch_bounds__(256)
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     const uint64_t nfull = n / 128; // whole warp tiles of 128 entities
-    for (uint64_t w = warp0; w < nfull; w += nwarps)
-    {
-        const uint64_t i = w * 128 + lane * 4;
-        const uint4 h = ld_stream_v4(heads + i), t = ld_stream_v4(tosses + i);
+    constexpr int kU = 4;           // tiles per warp iteration: eight 128-bit loads in flight per lane before any use
+    auto tile = [&](const uint4& h, const uint4& t) {
         const bool same = t.x == t.y && t.x == t.z && t.x == t.w && t.x == __shfl_sync(kFullMask, t.x, 0);
         if (__all_sync(kFullMask, same))
         {
@@ -165,6 +163,25 @@ __global__ void __launch_bounds__(256)
             sum += static_cast<double>(h.x) / static_cast<double>(t.x) + static_cast<double>(h.y) / static_cast<double>(t.y) +
                    static_cast<double>(h.z) / static_cast<double>(t.z) + static_cast<double>(h.w) / static_cast<double>(t.w);
         cnt += 4.0;
+    };
+    const uint64_t ngroups = nfull / kU;
+    for (uint64_t g = warp0; g < ngroups; g += nwarps)
+    {
+        uint4 h[kU], t[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+        {
+            const uint64_t i = (g * kU + u) * 128 + lane * 4;
+            h[u] = ld_stream_v4(heads + i);
+            t[u] = ld_stream_v4(tosses + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) tile(h[u], t[u]);
+    }
+    for (uint64_t w = ngroups * kU + warp0; w < nfull; w += nwarps)
+    {
+        const uint64_t i = w * 128 + lane * 4;
+        tile(ld_stream_v4(heads + i), ld_stream_v4(tosses + i));
     }
     for (uint64_t i = nfull * 128 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<uint64_t>(gridDim.x) * blockDim.x)

@@ -463,7 +463,7 @@ def check_replica_parity(ib, ex, np, ranks, local_rank):
 
 
 # --------------------------------------------------------------------------------------------------- CPU legs
-def cpu_baseline_sample(threads: int, seconds_target: float = 10.0):
+def cpu_baseline_sample(threads: int, seconds_target: float = 12.0):
     """The oracle (C++ restatement of the Bevy systems: hash-map grid, one serial pass per system) timed on
     the host cores on a bounded sample of the workload."""
     from oracle.lib import load
@@ -471,8 +471,12 @@ def cpu_baseline_sample(threads: int, seconds_target: float = 10.0):
     W = H = 1024
     t0 = time.perf_counter()
     lib.oracle_forest_bench(SEED, W, H, 2, threads)
-    per2 = time.perf_counter() - t0
-    steps = max(4, min(200, int(seconds_target / max(per2 / 2, 1e-3))))
+    t2 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lib.oracle_forest_bench(SEED, W, H, 10, threads)
+    t10 = time.perf_counter() - t0
+    per_step = max((t10 - t2) / 8.0, 1e-4)          # spawn + hash-grid build are in both: the difference is 8 steps
+    steps = max(20, min(300, int((seconds_target - t2) / per_step)))
     t0 = time.perf_counter()
     done = lib.oracle_forest_bench(SEED, W, H, steps, threads)
     dt = time.perf_counter() - t0
@@ -620,8 +624,13 @@ def main():
     per_rank_cells = cells / world
     achieved = 2.0 * per_rank_cells / (kernel_ms * 1e-3) / 1e9
     traffic = ncu_traffic().get("forest_fire_4096", {}).get("forest_step") if world == 1 else None
+    traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch under `ncu --set full` (profiles/r02_ncu_forestbench.txt): "
+                    "the 16.8 MB input buffer is read from DRAM; the 16.8 MB written stay in the 126 MB L2 until later launches evict "
+                    "them, so the write-back of a launch's output falls outside its own ncu window (at 16384^2, where the output "
+                    "cannot stay, ncu counts read + write = 495 MB for 537 MB algorithmic)")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "forest_step_kernel", "algorithmic_bytes_per_unit": 2,
+                "traffic": traffic, "traffic_note": traffic_note if traffic else None,
+                "kernel": "forest_step_kernel", "algorithmic_bytes_per_unit": 2,
                 "units_per_launch": per_rank_cells, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "l2_resident": {"achieved": 2.0 * per_rank_cells * warm_steps / (warm_ms * 1e-3) / 1e9,

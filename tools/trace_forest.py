@@ -18,11 +18,12 @@ from incerto_b200 import _ffi as F
 spec = next((a for a in sys.argv[1:] if "x" in a), "4096x4096")
 W, H = (int(v) for v in spec.split("x"))
 warm = "--warm" in sys.argv
+fires = int(sys.argv[sys.argv.index("--fires") + 1]) if "--fires" in sys.argv else 3
 b = ib.SimulationBuilder(seed=0x1CE27002025)
 pos = b.component("pos", F.I16, lanes=2)
 cell = b.component("cell", F.U8)
 b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
-b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_FOREST_GRID, F.SpawnForestParams(pos.handle, cell.handle, W, H, 0.7, 3, 3)))
+b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_FOREST_GRID, F.SpawnForestParams(pos.handle, cell.handle, W, H, 0.7, 3, fires)))
 b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.001))
 b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
 sim = b.build()
@@ -51,6 +52,9 @@ for rep in range(3):
     print("   warp end    (us) ", [round(float(np.percentile(end, p)) / 1e3, 2) for p in q])
     print("   load wait   (us) ", [round(float(np.percentile(loaded - start, p)) / 1e3, 2) for p in q])
     print("   after loads (us) ", [round(float(np.percentile(end - loaded, p)) / 1e3, 2) for p in q])
+    if nwarps <= 64:
+        for w in range(nwarps):
+            print(f"      warp {w:3d} (cta {w // warps_per_cta}, sm {sm[w]}): start {start[w] / 1e3:6.2f}  loaded {loaded[w] / 1e3:6.2f}  end {end[w] / 1e3:6.2f} us")
     # per SM: first start, last end, warps
     sms = np.unique(sm)
     first = np.array([start[sm == s].min() for s in sms]) / 1e3

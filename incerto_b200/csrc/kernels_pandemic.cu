@@ -139,15 +139,15 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
             if (a.do_move)
             {
                 // :121 stay put (bit 3 clear); :125 x axis (bit 2 clear) else y axis; :128/:147 negative (bit 1 clear)
-                // else positive direction; saturating at 0 and G-1 (the halves of the packed word never carry into
-                // each other because the move is refused at the walls)
+                // else positive direction; saturating at 0 and G-1.  Branch-free: the stepped coordinate t = c +- 1 is in
+                // range iff (unsigned) t < G (c - 1 wraps to 2^32 - 1 at the lower wall), and the halves of the packed
+                // word never carry into each other because the move is refused at the walls.
                 const uint32_t nib = nib8 >> (4 * k);
-                const uint32_t sh = (nib & 4u) << 2;                  // 0: x, 16: y
-                const uint32_t coord = (r.p[k] >> sh) & 0xffffu;
-                const bool pos_dir = (nib & 2u) != 0;
-                const bool ok = (fl & 1u) && (nib & 8u) && (pos_dir ? coord + 1 < G : coord > 0);
-                const uint32_t one = 1u << sh;
-                r.p[k] += ok ? (pos_dir ? one : 0u - one) : 0u;
+                const uint32_t sh = (nib & 4u) << 2;                               // 0: x, 16: y
+                const uint32_t dlt = (nib & 2u) - 1u;                              // +1 / -1
+                const uint32_t t = ((r.p[k] >> sh) & 0xffffu) + dlt;
+                const uint32_t go = (t < G ? 1u : 0u) & (nib >> 3) & fl;           // in range, moves, alive (bit 0)
+                r.p[k] += (dlt << sh) & (0u - (go & 1u));
             }
             if (a.do_infect && (fl & 1u) && (fl & a.bit_infected))
             {

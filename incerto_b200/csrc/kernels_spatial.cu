@@ -10,7 +10,7 @@
 // sees is the PreUpdate snapshot = the positions at the start of the step (the move comes last).
 //
 // Two passes per step over the person table (SoA: pos u32, disease u8, flags u8, quarantine u8, aux u8,
-// ContactHistory 20 x u32 slot-major):
+// ContactHistory 20 x u32 per person, contiguous):
 //   prepare : PreUpdate grid maintenance (per-cell occupancy counts patched with last step's moves and deaths,
 //             the device form of spatial_grid.rs:434-455), incubation, recovery/death draws, contact-history
 //             insert, and the two scatter sides of the pair interactions: infectious non-quarantined people
@@ -255,12 +255,19 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
             uint32_t hv[kSpatialHistorySlots];
             if (need_hist || take_back || put_all)
             {
-                // all remembered cells at once: independent, predicated loads (slot-major)
+                // all remembered cells at once: a person's 20 slots are contiguous (80 bytes), fetched as up to five
+                // independent 128-bit loads (round 1 stored the slots slot-major: 20 predicated 4-byte loads, a 32-byte
+                // sector each, and a fifth of this kernel's instructions)
+                const uint4* hp = reinterpret_cast<const uint4*>(a.hist + static_cast<uint64_t>(i) * kSpatialHistorySlots);
 #pragma unroll
-                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                for (uint32_t v4 = 0; v4 < kSpatialHistorySlots / 4; ++v4)
                 {
-                    hv[s2] = 0xffffffffu;
-                    if (s2 < len) hv[s2] = a.hist[static_cast<uint64_t>(s2) * a.n_cap + i];
+                    uint4 q = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                    if (4 * v4 < len) q = hp[v4];
+                    hv[4 * v4 + 0] = 4 * v4 + 0 < len ? q.x : 0xffffffffu;
+                    hv[4 * v4 + 1] = 4 * v4 + 1 < len ? q.y : 0xffffffffu;
+                    hv[4 * v4 + 2] = 4 * v4 + 2 < len ? q.z : 0xffffffffu;
+                    hv[4 * v4 + 3] = 4 * v4 + 3 < len ? q.w : 0xffffffffu;
                 }
             }
             if (take_back)
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
                     }
                     else
                     {
-                        a.hist[static_cast<uint64_t>(len) * a.n_cap + i] = p;
+                        a.hist[static_cast<uint64_t>(i) * kSpatialHistorySlots + len] = p;
 #pragma unroll
                         for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
                             if (s2 == len) hv[s2] = p;

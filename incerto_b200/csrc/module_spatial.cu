@@ -10,7 +10,7 @@ namespace incerto
 
 static bool valid_comp(const Sim& s, int c) { return c >= 0 && c < static_cast<int>(s.comps.size()); }
 
-// ContactHistory is engine-managed (20 packed positions per person, slot-major); called by run_spawners
+// ContactHistory is engine-managed (20 packed positions per person, contiguous: one 80-byte row); called by run_spawners
 // between counting and allocation.
 int32_t spatial_layout(Sim& s)
 {
@@ -287,7 +287,7 @@ int32_t spatial_read_history(Sim& s, int table, uint8_t* out, size_t out_size, s
         }
         uint32_t row[kSpatialHistorySlots + 1] = {0};
         row[0] = aux[r] & 31u;
-        for (uint32_t k = 0; k < row[0]; ++k) row[1 + k] = h[static_cast<size_t>(k) * t.n_spawned + r];
+        for (uint32_t k = 0; k < row[0]; ++k) row[1 + k] = h[static_cast<size_t>(r) * kSpatialHistorySlots + k];
         std::memcpy(out + w, row, rec);
         w += rec;
     }

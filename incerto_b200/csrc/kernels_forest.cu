@@ -261,7 +261,9 @@ __global__ void forest_publish_kernel(ForestArgs a, uint32_t slab_w, uint32_t bu
 // That shortens a grid of one or two waves, whose CTAs all start together and would sit idle until their loads
 // arrive (4096^2 cold: 19.2 -> 18.6 us); a long grid is bound by instruction issue in steady state and runs 4 %
 // slower that way (16384^2: 131 -> 136 us), so the launcher picks per grid size.
-template <bool ALIGNED, bool HOIST>
+// PEER: the fused halo transport is compiled in (row-partitioned grids with peer memory); the single-GPU kernel
+// carries none of its registers or branches.
+template <bool ALIGNED, bool HOIST, bool PEER>
 __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const __grid_constant__ ForestConst c)
 {
     const ForestArgs& a = c.a;
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // column group of this CTA.  With the fused halo transport the two boundary groups come first in launch order
     // (groups 1 and last swapped): they wait for the neighbours while the rest of the grid works.
     uint32_t by = blockIdx.y;
-    if (c.peer.mail && gridDim.y > 2) by = by == 1 ? gridDim.y - 1 : (by == gridDim.y - 1 ? 1 : by);
+    if (PEER && c.peer.mail && gridDim.y > 2) by = by == 1 ? gridDim.y - 1 : (by == gridDim.y - 1 ? 1 : by);
     const uint32_t lx0 = 1 + (by * kTY + threadIdx.y) * kColsPerThread;
     const uint32_t lane = threadIdx.x; // blockDim.x == 32: one warp per threadIdx.y
     const uint32_t tid = threadIdx.y * kTX + threadIdx.x;
@@ -292,50 +294,59 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         nr.n = 0;
     }
 
-    // ---- fused halo transport: the CTAs that read a halo column wait for the neighbour's stamp of the previous step
-    // and pull its boundary column into their own halo column (CTA-uniform; nothing else in this grid depends on
-    // these CTAs, so they may spin)
-    if (c.peer.mail)
-    {
-        const bool wait_lo = by == 0 && c.peer.need_lo, wait_hi = by == gridDim.y - 1 && c.peer.need_hi;
-        if (wait_lo || wait_hi)
-        {
-            if (tid == 0)
-            {
-                const volatile uint32_t* m = c.peer.mail;
-                const long long t0 = clock64();
-                // stamps only grow; wrap-around-safe comparison
-                while ((wait_lo && static_cast<int32_t>(m[0] - c.peer.need_lo) < 0) ||
-                       (wait_hi && static_cast<int32_t>(m[1] - c.peer.need_hi) < 0))
-                {
-                    __nanosleep(64);
-                    if (clock64() - t0 > 20000000000ll) // ~10 s: a neighbour died; never hang the device
-                    {
-                        if (c.error) atomicCAS(c.error, 0u, 39u); // INCERTO_ERR_COMM
-                        break;
-                    }
-                }
-                __threadfence_system();
-            }
-            __syncthreads();
-            if (threadIdx.y == 0)
-            {
-                uint8_t* mine = const_cast<uint8_t*>(a.cur);
-                if (wait_lo)
-                    *reinterpret_cast<uint4*>(mine + y0) = __ldcv(reinterpret_cast<const uint4*>(c.peer.src_lo + y0));
-                if (wait_hi)
-                    *reinterpret_cast<uint4*>(mine + static_cast<size_t>(c.slab_w + 1) * c.pitch + y0) =
-                        __ldcv(reinterpret_cast<const uint4*>(c.peer.src_hi + y0));
-            }
-            __syncthreads();
-        }
-    }
-
-    // ---- loads first: columns lx0-1 .. lx0+4
+    // ---- loads first.  With the fused halo transport the two warps (per boundary CTA) whose W / E neighbour column is
+    // the neighbour rank's boundary column do not read it from the local halo column: they pull it over NVLink below,
+    // after their other loads are in flight, straight into the register it is needed in.
+    const uint32_t hi_off = (c.slab_w - 1u) % (kTY * kColsPerThread);   // position of the last real column in its group
+    const bool pull_lo = PEER && c.peer.mail && c.peer.need_lo && by == 0 && threadIdx.y == 0;                // my v[0]
+    const bool pull_hi = PEER && c.peer.mail && c.peer.need_hi && by == gridDim.y - 1 && threadIdx.y == hi_off / kColsPerThread;
+    const uint32_t jh = hi_off % kColsPerThread + 2u;                                                          // my v[jh]
     const uint8_t* p0 = a.cur + static_cast<size_t>(lx0 - 1) * c.pitch + y0;
     uint4 v[kColsPerThread + 2];
 #pragma unroll
     for (int j = 0; j < kColsPerThread + 2; ++j) v[j] = *reinterpret_cast<const uint4*>(p0 + static_cast<size_t>(j) * c.pitch);
+    // (a pulling warp's load of the stale local halo column is simply overwritten below: no extra predicate or register
+    // on everybody else's path)
+    // ---- fused halo transport, pull side (warp-uniform: threadIdx.y is).  The pulling warp waits for the neighbour's
+    // stamp of the previous step (nothing else in this grid depends on it, so it may spin), fetches its chunk of the
+    // neighbour's boundary column and also leaves it in the local halo column: the rare-event and overlay paths of this
+    // CTA read single cells from there after the barrier below.  The other warps of the CTA never wait for NVLink.
+    if (PEER && (pull_lo || pull_hi))
+    {
+        if (lane == 0)
+        {
+            const volatile uint32_t* m = c.peer.mail;
+            const long long t0 = clock64();
+            // stamps only grow; wrap-around-safe comparison
+            while ((pull_lo && static_cast<int32_t>(m[0] - c.peer.need_lo) < 0) ||
+                   (pull_hi && static_cast<int32_t>(m[1] - c.peer.need_hi) < 0))
+            {
+                __nanosleep(64);
+                if (clock64() - t0 > 20000000000ll) // ~10 s: a neighbour died; never hang the device
+                {
+                    if (c.error) atomicCAS(c.error, 0u, 39u); // INCERTO_ERR_COMM
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        __syncwarp();
+        uint8_t* mine = const_cast<uint8_t*>(a.cur);
+        if (pull_lo)
+        {
+            v[0] = __ldcv(reinterpret_cast<const uint4*>(c.peer.src_lo + y0));
+            *reinterpret_cast<uint4*>(mine + y0) = v[0];
+        }
+        if (pull_hi)
+        {
+            const uint4 q = __ldcv(reinterpret_cast<const uint4*>(c.peer.src_hi + y0));
+#pragma unroll
+            for (int j = 1; j < kColsPerThread + 2; ++j)
+                if (static_cast<uint32_t>(j) == jh) v[j] = q;
+            *reinterpret_cast<uint4*>(mine + static_cast<size_t>(c.slab_w + 1) * c.pitch + y0) = q;
+        }
+        __syncwarp();
+    }
     // the word just outside the warp's y span, per column: lane 0 needs the cell y0-1 (top byte of the word
     // before its chunk), lane 31 the cell y0+16 (bottom byte of the word after it)
     uint32_t edge = 0; // bit j-1: that cell of my column j is burning
@@ -665,7 +676,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         g_forest_trace[4 * w + 3] = smid();
     }
 #endif
-    if (c.peer.mail_lo || c.peer.mail_hi) __syncwarp(); // lane 0 speaks for the whole warp's stores (the neighbours pull them)
+    if (PEER && (c.peer.mail_lo || c.peer.mail_hi)) __syncwarp(); // lane 0 speaks for the whole warp's stores (the neighbours pull them)
     if (lane != 0) return;
     __threadfence_block();
     if (atomicAdd(&s_done, 1u) != kTY - 1) return;
@@ -678,7 +689,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         if (b) atomicAdd(d + 1, static_cast<unsigned long long>(static_cast<long long>(b)));
         if (e) atomicAdd(d + 2, static_cast<unsigned long long>(static_cast<long long>(e)));
     }
-    if (!(c.peer.mail_lo || c.peer.mail_hi)) return;
+    if (!PEER || !(c.peer.mail_lo || c.peer.mail_hi)) return;
     // fused halo transport only.  What a neighbour pulls - the two boundary columns and the states of overlay entities
     // sitting in them - is written by the CTAs of the two boundary column groups alone, and those are the CTAs that
     // read the neighbours' columns.  So only they take the ticket: the last of them publishes this step's stamp in the
@@ -777,12 +788,22 @@ cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, con
     // at most four waves, and the loads actually take long (steps that find their cells in the L2 have no shadow worth
     // filling: 4096^2 graph replay 13.2 us with, 12.9 us without)
     const bool hoist = static_cast<uint64_t>(grid.x) * grid.y <= 4ull * kNumSMs * kMinBlocks && !a.l2_resident;
+    const bool peer_on = peer != nullptr;
+#define INC_FOREST_LAUNCH(AL, HO)                                        \
+    do                                                                   \
+    {                                                                    \
+        if (peer_on)                                                     \
+            forest_step_kernel<AL, HO, true><<<grid, block, 0, st>>>(c); \
+        else                                                             \
+            forest_step_kernel<AL, HO, false><<<grid, block, 0, st>>>(c); \
+    } while (0)
     if ((a.H % 16) != 0) // uid of a chunk's first cell is not a multiple of 16: no shared level-1 call per chunk
-        forest_step_kernel<false, false><<<grid, block, 0, st>>>(c);
+        INC_FOREST_LAUNCH(false, false);
     else if (hoist)
-        forest_step_kernel<true, true><<<grid, block, 0, st>>>(c);
+        INC_FOREST_LAUNCH(true, true);
     else
-        forest_step_kernel<true, false><<<grid, block, 0, st>>>(c);
+        INC_FOREST_LAUNCH(true, false);
+#undef INC_FOREST_LAUNCH
     return cudaGetLastError();
 }
 

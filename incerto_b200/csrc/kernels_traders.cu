@@ -152,13 +152,21 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
             unsigned long long cand[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) cand[c] = 0;
+            // (the 16-stock blocks of one 64-stock mask word run as a rolled loop: unrolling all of them made the kernel
+            // 41 KB of code - past the instruction cache - for no gain, ncu: stall no_instruction 2.0)
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
+            for (int c = 0; c < NC; ++c)
             {
-                if (static_cast<uint32_t>(b) >= nblk) continue; // (no break: the loop stays fully unrolled, the masks in registers)
-                const uint32_t hit = buy_lt.bits16(philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_buy));
-                const uint32_t listed = (s_listed[b >> 1] >> (16 * (b & 1))) & 0xffffu;
-                cand[b >> 2] |= static_cast<unsigned long long>(hit & listed & ~mask16<NC>(owned, b)) << (16 * (b & 3));
+#pragma unroll 1
+                for (uint32_t q = 0; q < 4; ++q)
+                {
+                    const uint32_t b = 4u * c + q;
+                    if (b >= nblk) break;
+                    const uint32_t hit = buy_lt.bits16(philox4x32_10(uid, b, a.step, 0u, a.rk_buy));
+                    const uint32_t listed = (s_listed[b >> 1] >> (16 * (b & 1))) & 0xffffu;
+                    const uint32_t own16 = static_cast<uint32_t>(owned[c] >> (16 * q)) & 0xffffu;
+                    cand[c] |= static_cast<unsigned long long>(hit & listed & ~own16) << (16 * q);
+                }
             }
             for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))
             {
@@ -181,12 +189,17 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
 #pragma unroll
             for (int c = 0; c < NC; ++c) cand[c] = 0;
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
+            for (int c = 0; c < NC; ++c)
             {
-                const uint32_t own16 = mask16<NC>(owned, b);
-                if (!own16) continue;
-                const uint32_t hit = sell_lt.bits16(philox4x32_10(uid, static_cast<uint32_t>(b), a.step, 0u, a.rk_sell));
-                cand[b >> 2] |= static_cast<unsigned long long>(hit & own16) << (16 * (b & 3));
+#pragma unroll 1
+                for (uint32_t q = 0; q < 4; ++q)
+                {
+                    const uint32_t b = 4u * c + q;
+                    const uint32_t own16 = static_cast<uint32_t>(owned[c] >> (16 * q)) & 0xffffu;
+                    if (!own16) continue;
+                    const uint32_t hit = sell_lt.bits16(philox4x32_10(uid, b, a.step, 0u, a.rk_sell));
+                    cand[c] |= static_cast<unsigned long long>(hit & own16) << (16 * q);
+                }
             }
             for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))
             {
@@ -203,13 +216,19 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
         if (a.do_net_worth)
         {
             // :250-261 portfolio value summed in ascending StockId order
-            unsigned long long rest[NC];
+            // (the owned stocks are walked 32 at a time: plain 32-bit find-first-set loops instead of the multi-word
+            // pop_lowest, which was a fifth of the kernel's instructions in this loop alone)
 #pragma unroll
-            for (int c = 0; c < NC; ++c) rest[c] = owned[c];
-            for (int s = pop_lowest<NC>(rest); s >= 0; s = pop_lowest<NC>(rest))
+            for (int h = 0; h < 2 * NC; ++h)
             {
-                const uint32_t n_sh = (s_pw[s >> 3][tid] >> (4 * (s & 7))) & 0xfu;
-                value = dm_add(value, dm_mul(static_cast<double>(n_sh), s_price[s]));
+                uint32_t rest = static_cast<uint32_t>(owned[h >> 1] >> (32 * (h & 1)));
+                while (rest)
+                {
+                    const uint32_t s = 32u * h + (__ffs(rest) - 1);
+                    rest &= rest - 1;
+                    const uint32_t n_sh = (s_pw[s >> 3][tid] >> (4 * (s & 7))) & 0xfu;
+                    value = dm_add(value, dm_mul(static_cast<double>(n_sh), s_price[s]));
+                }
             }
         }
 

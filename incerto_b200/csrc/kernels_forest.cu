@@ -13,7 +13,7 @@
 // [x_begin, x_end) ("column" = all cells with the same x, contiguous in y, as
 // the reference spawns them: uid = x*H + y, forest_fire.rs:239-257) plus one
 // halo column on either side:  col 0 = x_begin-1, cols 1..slab_w, col slab_w+1 = x_end.
-// Each column is `pitch` = round_up(H,16) bytes; pad bytes and out-of-grid halo
+// Each column is `pitch` = round_up(H, 512) bytes (whole warp spans; columns are padded to whole CTA tiles too); pad bytes and out-of-grid halo
 // columns hold BURNED (0), which is inert under all three systems.
 //
 // Cell encoding (u8): BURNED 0, BURNING{t} = t in 1..63, HEALTHY 0x40, EMPTY 0x80.
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // (c) cells an overlay entity can influence, and the overlay entities living in this thread's tile
     if (n_near && chunk_ok)
     {
-        const int gx0 = a.x_begin + static_cast<int>(lx0) - 1; // my columns: gx0 .. gx0+3
+        const int gx0 = a.x_begin + static_cast<int>(lx0) - 1; // my columns: gx0 .. gx0 + kColsPerThread - 1
         for (uint32_t i = 0; i < n_near; ++i)
         {
             const int ox = nr.x[i], oy = nr.y[i];

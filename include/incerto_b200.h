@@ -244,7 +244,7 @@ typedef struct incerto_spawn_coin_tossers_params
 
 typedef struct incerto_forest_params
 {
-    incerto_component position; /* GridPosition2D, I32 x 2 lanes at the ABI */
+    incerto_component position; /* GridPosition2D: 2 lanes of I16 (or U16 / I32 for a host-spawned grid) */
     incerto_component cell;     /* ForestCell.state, U8 */
     double probability;         /* FIRE_SPREAD_PROBABILITY :39 (spread) / REGROWTH_PROBABILITY :41 (regrowth); unused for progression */
     uint32_t burn_duration;     /* BURN_DURATION :40 (spread) */
@@ -281,7 +281,7 @@ typedef struct incerto_spawn_pandemic_params
 typedef struct incerto_air_params
 {
     incerto_component position;        /* GridPosition3D, I32 x 3 lanes at the ABI */
-    incerto_component target_altitude; /* Aircraft.target_altitude, I32 at the ABI */
+    incerto_component target_altitude; /* Aircraft.target_altitude, an I16 column (device layout; the façades narrow the reference's usize) */
     int32_t airspace_size;             /* AIRSPACE_SIZE :16 */
     int32_t airspace_height;           /* AIRSPACE_HEIGHT :17 */
     double chance_horizontal_move;     /* 0.7 :108 */

@@ -52,7 +52,10 @@ def test_param_struct_sizes(engine_lib):
              ("incerto_fire_stats", _ffi.FireStats), ("incerto_pandemic_stats", _ffi.PandemicStats),
              ("incerto_kernel_stat", _ffi.KernelStat), ("incerto_system_desc", _ffi.SystemDesc),
              ("incerto_column_data", _ffi.ColumnData),
-             ("incerto_spawn_coin_tossers_params", _ffi.SpawnCoinTossersParams)]
+             ("incerto_spawn_coin_tossers_params", _ffi.SpawnCoinTossersParams),
+             ("incerto_spatial_params", _ffi.SpatialParams), ("incerto_spawn_spatial_params", _ffi.SpawnSpatialParams),
+             ("incerto_traders_params", _ffi.TradersParams), ("incerto_spawn_traders_params", _ffi.SpawnTradersParams),
+             ("incerto_spawn_stocks_params", _ffi.SpawnStocksParams)]
     src = '#include <stdio.h>\n#include "incerto_b200.h"\nint main(void){' + "".join(
         f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:

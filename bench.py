@@ -25,7 +25,10 @@ Extra keys (round 2, VERDICT r01 "Next round" 1, 4, 5):
                 SHIPPED layout (csrc: KTimer), fractions are against MEASURED_PEAKS.json;
   `replicas`    configs[2] / [4]: independent Monte Carlo replicas of pandemic 10 M and traders 1 M, a fixed number
                 per GPU (weak scaling), two in flight per GPU, statistics all-reduced over NCCL;
-  `partition_parity`, `replica_parity` (N > 1)  untimed correctness checks of the multi-GPU paths;
+  `partition_parity`, `replica_parity`, `global_aggregate_parity` (N > 1)  untimed correctness checks of the
+                multi-GPU paths (row-split grid = undivided run; sharded + all-reduced replica statistics = one GPU
+                running them all; cross-replica Median / Percentile by distributed radix select = numpy on the
+                gathered columns);
   `same_slab_1gpu_us`, `fixed_cost_us` (N = 1)  the N > 1 slab (2048 x 16384) alone on one GPU, and the cold floor
                 of a 64 x 512 grid (launch + cold code / constant bank + event pair).
 """
@@ -462,6 +465,30 @@ def check_replica_parity(ib, ex, np, ranks, local_rank):
     return bool(ranks.max(0.0 if ok else 1.0) == 0.0)
 
 
+def check_global_aggregate_parity(ib, ex, np, ranks, local_rank):
+    """SURVEY §8 (f) 3, cross-replica quantiles: every rank holds one traders replica (200 k traders, 30 steps); Median,
+    Percentile<90>, Minimum, Maximum, Count and Mean of the net worth over the traders of ALL ranks through
+    incerto_sim_sample_aggregate_global (distributed radix select: per digit pass one NCCL all-reduce of the 256-bin
+    histogram) against numpy on the gathered columns."""
+    world, rank = ranks.world, ranks.rank
+    sim, h = ex.traders(200_000 + 1000 * rank, 100, replica=rank, device=local_rank)   # ragged rank sizes
+    sim.attach_comm(ranks.share_unique_id(ib), rank, world)
+    sim.run(30)
+    nw = h.tc.net_worth
+    got = {"count": sim.sample_aggregate_global(ib.Count(nw)), "min": sim.sample_aggregate_global(ib.Minimum(nw)),
+           "max": sim.sample_aggregate_global(ib.Maximum(nw)), "median": sim.sample_aggregate_global(ib.Median(nw)),
+           "p90": sim.sample_aggregate_global(ib.Percentile(nw, 90)), "mean": sim.sample_aggregate_global(ib.Mean(nw))}
+    cols = ranks.gather(sim.read_component(nw))
+    ok = True
+    if rank == 0:
+        allv = np.sort(np.concatenate(cols))
+        n = len(allv)
+        ok = (int(got["count"]) == n and got["min"] == allv[0] and got["max"] == allv[-1] and got["median"] == allv[n // 2]
+              and got["p90"] == allv[int(np.floor(90 / 100.0 * n))] and abs(got["mean"] - float(allv.mean())) <= 1e-9 * abs(float(allv.mean())))
+    sim.destroy()
+    return bool(ranks.max(0.0 if ok else 1.0) == 0.0)
+
+
 # --------------------------------------------------------------------------------------------------- CPU legs
 def cpu_baseline_sample(threads: int, seconds_target: float = 12.0):
     """The oracle (C++ restatement of the Bevy systems: hash-map grid, one serial pass per system) timed on
@@ -701,6 +728,7 @@ def main():
     if world > 1 and not args.only_headline:
         line["partition_parity"] = check_partition_parity(ib, ex, np, ranks, local_rank)
         line["replica_parity"] = check_replica_parity(ib, ex, np, ranks, local_rank)
+        line["global_aggregate_parity"] = check_global_aggregate_parity(ib, ex, np, ranks, local_rank)
 
     # ---- e2e through the C ABI with host buffers
     if not args.no_e2e:

@@ -6,7 +6,7 @@ d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 r = d["roofline"]
 print(f"headline: {d['config']['workload']}: {d['ms_per_step'] * 1e3:.2f} us/step, {d['value'] / 1e9:.1f} G/s, frac {r['frac']:.3f}; "
       f"L2-resident {d['value_l2_resident'] / 1e9:.1f} G/s; launches {d['gpu_launches']}")
-for k in ("same_slab_1gpu_us", "same_slab_1gpu_l2_resident_us", "fixed_cost_us", "fixed_cost_l2_resident_us", "partition_parity", "replica_parity"):
+for k in ("same_slab_1gpu_us", "same_slab_1gpu_l2_resident_us", "fixed_cost_us", "fixed_cost_l2_resident_us", "partition_parity", "replica_parity", "global_aggregate_parity"):
     if k in d:
         print(f"  {k}: {d[k]}")
 if "replica_stream" in d:

@@ -268,6 +268,39 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
                 p[k] = make_uint2((static_cast<uint32_t>(x) & 0xffffu) | (static_cast<uint32_t>(y) << 16),
                                   (static_cast<uint32_t>(z) & 0xffffu) | (p[k].y & 0xffff0000u));
             }
+            if (a.part)
+            {
+                // domain decomposition: the aircraft left the slab -> the neighbour takes it over (and it stays around as
+                // this rank's ghost: its bit below, its table entry from the sent list next step); it stands in a
+                // boundary column -> the neighbour needs it as a ghost
+                const int ngx = lane16(p[k].x, 0) - a.bmin[0];
+                AirMailbox* mig = ngx < a.x_lo ? a.out_lo : (ngx >= a.x_hi ? a.out_hi : nullptr);
+                if (ngx < a.x_lo || ngx >= a.x_hi)
+                {
+                    if (mig)
+                    {
+                        const uint32_t i = atomicAdd(&mig->n_migrants, 1u);
+                        if (i < mig->capacity)
+                            mig->migrants()[i] = make_uint4(a.uid ? a.uid[row] : static_cast<uint32_t>(row), p[k].x, p[k].y, 0u);
+                        else
+                            mig->overflow = 1u;
+                    }
+                    a.flags_rw[row] = 0; // no longer owned here
+                }
+                else
+                {
+                    if (ngx == a.x_lo && a.out_lo)
+                    {
+                        const uint32_t i = atomicAdd(&a.out_lo->n_ghosts, 1u);
+                        if (i < a.out_lo->capacity) a.out_lo->ghosts()[i] = p[k]; else a.out_lo->overflow = 1u;
+                    }
+                    if (ngx == a.x_hi - 1 && a.out_hi)
+                    {
+                        const uint32_t i = atomicAdd(&a.out_hi->n_ghosts, 1u);
+                        if (i < a.out_hi->capacity) a.out_hi->ghosts()[i] = p[k]; else a.out_hi->overflow = 1u;
+                    }
+                }
+            }
             if (a.bits_next)
             {
                 // the next PreUpdate's first pass, done here while the new position is in registers
@@ -303,6 +336,108 @@ __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------- domain decomposition
+// After the spawn (every rank spawned the whole airspace, same uids): "alive" becomes "owned by this rank", and the
+// aircraft standing just outside the slab are the first step's ghosts (written into the inboxes as if received).
+__global__ void __launch_bounds__(kThreads) air_own_init_kernel(AirArgs a, AirMailbox* in_lo, AirMailbox* in_hi)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += gstride)
+    {
+        const uint2 p = a.pos[i];
+        const int gx = lane16(p.x, 0) - a.bmin[0];
+        const bool mine = gx >= a.x_lo && gx < a.x_hi;
+        a.flags_rw[i] = mine ? 1u : 0u;
+        AirMailbox* g = (gx == a.x_lo - 1) ? in_lo : (gx == a.x_hi ? in_hi : nullptr);
+        if (g)
+        {
+            const uint32_t k = atomicAdd(&g->n_ghosts, 1u);
+            if (k < g->capacity) g->ghosts()[k] = p; else g->overflow = 1u;
+        }
+    }
+}
+
+// Start of a step: the ghosts - what the neighbours sent after the previous step plus the aircraft this rank handed over
+// itself (they stand in the neighbours' boundary columns now) - set their bits and enter the exact index.
+__global__ void __launch_bounds__(kThreads) air_ghosts_kernel(AirArgs a, const AirMailbox* sent_lo, const AirMailbox* sent_hi)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const AirMailbox* boxes[4] = {a.in_lo, a.in_hi, sent_lo, sent_hi};
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    {
+        const AirMailbox* m = boxes[b];
+        if (!m) continue;
+        const bool sent = b >= 2;
+        const uint32_t n = min(sent ? m->n_migrants : m->n_ghosts, m->capacity);
+        if (m->overflow && t == 0) atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_UNSUPPORTED));
+        for (uint32_t i = t; i < n; i += nt)
+        {
+            uint2 p;
+            if (sent)
+            {
+                const uint4 r = m->migrants()[i];
+                p = make_uint2(r.y, r.z);
+            }
+            else
+                p = m->ghosts()[i];
+            int gx, gy, gz;
+            uint32_t key;
+            if (!cell_of(a, p, gx, gy, gz, key)) continue;
+            const uint32_t h = bit_of(a, key);
+            atomicOr(&a.bits[h >> 5], 1u << (h & 31));
+            index_insert(a, key);
+        }
+    }
+}
+
+// After the exchange: the aircraft that crossed into this slab come alive here (row found through the uid), with the
+// position they moved to; their bit goes into the bitmap the last step kernel left for the next step.
+__global__ void __launch_bounds__(kThreads) air_unpack_kernel(AirArgs a, AirMailbox* in_lo, AirMailbox* in_hi)
+{
+    AirMailbox* boxes[2] = {in_lo, in_hi};
+    for (int b = 0; b < 2; ++b)
+    {
+        AirMailbox* m = boxes[b];
+        if (!m) continue;
+        const uint32_t n = min(m->n_migrants, m->capacity);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint4 r = m->migrants()[i];
+            const uint64_t row = a.row_of_uid ? a.row_of_uid[r.x] : r.x;
+            const uint2 p = make_uint2(r.y, r.z);
+            a.pos[row] = p;
+            a.flags_rw[row] = 1u;
+            int gx, gy, gz;
+            uint32_t key;
+            if (cell_of(a, p, gx, gy, gz, key))
+            {
+                const uint32_t h = bit_of(a, key);
+                atomicOr(&a.bits[h >> 5], 1u << (h & 31));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) m->n_migrants = 0; // consumed (the ghost list is read by the next step's ghost kernel)
+        __syncthreads();
+    }
+}
+
+__global__ void air_mail_reset_kernel(AirMailbox* a, AirMailbox* b, AirMailbox* c, AirMailbox* d)
+{
+    AirMailbox* boxes[4] = {a, b, c, d};
+    if (threadIdx.x < 4 && boxes[threadIdx.x])
+    {
+        boxes[threadIdx.x]->n_migrants = 0;
+        boxes[threadIdx.x]->n_ghosts = 0;
+    }
+}
+
+__global__ void invert_permutation_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ inv, uint64_t n)
+{
+    const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gstride) inv[perm[i]] = static_cast<uint32_t>(i);
+}
+
 inline int blocks_for(uint64_t items)
 {
     uint64_t b = (items + kThreads - 1) / kThreads;
@@ -323,6 +458,26 @@ void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_k
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
     air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);
+}
+void launch_air_own_init(const AirArgs& a, AirMailbox* in_lo, AirMailbox* in_hi, cudaStream_t st)
+{
+    air_own_init_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a, in_lo, in_hi);
+}
+void launch_air_ghosts(const AirArgs& a, const AirMailbox* sent_lo, const AirMailbox* sent_hi, cudaStream_t st)
+{
+    air_ghosts_kernel<<<8, kThreads, 0, st>>>(a, sent_lo, sent_hi);
+}
+void launch_air_unpack(const AirArgs& a, AirMailbox* in_lo, AirMailbox* in_hi, cudaStream_t st)
+{
+    air_unpack_kernel<<<1, kThreads, 0, st>>>(a, in_lo, in_hi);
+}
+void launch_air_mail_reset(AirMailbox* a, AirMailbox* b, AirMailbox* c, AirMailbox* d, cudaStream_t st)
+{
+    air_mail_reset_kernel<<<1, 32, 0, st>>>(a, b, c, d);
+}
+void launch_invert_permutation(const uint32_t* perm, uint32_t* inv, uint64_t n, cudaStream_t st)
+{
+    invert_permutation_kernel<<<blocks_for(n), kThreads, 0, st>>>(perm, inv, n);
 }
 
 } // namespace incerto

@@ -40,6 +40,8 @@ static int32_t air_check(Sim& s, AirModule& am, const incerto_air_params& p)
 }
 
 static int32_t air_sort_rows(Sim& s);
+static int32_t air_partition_setup(Sim& s);
+static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step);
 
 int32_t air_bind(Sim& s)
 {
@@ -107,7 +109,75 @@ int32_t air_bind(Sim& s)
         INC_CUDA(cudaMalloc(&am.d_bits_next, (1ull << fb) / 8));
         INC_CUDA(cudaMalloc(&am.d_cand, std::max<uint64_t>(t.n, 2)));
     }
-    return air_sort_rows(s);
+    INC_TRY(air_sort_rows(s));
+    return air_partition_setup(s);
+}
+
+// ---- domain decomposition: ONE airspace over the GPUs of a box, split by x.
+// Every rank spawns the whole population (same uids, same draws) and keeps the full table; the alive bit of a row means
+// "owned by this rank" (grid x inside [x_lo, x_hi)).  Rows are sorted by (x, y) column at spawn, so a rank's aircraft
+// are one contiguous run of rows plus, later, the few that wandered in.  After every step the ranks exchange one
+// fixed-size mailbox per neighbour (AirMailbox, kernels_air.hpp): the aircraft that crossed the cut - uid and new
+// position; the receiver revives its copy of the row, the sender marks its copy dead - and the positions of the
+// aircraft standing in the boundary column, which the neighbour needs as ghosts for the +-x probes of check_conflicts.
+// Draws are keyed by uid, so the union of the slabs is bit for bit the undivided world (tests/test_gpu_air_partition.py).
+static AirMailbox* air_mailbox(AirModule& am, int which) // 0 out_lo, 1 out_hi, 2 in_lo, 3 in_hi
+{
+    return reinterpret_cast<AirMailbox*>(am.d_mail + static_cast<size_t>(which) * ((AirMailbox::bytes(am.mail_cap) + 255) & ~size_t(255)));
+}
+
+static int32_t air_partition_setup(Sim& s)
+{
+    AirModule& am = s.mods->air;
+    am.part = false;
+    if (s.part_world <= 1 || am.table < 0) return INCERTO_OK;
+    if (am.grid < 0)
+    {
+        set_error("a row-partitioned air_traffic world needs the bounded 3-D spatial grid (its x extent is what gets split)");
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    const GridInst& g = s.grids[am.grid];
+    const int32_t ext_x = g.bmax[0] - g.bmin[0] + 1;
+    incerto_partition_range(ext_x, s.part_rank, s.part_world, &am.x_lo, &am.x_hi);
+    if (am.x_hi - am.x_lo < 2)
+    {
+        set_error("air_traffic partition: every rank needs at least two columns of x (extent %d over %u ranks)", ext_x, s.part_world);
+        return INCERTO_ERR_INVALID_ARGUMENT;
+    }
+    Table& t = s.tables[am.table];
+    // a boundary column holds n / ext_x aircraft on average; room for 8 x that + 1024 per list
+    const uint32_t cap = static_cast<uint32_t>(std::min<uint64_t>(8 * (t.n / static_cast<uint64_t>(ext_x) + 1) + 1024, std::max<uint64_t>(t.n, 1)));
+    if (!am.d_mail || cap != am.mail_cap)
+    {
+        cudaFree(am.d_mail);
+        am.d_mail = nullptr;
+        am.mail_cap = cap;
+        const size_t one = (AirMailbox::bytes(cap) + 255) & ~size_t(255);
+        INC_CUDA(cudaMalloc(&am.d_mail, 4 * one));
+    }
+    const size_t one = (AirMailbox::bytes(am.mail_cap) + 255) & ~size_t(255);
+    INC_CUDA(cudaMemsetAsync(am.d_mail, 0, 4 * one, s.stream));
+    for (int k = 0; k < 4; ++k)
+    {
+        const uint32_t hdr[4] = {0u, 0u, am.mail_cap, 0u};
+        INC_CUDA(cudaMemcpyAsync(air_mailbox(am, k), hdr, sizeof(hdr), cudaMemcpyHostToDevice, s.stream));
+    }
+    cudaFree(am.d_row_of_uid);
+    am.d_row_of_uid = nullptr;
+    if (t.d_uid)
+    {
+        INC_CUDA(cudaMalloc(&am.d_row_of_uid, std::max<uint64_t>(t.n_spawned, 1) * 4));
+        launch_invert_permutation(t.d_uid, am.d_row_of_uid, t.n, s.stream);
+    }
+    am.part = true;
+    t.all_alive = false;
+    AirArgs a;
+    air_fill(s, am, a, t, 0);
+    launch_air_own_init(a, s.part_rank > 0 ? air_mailbox(am, 2) : nullptr,
+                        s.part_rank + 1 < s.part_world ? air_mailbox(am, 3) : nullptr, s.stream);
+    INC_CUDA(cudaGetLastError());
+    am.bits_ready = false;
+    return INCERTO_OK;
 }
 
 // rows in (x, y) column order: neighbouring aircraft then probe neighbouring sectors of the pre-filter
@@ -132,7 +202,8 @@ int32_t air_reset(Sim& s)
     if (am.d_slots) INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
     if (am.d_acc) INC_CUDA(cudaMemsetAsync(am.d_acc, 0, 64, s.stream));
     am.bits_ready = false;
-    return air_sort_rows(s);
+    INC_TRY(air_sort_rows(s));
+    return air_partition_setup(s);
 }
 
 void air_free(Sim& s)
@@ -144,6 +215,10 @@ void air_free(Sim& s)
     cudaFree(am.d_bits_next);
     am.d_bits_next = nullptr;
     cudaFree(am.d_cand);
+    cudaFree(am.d_mail);
+    cudaFree(am.d_row_of_uid);
+    am.d_mail = nullptr;
+    am.d_row_of_uid = nullptr;
     am.d_bits = nullptr;
     am.d_cand = nullptr;
     am.d_slots = nullptr;
@@ -184,6 +259,41 @@ static void air_fill(Sim& s, AirModule& am, AirArgs& a, Table& t, uint64_t step)
     a.bits_shift = 32 - (am.filter_bits - 8); // 256-bit sectors are hashed, the low 8 key bits index inside
     a.cand = am.d_cand;
     a.error = s.d_error;
+    a.part = am.part ? 1u : 0u;
+    if (am.part)
+    {
+        a.x_lo = am.x_lo;
+        a.x_hi = am.x_hi;
+        a.flags = t.d_flags;
+        a.flags_rw = t.d_flags;
+        a.out_lo = s.part_rank > 0 ? air_mailbox(am, 0) : nullptr;
+        a.out_hi = s.part_rank + 1 < s.part_world ? air_mailbox(am, 1) : nullptr;
+        a.in_lo = s.part_rank > 0 ? air_mailbox(am, 2) : nullptr;
+        a.in_hi = s.part_rank + 1 < s.part_world ? air_mailbox(am, 3) : nullptr;
+        a.row_of_uid = am.d_row_of_uid;
+    }
+}
+
+// the per-step exchange over NCCL (one fixed-size message per neighbour and direction), then the arrivals come alive
+static int32_t air_exchange(Sim& s, AirModule& am, Table& t, uint64_t step)
+{
+    if (!am.part) return INCERTO_OK;
+    AirArgs a;
+    air_fill(s, am, a, t, step);
+    if (s.comm)
+    {
+        const void* send_lo[1] = {air_mailbox(am, 0)};
+        void* recv_lo[1] = {air_mailbox(am, 2)};
+        const void* send_hi[1] = {air_mailbox(am, 1)};
+        void* recv_hi[1] = {air_mailbox(am, 3)};
+        const size_t bytes[1] = {AirMailbox::bytes(am.mail_cap)};
+        KTimer kt(s, "air_exchange_nccl", 2.0 * bytes[0]);
+        INC_TRY(comm_halo(s, send_lo, recv_lo, send_hi, recv_hi, bytes, 1));
+        launch_air_unpack(a, const_cast<AirMailbox*>(a.in_lo), const_cast<AirMailbox*>(a.in_hi), s.stream);
+        INC_CUDA(cudaGetLastError());
+    }
+    // without a communicator the host moves the mailboxes (incerto_sim_halo_export / _import; the import unpacks)
+    return INCERTO_OK;
 }
 
 int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
@@ -208,11 +318,18 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
                 launch_air_bits(a, s.stream);
             }
             INC_CUDA(cudaMemsetAsync(am.d_bits_next, 0, (1ull << am.filter_bits) / 8, s.stream));
+            if (am.part)
+            {
+                // the ghosts: what the neighbours sent after the previous step + what this rank handed over itself
+                KTimer kt(s, "air_ghosts", 0.0);
+                launch_air_ghosts(a, a.out_lo, a.out_hi, s.stream);
+            }
             {
                 KTimer kt(s, "air_candidates", 9.0 * t.n);
                 launch_air_candidates(a, s.stream);
             }
         }
+        if (am.part) launch_air_mail_reset(a.out_lo, a.out_hi, nullptr, nullptr, s.stream); // the step kernel refills them
         {
             KTimer kt(s, "air_step", (am.do_move ? 18.0 : 8.0) * t.n + (am.do_check ? 1.0 : 0.0) * t.n);
             launch_air_step(a, s.stream);
@@ -223,7 +340,38 @@ int32_t air_step(Sim& s, uint64_t first_step, uint32_t nsteps)
             std::swap(am.d_bits, am.d_bits_next); // the step kernel left the next PreUpdate's bitmap behind
             am.bits_ready = true;
         }
+        INC_TRY(air_exchange(s, am, t, step));
     }
+    return INCERTO_OK;
+}
+
+// Manual transport of the mailboxes (single-process tests of the decomposition; with a communicator attached the
+// exchange runs over NCCL inside run): export = this rank's outbox for `side` (0 lower, 1 upper neighbour), import =
+// the neighbour's outbox into this rank's inbox, followed by the unpack of the arrivals.
+int32_t air_mail_export(Sim& s, uint32_t side, void* out, size_t capacity, size_t* n_out)
+{
+    AirModule& am = s.mods->air;
+    if (!am.part) return INCERTO_ERR_UNSUPPORTED;
+    const size_t n = AirMailbox::bytes(am.mail_cap);
+    if (n_out) *n_out = n;
+    if (capacity < n) return INCERTO_ERR_INVALID_ARGUMENT;
+    INC_CUDA(cudaMemcpyAsync(out, air_mailbox(am, side == 0 ? 0 : 1), n, cudaMemcpyDeviceToHost, s.stream));
+    INC_CUDA(cudaStreamSynchronize(s.stream));
+    return INCERTO_OK;
+}
+int32_t air_mail_import(Sim& s, uint32_t side, const void* in, size_t n)
+{
+    AirModule& am = s.mods->air;
+    if (!am.part) return INCERTO_ERR_UNSUPPORTED;
+    if (n != AirMailbox::bytes(am.mail_cap)) return INCERTO_ERR_INVALID_ARGUMENT;
+    Table& t = s.tables[am.table];
+    AirMailbox* box = air_mailbox(am, side == 0 ? 2 : 3);
+    INC_CUDA(cudaMemcpyAsync(box, in, n, cudaMemcpyHostToDevice, s.stream));
+    AirArgs a;
+    air_fill(s, am, a, t, s.step);
+    launch_air_unpack(a, side == 0 ? box : nullptr, side == 1 ? box : nullptr, s.stream);
+    INC_CUDA(cudaGetLastError());
+    INC_CUDA(cudaStreamSynchronize(s.stream));
     return INCERTO_OK;
 }
 

@@ -1032,8 +1032,9 @@ int32_t incerto_sim_halo_export(incerto_sim* sp, uint32_t side, void* out, size_
     Sim* S = reinterpret_cast<Sim*>(sp);
     if (!S || side > 1 || !out) return INCERTO_ERR_INVALID_ARGUMENT;
     ForestModule& fm = S->mods->forest;
-    if (!fm.active) return INCERTO_ERR_UNSUPPORTED;
     INC_CUDA(cudaSetDevice(S->device));
+    if (!fm.active && S->mods->air.part) return air_mail_export(*S, side, out, capacity, n_out);
+    if (!fm.active) return INCERTO_ERR_UNSUPPORTED;
     const size_t n = static_cast<size_t>(fm.H) + fm.n_overlay;
     if (n_out) *n_out = n;
     if (capacity < n) return INCERTO_ERR_INVALID_ARGUMENT;
@@ -1051,8 +1052,9 @@ int32_t incerto_sim_halo_import(incerto_sim* sp, uint32_t side, const void* in, 
     Sim* S = reinterpret_cast<Sim*>(sp);
     if (!S || side > 1 || !in) return INCERTO_ERR_INVALID_ARGUMENT;
     ForestModule& fm = S->mods->forest;
-    if (!fm.active) return INCERTO_ERR_UNSUPPORTED;
     INC_CUDA(cudaSetDevice(S->device));
+    if (!fm.active && S->mods->air.part) return air_mail_import(*S, side, in, n);
+    if (!fm.active) return INCERTO_ERR_UNSUPPORTED;
     if (n != static_cast<size_t>(fm.H) + fm.n_overlay) return INCERTO_ERR_INVALID_ARGUMENT;
     const uint32_t slab_w = static_cast<uint32_t>(fm.x_end - fm.x_begin);
     uint8_t* col = fm.d_slab[fm.cur] + static_cast<size_t>(side == 0 ? 0 : slab_w + 1) * fm.pitch;

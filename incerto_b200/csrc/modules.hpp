@@ -105,6 +105,12 @@ struct AirModule
     uint32_t filter_bits = 0;
     uint8_t* d_cand = nullptr;            // per row: neighbour cells that showed a set bit
     uint64_t* d_acc = nullptr;            // [0] conflicts of the last step (pairs counted twice), [1] aircraft indexed
+    // domain decomposition by x (incerto_builder_set_row_partition on an air_traffic world): see module_air.cu
+    bool part = false;
+    int32_t x_lo = 0, x_hi = 0;           // owned slab in grid coordinates
+    uint32_t mail_cap = 0;                // records per mailbox list
+    uint8_t* d_mail = nullptr;            // four AirMailbox blobs: out_lo, out_hi, in_lo, in_hi
+    uint32_t* d_row_of_uid = nullptr;     // inverse of the spawn-time row sort (nullptr: row == uid)
 };
 
 struct TradersModule
@@ -168,6 +174,8 @@ int32_t forest_stats_now(Sim& s, uint64_t out5[5]);
 void forest_free(Sim& s);
 int32_t forest_halo_exchange(Sim& s);
 int32_t forest_finalize(Sim& s);
+int32_t air_mail_export(Sim& s, uint32_t side, void* out, size_t capacity, size_t* n_out);
+int32_t air_mail_import(Sim& s, uint32_t side, const void* in, size_t n);
 int32_t forest_peer_setup(Sim& s);
 int32_t forest_peer_quiesce(Sim& s);
 void forest_peer_free(Sim& s);

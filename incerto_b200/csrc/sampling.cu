@@ -177,7 +177,8 @@ static int32_t select_allreduce_histogram(void* ctx)
 
 static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw, bool global = false)
 {
-    if (global && !is_generic_kind(a.kind) && a.kind != INCERTO_AGG_COIN_ODDS && a.kind != INCERTO_AGG_FIRE_STATS)
+    if (global && !is_generic_kind(a.kind) && a.kind != INCERTO_AGG_COIN_ODDS && a.kind != INCERTO_AGG_FIRE_STATS &&
+        a.kind != INCERTO_AGG_AIR_CONFLICTS)
     {
         set_error("sample_aggregate_global: aggregate kind %u is not available across ranks", a.kind);
         return INCERTO_ERR_UNSUPPORTED;
@@ -239,6 +240,9 @@ static int32_t aggregate_launch(Sim& s, const AggSpec& a, int ti, uint8_t* d_raw
             return INCERTO_ERR_UNSUPPORTED;
         }
         INC_CUDA(cudaMemcpyAsync(d_raw, am.d_acc, 16, cudaMemcpyDeviceToDevice, s.stream));
+        // one airspace split over the ranks: a pair across a cut is counted once on either side, so the halves only
+        // add up globally (conflicts = sum over the ranks / 2)
+        if (global) INC_TRY(comm_allreduce(s, d_raw, 2, 0, 0));
         return INCERTO_OK;
     }
     if (a.kind == INCERTO_AGG_COIN_ODDS)
@@ -353,8 +357,10 @@ static void narrow_store(int dt, uint64_t bits, void* out)
 
 // Combine the per-table raw records and convert to the ABI record.
 // Returns AGGREGATE_NO_ENTITIES when nothing matched.
+// `reduced`: the raw records were summed over the ranks of the communicator (only matters for AIR_CONFLICTS of an
+// x-partitioned airspace, whose per-rank records count conflict ENDS: a pair across a cut has one end on either side)
 static int32_t aggregate_finalize(const Sim& s, const AggSpec& a, const uint8_t* raws, size_t n_raws, void* out,
-                                  uint64_t* count_out)
+                                  uint64_t* count_out, bool reduced = false)
 {
     const int dt = s.comps[a.component].dtype;
     if (is_generic_kind(a.kind))
@@ -532,7 +538,9 @@ static int32_t aggregate_finalize(const Sim& s, const AggSpec& a, const uint8_t*
         }
         if (count_out) *count_out = indexed;
         if (!indexed) return INCERTO_ERR_AGGREGATE_NO_ENTITIES;
-        store_as<uint64_t>(out, twice / 2); // "Divide by 2 since each conflict is counted twice", air_traffic_3d.rs:160
+        // "Divide by 2 since each conflict is counted twice", air_traffic_3d.rs:160.  One rank of a partitioned
+        // airspace reports its conflict ends un-halved: only their sum over the ranks is even.
+        store_as<uint64_t>(out, (s.mods->air.part && !reduced) ? twice : twice / 2);
         return INCERTO_OK;
     }
     if (a.kind == INCERTO_AGG_PANDEMIC_STATS)
@@ -685,9 +693,12 @@ static int32_t series_materialize(Sim& s, SeriesInst& se)
         INC_CUDA(cudaMemcpyAsync(raw.data(), se.d_values, raw.size(), cudaMemcpyDeviceToHost, s.stream));
         INC_CUDA(cudaMemcpyAsync(counts.data(), se.d_counts, counts.size() * 8, cudaMemcpyDeviceToHost, s.stream));
         INC_CUDA(cudaStreamSynchronize(s.stream));
-        if (s.comm && se.agg.kind == INCERTO_AGG_FIRE_STATS && s.part_world > 1)
+        bool reduced = false;
+        if (s.comm && s.part_world > 1 &&
+            (se.agg.kind == INCERTO_AGG_FIRE_STATS || (se.agg.kind == INCERTO_AGG_AIR_CONFLICTS && s.mods->air.part)))
         {
-            // row-partitioned forest: every rank holds partial counts.  COLLECTIVE: every rank of the communicator must
+            reduced = true;
+            // row-partitioned forest / x-partitioned airspace: every rank holds partial counts.  COLLECTIVE: every rank of the communicator must
             // read the series the same number of times between runs (documented at incerto_sim_get_aggregate_time_series)
             uint64_t* d = nullptr;
             const size_t words = raw.size() / 8 + counts.size();
@@ -712,7 +723,7 @@ static int32_t series_materialize(Sim& s, SeriesInst& se)
         {
             if (counts[k] == 0) continue; // `if !component_values.is_empty()`, time_series.rs:79
             uint64_t cnt = 0;
-            const int32_t st = aggregate_finalize(s, se.agg, raw.data() + k * rs, 1, rec.data(), &cnt);
+            const int32_t st = aggregate_finalize(s, se.agg, raw.data() + k * rs, 1, rec.data(), &cnt, reduced);
             if (st == INCERTO_ERR_AGGREGATE_NO_ENTITIES) continue;
             INC_TRY(st);
             se.h_time.push_back((k + 1) * se.interval);
@@ -1121,7 +1132,7 @@ static int32_t sample_aggregate_impl(incerto_sim* s, const incerto_aggregate_des
         INC_TRY(incerto_sim_synchronize(s));
         return aggregate_finalize(S, a, reinterpret_cast<const uint8_t*>(&tot), 1, out, nullptr);
     }
-    return aggregate_finalize(S, a, h.data(), tabs.size(), out, nullptr);
+    return aggregate_finalize(S, a, h.data(), tabs.size(), out, nullptr, global);
 }
 
 static int32_t find_by_id(Sim& S, int component, int identifier, const void* id_value, int& table_out, uint64_t& row_out)

@@ -708,9 +708,15 @@ class Simulation:
         _check(self._lib.incerto_sim_run_cold(self._h, num_steps))
 
     def halo_export(self, side: int) -> np.ndarray:
+        """What the neighbour on `side` (0 lower, 1 upper) needs after the last step: the boundary column (+ overlay
+        states) of a row-partitioned forest, or the mailbox (migrated aircraft + ghosts) of an x-partitioned airspace."""
         n = C.c_size_t()
         buf = np.zeros(1 << 16, dtype=np.uint8)
-        _check(self._lib.incerto_sim_halo_export(self._h, side, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(n)))
+        code = self._lib.incerto_sim_halo_export(self._h, side, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(n))
+        if code == F.ERR_INVALID_ARGUMENT and n.value > buf.nbytes:      # the message is larger: the size came back
+            buf = np.zeros(n.value, dtype=np.uint8)
+            code = self._lib.incerto_sim_halo_export(self._h, side, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(n))
+        _check(code)
         return buf[:n.value].copy()
 
     def halo_import(self, side: int, data: np.ndarray) -> None:

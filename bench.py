@@ -28,7 +28,8 @@ Extra keys (round 2, VERDICT r01 "Next round" 1, 4, 5):
   `partition_parity`, `replica_parity`, `global_aggregate_parity` (N > 1)  untimed correctness checks of the
                 multi-GPU paths (row-split grid = undivided run; sharded + all-reduced replica statistics = one GPU
                 running them all; cross-replica Median / Percentile by distributed radix select = numpy on the
-                gathered columns);
+                gathered columns; `air_partition_parity`: one airspace split by x with migrating aircraft = the
+                undivided world); `air_one_world` (N > 1): the 5 M-aircraft airspace as ONE world over the N GPUs;
   `same_slab_1gpu_us`, `fixed_cost_us` (N = 1)  the N > 1 slab (2048 x 16384) alone on one GPU, and the cold floor
                 of a 64 x 512 grid (launch + cold code / constant bank + event pair).
 """
@@ -465,6 +466,58 @@ def check_replica_parity(ib, ex, np, ranks, local_rank):
     return bool(ranks.max(0.0 if ok else 1.0) == 0.0)
 
 
+def check_air_partition_parity(ib, ex, np, ranks, local_rank):
+    """ONE air_traffic_3d world (400 k aircraft at the reference density) split by x over the N GPUs -
+    aircraft migrate between the ranks, ghosts cross the cuts, all over NCCL - stepped 40 times: every aircraft's
+    position (gathered by uid) and the all-reduced conflict series must equal the undivided world on rank 0."""
+    world, rank = ranks.world, ranks.rank
+    n, size, steps = 400_000, 3266, 40
+    sim, h = ex.air_traffic_3d(n, size, device=local_rank, partition=(rank, world))
+    sim.attach_comm(ranks.share_unique_id(ib), rank, world)
+    sim.run(steps)
+    pos, uids = sim.read_component(h.position, with_uids=True)
+    ts = sim.get_aggregate_time_series(h.conflicts)                  # collective: summed over the ranks, then halved
+    ser = np.array(ts.values(), dtype=np.int64)
+    parts = ranks.gather((uids, pos))
+    ok = True
+    migrated = 0
+    if rank == 0:
+        whole, hw = ex.air_traffic_3d(n, size, device=local_rank)
+        whole.run(steps)
+        want = whole.read_component(hw.position)
+        ser0 = np.array(whole.get_aggregate_time_series(hw.conflicts).values(), dtype=np.int64)
+        got = np.full_like(want, -1)
+        seen = np.zeros(n, np.int32)
+        for u, p in parts:
+            got[u] = p
+            seen[u] += 1
+        ok = bool((seen == 1).all()) and bool(np.array_equal(got, want)) and bool(np.array_equal(ser, ser0)) and int(ser0.max()) > 0
+        whole.destroy()
+    sim.destroy()
+    return bool(ranks.max(0.0 if ok else 1.0) == 0.0)
+
+
+def run_air_one_world(ib, ex, ranks, local_rank, peak):
+    """The 5 M-aircraft airspace of configs[4b] as ONE world over the N GPUs (strong scaling of a single world; every rank
+    keeps the full table and steps the aircraft whose x lies in its slab)."""
+    world, rank = ranks.world, ranks.rank
+    n, size, steps = 5_000_000, 11547, 50
+    sim, h = ex.air_traffic_3d(n, size, device=local_rank, partition=(rank, world))
+    sim.attach_comm(ranks.share_unique_id(ib), rank, world)
+    sim.run(10)
+    ranks.barrier()
+    sim.run(steps)
+    ms, launches = sim.last_run_stats()
+    ms = ranks.max(ms)
+    conflicts = sim.sample_aggregate_global(h.conflicts)
+    owned = ranks.sum(float(sim.sample_aggregate(ib.Count(h.target))))
+    sim.destroy()
+    return {"entities": n, "steps": steps, "us_per_step": ms / steps * 1e3, "updates_per_s": n * steps / (ms * 1e-3),
+            "launches_per_step": launches / steps, "conflicts_last_step": int(conflicts), "aircraft_owned_by_all_ranks": int(owned),
+            "note": "one 11547^2 x 10 airspace split by x; per step: ghosts + candidates + step kernels on the owned rows, one "
+                    "fixed-size NCCL send/recv pair per neighbour (migrated aircraft + boundary-column ghosts), unpack"}
+
+
 def check_global_aggregate_parity(ib, ex, np, ranks, local_rank):
     """SURVEY §8 (f) 3, cross-replica quantiles: every rank holds one traders replica (200 k traders, 30 steps); Median,
     Percentile<90>, Minimum, Maximum, Count and Mean of the net worth over the traders of ALL ranks through
@@ -729,6 +782,7 @@ def main():
         line["partition_parity"] = check_partition_parity(ib, ex, np, ranks, local_rank)
         line["replica_parity"] = check_replica_parity(ib, ex, np, ranks, local_rank)
         line["global_aggregate_parity"] = check_global_aggregate_parity(ib, ex, np, ranks, local_rank)
+        line["air_partition_parity"] = check_air_partition_parity(ib, ex, np, ranks, local_rank)
 
     # ---- e2e through the C ABI with host buffers
     if not args.no_e2e:
@@ -739,6 +793,8 @@ def main():
         line["workloads"] = run_workloads(ib, ex, ranks, local_rank, peak)
     if not args.no_replicas:
         line["replicas"] = run_replicas(ib, ex, np, ranks, local_rank, peak)
+    if world > 1 and not args.no_workloads:
+        line["air_one_world"] = run_air_one_world(ib, ex, ranks, local_rank, peak)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -94,11 +94,14 @@ def traders(nt: int, ns: int = 100, replica: int = 0, device: int | None = None,
 
 
 def air_traffic_3d(n: int, size: int, height: int = 10, replica: int = 0, device: int | None = None, series: int = 1,
-                   seed: int = SEED):
-    """examples/air_traffic_3d.rs:201-220 (AIRSPACE_SIZE = size, AIRSPACE_HEIGHT = height)."""
+                   seed: int = SEED, partition: tuple[int, int] | None = None):
+    """examples/air_traffic_3d.rs:201-220 (AIRSPACE_SIZE = size, AIRSPACE_HEIGHT = height); `partition` = (rank, world)
+    splits the ONE airspace by x over the ranks (aircraft migrate between them)."""
     b = ib.SimulationBuilder(seed=seed, replica=replica, device=device)
     position = b.component("GridPosition3D", F.I16, lanes=3)
     target = b.component("Aircraft.target_altitude", F.I16)
+    if partition is not None and partition[1] > 1:
+        b.set_row_partition(*partition)
     b.add_spatial_grid_3d(position, target, bounds=((0, 0, 0), (size, size, height)))
     b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_AIRCRAFT, F.SpawnAircraftParams(position.handle, target.handle, n, size, height)))
     b.add_systems(ib.MoveAircraft(position, target, size, height), ib.CheckConflicts(position, target, size, height))

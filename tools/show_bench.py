@@ -6,7 +6,7 @@ d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 r = d["roofline"]
 print(f"headline: {d['config']['workload']}: {d['ms_per_step'] * 1e3:.2f} us/step, {d['value'] / 1e9:.1f} G/s, frac {r['frac']:.3f}; "
       f"L2-resident {d['value_l2_resident'] / 1e9:.1f} G/s; launches {d['gpu_launches']}")
-for k in ("same_slab_1gpu_us", "same_slab_1gpu_l2_resident_us", "fixed_cost_us", "fixed_cost_l2_resident_us", "partition_parity", "replica_parity", "global_aggregate_parity"):
+for k in ("same_slab_1gpu_us", "same_slab_1gpu_l2_resident_us", "fixed_cost_us", "fixed_cost_l2_resident_us", "partition_parity", "replica_parity", "global_aggregate_parity", "air_partition_parity"):
     if k in d:
         print(f"  {k}: {d[k]}")
 if "replica_stream" in d:
@@ -24,5 +24,8 @@ for name, w in d.get("workloads", {}).items():
               + (f"  dram {k['dram_bytes_per_launch_ncu'] / 1e6:.0f} MB" if "dram_bytes_per_launch_ncu" in k else ""))
 for name, w in d.get("replicas", {}).items():
     print(f"replicas {name}: {w['updates_per_s'] / 1e9:.2f} G/s, {w['replicas']} replicas, {w['us_per_replica_step']:.1f} us per replica-step, frac/GPU {w['frac_per_gpu']:.3f}")
+if "air_one_world" in d:
+    q = d["air_one_world"]
+    print(f"air_one_world: {q['us_per_step']:.1f} us/step, {q['updates_per_s'] / 1e9:.2f} G/s, conflicts {q['conflicts_last_step']}, owned {q['aircraft_owned_by_all_ranks']}")
 if "cpu_baseline" in d:
     print("cpu:", d["cpu_baseline"]["value"], d["cpu_baseline"]["sample"])

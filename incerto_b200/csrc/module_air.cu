@@ -102,8 +102,11 @@ int32_t air_bind(Sim& s)
         INC_CUDA(cudaMalloc(&am.d_slots, static_cast<size_t>(am.n_slots) * 8));
         INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
         // pre-filter bitmap: >= 32 bits per aircraft (at most ~3 % of the bits set)
+        // (one airspace split over the ranks: this rank sets bits for its own share of the aircraft only; twice the
+        // average share keeps the false-positive rate if the split is uneven - the filter has no capacity to overflow)
+        const uint64_t filter_n = s.part_world > 1 ? std::max<uint64_t>(2 * t.n / s.part_world, 1024) : t.n;
         uint32_t fb = 16;
-        while ((1ull << fb) < 32 * t.n && fb < 32) ++fb;
+        while ((1ull << fb) < 32 * filter_n && fb < 32) ++fb;
         am.filter_bits = fb;
         INC_CUDA(cudaMalloc(&am.d_bits, (1ull << fb) / 8));
         INC_CUDA(cudaMalloc(&am.d_bits_next, (1ull << fb) / 8));

@@ -104,8 +104,17 @@ void incerto_builder_free(incerto_builder* b); /* drop without build */
 int32_t incerto_builder_set_seed(incerto_builder* b, uint64_t seed, uint32_t replica);
 int32_t incerto_builder_set_device(incerto_builder* b, int32_t cuda_device_ordinal);
 
-/* Row partition for one oversized forest-fire grid split by rows over `world`
- * processes.  rank r owns grid x in [x_begin, x_end). */
+/* Spatial decomposition of ONE world over `world` processes (one per GPU): rank r owns grid x in
+ * [extent * r / world, extent * (r + 1) / world).
+ *  - forest_fire: the dense grid is split by columns of x; each rank holds its slab + one halo column per side, the
+ *    halo exchange is fused into the step kernel (peer memory) or runs over NCCL.
+ *  - air_traffic_3d: the airspace is split by x.  Every rank spawns the whole population and keeps the full table;
+ *    a row is alive on the rank that owns the aircraft's position.  After every step the ranks exchange one fixed-size
+ *    mailbox per neighbour: the aircraft that crossed the cut (they come alive on the receiver) and the positions of the
+ *    boundary-column aircraft (ghosts for check_conflicts).  Needs a communicator (incerto_sim_attach_comm) or the
+ *    manual transport below with one step per run.  The local AIR_CONFLICTS aggregate of one rank is its number of
+ *    conflict ENDS (a pair across a cut has one end on either side); incerto_sim_sample_aggregate_global and the
+ *    aggregate time series (collective) report the world's conflicts. */
 int32_t incerto_builder_set_row_partition(incerto_builder* b, uint32_t rank, uint32_t world);
 
 /* One column of a bulk spawn. `data` holds n*lanes values of the component's
@@ -539,7 +548,11 @@ int32_t incerto_sim_attach_comm(incerto_sim* s, const uint8_t unique_id[128], ui
  * the partition is tested on a single GPU).  When no communicator is attached, `run` leaves the halo
  * columns alone and the host moves them between steps: export the boundary of side 0 (lowest owned
  * column) / 1 (highest) — H cell bytes followed by the overlay-entity states — and import it into the
- * neighbour's halo of the opposite side. */
+ * neighbour's halo of the opposite side.
+ * For an x-partitioned air_traffic_3d world the same two calls move the per-step mailboxes: export = this rank's outbox
+ * for the neighbour on `side` after a step (call with a small `capacity` to learn the size through *n_out), import =
+ * the neighbour's outbox into this rank's inbox of that side; the import revives the aircraft that migrated in.  One
+ * step per `run` call, then both directions of every cut, before the next step. */
 int32_t incerto_sim_halo_export(incerto_sim* s, uint32_t side, void* out, size_t capacity, size_t* n_out);
 int32_t incerto_sim_halo_import(incerto_sim* s, uint32_t side, const void* in, size_t n);
 /* Columns [begin, end) of a W-column grid owned by `rank` of `world` (pure host arithmetic). */

@@ -163,19 +163,25 @@ __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, uint32_t& to
 
 // The persons of a 256-row warp tile that need any work this step, compacted: row, its four state bytes
 // (flags | aux << 8 | quarantine << 16 | disease << 24) and its position.
+// Entries wait in the queue until a full warp's worth (32) has accumulated, across tiles: a tile holds ~13 persons with
+// work in the steady state, and dealing out each tile's entries on its own ran the whole slow path with 13 of 32 lanes
+// (ncu, round 2: 12.9 active threads per instruction).  The queue is a stack: the top 32 entries are taken whenever there
+// are that many; what is left when the warp runs out of tiles is processed at the end.
+constexpr uint32_t kQueueCap = 31 + 256;
 struct WorkQueue
 {
-    uint32_t row[kThreads / 32][256];
-    uint32_t bytes[kThreads / 32][256];
-    uint32_t pos[kThreads / 32][256];
-    uint8_t marked[kThreads / 32][256]; // prepare only: the person's marks are in the mark table
+    uint32_t row[kThreads / 32][kQueueCap + 1];
+    uint32_t bytes[kThreads / 32][kQueueCap + 1];
+    uint32_t pos[kThreads / 32][kQueueCap + 1];
+    uint8_t marked[kThreads / 32][kQueueCap + 1]; // prepare only: the person's marks are in the mark table
 };
 
+// appends this tile's entries above the `have` entries already waiting; returns the new count
 __device__ __forceinline__ uint32_t enqueue(WorkQueue& wq, uint32_t warp, const Tile8& t, uint64_t i0, uint32_t todo,
-                                            uint32_t marked_bits = 0)
+                                            uint32_t have, uint32_t marked_bits = 0)
 {
     uint32_t total;
-    uint32_t off = warp_exclusive_scan(__popc(todo), total);
+    uint32_t off = have + warp_exclusive_scan(__popc(todo), total);
     if (total)
     {
 #pragma unroll
@@ -190,7 +196,7 @@ __device__ __forceinline__ uint32_t enqueue(WorkQueue& wq, uint32_t warp, const 
             }
     }
     __syncwarp();
-    return total;
+    return have + total;
 }
 
 // Streaming pass with a rare slow path.  A lane owns eight consecutive persons (128 bytes in flight per lane);
@@ -208,6 +214,147 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats_acc)
         for (int k = 0; k < 4; ++k) a.stats_acc[k] = 0;
+    // the slow path of one person (entry j of this warp's queue)
+    auto work = [&](uint32_t j) {
+        const uint64_t i = wq.row[warp][j];
+        const uint32_t bytes = wq.bytes[warp][j], p = wq.pos[warp][j];
+        const uint32_t fl = bytes & 0xffu, ax = (bytes >> 8) & 0xffu, q = (bytes >> 16) & 0xffu;
+        uint32_t d = bytes >> 24;
+        const uint32_t d0 = d;
+        const uint32_t op = ax >> 5;
+        uint32_t len = ax & 31u;
+        const uint32_t x = p & 0xffffu, y = p >> 16;
+        const uint32_t cell = x * G + y;
+        bool marked = wq.marked[warp][j] != 0;
+        const bool alive = (fl & 1u) != 0;
+        const bool free_ = q == 0;
+        const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
+        const bool moved = alive && op >= OP_UP && op <= OP_DOWN;
+        // :544-562 update_contact_history: a person who did not move already remembers this cell (it was
+        // inserted last step) unless that insert emptied the set
+        const bool need_hist = alive && (a.systems & 8u) && (len == 0 || moved);
+        // :565-608 scatter side of the tracing, kept incrementally: the mark table holds the remembered cells of
+        // exactly the non-quarantined live people
+        const bool take_back = marked && !(alive && free_);
+        const bool put_all = alive && (a.systems & 16u) && free_ && !marked;
+        uint32_t hv[kSpatialHistorySlots];
+        if (need_hist || take_back || put_all)
+        {
+            // all remembered cells at once: a person's 20 slots are contiguous (80 bytes), fetched as up to five
+            // independent 128-bit loads (round 1 stored the slots slot-major: 20 predicated 4-byte loads, a 32-byte
+            // sector each, and a fifth of this kernel's instructions)
+            const uint4* hp = reinterpret_cast<const uint4*>(a.hist + static_cast<uint64_t>(i) * kSpatialHistorySlots);
+#pragma unroll
+            for (uint32_t v4 = 0; v4 < kSpatialHistorySlots / 4; ++v4)
+            {
+                uint4 q = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                if (4 * v4 < len) q = hp[v4];
+                hv[4 * v4 + 0] = 4 * v4 + 0 < len ? q.x : 0xffffffffu;
+                hv[4 * v4 + 1] = 4 * v4 + 1 < len ? q.y : 0xffffffffu;
+                hv[4 * v4 + 2] = 4 * v4 + 2 < len ? q.z : 0xffffffffu;
+                hv[4 * v4 + 3] = 4 * v4 + 3 < len ? q.w : 0xffffffffu;
+            }
+        }
+        if (take_back)
+        {
+            // quarantined at the last flush, or despawned: its marks (the set as it was while it was free) go
+#pragma unroll
+            for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                if (s2 < len) unmark_cell(a, hv[s2], uid + 1u);
+            marked = false;
+        }
+        if (!alive)
+        {
+            // spatial_grid_cleanup_system (spatial_grid.rs:446-455): despawned at the last flush
+            atomicSub(&a.count[cell], 1u);
+            a.aux[i] = 0;
+            return;
+        }
+        // spatial_grid_update_system (spatial_grid.rs:434-443) for Changed<GridPosition>
+        if (op == OP_NEW)
+        {
+            if (x >= G || y >= G)
+            {
+                if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u) a.error[1] = static_cast<uint32_t>(i);
+                return; // left untouched
+            }
+            atomicAdd(&a.count[cell], 1u);
+        }
+        if (moved)
+        {
+            const uint32_t old = op == OP_UP ? cell + 1 : (op == OP_DOWN ? cell - 1 : (op == OP_LEFT ? cell + G : cell - G));
+            atomicSub(&a.count[old], 1u);
+            atomicAdd(&a.count[cell], 1u);
+        }
+        bool dying = false;
+        // :414-433
+        if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
+        // :446-459 the infectious, non-quarantined people are the sources of this step
+        if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
+        {
+            atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
+            const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
+            a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
+        }
+        // :521-541
+        if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
+        {
+            const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
+            if (bernoulli(r.x, a.thr_die))
+                dying = true;
+            else if (bernoulli(r.y, a.thr_recover))
+                d = INCERTO_DISEASE_RECOVERED;
+        }
+        if (need_hist)
+        {
+            bool found = false;
+#pragma unroll
+            for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2) found = found || hv[s2] == p;
+            if (!found)
+            {
+                if (len >= a.history_cap)
+                {
+                    // the insert made the set larger than 20: clear() (:555-558)
+                    if (marked)
+                    {
+#pragma unroll
+                        for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                            if (s2 < len) unmark_cell(a, hv[s2], uid + 1u);
+                    }
+                    len = 0;
+                }
+                else
+                {
+                    a.hist[static_cast<uint64_t>(i) * kSpatialHistorySlots + len] = p;
+#pragma unroll
+                    for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                        if (s2 == len) hv[s2] = p;
+                    len += 1;
+                    if (marked) mark_cell(a, p, uid + 1u);
+                }
+            }
+        }
+        if (put_all)
+        {
+#pragma unroll
+            for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
+                if (s2 < len) mark_cell(a, hv[s2], uid + 1u);
+            marked = true;
+        }
+        if (marked != (wq.marked[warp][j] != 0))
+        {
+            // flip this person's bit (rare: once per quarantine / release)
+            uint32_t* word = reinterpret_cast<uint32_t*>(a.marked) + (i >> 5);
+            if (marked)
+                atomicOr(word, 1u << (i & 31));
+            else
+                atomicAnd(word, ~(1u << (i & 31)));
+        }
+        if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
+        const uint32_t nax = len | ((dying ? OP_DYING : OP_NONE) << 5);
+        if (nax != ax) a.aux[i] = static_cast<uint8_t>(nax);
+    };
+    uint32_t waiting = 0; // entries in this warp's queue (warp-uniform)
     for (uint64_t base = warp0 * 256; base < a.n; base += nwarps * 256)
     {
         const uint64_t i0 = base + lane * 8;
@@ -228,149 +375,15 @@ __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a
         if (a.systems & 16u) want |= alive8 & (free8 ^ marked8); // became free: add its marks; quarantined: take them back
         if (a.systems & 8u) want |= alive8 & len0;
         want |= (alive8 ^ kOnes) & died;
-        const uint32_t total = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(want) : 0u, mk);
-        for (uint32_t j = lane; j < total; j += 32)
+        waiting = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(want) : 0u, waiting, mk);
+        while (waiting >= 32) // a full warp's worth: take the top 32
         {
-            const uint64_t i = wq.row[warp][j];
-            const uint32_t bytes = wq.bytes[warp][j], p = wq.pos[warp][j];
-            const uint32_t fl = bytes & 0xffu, ax = (bytes >> 8) & 0xffu, q = (bytes >> 16) & 0xffu;
-            uint32_t d = bytes >> 24;
-            const uint32_t d0 = d;
-            const uint32_t op = ax >> 5;
-            uint32_t len = ax & 31u;
-            const uint32_t x = p & 0xffffu, y = p >> 16;
-            const uint32_t cell = x * G + y;
-            bool marked = wq.marked[warp][j] != 0;
-            const bool alive = (fl & 1u) != 0;
-            const bool free_ = q == 0;
-            const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
-            const bool moved = alive && op >= OP_UP && op <= OP_DOWN;
-            // :544-562 update_contact_history: a person who did not move already remembers this cell (it was
-            // inserted last step) unless that insert emptied the set
-            const bool need_hist = alive && (a.systems & 8u) && (len == 0 || moved);
-            // :565-608 scatter side of the tracing, kept incrementally: the mark table holds the remembered cells of
-            // exactly the non-quarantined live people
-            const bool take_back = marked && !(alive && free_);
-            const bool put_all = alive && (a.systems & 16u) && free_ && !marked;
-            uint32_t hv[kSpatialHistorySlots];
-            if (need_hist || take_back || put_all)
-            {
-                // all remembered cells at once: a person's 20 slots are contiguous (80 bytes), fetched as up to five
-                // independent 128-bit loads (round 1 stored the slots slot-major: 20 predicated 4-byte loads, a 32-byte
-                // sector each, and a fifth of this kernel's instructions)
-                const uint4* hp = reinterpret_cast<const uint4*>(a.hist + static_cast<uint64_t>(i) * kSpatialHistorySlots);
-#pragma unroll
-                for (uint32_t v4 = 0; v4 < kSpatialHistorySlots / 4; ++v4)
-                {
-                    uint4 q = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-                    if (4 * v4 < len) q = hp[v4];
-                    hv[4 * v4 + 0] = 4 * v4 + 0 < len ? q.x : 0xffffffffu;
-                    hv[4 * v4 + 1] = 4 * v4 + 1 < len ? q.y : 0xffffffffu;
-                    hv[4 * v4 + 2] = 4 * v4 + 2 < len ? q.z : 0xffffffffu;
-                    hv[4 * v4 + 3] = 4 * v4 + 3 < len ? q.w : 0xffffffffu;
-                }
-            }
-            if (take_back)
-            {
-                // quarantined at the last flush, or despawned: its marks (the set as it was while it was free) go
-#pragma unroll
-                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
-                    if (s2 < len) unmark_cell(a, hv[s2], uid + 1u);
-                marked = false;
-            }
-            if (!alive)
-            {
-                // spatial_grid_cleanup_system (spatial_grid.rs:446-455): despawned at the last flush
-                atomicSub(&a.count[cell], 1u);
-                a.aux[i] = 0;
-                continue;
-            }
-            // spatial_grid_update_system (spatial_grid.rs:434-443) for Changed<GridPosition>
-            if (op == OP_NEW)
-            {
-                if (x >= G || y >= G)
-                {
-                    if (atomicCAS(a.error, 0u, static_cast<uint32_t>(INCERTO_ERR_OUT_OF_BOUNDS)) == 0u) a.error[1] = static_cast<uint32_t>(i);
-                    continue; // left untouched
-                }
-                atomicAdd(&a.count[cell], 1u);
-            }
-            if (moved)
-            {
-                const uint32_t old = op == OP_UP ? cell + 1 : (op == OP_DOWN ? cell - 1 : (op == OP_LEFT ? cell + G : cell - G));
-                atomicSub(&a.count[old], 1u);
-                atomicAdd(&a.count[cell], 1u);
-            }
-            bool dying = false;
-            // :414-433
-            if ((a.systems & 1u) && d >= 1u && d < 0x80u) d = d > 1u ? d - 1u : INCERTO_DISEASE_INFECTIOUS;
-            // :446-459 the infectious, non-quarantined people are the sources of this step
-            if ((a.systems & 2u) && d == INCERTO_DISEASE_INFECTIOUS && free_)
-            {
-                atomicOr(&a.src_bits[cell >> 5], 1u << (cell & 31));
-                const uint32_t old = atomicExch(&a.src_head[cell], (a.tag << kSpatialRowBits) | static_cast<uint32_t>(i));
-                a.src_next[i] = ((old >> kSpatialRowBits) == a.tag) ? (old & kRowMask) : kRowMask;
-            }
-            // :521-541
-            if ((a.systems & 4u) && d == INCERTO_DISEASE_INFECTIOUS)
-            {
-                const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_fate);
-                if (bernoulli(r.x, a.thr_die))
-                    dying = true;
-                else if (bernoulli(r.y, a.thr_recover))
-                    d = INCERTO_DISEASE_RECOVERED;
-            }
-            if (need_hist)
-            {
-                bool found = false;
-#pragma unroll
-                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2) found = found || hv[s2] == p;
-                if (!found)
-                {
-                    if (len >= a.history_cap)
-                    {
-                        // the insert made the set larger than 20: clear() (:555-558)
-                        if (marked)
-                        {
-#pragma unroll
-                            for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
-                                if (s2 < len) unmark_cell(a, hv[s2], uid + 1u);
-                        }
-                        len = 0;
-                    }
-                    else
-                    {
-                        a.hist[static_cast<uint64_t>(i) * kSpatialHistorySlots + len] = p;
-#pragma unroll
-                        for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
-                            if (s2 == len) hv[s2] = p;
-                        len += 1;
-                        if (marked) mark_cell(a, p, uid + 1u);
-                    }
-                }
-            }
-            if (put_all)
-            {
-#pragma unroll
-                for (uint32_t s2 = 0; s2 < kSpatialHistorySlots; ++s2)
-                    if (s2 < len) mark_cell(a, hv[s2], uid + 1u);
-                marked = true;
-            }
-            if (marked != (wq.marked[warp][j] != 0))
-            {
-                // flip this person's bit (rare: once per quarantine / release)
-                uint32_t* word = reinterpret_cast<uint32_t*>(a.marked) + (i >> 5);
-                if (marked)
-                    atomicOr(word, 1u << (i & 31));
-                else
-                    atomicAnd(word, ~(1u << (i & 31)));
-            }
-            if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
-            const uint32_t nax = len | ((dying ? OP_DYING : OP_NONE) << 5);
-            if (nax != ax) a.aux[i] = static_cast<uint8_t>(nax);
+            waiting -= 32;
+            work(waiting + lane);
+            __syncwarp();
         }
-        __syncwarp();
     }
+    if (lane < waiting) work(lane); // what was left when the tiles ran out
 }
 
 // (dx, dy) of the 13 cells within Manhattan distance 2: index 0 -> distance 0, 1..4 -> distance 1, 5..12 -> distance 2
@@ -384,6 +397,143 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     uint32_t st[4] = {0, 0, 0, 0}; // PandemicStats of the state after this step: healthy, exposed, infectious, recovered
+    // the slow path of one person (entry j of this warp's queue)
+    auto work = [&](uint32_t j) {
+        const uint64_t i = wq.row[warp][j];
+        const uint32_t bytes = wq.bytes[warp][j];
+        uint32_t p = wq.pos[warp][j];
+        uint32_t fl = bytes & 0xffu;
+        const uint32_t ax = (bytes >> 8) & 0xffu, q = (bytes >> 16) & 0xffu;
+        uint32_t d = bytes >> 24;
+        const uint32_t d0 = d;
+        const bool dying = (ax >> 5) == OP_DYING;
+        const bool free_ = q == 0;
+        const int x = static_cast<int>(p & 0xffffu), y = static_cast<int>(p >> 16);
+        const uint32_t cell = static_cast<uint32_t>(x) * G + static_cast<uint32_t>(y);
+        const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
+
+        // :461-508 gather side of the transmission: probe the 13 cells within Manhattan distance 2 (independent,
+        // predicated bit loads), then walk the source lists of the few cells that hold a source
+        if ((a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY)
+        {
+            uint32_t hits = 0;
+#pragma unroll
+            for (int c13 = 0; c13 < 13; ++c13)
+            {
+                const int dx = kOff13[c13][0], dy = kOff13[c13][1];
+                const int cx = x + dx, cy = y + dy;
+                const uint32_t dist = static_cast<uint32_t>((dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy));
+                if (dist <= a.radius && cx >= 0 && cx < G && cy >= 0 && cy < G)
+                {
+                    const uint32_t c = static_cast<uint32_t>(cx) * G + static_cast<uint32_t>(cy);
+                    hits |= ((a.src_bits[c >> 5] >> (c & 31)) & 1u) << c13;
+                }
+            }
+            bool exposed = false;
+            while (hits)
+            {
+                const int c13 = __ffs(hits) - 1;
+                hits &= hits - 1;
+                int dx = 0, dy = 0;
+#pragma unroll
+                for (int k = 0; k < 13; ++k)
+                    if (c13 == k)
+                    {
+                        dx = kOff13[k][0];
+                        dy = kOff13[k][1];
+                    }
+                const uint32_t c = static_cast<uint32_t>(x + dx) * G + static_cast<uint32_t>(y + dy);
+                const uint64_t thr = c13 <= 4 ? a.thr_infect1 : a.thr_infect2; // distance 0 | 1, else 2 (:495-499)
+                const uint32_t h = a.src_head[c];
+                uint32_t cur = ((h >> kSpatialRowBits) == a.tag) ? (h & kRowMask) : kRowMask;
+                for (uint32_t guard = 0; cur != kRowMask && guard <= kRowMask; ++guard)
+                {
+                    const uint32_t suid = a.uid ? a.uid[cur] : cur;
+                    exposed = exposed || bernoulli(philox4x32_10(uid, suid, a.step, 0u, a.rk_transmit).x, thr);
+                    cur = a.src_next[cur];
+                }
+            }
+            if (exposed) d = a.incubation; // :510-517
+        }
+
+        // :580-606 gather side of the tracing
+        bool quarantine = false;
+        if ((a.systems & 16u) && free_)
+        {
+            const unsigned long long m = a.mark[cell];
+            const uint32_t markers = static_cast<uint32_t>(m >> 32);
+            quarantine = markers >= 2u || (markers == 1u && static_cast<uint32_t>(m) != uid + 1u);
+        }
+
+        // :316-411 (a person despawned at this flush is left where it is: its move is unobservable)
+        uint32_t newop = OP_NONE;
+        if ((a.systems & 64u) && free_ && !dying)
+        {
+            const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_move);
+            if (bernoulli(r.x, a.thr_attempt)) // :332
+            {
+                const bool social = (fl & a.bit_social) != 0;
+                // candidates in the order up, left, right, down (:338-343); bit k of `ok`: candidate k passes
+                // the bounds (:348-355) and quarantine-zone (:360-371) filters
+                uint32_t ok = 0, cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    const int nx = c == 1 ? x - 1 : (c == 2 ? x + 1 : x), ny = c == 0 ? y - 1 : (c == 3 ? y + 1 : y);
+                    if (nx < 0 || nx >= G || ny < 0 || ny >= G) continue;
+                    const int zd = (nx > a.zone_x ? nx - a.zone_x : a.zone_x - nx) + (ny > a.zone_y ? ny - a.zone_y : a.zone_y - ny);
+                    if (zd <= a.zone_radius && social) continue;
+                    ok |= 1u << c;
+                    cnt[c] = a.count[static_cast<uint32_t>(nx) * G + static_cast<uint32_t>(ny)];
+                }
+                if (social)
+                {
+                    // keep the least crowded candidates (:377-390)
+                    uint32_t mn = 0xffffffffu;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if ((ok >> c) & 1u) mn = min(mn, cnt[c]);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (cnt[c] != mn) ok &= ~(1u << c);
+                }
+                if (ok)
+                {
+                    const uint32_t pick = uniform_below(r.y, static_cast<uint32_t>(__popc(ok))); // best_moves.choose (:401)
+                    const uint32_t dir = __fns(ok, 0, static_cast<int>(pick) + 1);
+                    const uint32_t people = dir == 0 ? cnt[0] : (dir == 1 ? cnt[1] : (dir == 2 ? cnt[2] : cnt[3]));
+                    if (people < a.crowding) // :403-408
+                    {
+                        const int mx = dir == 1 ? x - 1 : (dir == 2 ? x + 1 : x), my = dir == 0 ? y - 1 : (dir == 3 ? y + 1 : y);
+                        p = static_cast<uint32_t>(mx) | (static_cast<uint32_t>(my) << 16);
+                        newop = dir + 1;
+                    }
+                }
+            }
+        }
+
+        // end of Update: despawn (:530), try_insert(Quarantined) (:600-603); a quarantined dying person had its
+        // counter decremented above, which nobody can observe
+        if (dying)
+        {
+            fl &= ~1u;
+            newop = OP_DIED;
+            a.flags[i] = static_cast<uint8_t>(fl);
+        }
+        else if (quarantine)
+            a.quar[i] = static_cast<uint8_t>(a.quarantine_duration);
+        if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
+        if (newop >= OP_UP && newop <= OP_DOWN) a.pos[i] = p;
+        if (newop != (ax >> 5)) a.aux[i] = static_cast<uint8_t>((ax & 31u) | (newop << 5));
+        if (fl & 1u)
+        {
+            st[0] += d == INCERTO_DISEASE_HEALTHY;
+            st[1] += d >= 1u && d < 0x80u;
+            st[2] += d == INCERTO_DISEASE_INFECTIOUS;
+            st[3] += d == INCERTO_DISEASE_RECOVERED;
+        }
+    };
+    uint32_t waiting = 0; // entries in this warp's queue (warp-uniform)
     for (uint64_t base = warp0 * 256; base < a.n; base += nwarps * 256)
     {
         const uint64_t i0 = base + lane * 8;
@@ -412,145 +562,15 @@ __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs 
             st[1] += __popcll(al) - __popcll(healthy) - __popcll(infectious) - __popcll(recovered);
         }
         // the packed quarantine store above is ordered before the byte stores below by the barrier inside enqueue()
-        const uint32_t total = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(busy8) : 0u);
-        for (uint32_t j = lane; j < total; j += 32)
+        waiting = enqueue(wq, warp, t, i0, i0 < a.n ? collect_lsb(busy8) : 0u, waiting);
+        while (waiting >= 32) // a full warp's worth: take the top 32
         {
-            const uint64_t i = wq.row[warp][j];
-            const uint32_t bytes = wq.bytes[warp][j];
-            uint32_t p = wq.pos[warp][j];
-            uint32_t fl = bytes & 0xffu;
-            const uint32_t ax = (bytes >> 8) & 0xffu, q = (bytes >> 16) & 0xffu;
-            uint32_t d = bytes >> 24;
-            const uint32_t d0 = d;
-            const bool dying = (ax >> 5) == OP_DYING;
-            const bool free_ = q == 0;
-            const int x = static_cast<int>(p & 0xffffu), y = static_cast<int>(p >> 16);
-            const uint32_t cell = static_cast<uint32_t>(x) * G + static_cast<uint32_t>(y);
-            const uint32_t uid = a.uid ? a.uid[i] : static_cast<uint32_t>(i);
-
-            // :461-508 gather side of the transmission: probe the 13 cells within Manhattan distance 2 (independent,
-            // predicated bit loads), then walk the source lists of the few cells that hold a source
-            if ((a.systems & 2u) && free_ && d == INCERTO_DISEASE_HEALTHY)
-            {
-                uint32_t hits = 0;
-#pragma unroll
-                for (int c13 = 0; c13 < 13; ++c13)
-                {
-                    const int dx = kOff13[c13][0], dy = kOff13[c13][1];
-                    const int cx = x + dx, cy = y + dy;
-                    const uint32_t dist = static_cast<uint32_t>((dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy));
-                    if (dist <= a.radius && cx >= 0 && cx < G && cy >= 0 && cy < G)
-                    {
-                        const uint32_t c = static_cast<uint32_t>(cx) * G + static_cast<uint32_t>(cy);
-                        hits |= ((a.src_bits[c >> 5] >> (c & 31)) & 1u) << c13;
-                    }
-                }
-                bool exposed = false;
-                while (hits)
-                {
-                    const int c13 = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    int dx = 0, dy = 0;
-#pragma unroll
-                    for (int k = 0; k < 13; ++k)
-                        if (c13 == k)
-                        {
-                            dx = kOff13[k][0];
-                            dy = kOff13[k][1];
-                        }
-                    const uint32_t c = static_cast<uint32_t>(x + dx) * G + static_cast<uint32_t>(y + dy);
-                    const uint64_t thr = c13 <= 4 ? a.thr_infect1 : a.thr_infect2; // distance 0 | 1, else 2 (:495-499)
-                    const uint32_t h = a.src_head[c];
-                    uint32_t cur = ((h >> kSpatialRowBits) == a.tag) ? (h & kRowMask) : kRowMask;
-                    for (uint32_t guard = 0; cur != kRowMask && guard <= kRowMask; ++guard)
-                    {
-                        const uint32_t suid = a.uid ? a.uid[cur] : cur;
-                        exposed = exposed || bernoulli(philox4x32_10(uid, suid, a.step, 0u, a.rk_transmit).x, thr);
-                        cur = a.src_next[cur];
-                    }
-                }
-                if (exposed) d = a.incubation; // :510-517
-            }
-
-            // :580-606 gather side of the tracing
-            bool quarantine = false;
-            if ((a.systems & 16u) && free_)
-            {
-                const unsigned long long m = a.mark[cell];
-                const uint32_t markers = static_cast<uint32_t>(m >> 32);
-                quarantine = markers >= 2u || (markers == 1u && static_cast<uint32_t>(m) != uid + 1u);
-            }
-
-            // :316-411 (a person despawned at this flush is left where it is: its move is unobservable)
-            uint32_t newop = OP_NONE;
-            if ((a.systems & 64u) && free_ && !dying)
-            {
-                const uint4 r = philox4x32_10(uid, 0u, a.step, 0u, a.rk_move);
-                if (bernoulli(r.x, a.thr_attempt)) // :332
-                {
-                    const bool social = (fl & a.bit_social) != 0;
-                    // candidates in the order up, left, right, down (:338-343); bit k of `ok`: candidate k passes
-                    // the bounds (:348-355) and quarantine-zone (:360-371) filters
-                    uint32_t ok = 0, cnt[4] = {0, 0, 0, 0};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                    {
-                        const int nx = c == 1 ? x - 1 : (c == 2 ? x + 1 : x), ny = c == 0 ? y - 1 : (c == 3 ? y + 1 : y);
-                        if (nx < 0 || nx >= G || ny < 0 || ny >= G) continue;
-                        const int zd = (nx > a.zone_x ? nx - a.zone_x : a.zone_x - nx) + (ny > a.zone_y ? ny - a.zone_y : a.zone_y - ny);
-                        if (zd <= a.zone_radius && social) continue;
-                        ok |= 1u << c;
-                        cnt[c] = a.count[static_cast<uint32_t>(nx) * G + static_cast<uint32_t>(ny)];
-                    }
-                    if (social)
-                    {
-                        // keep the least crowded candidates (:377-390)
-                        uint32_t mn = 0xffffffffu;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if ((ok >> c) & 1u) mn = min(mn, cnt[c]);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (cnt[c] != mn) ok &= ~(1u << c);
-                    }
-                    if (ok)
-                    {
-                        const uint32_t pick = uniform_below(r.y, static_cast<uint32_t>(__popc(ok))); // best_moves.choose (:401)
-                        const uint32_t dir = __fns(ok, 0, static_cast<int>(pick) + 1);
-                        const uint32_t people = dir == 0 ? cnt[0] : (dir == 1 ? cnt[1] : (dir == 2 ? cnt[2] : cnt[3]));
-                        if (people < a.crowding) // :403-408
-                        {
-                            const int mx = dir == 1 ? x - 1 : (dir == 2 ? x + 1 : x), my = dir == 0 ? y - 1 : (dir == 3 ? y + 1 : y);
-                            p = static_cast<uint32_t>(mx) | (static_cast<uint32_t>(my) << 16);
-                            newop = dir + 1;
-                        }
-                    }
-                }
-            }
-
-            // end of Update: despawn (:530), try_insert(Quarantined) (:600-603); a quarantined dying person had its
-            // counter decremented above, which nobody can observe
-            if (dying)
-            {
-                fl &= ~1u;
-                newop = OP_DIED;
-                a.flags[i] = static_cast<uint8_t>(fl);
-            }
-            else if (quarantine)
-                a.quar[i] = static_cast<uint8_t>(a.quarantine_duration);
-            if (d != d0) a.disease[i] = static_cast<uint8_t>(d);
-            if (newop >= OP_UP && newop <= OP_DOWN) a.pos[i] = p;
-            if (newop != (ax >> 5)) a.aux[i] = static_cast<uint8_t>((ax & 31u) | (newop << 5));
-            if (fl & 1u)
-            {
-                st[0] += d == INCERTO_DISEASE_HEALTHY;
-                st[1] += d >= 1u && d < 0x80u;
-                st[2] += d == INCERTO_DISEASE_INFECTIOUS;
-                st[3] += d == INCERTO_DISEASE_RECOVERED;
-            }
+            waiting -= 32;
+            work(waiting + lane);
+            __syncwarp();
         }
-        __syncwarp();
     }
+    if (lane < waiting) work(lane); // what was left when the tiles ran out
     if (a.stats_acc)
     {
         __shared__ uint32_t smem[4 * 32];

@@ -25,13 +25,15 @@
 //   spread, source S an overlay entity (uid >= W*H):
 //     word 0 of philox(key[SPREAD], (uid_T, uid_S, step, 1)) < thr_spread
 //   regrow, empty entity uid, p*256 <= 1 (two-level, exact product of probabilities):
-//     byte (uid & 15) of philox(key[REGROW], (uid >> 4, 0, step, 0)) == 0
+//     uid is a winner of the block lottery of block uid >> 8 at this step (lottery.cuh: 256 independent
+//     Bernoulli(2^-8) draws realised by ONE call philox(key[REGROW], (uid >> 8, 0, step, 0)))
 //     AND word (uid & 3) of philox(key[REGROW], (uid >> 2, 0, step, 1)) < floor(256*p*2^32)
 //   regrow, p*256 > 1: word (uid & 3) of philox(key[REGROW], (uid >> 2, 0, step, 1)) < floor(p*2^32)
 #include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.hpp"
+#include "lottery.cuh"
 
 namespace incerto
 {
@@ -44,11 +46,11 @@ constexpr int kTX = 32;  // chunks (16 cells) along y per CTA
 #endif
 constexpr int kTY = INCERTO_FOREST_TY;   // column groups (warps) per CTA
 #ifndef INCERTO_FOREST_COLS
-#define INCERTO_FOREST_COLS 6
+#define INCERTO_FOREST_COLS 7
 #endif
 constexpr int kColsPerThread = INCERTO_FOREST_COLS; // adjacent columns per thread
 #ifndef INCERTO_FOREST_MIN_BLOCKS
-#define INCERTO_FOREST_MIN_BLOCKS 9
+#define INCERTO_FOREST_MIN_BLOCKS 8
 #endif
 constexpr int kMinBlocks = INCERTO_FOREST_MIN_BLOCKS;
 
@@ -65,7 +67,7 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t v)
 
 #ifdef INCERTO_FOREST_TRACE
 // developer instrumentation (tools/trace_forest.py): per warp {start, loads consumed, end} in globaltimer ns + SM id
-__device__ unsigned long long g_forest_trace[4 * (1 << 18)];
+__device__ unsigned long long g_forest_trace[8 * (1 << 16)];
 __device__ __forceinline__ unsigned long long gtime()
 {
     unsigned long long t;
@@ -108,12 +110,7 @@ __device__ __forceinline__ uint32_t ignited_value(const ForestArgs& a)
 
 __device__ __forceinline__ bool regrow_draw(const ForestConst& c, uint32_t uid, uint32_t step)
 {
-    if (c.regrow_two_level)
-    {
-        const uint4 l1 = philox4x32_10(uid >> 4, 0u, step, 0u, c.rk_regrow);
-        const uint32_t w = word_of(l1, (uid >> 2) & 3u);
-        if ((w >> (8 * (uid & 3u))) & 0xffu) return false;
-    }
+    if (c.regrow_two_level && !lottery256_wins(c.rk_regrow, uid, step)) return false;
     const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.rk_regrow);
     return bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2);
 }
@@ -257,13 +254,13 @@ __global__ void forest_publish_kernel(ForestArgs a, uint32_t slab_w, uint32_t bu
     if (bump && a.d_step) *const_cast<uint32_t*>(a.d_step) += bump;
 }
 
-// HOIST: the level-1 regrowth draws are computed before the cells are looked at, i.e. while the loads are in flight.
-// That shortens a grid of one or two waves, whose CTAs all start together and would sit idle until their loads
-// arrive (4096^2 cold: 19.2 -> 18.6 us); a long grid is bound by instruction issue in steady state and runs 4 %
-// slower that way (16384^2: 131 -> 136 us), so the launcher picks per grid size.
+// Regrowth level 1 is the block lottery (lottery.cuh): one Philox call per 256 cells, made by up to 3 lanes per column
+// (the blocks that intersect the warp's 512 cells of it) while the loads are in flight; the winners go straight into
+// the warp's rare-event queue.  (Until round 2 every thread made one call per 16 cells and turned the 16 bytes into
+// masks: 45 % of the kernel's instructions.)
 // PEER: the fused halo transport is compiled in (row-partitioned grids with peer memory); the single-GPU kernel
 // carries none of its registers or branches.
-template <bool ALIGNED, bool HOIST, bool PEER>
+template <bool PEER>
 __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const __grid_constant__ ForestConst c)
 {
     const ForestArgs& a = c.a;
@@ -287,6 +284,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     __shared__ uint32_t s_done; // warps of this block that finished (see the end of the kernel)
     __shared__ int32_t s_delta[3];
     __shared__ NearOverlays nr;
+    __shared__ uint16_t s_evq[kTY][kEventQueue];                                   // rare events of a warp's tile
     if (tid < 3) s_delta[tid] = 0;
     if (tid == 0)
     {
@@ -360,19 +358,23 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     }
     // StepNumber of this launch: by value, or (captured graphs) the device counter + the launch's offset in the graph
     const uint32_t step = (a.d_step ? *a.d_step : 0u) + a.step_base;
-    // ---- level-1 regrowth draws (one Philox call per 16 cells, uid0 % 16 == 0): nothing here depends on the cells,
-    // so the four calls of the thread run while its loads are in flight.  Their multiply chains interleave; per
-    // column one word survives: bit 8b+4+k set = cell 4k+b passed level 1 (~1/256 of the cells; the empty ones
-    // among them take the level-2 draw in the rare-event loop).
-    uint32_t zmask[kColsPerThread];
-    if (HOIST && ALIGNED && a.do_regrow && c.regrow_two_level)
+    // ---- level-1 regrowth draws (block lottery): nothing here depends on the cells, so the call runs while the loads
+    // are in flight.  Lane 3(j-1)+i draws the i-th block of 256 uids that intersects the warp's cells of column j and
+    // keeps the number of winners and the head of the position stream; the events are made after the stores.
+    uint32_t lot_k = 0, lot_z = 0, lot_w = 0;
+    if (a.do_regrow && c.regrow_two_level)
     {
-#pragma unroll
-        for (int j = 1; j <= kColsPerThread; ++j)
+        const uint32_t j = lane / 3 + 1, bi = lane - 3 * (j - 1);
+        const uint32_t yw = blockIdx.x * (kTX * 16);
+        const uint32_t lo = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + yw;
+        const uint32_t len = yw < H ? min(H - yw, static_cast<uint32_t>(kTX * 16)) : 0u;
+        const uint32_t blk = (lo >> 8) + bi;
+        if (lane < 3 * kColsPerThread && lx0 - 1 + j <= c.slab_w && len != 0 && blk <= ((lo + len - 1) >> 8))
         {
-            const uint32_t uid0 = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + y0;
-            const uint4 l1 = philox4x32_10(uid0 >> 4, 0u, step, 0u, c.rk_regrow);
-            zmask[j - 1] = (zero_bytes(l1.x) >> 3) | (zero_bytes(l1.y) >> 2) | (zero_bytes(l1.z) >> 1) | zero_bytes(l1.w);
+            const uint4 r = philox4x32_10(blk, 0u, step, 0u, c.rk_regrow);
+            lot_k = lottery_count((static_cast<uint64_t>(r.x) << 32) | r.y);
+            lot_z = r.z;
+            lot_w = r.w;
         }
     }
     // the previous step's FireStats go on record now, off every critical path (see forest_publish)
@@ -500,45 +502,78 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         }
     }
 
-    // ---- regrowth (:354-365): only EMPTY cells draw
-    if (a.do_regrow)
+    // ---- regrowth (:354-365): only EMPTY cells draw.  Two-level: the lottery winners are already queued; a
+    // probability above 1/256 has no level 1 and every Empty cell takes its draw in the rare-event loop.
+    if (a.do_regrow && !c.regrow_two_level)
     {
 #pragma unroll
         for (int j = 1; j <= kColsPerThread; ++j)
         {
             const uint32_t e0 = v[j].x & 0x80808080u, e1 = v[j].y & 0x80808080u, e2 = v[j].z & 0x80808080u,
                            e3 = v[j].w & 0x80808080u;
-            uint32_t evj;
-            if (HOIST && ALIGNED && c.regrow_two_level)
-                evj = ((e0 >> 3) | (e1 >> 2) | (e2 >> 1) | e3) & zmask[j - 1]; // level 1 was drawn in the shadow of the loads
-            else if (ALIGNED && c.regrow_two_level)
-            {
-                // uid0 % 16 == 0: one level-1 call covers the 16 cells of this chunk; ~1/256 of the empty
-                // cells pass it and take the level-2 draw in the rare-event loop.  The calls of the thread's
-                // columns sit in one basic block so that their dependent multiply chains interleave.
-                const uint32_t uid0 = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + y0;
-                const uint4 l1 = philox4x32_10(uid0 >> 4, 0u, step, 0u, c.rk_regrow);
-                evj = ((zero_bytes(l1.x) & e0) >> 3) | ((zero_bytes(l1.y) & e1) >> 2) | ((zero_bytes(l1.z) & e2) >> 1) |
-                      (zero_bytes(l1.w) & e3);
-            }
-            else
-                evj = (e0 >> 3) | (e1 >> 2) | (e2 >> 1) | e3;
-            if (lx0 - 1 + j <= c.slab_w) ev[j - 1] |= evj;
+            if (lx0 - 1 + j <= c.slab_w) ev[j - 1] |= (e0 >> 3) | (e1 >> 2) | (e2 >> 1) | e3;
         }
     }
 
-    // ================= rare events: patch single cells of the buffer just written =================
-    // Events are rare and scattered over the lanes (an empty cell that passed the level-1 regrowth draw, a healthy
-    // cell at a fire front), and each costs a Philox call: the warp compacts them into a shared-memory queue and
-    // deals them out one per lane, so that the expensive path runs once per 32 events instead of once per event
-    // position of the busiest lane.  The queue is bounded; leftovers go through another round.
-    __shared__ uint16_t s_evq[kTY][kEventQueue];
-    for (;;)
+#ifdef INCERTO_FOREST_TRACE
+    const unsigned long long tr_stored = gtime();
+#endif
+    // ---- regrowth events of the lottery drawn above.  One warp-uniform loop over the position stream: per round every
+    // drawing lane takes its next stream byte, skips it if it repeats an earlier one (the first eight bytes sit in two
+    // registers: byte-parallel compare), else has a winner; winners that lie in the span AND are Empty (a byte load from
+    // a line this warp has just read) are queued, slots by ballot.  Typically 2-4 rounds; no out-of-line path (a
+    // rarely executed stretch of code costs a small grid microseconds of instruction fetches).  This half sits after
+    // the stores: the cell registers are dead here (with all of it in the shadow of the loads the compiler spilled two
+    // of the eight cell vectors, i.e. made the warp wait for them first).
+    uint32_t queued = 0; // warp-uniform
+    if (a.do_regrow && c.regrow_two_level)
+    {
+        const uint32_t j = lane / 3 + 1, bi = lane - 3 * (j - 1);
+        const uint32_t yw = blockIdx.x * (kTX * 16);
+        const uint32_t lo = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + yw; // uid of the span's first cell
+        const uint32_t len = yw < H ? min(H - yw, static_cast<uint32_t>(kTX * 16)) : 0u;
+        const uint32_t blk = (lo >> 8) + bi;
+        const uint8_t* colp = a.cur + static_cast<size_t>(lx0 - 1 + j) * c.pitch + yw; // the span's first cell
+        uint32_t need = lot_k; // stream bytes this lane still has to look at: winners left + repeats met
+        for (uint32_t t = 0; __any_sync(kFullMask, t < need); ++t)
+        {
+            uint32_t b;
+            bool rep;
+            if (t < 8)
+            {
+                b = ((t < 4 ? lot_z : lot_w) >> (8 * (t & 3u))) & 0xffu;
+                const uint32_t r4 = b * 0x01010101u;
+                const uint32_t mz = t >= 4 ? 0xffffffffu : ((1u << (8 * t)) - 1u), mw = t > 4 ? ((1u << (8 * (t - 4))) - 1u) : 0u;
+                rep = ((zero_bytes(lot_z ^ r4) & mz) | (zero_bytes(lot_w ^ r4) & mw)) != 0;
+            }
+            else // beyond the first eight bytes (about one block in a million)
+            {
+                b = t < need ? lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, t) : 0u;
+                rep = false;
+                for (uint32_t h = 0; h < t && t < need; ++h) rep = rep || lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, h) == b;
+            }
+            if (rep && t < need) ++need;
+            const uint32_t yo = ((blk << 8) | b) - lo;
+            const bool ev_here = t < need && !rep && yo < len && colp[yo] == 0x80u;
+            const uint32_t m = __ballot_sync(kFullMask, ev_here);
+            if (ev_here)
+            {
+                const uint32_t cc = yo & 15u;
+                s_evq[threadIdx.y][queued + __popc(m & ((1u << lane) - 1u))] =
+                    static_cast<uint16_t>(((yo >> 4) << 10) | ((j - 1) << 5) | (8 * (cc & 3u) + 4 + (cc >> 2)));
+            }
+            queued += __popc(m);
+        }
+    }
+#ifdef INCERTO_FOREST_TRACE
+    const unsigned long long tr_lot = gtime();
+#endif
+    for (;;) // `queued` lottery winners are waiting in the queue (first round only)
     {
         uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < kColsPerThread; ++j) mine += __popc(ev[j]);
-        if (!__any_sync(kFullMask, mine != 0)) break;
+        if (!__any_sync(kFullMask, mine != 0) && !queued) break;
         // exclusive prefix sum of the per-lane event counts
         uint32_t incl = mine;
 #pragma unroll
@@ -547,8 +582,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
             if (lane >= static_cast<uint32_t>(o)) incl += up;
         }
-        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-        uint32_t slot = incl - mine;
+        const uint32_t total = __shfl_sync(kFullMask, incl, 31) + queued;
+        uint32_t slot = incl - mine + queued;
+        queued = 0;
 #pragma unroll
         for (int j = 0; j < kColsPerThread; ++j)
             while (ev[j] && slot < kEventQueue)
@@ -588,16 +624,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             }
             else
             {
-                // (b) regrowth draw still owed
-                bool grow;
-                if (ALIGNED && c.regrow_two_level)
-                {
-                    const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.rk_regrow);
-                    grow = bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2);
-                }
-                else
-                    grow = regrow_draw(c, uid, step);
-                if (grow)
+                // (b) regrowth draw still owed by an Empty cell: level 2 (or the only level)
+                const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.rk_regrow);
+                if (bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2))
                 {
                     a.next[off] = 0x40;
                     dl.e -= 1;
@@ -607,6 +636,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         }
         __syncwarp();
     }
+#ifdef INCERTO_FOREST_TRACE
+    const unsigned long long tr_events = gtime();
+#endif
     // (c) cells an overlay entity can influence, and the overlay entities living in this thread's tile
     if (n_near && chunk_ok)
     {
@@ -652,6 +684,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         }
     }
 
+#ifdef INCERTO_FOREST_TRACE
+    const unsigned long long tr_overlays = gtime();
+#endif
     // ---- incremental FireStats: warps that saw a transition add their deltas to the block's counters
     if (__any_sync(kFullMask, (dl.h | dl.b | dl.e) != 0))
     {
@@ -669,11 +704,15 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
 #ifdef INCERTO_FOREST_TRACE
     if (lane == 0)
     {
-        const uint32_t w = ((blockIdx.y * gridDim.x + blockIdx.x) * kTY + threadIdx.y) & ((1u << 18) - 1);
-        g_forest_trace[4 * w + 0] = tr_start;
-        g_forest_trace[4 * w + 1] = tr_loaded;
-        g_forest_trace[4 * w + 2] = gtime();
-        g_forest_trace[4 * w + 3] = smid();
+        const uint32_t w = ((blockIdx.y * gridDim.x + blockIdx.x) * kTY + threadIdx.y) & ((1u << 16) - 1);
+        g_forest_trace[8 * w + 0] = tr_start;
+        g_forest_trace[8 * w + 1] = tr_loaded;
+        g_forest_trace[8 * w + 2] = gtime();
+        g_forest_trace[8 * w + 3] = smid() | (static_cast<unsigned long long>(fire) << 32);
+        g_forest_trace[8 * w + 4] = tr_stored;
+        g_forest_trace[8 * w + 5] = tr_lot;
+        g_forest_trace[8 * w + 6] = tr_events;
+        g_forest_trace[8 * w + 7] = tr_overlays;
     }
 #endif
     if (PEER && (c.peer.mail_lo || c.peer.mail_hi)) __syncwarp(); // lane 0 speaks for the whole warp's stores (the neighbours pull them)
@@ -785,25 +824,10 @@ cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, con
     c.rk_regrow = make_round_keys(a.key_regrow);
     dim3 block(kTX, kTY);
     dim3 grid((c.chunks_per_col + kTX - 1) / kTX, (c.slab_w + kTY * kColsPerThread - 1) / (kTY * kColsPerThread));
-    // at most four waves, and the loads actually take long (steps that find their cells in the L2 have no shadow worth
-    // filling: 4096^2 graph replay 13.2 us with, 12.9 us without)
-    const bool hoist = static_cast<uint64_t>(grid.x) * grid.y <= 4ull * kNumSMs * kMinBlocks && !a.l2_resident;
-    const bool peer_on = peer != nullptr;
-#define INC_FOREST_LAUNCH(AL, HO)                                        \
-    do                                                                   \
-    {                                                                    \
-        if (peer_on)                                                     \
-            forest_step_kernel<AL, HO, true><<<grid, block, 0, st>>>(c); \
-        else                                                             \
-            forest_step_kernel<AL, HO, false><<<grid, block, 0, st>>>(c); \
-    } while (0)
-    if ((a.H % 16) != 0) // uid of a chunk's first cell is not a multiple of 16: no shared level-1 call per chunk
-        INC_FOREST_LAUNCH(false, false);
-    else if (hoist)
-        INC_FOREST_LAUNCH(true, true);
+    if (peer != nullptr)
+        forest_step_kernel<true><<<grid, block, 0, st>>>(c);
     else
-        INC_FOREST_LAUNCH(true, false);
-#undef INC_FOREST_LAUNCH
+        forest_step_kernel<false><<<grid, block, 0, st>>>(c);
     return cudaGetLastError();
 }
 

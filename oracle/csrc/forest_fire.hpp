@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "library.hpp"
+#include "lottery.hpp"
 #include "philox.hpp"
 
 namespace oracle
@@ -192,14 +193,14 @@ struct ForestSim
     }
 
     // regrowth draw of entity uid: two-level when p*256 <= 1
+    mutable LotteryCache regrow_lottery;
     bool regrow_draw(const Stream& rng, Entity uid) const
     {
         const double p = P.regrowth_probability;
         if (p * 256.0 <= 1.0)
         {
-            const U4 l1 = rng.block(uid >> 4, 0, static_cast<uint32_t>(step), 0);
-            const uint32_t byte = (l1.w[(uid >> 2) & 3] >> (8 * (uid & 3))) & 0xffu;
-            if (byte != 0) return false;
+            // level 1: uid is a winner of its block's lottery (256 independent Bernoulli(2^-8) draws, one call)
+            if (!regrow_lottery.wins(rng, static_cast<uint32_t>(uid), static_cast<uint32_t>(step))) return false;
             const U4 l2 = rng.block(uid >> 2, 0, static_cast<uint32_t>(step), 1);
             return bern(l2.w[uid & 3], threshold(p * 256.0));
         }

@@ -3,7 +3,7 @@
 import numpy as np
 
 SEED = 0x1CE27002025
-CASES = ["coin_toss", "forest_fire", "pandemic", "pandemic_spatial", "traders", "air_traffic_3d", "normal_draws"]
+CASES = ["coin_toss", "forest_fire", "forest_fire_lottery", "pandemic", "pandemic_spatial", "traders", "air_traffic_3d", "normal_draws"]
 
 
 def run_oracle(name):
@@ -14,6 +14,12 @@ def run_oracle(name):
     if name == "forest_fire":
         from oracle.forest import ForestOracle
         o = ForestOracle(SEED, 1, 48, 40, density=0.7, p_regrow=0.004, fires=3).spawn().run(60)
+        return dict(cells=o.cells()[0], series=o.series())
+    if name == "forest_fire_lottery":
+        # p_regrow <= 1/256: level 1 of the regrowth draw is the block lottery (256 uids per call; H = 100 puts the
+        # blocks across column ends)
+        from oracle.forest import ForestOracle
+        o = ForestOracle(SEED, 7, 36, 100, density=0.6, p_regrow=0.002, fires=3).spawn().run(90)
         return dict(cells=o.cells()[0], series=o.series())
     if name == "pandemic":
         from oracle.pandemic import PandemicOracle
@@ -61,16 +67,16 @@ def run_engine(name):
         sim.run(200)
         return dict(heads=sim.read_component(heads), tosses=sim.read_component(tosses),
                     odds=np.array([sim.sample_aggregate(ib.CoinOdds(heads, tosses))]))
-    if name == "forest_fire":
-        W, H = 48, 40
-        b = ib.SimulationBuilder(seed=SEED, replica=1)
+    if name in ("forest_fire", "forest_fire_lottery"):
+        W, H, replica, density, p_regrow, steps = (48, 40, 1, 0.7, 0.004, 60) if name == "forest_fire" else (36, 100, 7, 0.6, 0.002, 90)
+        b = ib.SimulationBuilder(seed=SEED, replica=replica)
         pos, cell = b.component("GridPosition2D", F.I16, lanes=2), b.component("ForestCell.state", F.U8)
         b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
-        b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_FOREST_GRID, F.SpawnForestParams(pos.handle, cell.handle, W, H, 0.7, 3, 3)))
-        b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.004))
+        b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_FOREST_GRID, F.SpawnForestParams(pos.handle, cell.handle, W, H, density, 3, 3)))
+        b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, p_regrow))
         b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
         sim = b.build()
-        sim.run(60)
+        sim.run(steps)
         ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
         ser = np.array([(v.healthy_count, v.burning_count, v.burned_count, v.empty_count, v.total_cells) for v in ts.values()], np.uint64)
         return dict(cells=sim.read_component(cell), series=ser)

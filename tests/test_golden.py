@@ -27,6 +27,8 @@ def test_oracle_reproduces_golden(name, oracle_lib):
 
 def test_golden_is_not_trivial():
     assert GOLD["forest_fire/series"][-1][2] > 0            # something burned down
+    lot = GOLD["forest_fire_lottery/series"]
+    assert lot[-1][2] > 0 and 150 < int(lot[0][3]) - int(lot[-1][3]) < 350   # Empty cells regrew through the block lottery
     assert (~GOLD["pandemic/alive"]).any() and (~GOLD["pandemic_spatial/alive"]).any()   # despawns happened
     assert GOLD["traders/delisted"].any() or GOLD["traders/price"].min() < 5.0
     assert GOLD["air_traffic_3d/conflicts"].max() > 0

@@ -35,15 +35,17 @@ for rep in range(3):
         sim.run_cold(1)
     ms, _ = sim.last_run_stats()
     lib = F.load()
-    tile_rows, warps_per_cta, cols_per_thread = 512, 4, 6     # kTX * 16, kTY, kColsPerThread of kernels_forest.cu
+    tile_rows, warps_per_cta, cols_per_thread = 512, 4, 7     # kTX * 16, kTY, kColsPerThread of kernels_forest.cu
     ctas = ((H + tile_rows - 1) // tile_rows) * ((W + warps_per_cta * cols_per_thread - 1) // (warps_per_cta * cols_per_thread))
-    nwarps = min(ctas * warps_per_cta, 1 << 18)
-    buf = np.zeros(4 * nwarps, np.uint64)
+    nwarps = min(ctas * warps_per_cta, 1 << 16)
+    buf = np.zeros(8 * nwarps, np.uint64)
     lib.incerto_debug_forest_trace.argtypes = [C.c_void_p, C.c_uint64]
-    assert lib.incerto_debug_forest_trace(buf.ctypes.data, 4 * nwarps) == 0
-    t = buf.reshape(-1, 4).astype(np.int64)
+    assert lib.incerto_debug_forest_trace(buf.ctypes.data, 8 * nwarps) == 0
+    t = buf.reshape(-1, 8).astype(np.int64)
     t0 = t[:, 0].min()
-    start, loaded, end, sm = t[:, 0] - t0, t[:, 1] - t0, t[:, 2] - t0, t[:, 3]
+    start, loaded, end, sm = t[:, 0] - t0, t[:, 1] - t0, t[:, 2] - t0, t[:, 3] & 0xffffffff
+    fire = t[:, 3] >> 32
+    stored, lot, events, overlays = t[:, 4] - t0, t[:, 5] - t0, t[:, 6] - t0, t[:, 7] - t0
     q = [0, 1, 10, 25, 50, 75, 90, 99, 100]
     print(f"== {W}x{H} {'warm' if warm else 'cold'}: event time {ms * 1e3:.2f} us; warps {nwarps}; span first start -> last end {end.max() / 1e3:.2f} us")
     print("   percentiles      ", q)
@@ -52,9 +54,18 @@ for rep in range(3):
     print("   warp end    (us) ", [round(float(np.percentile(end, p)) / 1e3, 2) for p in q])
     print("   load wait   (us) ", [round(float(np.percentile(loaded - start, p)) / 1e3, 2) for p in q])
     print("   after loads (us) ", [round(float(np.percentile(end - loaded, p)) / 1e3, 2) for p in q])
+    for name, a, b_ in (("compute+store", loaded, stored), ("lottery tail", stored, lot), ("event loop", lot, events), ("overlays", events, overlays),
+                        ("stats+exit", overlays, end)):
+        print(f"   {name:14s}(us) ", [round(float(np.percentile(b_ - a, p)) / 1e3, 2) for p in q], " fire warps:",
+              [round(float(np.percentile((b_ - a)[fire > 0], p)) / 1e3, 2) for p in (50, 100)] if (fire > 0).any() else "-")
+    late = np.argsort(end)[-6:]
+    for w in late:
+        print(f"      late warp {w} (cta {w // warps_per_cta}, sm {sm[w]}, fire {fire[w]}): start {start[w] / 1e3:.2f} loaded {loaded[w] / 1e3:.2f} stored {stored[w] / 1e3:.2f} "
+              f"lottery {lot[w] / 1e3:.2f} events {events[w] / 1e3:.2f} overlays {overlays[w] / 1e3:.2f} end {end[w] / 1e3:.2f}")
     if nwarps <= 64:
         for w in range(nwarps):
-            print(f"      warp {w:3d} (cta {w // warps_per_cta}, sm {sm[w]}): start {start[w] / 1e3:6.2f}  loaded {loaded[w] / 1e3:6.2f}  end {end[w] / 1e3:6.2f} us")
+            print(f"      warp {w:3d} (cta {w // warps_per_cta}, sm {sm[w]}, fire {fire[w]}): start {start[w] / 1e3:6.2f}  loaded {loaded[w] / 1e3:6.2f}  stored {stored[w] / 1e3:6.2f}  "
+                  f"lottery {lot[w] / 1e3:6.2f}  events {events[w] / 1e3:6.2f}  overlays {overlays[w] / 1e3:6.2f}  end {end[w] / 1e3:6.2f} us")
     # per SM: first start, last end, warps
     sms = np.unique(sm)
     first = np.array([start[sm == s].min() for s in sms]) / 1e3

@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t smid()
 #endif
 
 constexpr int kEventQueue = 512;   // rare events of one warp tile handled per round
+constexpr uint16_t kNullEvent = 0xffffu;
 constexpr int kMaxNear = 64;       // overlay entities within one cell of a CTA tile
 
 struct ForestConst
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // ---- level-1 regrowth draws (block lottery): nothing here depends on the cells, so the call runs while the loads
     // are in flight.  Lane 3(j-1)+i draws the i-th block of 256 uids that intersects the warp's cells of column j and
     // keeps the number of winners and the head of the position stream; the events are made after the stores.
-    uint32_t lot_k = 0, lot_z = 0, lot_w = 0;
+    uint32_t lot_k = 0, lot_z = 0, lot_w = 0, lot_off = 0, lot_total = 0;
     if (a.do_regrow && c.regrow_two_level)
     {
         const uint32_t j = lane / 3 + 1, bi = lane - 3 * (j - 1);
@@ -376,6 +377,17 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             lot_z = r.z;
             lot_w = r.w;
         }
+        // queue slots of the lane's winners: exclusive prefix sum of the counts (a winner outside the span leaves a
+        // null item), so that the lanes can write their events later without talking to each other
+        uint32_t incl = lot_k;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= static_cast<uint32_t>(o)) incl += up;
+        }
+        lot_total = __shfl_sync(kFullMask, incl, 31);
+        lot_off = incl - lot_k;
     }
     // the previous step's FireStats go on record now, off every critical path (see forest_publish)
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) forest_publish(a, c.slab_w, step - 1);
@@ -437,11 +449,13 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         n_near = nr.n < kMaxNear ? nr.n : kMaxNear;
     }
 
-    // ---- is there any fire in what this warp loaded?
-    uint32_t ob = edge;
+    // ---- is there any fire in what this warp loaded, and in which columns?  Bit j of `wf` (one warp-wide OR): some
+    // lane holds a burning cell in column j of its eight (the edge cells count for their column).
+    uint32_t fl = edge << 1;
 #pragma unroll
-    for (int j = 0; j < kColsPerThread + 2; ++j) ob |= (v[j].x | v[j].y | v[j].z | v[j].w) & 0x3f3f3f3fu;
-    const bool fire = __any_sync(kFullMask, ob != 0);
+    for (int j = 0; j < kColsPerThread + 2; ++j) fl |= (((v[j].x | v[j].y | v[j].z | v[j].w) & 0x3f3f3f3fu) ? 1u : 0u) << j;
+    const uint32_t wf = __reduce_or_sync(kFullMask, fl);
+    const bool fire = wf != 0;
 #ifdef INCERTO_FOREST_TRACE
     const unsigned long long tr_loaded = gtime();
 #endif
@@ -462,6 +476,11 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
 #pragma unroll
         for (int j = 1; j <= kColsPerThread; ++j)
         {
+            if (!((wf >> (j - 1)) & 7u)) // warp-uniform: no fire in this column nor in its W / E neighbours - copied
+            {
+                if (lx0 - 1 + j <= c.slab_w) *reinterpret_cast<uint4*>(q0 + static_cast<size_t>(j) * c.pitch) = v[j];
+                continue;
+            }
             const uint32_t cw[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
             uint32_t B[4];
 #pragma unroll
@@ -518,24 +537,22 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
 #ifdef INCERTO_FOREST_TRACE
     const unsigned long long tr_stored = gtime();
 #endif
-    // ---- regrowth events of the lottery drawn above.  One warp-uniform loop over the position stream: per round every
-    // drawing lane takes its next stream byte, skips it if it repeats an earlier one (the first eight bytes sit in two
-    // registers: byte-parallel compare), else has a winner; winners that lie in the span AND are Empty (a byte load from
-    // a line this warp has just read) are queued, slots by ballot.  Typically 2-4 rounds; no out-of-line path (a
-    // rarely executed stretch of code costs a small grid microseconds of instruction fetches).  This half sits after
-    // the stores: the cell registers are dead here (with all of it in the shadow of the loads the compiler spilled two
-    // of the eight cell vectors, i.e. made the warp wait for them first).
-    uint32_t queued = 0; // warp-uniform
-    if (a.do_regrow && c.regrow_two_level)
+    // ---- regrowth events of the lottery drawn above: every drawing lane walks its position stream - skipping a byte
+    // that repeats an earlier one (the first eight bytes sit in two registers: byte-parallel compare) - and writes its
+    // winners into its own slots of the warp's event queue (a null item for a winner outside the span).  No loads, no
+    // votes; whether the cell is Empty is looked at when the event is handled.  No out-of-line path either: a rarely
+    // executed stretch of code costs a small grid microseconds of instruction fetches.  This half sits after the
+    // stores (with the walk in the shadow of the loads the compiler spilled two of the eight cell vectors, i.e. made
+    // the warp wait for them first).
+    uint32_t queued = lot_total; // warp-uniform
     {
         const uint32_t j = lane / 3 + 1, bi = lane - 3 * (j - 1);
         const uint32_t yw = blockIdx.x * (kTX * 16);
         const uint32_t lo = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + yw; // uid of the span's first cell
         const uint32_t len = yw < H ? min(H - yw, static_cast<uint32_t>(kTX * 16)) : 0u;
         const uint32_t blk = (lo >> 8) + bi;
-        const uint8_t* colp = a.cur + static_cast<size_t>(lx0 - 1 + j) * c.pitch + yw; // the span's first cell
         uint32_t need = lot_k; // stream bytes this lane still has to look at: winners left + repeats met
-        for (uint32_t t = 0; __any_sync(kFullMask, t < need); ++t)
+        for (uint32_t t = 0; t < need; ++t)
         {
             uint32_t b;
             bool rep;
@@ -548,56 +565,62 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             }
             else // beyond the first eight bytes (about one block in a million)
             {
-                b = t < need ? lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, t) : 0u;
+                b = lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, t);
                 rep = false;
-                for (uint32_t h = 0; h < t && t < need; ++h) rep = rep || lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, h) == b;
+                for (uint32_t h = 0; h < t; ++h) rep = rep || lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, h) == b;
             }
-            if (rep && t < need) ++need;
-            const uint32_t yo = ((blk << 8) | b) - lo;
-            const bool ev_here = t < need && !rep && yo < len && colp[yo] == 0x80u;
-            const uint32_t m = __ballot_sync(kFullMask, ev_here);
-            if (ev_here)
+            if (rep)
             {
-                const uint32_t cc = yo & 15u;
-                s_evq[threadIdx.y][queued + __popc(m & ((1u << lane) - 1u))] =
-                    static_cast<uint16_t>(((yo >> 4) << 10) | ((j - 1) << 5) | (8 * (cc & 3u) + 4 + (cc >> 2)));
+                ++need;
+                continue;
             }
-            queued += __popc(m);
+            const uint32_t yo = ((blk << 8) | b) - lo, cc = yo & 15u;
+            s_evq[threadIdx.y][lot_off++] =
+                yo < len ? static_cast<uint16_t>(((yo >> 4) << 10) | ((j - 1) << 5) | (8 * (cc & 3u) + 4 + (cc >> 2))) : kNullEvent;
         }
     }
 #ifdef INCERTO_FOREST_TRACE
     const unsigned long long tr_lot = gtime();
 #endif
-    for (;;) // `queued` lottery winners are waiting in the queue (first round only)
+    // `queued` lottery winners are waiting in the queue (first round only).  Warps without fire (nearly all) have nothing
+    // else: they skip the compaction of the event words.
+    bool packing = fire || (a.do_regrow && !c.regrow_two_level); // warp-uniform: event words may hold something
+    for (;;)
     {
-        uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < kColsPerThread; ++j) mine += __popc(ev[j]);
-        if (!__any_sync(kFullMask, mine != 0) && !queued) break;
-        // exclusive prefix sum of the per-lane event counts
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
+        uint32_t total = queued;
+        if (packing)
         {
-            const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
-            if (lane >= static_cast<uint32_t>(o)) incl += up;
-        }
-        const uint32_t total = __shfl_sync(kFullMask, incl, 31) + queued;
-        uint32_t slot = incl - mine + queued;
-        queued = 0;
+            uint32_t mine = 0;
 #pragma unroll
-        for (int j = 0; j < kColsPerThread; ++j)
-            while (ev[j] && slot < kEventQueue)
+            for (int j = 0; j < kColsPerThread; ++j) mine += __popc(ev[j]);
+            // exclusive prefix sum of the per-lane event counts
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                const uint32_t bit = __ffs(ev[j]) - 1;
-                ev[j] &= ev[j] - 1;
-                s_evq[threadIdx.y][slot++] = static_cast<uint16_t>((lane << 10) | (static_cast<uint32_t>(j) << 5) | bit);
+                const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= static_cast<uint32_t>(o)) incl += up;
             }
+            total += __shfl_sync(kFullMask, incl, 31);
+            uint32_t slot = incl - mine + queued;
+#pragma unroll
+            for (int j = 0; j < kColsPerThread; ++j)
+                while (ev[j] && slot < kEventQueue)
+                {
+                    const uint32_t bit = __ffs(ev[j]) - 1;
+                    ev[j] &= ev[j] - 1;
+                    s_evq[threadIdx.y][slot++] = static_cast<uint16_t>((lane << 10) | (static_cast<uint32_t>(j) << 5) | bit);
+                }
+            packing = total > kEventQueue; // leftovers go through another round
+        }
+        queued = 0;
+        if (!total) break;
         __syncwarp(); // also orders the owners' vector stores of `next` before the byte patches below
         const uint32_t n_ev = total < kEventQueue ? total : kEventQueue;
         for (uint32_t k = lane; k < n_ev; k += 32)
         {
             const uint32_t item = s_evq[threadIdx.y][k];
+            if (item == kNullEvent) continue;
             const uint32_t bit = item & 31u;
             const uint32_t lx = lx0 + ((item >> 5) & 31u);
             const uint32_t y = (blockIdx.x * kTX + (item >> 10)) * 16 + 4 * (bit & 3) + ((bit >> 3) & 3);
@@ -626,7 +649,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             {
                 // (b) regrowth draw still owed by an Empty cell: level 2 (or the only level)
                 const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.rk_regrow);
-                if (bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2))
+                if (a.cur[off] == 0x80u && bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2))
                 {
                     a.next[off] = 0x40;
                     dl.e -= 1;

@@ -84,6 +84,7 @@ __device__ __forceinline__ uint32_t smid()
 
 constexpr int kEventQueue = 512;   // rare events of one warp tile handled per round
 constexpr uint16_t kNullEvent = 0xffffu;
+static_assert(INCERTO_FOREST_COLS <= 7, "a lottery event carries its column in three bits, and 0xffff must stay free");
 constexpr int kMaxNear = 64;       // overlay entities within one cell of a CTA tile
 
 struct ForestConst
@@ -348,14 +349,21 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     }
     // the word just outside the warp's y span, per column: lane 0 needs the cell y0-1 (top byte of the word
     // before its chunk), lane 31 the cell y0+16 (bottom byte of the word after it)
-    uint32_t edge = 0; // bit j-1: that cell of my column j is burning
-    if ((lane == 0 && cy > 0) || (lane == 31 && cy + 1 < c.chunks_per_col))
+    // (bit j-1 of `edge`: that cell of my column j is burning).  The 2 x kColsPerThread words are fetched by as many
+    // lanes with ONE load instruction - lane i < C the word above column i+1, lane C+i the word below it - and handed to
+    // lanes 0 and 31 by a vote.
+    uint32_t edge;
     {
-        const ptrdiff_t d = lane == 0 ? -4 : 16;
-        const uint32_t m = lane == 0 ? 0x3f000000u : 0x0000003fu;
-#pragma unroll
-        for (int j = 1; j <= kColsPerThread; ++j)
-            edge |= ((*reinterpret_cast<const uint32_t*>(p0 + static_cast<size_t>(j) * c.pitch + d) & m) ? 1u : 0u) << (j - 1);
+        const bool top = lane < kColsPerThread, bot = !top && lane < 2 * kColsPerThread;
+        const uint32_t jj = top ? lane + 1 : lane + 1 - kColsPerThread;
+        bool burning = false;
+        if ((top && blockIdx.x > 0) || (bot && blockIdx.x + 1 < gridDim.x))
+        {
+            const uint8_t* span = p0 - lane * 16 + static_cast<size_t>(jj) * c.pitch; // the warp's first cell of column jj
+            burning = (*reinterpret_cast<const uint32_t*>(span + (top ? -4 : kTX * 16)) & (top ? 0x3f000000u : 0x0000003fu)) != 0;
+        }
+        const uint32_t eb = __ballot_sync(kFullMask, burning);
+        edge = lane == 0 ? (eb & ((1u << kColsPerThread) - 1u)) : (lane == 31 ? ((eb >> kColsPerThread) & ((1u << kColsPerThread) - 1u)) : 0u);
     }
     // StepNumber of this launch: by value, or (captured graphs) the device counter + the launch's offset in the graph
     const uint32_t step = (a.d_step ? *a.d_step : 0u) + a.step_base;
@@ -552,16 +560,31 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         const uint32_t len = yw < H ? min(H - yw, static_cast<uint32_t>(kTX * 16)) : 0u;
         const uint32_t blk = (lo >> 8) + bi;
         uint32_t need = lot_k; // stream bytes this lane still has to look at: winners left + repeats met
-        for (uint32_t t = 0; t < need; ++t)
+        // regrowth event of a winner: bit 15 | column << 9 | offset in the warp's span (null when outside the span)
+        auto winner = [&](uint32_t b) {
+            const uint32_t yo = ((blk << 8) | b) - lo;
+            s_evq[threadIdx.y][lot_off++] = yo < len ? static_cast<uint16_t>(0x8000u | ((j - 1) << 9) | yo) : kNullEvent;
+        };
+        // the first four bytes (one register) with compile-time masks: all there is for 99 % of the blocks
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (static_cast<uint32_t>(t) < need)
+            {
+                const uint32_t b = (lot_z >> (8 * t)) & 0xffu;
+                if (t > 0 && (zero_bytes(lot_z ^ (b * 0x01010101u)) & ((1u << (8 * t)) - 1u)))
+                    ++need;
+                else
+                    winner(b);
+            }
+        for (uint32_t t = 4; t < need; ++t)
         {
             uint32_t b;
             bool rep;
             if (t < 8)
             {
-                b = ((t < 4 ? lot_z : lot_w) >> (8 * (t & 3u))) & 0xffu;
+                b = (lot_w >> (8 * (t & 3u))) & 0xffu;
                 const uint32_t r4 = b * 0x01010101u;
-                const uint32_t mz = t >= 4 ? 0xffffffffu : ((1u << (8 * t)) - 1u), mw = t > 4 ? ((1u << (8 * (t - 4))) - 1u) : 0u;
-                rep = ((zero_bytes(lot_z ^ r4) & mz) | (zero_bytes(lot_w ^ r4) & mw)) != 0;
+                rep = (zero_bytes(lot_z ^ r4) | (zero_bytes(lot_w ^ r4) & ((1u << (8 * (t - 4))) - 1u))) != 0;
             }
             else // beyond the first eight bytes (about one block in a million)
             {
@@ -570,13 +593,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
                 for (uint32_t h = 0; h < t; ++h) rep = rep || lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, h) == b;
             }
             if (rep)
-            {
                 ++need;
-                continue;
-            }
-            const uint32_t yo = ((blk << 8) | b) - lo, cc = yo & 15u;
-            s_evq[threadIdx.y][lot_off++] =
-                yo < len ? static_cast<uint16_t>(((yo >> 4) << 10) | ((j - 1) << 5) | (8 * (cc & 3u) + 4 + (cc >> 2))) : kNullEvent;
+            else
+                winner(b);
         }
     }
 #ifdef INCERTO_FOREST_TRACE
@@ -621,9 +640,11 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         {
             const uint32_t item = s_evq[threadIdx.y][k];
             if (item == kNullEvent) continue;
-            const uint32_t bit = item & 31u;
-            const uint32_t lx = lx0 + ((item >> 5) & 31u);
-            const uint32_t y = (blockIdx.x * kTX + (item >> 10)) * 16 + 4 * (bit & 3) + ((bit >> 3) & 3);
+            // spread / one-level regrowth event: lane << 10 | column << 5 | bit of the event word; lottery winner: see above
+            const bool won = (item & 0x8000u) != 0;
+            const uint32_t bit = won ? 4u : (item & 31u);
+            const uint32_t lx = lx0 + (won ? ((item >> 9) & 7u) : ((item >> 5) & 31u));
+            const uint32_t y = blockIdx.x * (kTX * 16) + (won ? (item & 511u) : ((item >> 10) * 16 + 4 * (bit & 3) + ((bit >> 3) & 3)));
             const size_t off = static_cast<size_t>(lx) * c.pitch + y;
             const uint32_t uid = (static_cast<uint32_t>(a.x_begin) + lx - 1) * H + y;
             if (!(bit & 4))
@@ -713,7 +734,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // ---- incremental FireStats: warps that saw a transition add their deltas to the block's counters
     if (__any_sync(kFullMask, (dl.h | dl.b | dl.e) != 0))
     {
-        const int32_t h = warp_sum(dl.h), b = warp_sum(dl.b), e = warp_sum(dl.e);
+        const int32_t h = __reduce_add_sync(kFullMask, dl.h), b = __reduce_add_sync(kFullMask, dl.b), e = __reduce_add_sync(kFullMask, dl.e);
         if (lane == 0)
         {
             if (h) atomicAdd(&s_delta[0], h);

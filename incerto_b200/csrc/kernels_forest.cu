@@ -112,7 +112,7 @@ __device__ __forceinline__ uint32_t ignited_value(const ForestArgs& a)
 
 __device__ __forceinline__ bool regrow_draw(const ForestConst& c, uint32_t uid, uint32_t step)
 {
-    if (c.regrow_two_level && !lottery256_wins(c.rk_regrow, uid, step)) return false;
+    if (c.regrow_two_level && !lottery256_wins(c.rk_regrow, uid, 0u, step)) return false;
     const uint4 l2 = philox4x32_10(uid >> 2, 0u, step, 1u, c.rk_regrow);
     return bernoulli(word_of(l2, uid & 3u), c.thr_regrow_l2);
 }
@@ -588,9 +588,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             }
             else // beyond the first eight bytes (about one block in a million)
             {
-                b = lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, t);
+                b = lottery_stream_byte(c.rk_regrow, blk, 0u, step, lot_z, lot_w, t);
                 rep = false;
-                for (uint32_t h = 0; h < t; ++h) rep = rep || lottery_stream_byte(c.rk_regrow, blk, step, lot_z, lot_w, h) == b;
+                for (uint32_t h = 0; h < t; ++h) rep = rep || lottery_stream_byte(c.rk_regrow, blk, 0u, step, lot_z, lot_w, h) == b;
             }
             if (rep)
                 ++need;

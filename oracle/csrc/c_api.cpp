@@ -24,13 +24,13 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     std::memcpy(out, r.w, 16);
 }
 uint64_t oracle_threshold(double p) { return threshold(p); }
-// winners of one block lottery (lottery.hpp) under key (k0, k1); returns their number, positions into out[<= 21]
-uint32_t oracle_lottery256(uint32_t k0, uint32_t k1, uint32_t block, uint32_t step, uint8_t* out)
+// winners of one block lottery (lottery.hpp) under key (k0, k1); returns their number, positions into out[<= 48]
+uint32_t oracle_lottery256(uint32_t k0, uint32_t k1, uint32_t block, uint32_t sub, uint32_t step, int kexp, uint8_t* out)
 {
     Stream s(0, 0, 0);
     s.k0 = k0;
     s.k1 = k1;
-    const std::vector<uint8_t> w = lottery256(s, block, step);
+    const std::vector<uint8_t> w = lottery256(s, block, sub, step, kexp);
     for (size_t i = 0; i < w.size(); ++i) out[i] = w[i];
     return static_cast<uint32_t>(w.size());
 }

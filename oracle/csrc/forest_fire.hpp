@@ -200,7 +200,7 @@ struct ForestSim
         if (p * 256.0 <= 1.0)
         {
             // level 1: uid is a winner of its block's lottery (256 independent Bernoulli(2^-8) draws, one call)
-            if (!regrow_lottery.wins(rng, static_cast<uint32_t>(uid), static_cast<uint32_t>(step))) return false;
+            if (!regrow_lottery.wins(rng, static_cast<uint32_t>(uid), 0, static_cast<uint32_t>(step))) return false;
             const U4 l2 = rng.block(uid >> 2, 0, static_cast<uint32_t>(step), 1);
             return bern(l2.w[uid & 3], threshold(p * 256.0));
         }

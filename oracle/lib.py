@@ -32,7 +32,7 @@ def load() -> C.CDLL:
     lib.oracle_threshold.restype = C.c_uint64
     lib.oracle_below.argtypes = [C.c_uint32, C.c_uint32]
     lib.oracle_below.restype = C.c_uint32
-    lib.oracle_lottery256.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p]
+    lib.oracle_lottery256.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p]
     lib.oracle_lottery256.restype = C.c_uint32
     lib.oracle_coin_toss_run.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, u64p, u64p]
     lib.oracle_coin_toss_run.restype = C.c_double

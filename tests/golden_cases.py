@@ -3,7 +3,7 @@
 import numpy as np
 
 SEED = 0x1CE27002025
-CASES = ["coin_toss", "forest_fire", "forest_fire_lottery", "pandemic", "pandemic_spatial", "traders", "air_traffic_3d", "normal_draws"]
+CASES = ["coin_toss", "forest_fire", "forest_fire_lottery", "pandemic", "pandemic_two_level", "pandemic_spatial", "traders", "air_traffic_3d", "normal_draws"]
 
 
 def run_oracle(name):
@@ -21,9 +21,12 @@ def run_oracle(name):
         from oracle.forest import ForestOracle
         o = ForestOracle(SEED, 7, 36, 100, density=0.6, p_regrow=0.002, fires=3).spawn().run(90)
         return dict(cells=o.cells()[0], series=o.series())
-    if name == "pandemic":
+    if name in ("pandemic", "pandemic_two_level"):
         from oracle.pandemic import PandemicOracle
-        o = PandemicOracle(SEED, 2, 1500, 20, p_infect=0.05, p_recover=0.01, p_die=0.005, nested_loop=False).spawn().run(120)
+        if name == "pandemic":
+            o = PandemicOracle(SEED, 2, 1500, 20, p_infect=0.05, p_recover=0.01, p_die=0.005, nested_loop=False).spawn().run(120)
+        else:  # both fate probabilities <= 1/256: the two-level fate draws of the contract
+            o = PandemicOracle(SEED, 8, 3000, 30, p_infect=0.05, p_recover=0.003, p_die=0.002, nested_loop=False).spawn().run(150)
         xy, alive, inf = o.state()
         return dict(xy=xy, alive=alive, infected=inf, counts=np.array(o.counts(), np.uint64))
     if name == "pandemic_spatial":
@@ -80,16 +83,16 @@ def run_engine(name):
         ts = sim.get_aggregate_time_series(ib.FireStatsOf(cell))
         ser = np.array([(v.healthy_count, v.burning_count, v.burned_count, v.empty_count, v.total_cells) for v in ts.values()], np.uint64)
         return dict(cells=sim.read_component(cell), series=ser)
-    if name == "pandemic":
-        n, G = 1500, 20
-        b = ib.SimulationBuilder(seed=SEED, replica=2)
+    if name in ("pandemic", "pandemic_two_level"):
+        n, G, replica, p_rec, p_die, steps = (1500, 20, 2, 0.01, 0.005, 120) if name == "pandemic" else (3000, 30, 8, 0.003, 0.002, 150)
+        b = ib.SimulationBuilder(seed=SEED, replica=replica)
         person, infected = b.component("Person"), b.component("Infected")
         position = b.component("Position", F.U16, lanes=2)
         b.add_entity_spawner(ib.DeviceSpawner(F.SPAWN_PANDEMIC_PEOPLE, F.SpawnPandemicParams(person.handle, position.handle, infected.handle, n, G, 0.05)))
         b.add_systems(ib.PeopleMove(person, position, infected, G), ib.PeopleInfectOthers(person, position, infected, G, 0.05),
-                      ib.PeopleInfectedMayDie(person, position, infected, G, 0.005), ib.PeopleInfectedMayRecover(person, position, infected, G, 0.01))
+                      ib.PeopleInfectedMayDie(person, position, infected, G, p_die), ib.PeopleInfectedMayRecover(person, position, infected, G, p_rec))
         sim = b.build()
-        sim.run(120)
+        sim.run(steps)
         xy_live, uids = sim.read_component(position, with_uids=True)
         inf_live = sim.read_component(infected, rows_of=position)
         alive = np.zeros(n, bool)
@@ -165,11 +168,11 @@ def compare_engine_to_golden(name, got, gold):
         if a.dtype.kind == "f" or b.dtype.kind == "f":
             return np.array_equal(a.astype(np.float64).view(np.uint64), b.astype(np.float64).view(np.uint64))
         return a.shape == b.shape and np.array_equal(a.astype(np.int64), b.astype(np.int64))
-    if name in ("pandemic", "pandemic_spatial"):
+    if name in ("pandemic", "pandemic_two_level", "pandemic_spatial"):
         alive = gold["alive"].astype(bool)
         assert eq(got["alive"], alive), "survivors differ"
         assert eq(got["xy_live"], gold["xy"][alive])
-        if name == "pandemic":
+        if name != "pandemic_spatial":
             assert eq(got["infected_live"], gold["infected"][alive]) and eq(got["counts"], gold["counts"])
         else:
             assert eq(got["disease_live"], gold["disease"][alive]) and eq(got["quarantined_live"], gold["quarantined"][alive])

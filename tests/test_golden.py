@@ -29,6 +29,7 @@ def test_golden_is_not_trivial():
     assert GOLD["forest_fire/series"][-1][2] > 0            # something burned down
     lot = GOLD["forest_fire_lottery/series"]
     assert lot[-1][2] > 0 and 150 < int(lot[0][3]) - int(lot[-1][3]) < 350   # Empty cells regrew through the block lottery
+    assert 200 < (~GOLD["pandemic_two_level/alive"]).sum() < 1500 and GOLD["pandemic_two_level/counts"][1] > 100   # deaths through the two-level fate draw
     assert (~GOLD["pandemic/alive"]).any() and (~GOLD["pandemic_spatial/alive"]).any()   # despawns happened
     assert GOLD["traders/delisted"].any() or GOLD["traders/price"].min() < 5.0
     assert GOLD["air_traffic_3d/conflicts"].max() > 0

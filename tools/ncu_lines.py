@@ -2,7 +2,8 @@
 import csv, subprocess, sys
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []   # optional: kernel name pattern
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", *kern], capture_output=True, text=True).stdout
 rows, fname, func, hdr, first_func = [], None, None, None, None
 for r in csv.reader(out.splitlines()):
     if not r:

@@ -13,15 +13,19 @@
 // up to 52 w - only changed words are written -, cash 8 + 8, net worth 8 w).  The kernel is bound by
 // the integer pipe (Philox), not by HBM: see DESIGN.md §5.
 //
-// Draw contract: two-level Bernoulli with byte granularity, T1 = min(256, ceil(256 p)):
-//   buy   (trader t, stock s): L1 = byte (s & 15) of philox(key[TBUY], (t, s >> 4, step, 0)) < T1;
-//         L2 = philox(key[TBUY], (t, s, step, 1)): decides = L2.x < floor(256 p / T1 * 2^32),
+// Draw contract: two-level Bernoulli.
+//   buy   (trader t, stock s), p <= 1/32: L1 = s wins the block lottery (lottery.cuh, P = 2^-k with the largest k in
+//         5..8 such that 2^k p <= 1) of block t, sub-stream 0, key[TBUY] - ONE call per trader and step;
+//         L2 = philox(key[TBUY], (t, s, step, 1)): decides = L2.x < floor(2^k p * 2^32),
 //         num_shares = min + mulhi(L2.y, max - min + 1)                              (:178, :182)
+//         p > 1/32: L1 = byte (s & 15) of philox(key[TBUY], (t, s >> 4, step, 0)) < T1 = min(256, ceil(256 p)),
+//         L2 against floor(256 p / T1 * 2^32)
 //   sell  same with key[TSEL]; drawn for owned stocks only                          (:218)
 //   price stock s: z = det_normal(philox(key[TPRC], (s, 0, step, 0))) (detmath.cuh); change = mean + sd * z (:148-155)
 #include "common.cuh"
 #include "detmath.cuh"
 #include "kernels_traders.hpp"
+#include "lottery.cuh"
 
 namespace incerto
 {
@@ -152,20 +156,30 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
             unsigned long long cand[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) cand[c] = 0;
-            // (the 16-stock blocks of one 64-stock mask word run as a rolled loop: unrolling all of them made the kernel
-            // 41 KB of code - past the instruction cache - for no gain, ncu: stall no_instruction 2.0)
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
+            if (a.buy_kexp) // warp-uniform: the trader's lottery, winners that are listed and not owned
             {
-#pragma unroll 1
-                for (uint32_t q = 0; q < 4; ++q)
+                lottery256_k(a.rk_buy, a.buy_kexp, uid, 0u, a.step, [&](uint32_t b) { mask_set<NC>(cand, b, true); });
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    cand[c] &= (static_cast<unsigned long long>(s_listed[2 * c]) | (static_cast<unsigned long long>(s_listed[2 * c + 1]) << 32)) & ~owned[c];
+            }
+            else
+            {
+                // (the 16-stock blocks of one 64-stock mask word run as a rolled loop: unrolling all of them made the
+                // kernel 41 KB of code - past the instruction cache - for no gain, ncu: stall no_instruction 2.0)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
                 {
-                    const uint32_t b = 4u * c + q;
-                    if (b >= nblk) break;
-                    const uint32_t hit = buy_lt.bits16(philox4x32_10(uid, b, a.step, 0u, a.rk_buy));
-                    const uint32_t listed = (s_listed[b >> 1] >> (16 * (b & 1))) & 0xffffu;
-                    const uint32_t own16 = static_cast<uint32_t>(owned[c] >> (16 * q)) & 0xffffu;
-                    cand[c] |= static_cast<unsigned long long>(hit & listed & ~own16) << (16 * q);
+#pragma unroll 1
+                    for (uint32_t q = 0; q < 4; ++q)
+                    {
+                        const uint32_t b = 4u * c + q;
+                        if (b >= nblk) break;
+                        const uint32_t hit = buy_lt.bits16(philox4x32_10(uid, b, a.step, 0u, a.rk_buy));
+                        const uint32_t listed = (s_listed[b >> 1] >> (16 * (b & 1))) & 0xffffu;
+                        const uint32_t own16 = static_cast<uint32_t>(owned[c] >> (16 * q)) & 0xffffu;
+                        cand[c] |= static_cast<unsigned long long>(hit & listed & ~own16) << (16 * q);
+                    }
                 }
             }
             for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))
@@ -188,17 +202,32 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
             unsigned long long cand[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) cand[c] = 0;
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
+            if (a.sell_kexp)
             {
-#pragma unroll 1
-                for (uint32_t q = 0; q < 4; ++q)
+                unsigned long long any = 0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) any |= owned[c];
+                if (any) // a trader without shares draws nothing
                 {
-                    const uint32_t b = 4u * c + q;
-                    const uint32_t own16 = static_cast<uint32_t>(owned[c] >> (16 * q)) & 0xffffu;
-                    if (!own16) continue;
-                    const uint32_t hit = sell_lt.bits16(philox4x32_10(uid, b, a.step, 0u, a.rk_sell));
-                    cand[c] |= static_cast<unsigned long long>(hit & own16) << (16 * q);
+                    lottery256_k(a.rk_sell, a.sell_kexp, uid, 0u, a.step, [&](uint32_t b) { mask_set<NC>(cand, b, true); });
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) cand[c] &= owned[c];
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                {
+#pragma unroll 1
+                    for (uint32_t q = 0; q < 4; ++q)
+                    {
+                        const uint32_t b = 4u * c + q;
+                        const uint32_t own16 = static_cast<uint32_t>(owned[c] >> (16 * q)) & 0xffffu;
+                        if (!own16) continue;
+                        const uint32_t hit = sell_lt.bits16(philox4x32_10(uid, b, a.step, 0u, a.rk_sell));
+                        cand[c] |= static_cast<unsigned long long>(hit & own16) << (16 * q);
+                    }
                 }
             }
             for (int s = pop_lowest<NC>(cand); s >= 0; s = pop_lowest<NC>(cand))

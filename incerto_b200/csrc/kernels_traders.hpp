@@ -28,7 +28,8 @@ struct TradersArgs
     uint32_t step;
     uint32_t do_buy, do_sell, do_net_worth;
     uint32_t buy_t1, sell_t1;   // level-1 byte thresholds: min(256, ceil(256 p))
-    uint64_t buy_thr2, sell_thr2; // level-2: floor(256 p / T1 * 2^32)
+    uint64_t buy_thr2, sell_thr2; // level-2: floor(256 p / T1 * 2^32), or floor(2^k p * 2^32) with the lottery
+    uint32_t buy_kexp, sell_kexp; // level 1 by block lottery with P = 2^-k (k = 5..8); 0: byte thresholds
     uint32_t shares_min, shares_range; // num_shares = shares_min + mulhi(u, shares_range)
     double change_mean, change_std_dev;
     PhiloxRoundKeys rk_buy, rk_sell, rk_price;

@@ -107,6 +107,7 @@ __device__ __forceinline__ void lottery_walk(const PhiloxRoundKeys& rk, uint32_t
 {
     auto zero_bytes = [](uint32_t v) { return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; };
     uint32_t need = count; // stream bytes still to look at: winners left + repeats met
+    uint4 e = make_uint4(0u, 0u, 0u, 0u); // bytes 8..23: the first continuation call, made once when the walk gets there
     for (uint32_t t = 0; t < need; ++t)
     {
         uint32_t b;
@@ -118,7 +119,20 @@ __device__ __forceinline__ void lottery_walk(const PhiloxRoundKeys& rk, uint32_t
             const uint32_t mz = t >= 4 ? 0xffffffffu : ((1u << (8 * t)) - 1u), mw = t > 4 ? ((1u << (8 * (t - 4))) - 1u) : 0u;
             rep = ((zero_bytes(z ^ r4) & mz) | (zero_bytes(w ^ r4) & mw)) != 0;
         }
-        else
+        else if (t < 24)
+        {
+            if (t == 8) e = philox4x32_10(block, sub, step, 2u, rk);
+            const uint32_t j = t - 8, ws = j >> 2, part = (1u << (8 * (j & 3u))) - 1u; // word of the byte, earlier bytes of that word
+            b = (word_of(e, ws) >> (8 * (j & 3u))) & 0xffu;
+            const uint32_t r4 = b * 0x01010101u;
+            uint32_t hit = zero_bytes(z ^ r4) | zero_bytes(w ^ r4);
+            hit |= zero_bytes(e.x ^ r4) & (ws > 0 ? 0xffffffffu : part);
+            hit |= zero_bytes(e.y ^ r4) & (ws > 1 ? 0xffffffffu : (ws == 1 ? part : 0u));
+            hit |= zero_bytes(e.z ^ r4) & (ws > 2 ? 0xffffffffu : (ws == 2 ? part : 0u));
+            hit |= zero_bytes(e.w ^ r4) & (ws == 3 ? part : 0u);
+            rep = hit != 0;
+        }
+        else // 24 stream bytes used up: out of reach in practice
         {
             b = lottery_stream_byte(rk, block, sub, step, z, w, t);
             rep = false;

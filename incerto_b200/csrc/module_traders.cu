@@ -120,14 +120,26 @@ int32_t traders_bind(Sim& s)
     return INCERTO_OK;
 }
 
-static void two_level(double p, uint32_t& t1, uint64_t& thr2)
+// Level 1 of a buy / sell decision: for p <= 1/32 the block lottery with the largest k in 5..8 such
+// that 2^k p <= 1 (`kexp`, one Philox call per trader and step), level 2 then draws against 2^k p; above 1/32 one byte
+// per stock below T1 = min(256, ceil(256 p)) (`kexp` = 0), level 2 against 256 p / T1.
+static void two_level(double p, uint32_t& t1, uint64_t& thr2, uint32_t& kexp)
 {
+    kexp = 0;
     if (!(p > 0.0))
     {
         t1 = 0;
         thr2 = 0;
         return;
     }
+    for (uint32_t k = 8; k >= 5; --k)
+        if (p * static_cast<double>(1u << k) <= 1.0)
+        {
+            kexp = k;
+            t1 = 0;
+            thr2 = bernoulli_threshold(p * static_cast<double>(1u << k));
+            return;
+        }
     const double c = std::ceil(256.0 * p);
     t1 = c >= 256.0 ? 256u : static_cast<uint32_t>(c);
     thr2 = bernoulli_threshold(256.0 * p / static_cast<double>(t1));
@@ -157,8 +169,8 @@ static bool traders_fill(Sim& s, TradersModule& tm, TradersArgs& a, uint64_t ste
     a.do_buy = tm.do_buy;
     a.do_sell = tm.do_sell;
     a.do_net_worth = tm.do_net_worth;
-    two_level(tm.p.chance_buy, a.buy_t1, a.buy_thr2);
-    two_level(tm.p.chance_sell, a.sell_t1, a.sell_thr2);
+    two_level(tm.p.chance_buy, a.buy_t1, a.buy_thr2, a.buy_kexp);
+    two_level(tm.p.chance_sell, a.sell_t1, a.sell_thr2, a.sell_kexp);
     a.shares_min = tm.p.buy_shares_min;
     a.shares_range = tm.p.buy_shares_max - tm.p.buy_shares_min + 1;
     a.change_mean = tm.p.price_change_mean;

@@ -96,16 +96,20 @@ struct LotteryCache
     bool win[256] = {};
     bool wins(const Stream& rng, uint32_t id, uint32_t at_sub, uint32_t at_step, int at_kexp = 8)
     {
-        if ((id >> 8) != block || at_sub != sub || at_step != step || at_kexp != kexp)
+        return wins_at(rng, id >> 8, id & 255u, at_sub, at_step, at_kexp);
+    }
+    bool wins_at(const Stream& rng, uint32_t at_block, uint32_t pos, uint32_t at_sub, uint32_t at_step, int at_kexp = 8)
+    {
+        if (at_block != block || at_sub != sub || at_step != step || at_kexp != kexp)
         {
-            block = id >> 8;
+            block = at_block;
             sub = at_sub;
             step = at_step;
             kexp = at_kexp;
             for (bool& w : win) w = false;
             for (uint8_t b : lottery256(rng, block, sub, step, kexp)) win[b] = true;
         }
-        return win[id & 255u];
+        return win[pos];
     }
 };
 

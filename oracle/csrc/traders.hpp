@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "detmath.hpp"
+#include "lottery.hpp"
 #include "philox.hpp"
 
 namespace oracle
@@ -35,10 +36,20 @@ struct TradersParams
 
 // two-level Bernoulli of the contract: level 1 = one byte < T1 with T1 = min(256, ceil(256 p)),
 // level 2 = a 32-bit draw below floor(256 p / T1 * 2^32)
+// (for p <= 1/32 level 1 is the block lottery with P = 2^-k, the largest k in 5..8 such that 2^k p <= 1 - one call
+// per trader and step, lottery.hpp - and level 2 draws against 2^k p)
 struct TwoLevel
 {
     uint32_t t1;
     uint64_t thr2;
+    int kexp = 0;
+    // level 1 for stock s of trader t
+    bool level1(const Stream& rng, uint32_t t, uint32_t s, uint32_t step, LotteryCache& cache) const
+    {
+        if (kexp) return cache.wins_at(rng, t, s, 0, step, kexp); // block t, position s
+        const U4 b = rng.block(t, s >> 4, step, 0);
+        return ((b.w[(s & 15) >> 2] >> (8 * (s & 3))) & 0xffu) < t1;
+    }
     explicit TwoLevel(double p)
     {
         if (!(p > 0.0))
@@ -47,6 +58,14 @@ struct TwoLevel
             thr2 = 0;
             return;
         }
+        for (int k = 8; k >= 5; --k)
+            if (p * static_cast<double>(1u << k) <= 1.0)
+            {
+                kexp = k;
+                t1 = 0;
+                thr2 = threshold(p * static_cast<double>(1u << k));
+                return;
+            }
         const double c = std::ceil(256.0 * p);
         t1 = c >= 256.0 ? 256u : static_cast<uint32_t>(c);
         thr2 = threshold(256.0 * p / static_cast<double>(t1));
@@ -95,6 +114,7 @@ struct TradersSim
     {
         const Stream rng(seed, replica, T_TBUY);
         const TwoLevel tl(P.chance_buy);
+        LotteryCache lottery;
         for (uint32_t t = 0; t < traders.size(); ++t)
         {
             Trader& tr = traders[t];
@@ -103,7 +123,7 @@ struct TradersSim
                 if (delisted[s]) continue; // Without<StockDelisted>
                 const double p = price[s];
                 const bool already_owned = tr.portfolio.count(s) != 0;
-                bool decides_to_buy = byte_of(rng.block(t, s >> 4, static_cast<uint32_t>(step), 0), s & 15) < tl.t1;
+                bool decides_to_buy = tl.level1(rng, t, s, static_cast<uint32_t>(step), lottery);
                 U4 l2{};
                 if (decides_to_buy)
                 {
@@ -126,6 +146,7 @@ struct TradersSim
     {
         const Stream rng(seed, replica, T_TSEL);
         const TwoLevel tl(P.chance_sell);
+        LotteryCache lottery;
         std::unordered_map<uint32_t, double> stock_prices;
         for (uint32_t s = 0; s < price.size(); ++s) stock_prices[s] = price[s];
         for (uint32_t t = 0; t < traders.size(); ++t)
@@ -137,7 +158,7 @@ struct TradersSim
             std::vector<std::pair<uint32_t, uint32_t>> to_sell;
             for (uint32_t s : owned)
             {
-                bool decides_to_sell = byte_of(rng.block(t, s >> 4, static_cast<uint32_t>(step), 0), s & 15) < tl.t1;
+                bool decides_to_sell = tl.level1(rng, t, s, static_cast<uint32_t>(step), lottery);
                 if (decides_to_sell) decides_to_sell = bern(rng.block(t, s, static_cast<uint32_t>(step), 1).w[0], tl.thr2);
                 if (decides_to_sell) to_sell.push_back({s, tr.portfolio[s]});
             }

@@ -47,12 +47,52 @@ pub fn forest_spread(seed: u64, replica: u32, t: u32, s: u32, dir: u32, base_cel
     if s < base_cells { bern(st.block(t, 0, step, 0)[dir as usize], threshold(p)) } else { bern(st.block(t, s, step, 1)[0], threshold(p)) }
 }
 
+/// Block lottery, k = 8: floor(P(Binomial(256, 1/256) <= j) * 2^64), j = 0..20
+/// (the tables for k = 5..7 are in tools/gen_lottery_tables.py; the shim only needs this one).
+pub const LOTTERY_CDF_K8: [u64; 21] = [
+    0x5dfe2e83aaa155df, 0xbc5ab99263fc066e, 0xeb88ff19c0a95eb6,
+    0xfb334c65d160bff4, 0xff1602b52bdc8a86, 0xffda9ccd49cad7e7,
+    0xfffadd91a9b98cec, 0xffff61fa9ca0e619, 0xffffef2105923822,
+    0xfffffe61be083611, 0xffffffdbf6da03df, 0xfffffffd2270a8ad,
+    0xffffffffca5278cd, 0xfffffffffc5d60d0, 0xffffffffffc5618b,
+    0xfffffffffffc8d07, 0xffffffffffffcf48, 0xfffffffffffffd78,
+    0xffffffffffffffe0, 0xfffffffffffffffe, 0xffffffffffffffff,
+];
+
+/// Winners (positions 0..255) of block `block`, sub-stream `sub`, at `step`: 256 independent Bernoulli(2^-8) draws
+/// realised with one call - the number of winners by inverse CDF, then distinct bytes of the block's byte stream
+/// (words 2, 3 of the first call, then all four words of the calls with counter word 3 = 2, 3, ...).
+pub fn lottery256(st: &Stream, block: u32, sub: u32, step: u32) -> Vec<u8> {
+    let first = st.block(block, sub, step, 0);
+    let u = ((first[0] as u64) << 32) | first[1] as u64;
+    let k = LOTTERY_CDF_K8.iter().take_while(|&&t| u >= t).count();
+    let (mut winners, mut seen, mut cur, mut word, mut byte, mut extra) = (Vec::new(), [false; 256], first, 2usize, 0u32, 0u32);
+    while winners.len() < k {
+        if word == 4 {
+            cur = st.block(block, sub, step, 2 + extra);
+            extra += 1;
+            word = 0;
+        }
+        let b = (cur[word] >> (8 * byte)) as u8;
+        byte += 1;
+        if byte == 4 {
+            byte = 0;
+            word += 1;
+        }
+        if !seen[b as usize] {
+            seen[b as usize] = true;
+            winners.push(b);
+        }
+    }
+    winners
+}
+
 /// examples/forest_fire.rs:360  `rng.random_bool(REGROWTH_PROBABILITY)` for an Empty entity
 pub fn forest_regrow(seed: u64, replica: u32, uid: u32, step: u32, p: f64) -> bool {
     let st = Stream::new(seed, replica, b"FREG");
     if p * 256.0 <= 1.0 {
-        let l1 = st.block(uid >> 4, 0, step, 0);
-        if (l1[((uid >> 2) & 3) as usize] >> (8 * (uid & 3))) & 0xff != 0 { return false; }
+        // level 1: uid wins the lottery of its block of 256 uids (a real run would cache the block's winners)
+        if !lottery256(&st, uid >> 8, 0, step).contains(&((uid & 255) as u8)) { return false; }
         bern(st.block(uid >> 2, 0, step, 1)[(uid & 3) as usize], threshold(p * 256.0))
     } else {
         bern(st.block(uid >> 2, 0, step, 1)[(uid & 3) as usize], threshold(p))

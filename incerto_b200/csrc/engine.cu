@@ -1297,6 +1297,10 @@ int32_t incerto_sim_run_cold(incerto_sim* s, uint64_t num_steps)
             // GPU to GPU — otherwise that skew would be charged to the step as time spent waiting for the neighbour
             rc = comm_allreduce(S, S.d_scratch, 1, 0, 0);
             if (rc != INCERTO_OK) break;
+            // ... and the neighbours once more over peer memory (they leave within one NVLink latency of each other;
+            // the collective's kernels end a few microseconds apart, and a step waits for its neighbours' launch)
+            rc = forest_cold_rendezvous(S);
+            if (rc != INCERTO_OK) break;
         }
         fail(cudaEventRecord(ev[2 * i], S.stream));
         if (rc == INCERTO_OK) rc = do_run_enqueue(S, 1);

@@ -133,26 +133,28 @@ struct ForestArgs
     uint64_t series_interval, series_capacity;
 };
 // Halo transport fused into the step kernel (row partition, neighbours' slabs mapped through CUDA IPC).  A stamp k in
-// my mailbox says "that neighbour finished step k: the buffer that step wrote is complete".  The CTAs that read a halo
-// column wait for the stamp of the previous step and then PULL the neighbour's boundary column over NVLink into their
-// own halo column (nothing on the writer's side but one system-scope fence and the stamp, issued by the last of the
-// boundary CTAs: only they write what a neighbour pulls); they are scheduled first, so that the wait, the NVLink round
-// trip and the stamp all happen while the rest of the grid works.  The
-// neighbour cannot overwrite what is being pulled: the warps that write its boundary column are the ones that wait
-// for MY stamp of this step.
+// a rank's mailbox says "I finished step k: the buffer that step wrote is complete".  The warps that read a halo column
+// wait for the neighbour's stamp of the previous step (read over NVLink) and then PULL its boundary column.  The writer's
+// side is one plain store into its OWN mailbox by the first thread of the launch that FOLLOWS step k (the next step's
+// grid, or the publish kernel at the end of a run): the kernel boundary has made step k's cells visible; a step never
+// writes a neighbour's memory (a grid that does completes ~5 us later, kernels_forest.cu: forest_stamp).
+// The CTAs of the two boundary column groups are scheduled first, so that the wait and the NVLink round trip happen
+// while the rest of the grid works.  The neighbour cannot overwrite what is being pulled: the warps that write its
+// boundary column in step k+2 wait for MY stamp k+1, which leaves after my step k+1 (and its pulls) completed.
 struct ForestPeer
 {
-    const uint32_t* mail = nullptr;      // my mailbox: [0] last step stamped by the lower neighbour, [1] by the upper one
+    uint32_t* my_mail = nullptr;         // my mailbox (slot 4: the last step of mine that is complete; slot 5: rendezvous epoch)
     uint32_t need_lo = 0, need_hi = 0;   // stamp the neighbour's buffer must carry (0: first step, halos spawned locally)
     const uint8_t* src_lo = nullptr;     // lower neighbour's last own column in the buffer this step reads
     const uint8_t* src_hi = nullptr;     // upper neighbour's first own column
-    uint32_t* mail_lo = nullptr;         // my slot in the lower / upper neighbour's mailbox
-    uint32_t* mail_hi = nullptr;
-    uint32_t stamp = 0;
+    const uint32_t* mail_lo = nullptr;   // the lower / upper neighbour's mailbox, read over NVLink
+    const uint32_t* mail_hi = nullptr;
+    uint32_t stamp = 0;                  // step to announce at the start of this launch (0: none yet)
+    uint32_t debug = 0;                  // timing experiments (INCERTO_B200_DEBUG_HALO): 1 no boundary-first order, 2 no pulls
 };
 cudaError_t launch_forest_step(const ForestArgs& a, cudaStream_t st);
 // put step (d_step ? *d_step : 0) + step_base on record (idempotent) and add `bump` to the device StepNumber
-cudaError_t launch_forest_publish(const ForestArgs& a, uint32_t bump, cudaStream_t st);
+cudaError_t launch_forest_publish(const ForestArgs& a, uint32_t bump, cudaStream_t st, const ForestPeer* peer = nullptr);
 cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
                                   cudaStream_t st, const ForestPeer* peer = nullptr);
 int forest_step_grid_blocks(int32_t slab_w, int32_t H);
@@ -165,6 +167,9 @@ void launch_forest_halo_push(const uint8_t* col_lo, uint8_t* peer_lo, const uint
                              uint32_t col_bytes, const uint8_t* ov, uint8_t* peer_ov_lo, uint8_t* peer_ov_hi, uint32_t n_ov,
                              uint32_t* peer_mail_lo, uint32_t* peer_mail_hi, uint32_t stamp, cudaStream_t st);
 void launch_forest_halo_wait(const uint32_t* mail, uint32_t need_lo, uint32_t need_hi, uint32_t* error, cudaStream_t st);
+// neighbour rendezvous over the peer mailboxes (slot 5), epoch strictly increasing
+void launch_forest_rendezvous(uint32_t* mail, const uint32_t* peer_mail_lo, const uint32_t* peer_mail_hi, uint32_t epoch, uint32_t* error, cudaStream_t st);
+void launch_forest_stamp_wait(const uint32_t* peer_mail_lo, const uint32_t* peer_mail_hi, uint32_t need, uint32_t* error, cudaStream_t st);
 void launch_forest_spawn(uint8_t* cells, int32_t W, int32_t H, int32_t x_begin, int32_t x_end, PhiloxKey key,
                          uint64_t thr_density, cudaStream_t st);
 // FireStats of the owned columns of a pitched slab (standalone sample_aggregate)

@@ -82,6 +82,40 @@ __device__ __forceinline__ uint32_t smid()
 }
 #endif
 
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Fused halo transport, stamp side.  "Step k of this rank is complete" is announced by the launch that FOLLOWS step k
+// (the first thread of step k+1's grid, or the publish kernel at the end of a run): the kernel boundary has already made
+// every cell and overlay state of step k visible, so the stamp is one plain store - into this rank's OWN mailbox (slot
+// kStampSlot), where the neighbours read it over NVLink.  No remote write, no fence, no ticket inside a step: measured
+// by switching the halves of the transport off separately, ONE 4-byte store into a neighbour's memory - wherever in the
+// kernel, whatever its ordering - made every step of a row-split grid 5 us longer (28.0 against 23.2 us; a grid that
+// wrote peer memory completes later), as did the round-1 design (device-scope fence + ticket in each boundary CTA,
+// system-scope fence + remote stamp by the last of them).  Remote READS cost nothing of the kind.
+constexpr uint32_t kStampSlot = 4, kEpochSlot = 5;
+__device__ __forceinline__ void forest_stamp(const ForestPeer& pr)
+{
+    if (pr.stamp && pr.my_mail) *reinterpret_cast<volatile uint32_t*>(pr.my_mail + kStampSlot) = pr.stamp;
+}
+
 constexpr int kEventQueue = 512;   // rare events of one warp tile handled per round
 constexpr uint16_t kNullEvent = 0xffffu;
 static_assert(INCERTO_FOREST_COLS <= 7, "a lottery event carries its column in three bits, and 0xffff must stay free");
@@ -249,8 +283,9 @@ __device__ __forceinline__ void forest_publish(const ForestArgs& a, uint32_t sla
 
 // After the last step of a run (and at the end of every captured graph of steps): put that step on record and,
 // for a graph, advance the device-side StepNumber (src/plugins/step_number.rs:20-23) by the steps it held.
-__global__ void forest_publish_kernel(ForestArgs a, uint32_t slab_w, uint32_t bump)
+__global__ void forest_publish_kernel(ForestArgs a, uint32_t slab_w, uint32_t bump, ForestPeer pr)
 {
+    forest_stamp(pr); // row-split grids: the last step of the run is complete
     const uint32_t p = (a.d_step ? *a.d_step : 0u) + a.step_base;
     forest_publish(a, slab_w, p);
     if (bump && a.d_step) *const_cast<uint32_t*>(a.d_step) += bump;
@@ -272,7 +307,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // column group of this CTA.  With the fused halo transport the two boundary groups come first in launch order
     // (groups 1 and last swapped): they wait for the neighbours while the rest of the grid works.
     uint32_t by = blockIdx.y;
-    if (PEER && c.peer.mail && gridDim.y > 2) by = by == 1 ? gridDim.y - 1 : (by == gridDim.y - 1 ? 1 : by);
+    if (PEER && c.peer.my_mail && gridDim.y > 2 && !(c.peer.debug & 1u)) by = by == 1 ? gridDim.y - 1 : (by == gridDim.y - 1 ? 1 : by);
     const uint32_t lx0 = 1 + (by * kTY + threadIdx.y) * kColsPerThread;
     const uint32_t lane = threadIdx.x; // blockDim.x == 32: one warp per threadIdx.y
     const uint32_t tid = threadIdx.y * kTX + threadIdx.x;
@@ -287,6 +322,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     __shared__ int32_t s_delta[3];
     __shared__ NearOverlays nr;
     __shared__ uint16_t s_evq[kTY][kEventQueue];                                   // rare events of a warp's tile
+    // row-split grid: the neighbours learn that my previous step is complete - first thing, before this very thread may
+    // have to wait for THEIR stamp below (both ranks stamp, then wait)
+    if (PEER && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) forest_stamp(c.peer);
     if (tid < 3) s_delta[tid] = 0;
     if (tid == 0)
     {
@@ -298,8 +336,8 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     // the neighbour rank's boundary column do not read it from the local halo column: they pull it over NVLink below,
     // after their other loads are in flight, straight into the register it is needed in.
     const uint32_t hi_off = (c.slab_w - 1u) % (kTY * kColsPerThread);   // position of the last real column in its group
-    const bool pull_lo = PEER && c.peer.mail && c.peer.need_lo && by == 0 && threadIdx.y == 0;                // my v[0]
-    const bool pull_hi = PEER && c.peer.mail && c.peer.need_hi && by == gridDim.y - 1 && threadIdx.y == hi_off / kColsPerThread;
+    const bool pull_lo = PEER && c.peer.my_mail && c.peer.need_lo && by == 0 && threadIdx.y == 0 && !(c.peer.debug & 2u);                // my v[0]
+    const bool pull_hi = PEER && c.peer.my_mail && c.peer.need_hi && by == gridDim.y - 1 && threadIdx.y == hi_off / kColsPerThread && !(c.peer.debug & 2u);
     const uint32_t jh = hi_off % kColsPerThread + 2u;                                                          // my v[jh]
     const uint8_t* p0 = a.cur + static_cast<size_t>(lx0 - 1) * c.pitch + y0;
     uint4 v[kColsPerThread + 2];
@@ -315,11 +353,13 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     {
         if (lane == 0)
         {
-            const volatile uint32_t* m = c.peer.mail;
+            // Acquire loads of the stamp, not a volatile poll + system-scope fence: the fence also waited for this
+            // warp's own cell loads (just issued, microseconds from a cold L2) before the pull could even start, which
+            // put the boundary warps - and with them the end of the step - 3-5 us behind everybody else.
             const long long t0 = clock64();
-            // stamps only grow; wrap-around-safe comparison
-            while ((pull_lo && static_cast<int32_t>(m[0] - c.peer.need_lo) < 0) ||
-                   (pull_hi && static_cast<int32_t>(m[1] - c.peer.need_hi) < 0))
+            // stamps only grow; wrap-around-safe comparison (the stamp words live in the neighbours' memory)
+            while ((pull_lo && static_cast<int32_t>(ld_acquire_sys(c.peer.mail_lo + kStampSlot) - c.peer.need_lo) < 0) ||
+                   (pull_hi && static_cast<int32_t>(ld_acquire_sys(c.peer.mail_hi + kStampSlot) - c.peer.need_hi) < 0))
             {
                 __nanosleep(64);
                 if (clock64() - t0 > 20000000000ll) // ~10 s: a neighbour died; never hang the device
@@ -328,9 +368,8 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
                     break;
                 }
             }
-            __threadfence_system();
         }
-        __syncwarp();
+        __syncwarp(); // orders the other lanes' pulls after lane 0's acquire
         uint8_t* mine = const_cast<uint8_t*>(a.cur);
         if (pull_lo)
         {
@@ -419,7 +458,9 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
             pf_x = a.ov_pos[2 * tid];
             pf_y = a.ov_pos[2 * tid + 1];
             pf_owner = c.ov_owner ? c.ov_owner[tid] : 0;
-            pf_old = pf_owner == 0 ? a.ov_cur[tid] : (pf_owner == 1 ? (c.ov_lo ? c.ov_lo[tid] : 0) : (pf_owner == 2 ? (c.ov_hi ? c.ov_hi[tid] : 0) : 0));
+            // (a neighbour rank's overlay state lives in ITS memory: fetched below, by the few CTAs that have the entity
+            // nearby - as a prefetch in every CTA it was an NVLink round trip no warp 0 of the grid could retire before)
+            pf_old = pf_owner == 0 ? a.ov_cur[tid] : 0u;
         }
     }
     __syncthreads(); // s_done and nr.n are initialised; all warps are still in step here, so this barrier is cheap
@@ -431,6 +472,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         {
             int ox = pf_x, oy = pf_y;
             uint32_t o = pf_owner, old = pf_old;
+            if (k == tid && (o == 1 || o == 2)) old = o == 1 ? (c.ov_lo ? c.ov_lo[k] : 0) : (c.ov_hi ? c.ov_hi[k] : 0);
             if (k != tid) // more overlays than threads: the rest is fetched here
             {
                 ox = a.ov_pos[2 * k];
@@ -759,7 +801,6 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         g_forest_trace[8 * w + 7] = tr_overlays;
     }
 #endif
-    if (PEER && (c.peer.mail_lo || c.peer.mail_hi)) __syncwarp(); // lane 0 speaks for the whole warp's stores (the neighbours pull them)
     if (lane != 0) return;
     __threadfence_block();
     if (atomicAdd(&s_done, 1u) != kTY - 1) return;
@@ -772,21 +813,6 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         if (b) atomicAdd(d + 1, static_cast<unsigned long long>(static_cast<long long>(b)));
         if (e) atomicAdd(d + 2, static_cast<unsigned long long>(static_cast<long long>(e)));
     }
-    if (!PEER || !(c.peer.mail_lo || c.peer.mail_hi)) return;
-    // fused halo transport only.  What a neighbour pulls - the two boundary columns and the states of overlay entities
-    // sitting in them - is written by the CTAs of the two boundary column groups alone, and those are the CTAs that
-    // read the neighbours' columns.  So only they take the ticket: the last of them publishes this step's stamp in the
-    // neighbours' mailboxes.  They are scheduled first, hence the stamp leaves long before the grid ends and neither
-    // the fence nor the stamp sits on this kernel's tail.
-    if (by != 0 && by != gridDim.y - 1) return;
-    __threadfence(); // this block's cells and overlay states, before it is counted
-    const uint32_t nblocks = gridDim.y > 1 ? 2 * gridDim.x : gridDim.x;
-    const uint32_t t = atomicAdd(a.ticket, 1u);
-    if (t != nblocks - 1) return;
-    *a.ticket = 0u; // ready for the next launch
-    __threadfence_system();
-    if (c.peer.mail_lo) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_lo) = c.peer.stamp;
-    if (c.peer.mail_hi) *reinterpret_cast<volatile uint32_t*>(c.peer.mail_hi) = c.peer.stamp;
 }
 
 __global__ void forest_spawn_kernel(uint8_t* cells, int32_t H, uint32_t pitch, int32_t x_begin, uint32_t slab_w,
@@ -875,9 +901,11 @@ cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_forest_publish(const ForestArgs& a, uint32_t bump, cudaStream_t st)
+cudaError_t launch_forest_publish(const ForestArgs& a, uint32_t bump, cudaStream_t st, const ForestPeer* peer)
 {
-    forest_publish_kernel<<<1, 1, 0, st>>>(a, static_cast<uint32_t>(a.x_end - a.x_begin), bump);
+    ForestPeer pr;
+    if (peer) pr = *peer;
+    forest_publish_kernel<<<1, 1, 0, st>>>(a, static_cast<uint32_t>(a.x_end - a.x_begin), bump, pr);
     return cudaGetLastError();
 }
 
@@ -946,6 +974,52 @@ void launch_forest_halo_push(const uint8_t* col_lo, uint8_t* peer_lo, const uint
     forest_halo_push_kernel<<<2, 256, 0, st>>>(col_lo, peer_lo, col_hi, peer_hi, col_bytes, ov, peer_ov_lo, peer_ov_hi, n_ov,
                                                peer_mail_lo, peer_mail_hi, stamp);
 }
+namespace
+{
+// Neighbour rendezvous over the peer mailboxes (slot kEpochSlot: the owner's epoch, read by its neighbours over NVLink):
+// the ranks of a row-split grid leave it within one NVLink latency of each other.  Bench hygiene (run_cold): the flush
+// before a timed step takes a different time on every GPU.
+__global__ void forest_rendezvous_kernel(uint32_t* mail, const uint32_t* peer_mail_lo, const uint32_t* peer_mail_hi, uint32_t epoch, uint32_t* error)
+{
+    *reinterpret_cast<volatile uint32_t*>(mail + kEpochSlot) = epoch;
+    __threadfence_system();
+    const long long t0 = clock64();
+    while ((peer_mail_lo && static_cast<int32_t>(ld_acquire_sys(peer_mail_lo + kEpochSlot) - epoch) < 0) ||
+           (peer_mail_hi && static_cast<int32_t>(ld_acquire_sys(peer_mail_hi + kEpochSlot) - epoch) < 0))
+    {
+        __nanosleep(64);
+        if (clock64() - t0 > 20000000000ll) // ~10 s: a neighbour died; never hang the device
+        {
+            atomicCAS(error, 0u, static_cast<uint32_t>(39 /* INCERTO_ERR_COMM */));
+            return;
+        }
+    }
+}
+// wait until both neighbours announced step `need` (fused transport: reset must not respawn under a neighbour's pull)
+__global__ void forest_stamp_wait_kernel(const uint32_t* peer_mail_lo, const uint32_t* peer_mail_hi, uint32_t need, uint32_t* error)
+{
+    const long long t0 = clock64();
+    while ((peer_mail_lo && static_cast<int32_t>(ld_acquire_sys(peer_mail_lo + kStampSlot) - need) < 0) ||
+           (peer_mail_hi && static_cast<int32_t>(ld_acquire_sys(peer_mail_hi + kStampSlot) - need) < 0))
+    {
+        __nanosleep(200);
+        if (clock64() - t0 > 20000000000ll)
+        {
+            atomicCAS(error, 0u, static_cast<uint32_t>(39 /* INCERTO_ERR_COMM */));
+            return;
+        }
+    }
+}
+} // namespace
+void launch_forest_stamp_wait(const uint32_t* peer_mail_lo, const uint32_t* peer_mail_hi, uint32_t need, uint32_t* error, cudaStream_t st)
+{
+    forest_stamp_wait_kernel<<<1, 1, 0, st>>>(peer_mail_lo, peer_mail_hi, need, error);
+}
+void launch_forest_rendezvous(uint32_t* mail, const uint32_t* peer_mail_lo, const uint32_t* peer_mail_hi, uint32_t epoch, uint32_t* error, cudaStream_t st)
+{
+    forest_rendezvous_kernel<<<1, 1, 0, st>>>(mail, peer_mail_lo, peer_mail_hi, epoch, error);
+}
+
 void launch_forest_halo_wait(const uint32_t* mail, uint32_t need_lo, uint32_t need_hi, uint32_t* error, cudaStream_t st)
 {
     forest_halo_wait_kernel<<<1, 1, 0, st>>>(mail, need_lo, need_hi, error);

@@ -86,6 +86,7 @@ void forest_peer_free(Sim& s)
     fm.peer_ovs_lo[0] = fm.peer_ovs_lo[1] = fm.peer_ovs_hi[0] = fm.peer_ovs_hi[1] = nullptr;
     fm.peer_mail_lo = fm.peer_mail_hi = nullptr;
     fm.pushes = 0;
+    fm.rendezvous = 0;
 }
 
 // Map the neighbours' slabs through CUDA IPC (handles exchanged with one NCCL all-gather).  Any failure leaves the NCCL
@@ -178,6 +179,7 @@ int32_t forest_peer_setup(Sim& s)
     }
     fm.peer = true;
     fm.pushes = 0;
+    fm.rendezvous = 0;
     return INCERTO_OK;
 }
 
@@ -701,8 +703,20 @@ int32_t forest_peer_quiesce(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
     if (!fm.peer || !s.comm || !fm.pushes) return INCERTO_OK;
-    launch_forest_halo_wait(fm.d_mail, fm.peer_mail_lo ? fm.pushes : 0u, fm.peer_mail_hi ? fm.pushes : 0u, s.d_error, s.stream);
+    if (fm.fused) // the neighbours announce their steps in their own mailboxes
+        launch_forest_stamp_wait(fm.peer_mail_lo, fm.peer_mail_hi, fm.pushes, s.d_error, s.stream);
+    else
+        launch_forest_halo_wait(fm.d_mail, fm.peer_mail_lo ? fm.pushes : 0u, fm.peer_mail_hi ? fm.pushes : 0u, s.d_error, s.stream);
     INC_CUDA(cudaStreamSynchronize(s.stream));
+    return INCERTO_OK;
+}
+
+int32_t forest_cold_rendezvous(Sim& s)
+{
+    ForestModule& fm = s.mods->forest;
+    if (!fm.active || !fm.peer || !fm.fused || !s.comm) return INCERTO_OK;
+    launch_forest_rendezvous(fm.d_mail, fm.peer_mail_lo, fm.peer_mail_hi, ++fm.rendezvous, s.d_error, s.stream);
+    INC_CUDA(cudaGetLastError());
     return INCERTO_OK;
 }
 
@@ -817,14 +831,33 @@ static int32_t forest_launch_one(Sim& s, uint64_t step, int graph_offset, Forest
     {
         // pull protocol (kernels.hpp: ForestPeer): this step reads the neighbours' boundary columns and overlay states
         // straight from the buffers their previous step wrote
-        pr.mail = fm.d_mail;
+        pr.my_mail = fm.d_mail;
         pr.need_lo = fm.peer_mail_lo ? fm.pushes : 0u;
         pr.need_hi = fm.peer_mail_hi ? fm.pushes : 0u;
-        pr.stamp = ++fm.pushes;
+        pr.stamp = fm.pushes; // this launch announces the step before it; forest_finalize the last one of a run
+        fm.pushes += 1;
         pr.src_lo = fm.peer_alloc_lo[fm.cur] ? fm.peer_alloc_lo[fm.cur] + kLead + static_cast<size_t>(fm.peer_slab_w_lo) * fm.pitch : nullptr;
         pr.src_hi = fm.peer_alloc_hi[fm.cur] ? fm.peer_alloc_hi[fm.cur] + kLead + fm.pitch : nullptr;
-        pr.mail_lo = fm.peer_mail_lo ? fm.peer_mail_lo + 1 : nullptr; // the lower neighbour knows me as its upper one
+        pr.mail_lo = fm.peer_mail_lo;
         pr.mail_hi = fm.peer_mail_hi;
+        if (const char* dbg = std::getenv("INCERTO_B200_DEBUG_HALO")) // timing experiments only (results are wrong)
+        {
+            if (dbg[0] == 's') pr.my_mail = nullptr, pr.need_lo = pr.need_hi = 0; // no stamps, no pulls
+            if (dbg[0] == 'z') pr.debug = 1; // natural launch order
+            if (dbg[0] == 'q') pr.debug = 2; // boundary-first order and stamps, but no pulls
+            if (dbg[0] == 'l') // the same code path on LOCAL memory: my own stamp and columns instead of the neighbours'
+            {
+                pr.mail_lo = pr.mail_hi = fm.d_mail;
+                if (pr.src_lo) pr.src_lo = fm.d_slab[fm.cur] + fm.pitch;
+                if (pr.src_hi) pr.src_hi = fm.d_slab[fm.cur] + fm.pitch;
+            }
+            if (dbg[0] == 'm') pr.mail_lo = pr.mail_hi = fm.d_mail; // local stamps, remote pulls
+            if (dbg[0] == 'c') // remote stamps, local pulls
+            {
+                if (pr.src_lo) pr.src_lo = fm.d_slab[fm.cur] + fm.pitch;
+                if (pr.src_hi) pr.src_hi = fm.d_slab[fm.cur] + fm.pitch;
+            }
+        }
         if (pr.need_lo && fm.peer_ovs_lo[fm.cur]) ov_lo = fm.peer_ovs_lo[fm.cur];
         if (pr.need_hi && fm.peer_ovs_hi[fm.cur]) ov_hi = fm.peer_ovs_hi[fm.cur];
     }
@@ -864,8 +897,15 @@ int32_t forest_finalize(Sim& s)
         a.series_capacity = se.capacity;
     }
     {
+        // row-split grid with the fused halo transport: the neighbours learn that the run's last step is complete
+        ForestPeer pr;
+        if (fm.peer && fm.fused && s.comm && fm.pushes)
+        {
+            pr.my_mail = fm.d_mail;
+            pr.stamp = fm.pushes;
+        }
         KTimer kt(s, "forest_publish", 0.0);
-        INC_CUDA(launch_forest_publish(a, 0u, s.stream));
+        INC_CUDA(launch_forest_publish(a, 0u, s.stream, &pr));
     }
     fm.unpublished_step = 0;
     return INCERTO_OK;

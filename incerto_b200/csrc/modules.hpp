@@ -69,6 +69,7 @@ struct ForestModule
     uint32_t* d_mail = nullptr;      // [0] steps pushed by the lower neighbour, [1] by the upper one
     uint32_t peer_slab_w_lo = 0;     // lower neighbour's slab width (to find its upper halo column)
     uint32_t pushes = 0;             // steps whose boundary I pushed so far
+    uint32_t rendezvous = 0;         // epochs of forest_cold_rendezvous
     void* ipc_opened[12] = {};
 };
 
@@ -178,6 +179,7 @@ int32_t air_mail_export(Sim& s, uint32_t side, void* out, size_t capacity, size_
 int32_t air_mail_import(Sim& s, uint32_t side, const void* in, size_t n);
 int32_t forest_peer_setup(Sim& s);
 int32_t forest_peer_quiesce(Sim& s);
+int32_t forest_cold_rendezvous(Sim& s); // run_cold: line the neighbours of a row-split grid up before a timed step
 void forest_peer_free(Sim& s);
 
 // module_pandemic.cu

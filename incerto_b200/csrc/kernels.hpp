@@ -155,8 +155,9 @@ struct ForestPeer
 cudaError_t launch_forest_step(const ForestArgs& a, cudaStream_t st);
 // put step (d_step ? *d_step : 0) + step_base on record (idempotent) and add `bump` to the device StepNumber
 cudaError_t launch_forest_publish(const ForestArgs& a, uint32_t bump, cudaStream_t st, const ForestPeer* peer = nullptr);
+// pdl: launch as a programmatic dependent of the previous launch on the stream (captured runs of steps on one GPU)
 cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
-                                  cudaStream_t st, const ForestPeer* peer = nullptr);
+                                  cudaStream_t st, const ForestPeer* peer = nullptr, bool pdl = false);
 int forest_step_grid_blocks(int32_t slab_w, int32_t H);
 uint32_t forest_pitch(int32_t H);            // bytes per column: H rounded up to whole CTA tiles
 uint32_t forest_alloc_cols(int32_t slab_w);  // columns allocated: slab_w rounded up to whole CTA tiles + 2 halos

@@ -297,9 +297,14 @@ __global__ void forest_publish_kernel(ForestArgs a, uint32_t slab_w, uint32_t bu
 // masks: 45 % of the kernel's instructions.)
 // PEER: the fused halo transport is compiled in (row-partitioned grids with peer memory); the single-GPU kernel
 // carries none of its registers or branches.
-template <bool PEER>
+// PDL: the launch is a node of a captured run of steps with programmatic dependencies (run(n) on one GPU).  The grid lets
+// its successor's CTAs be scheduled as soon as SM slots free up, and everything that does not depend on the previous
+// step - the launch itself, the index arithmetic, the regrowth lottery of the step - runs before `griddepcontrol.wait`,
+// i.e. under the previous step's tail; the wait returns when the previous grid has completed and its cells are visible.
+template <bool PEER, bool PDL>
 __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const __grid_constant__ ForestConst c)
 {
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;");
     const ForestArgs& a = c.a;
     // The slab is padded to whole CTA tiles (pitch a multiple of 512 B, columns a multiple of 32 plus the
     // two halo columns; pad bytes are BURNED = inert), so no load or store below needs a bounds predicate.
@@ -330,6 +335,47 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
     {
         s_done = 0;
         nr.n = 0;
+    }
+
+    // StepNumber of this launch: by value, or (captured graphs) the device counter + the launch's offset in the graph
+    // (the counter only changes between graphs)
+    const uint32_t step = (a.d_step ? *a.d_step : 0u) + a.step_base;
+    uint32_t lot_k = 0, lot_z = 0, lot_w = 0, lot_off = 0, lot_total = 0;
+    auto draw_lottery = [&]() {
+        // ---- level-1 regrowth draws (block lottery): nothing here depends on the cells, so the call runs while the loads
+        // are in flight.  Lane 3(j-1)+i draws the i-th block of 256 uids that intersects the warp's cells of column j and
+        // keeps the number of winners and the head of the position stream; the events are made after the stores.
+        if (a.do_regrow && c.regrow_two_level)
+        {
+            const uint32_t j = lane / 3 + 1, bi = lane - 3 * (j - 1);
+            const uint32_t yw = blockIdx.x * (kTX * 16);
+            const uint32_t lo = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + yw;
+            const uint32_t len = yw < H ? min(H - yw, static_cast<uint32_t>(kTX * 16)) : 0u;
+            const uint32_t blk = (lo >> 8) + bi;
+            if (lane < 3 * kColsPerThread && lx0 - 1 + j <= c.slab_w && len != 0 && blk <= ((lo + len - 1) >> 8))
+            {
+                const uint4 r = philox4x32_10(blk, 0u, step, 0u, c.rk_regrow);
+                lot_k = lottery_count((static_cast<uint64_t>(r.x) << 32) | r.y);
+                lot_z = r.z;
+                lot_w = r.w;
+            }
+            // queue slots of the lane's winners: exclusive prefix sum of the counts (a winner outside the span leaves a
+            // null item), so that the lanes can write their events later without talking to each other
+            uint32_t incl = lot_k;
+    #pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= static_cast<uint32_t>(o)) incl += up;
+            }
+            lot_total = __shfl_sync(kFullMask, incl, 31);
+            lot_off = incl - lot_k;
+        }
+    };
+    if (PDL)
+    {
+        draw_lottery();
+        asm volatile("griddepcontrol.wait;" ::: "memory"); // the previous step is complete: its cells may be read
     }
 
     // ---- loads first.  With the fused halo transport the two warps (per boundary CTA) whose W / E neighbour column is
@@ -404,38 +450,7 @@ __global__ void __launch_bounds__(kTX* kTY, kMinBlocks) forest_step_kernel(const
         const uint32_t eb = __ballot_sync(kFullMask, burning);
         edge = lane == 0 ? (eb & ((1u << kColsPerThread) - 1u)) : (lane == 31 ? ((eb >> kColsPerThread) & ((1u << kColsPerThread) - 1u)) : 0u);
     }
-    // StepNumber of this launch: by value, or (captured graphs) the device counter + the launch's offset in the graph
-    const uint32_t step = (a.d_step ? *a.d_step : 0u) + a.step_base;
-    // ---- level-1 regrowth draws (block lottery): nothing here depends on the cells, so the call runs while the loads
-    // are in flight.  Lane 3(j-1)+i draws the i-th block of 256 uids that intersects the warp's cells of column j and
-    // keeps the number of winners and the head of the position stream; the events are made after the stores.
-    uint32_t lot_k = 0, lot_z = 0, lot_w = 0, lot_off = 0, lot_total = 0;
-    if (a.do_regrow && c.regrow_two_level)
-    {
-        const uint32_t j = lane / 3 + 1, bi = lane - 3 * (j - 1);
-        const uint32_t yw = blockIdx.x * (kTX * 16);
-        const uint32_t lo = (static_cast<uint32_t>(a.x_begin) + lx0 - 2 + j) * H + yw;
-        const uint32_t len = yw < H ? min(H - yw, static_cast<uint32_t>(kTX * 16)) : 0u;
-        const uint32_t blk = (lo >> 8) + bi;
-        if (lane < 3 * kColsPerThread && lx0 - 1 + j <= c.slab_w && len != 0 && blk <= ((lo + len - 1) >> 8))
-        {
-            const uint4 r = philox4x32_10(blk, 0u, step, 0u, c.rk_regrow);
-            lot_k = lottery_count((static_cast<uint64_t>(r.x) << 32) | r.y);
-            lot_z = r.z;
-            lot_w = r.w;
-        }
-        // queue slots of the lane's winners: exclusive prefix sum of the counts (a winner outside the span leaves a
-        // null item), so that the lanes can write their events later without talking to each other
-        uint32_t incl = lot_k;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
-            if (lane >= static_cast<uint32_t>(o)) incl += up;
-        }
-        lot_total = __shfl_sync(kFullMask, incl, 31);
-        lot_off = incl - lot_k;
-    }
+    if (!PDL) draw_lottery();
     // the previous step's FireStats go on record now, off every critical path (see forest_publish)
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) forest_publish(a, c.slab_w, step - 1);
 
@@ -875,7 +890,7 @@ __global__ void __launch_bounds__(256)
 
 // Extended launch: the engine passes the neighbour overlay arrays separately.
 cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, const uint8_t* ov_hi, const uint8_t* ov_owner,
-                                  cudaStream_t st, const ForestPeer* peer)
+                                  cudaStream_t st, const ForestPeer* peer, bool pdl)
 {
     ForestConst c;
     if (peer) c.peer = *peer;
@@ -895,9 +910,24 @@ cudaError_t launch_forest_step_ex(const ForestArgs& a, const uint8_t* ov_lo, con
     dim3 block(kTX, kTY);
     dim3 grid((c.chunks_per_col + kTX - 1) / kTX, (c.slab_w + kTY * kColsPerThread - 1) / (kTY * kColsPerThread));
     if (peer != nullptr)
-        forest_step_kernel<true><<<grid, block, 0, st>>>(c);
+        forest_step_kernel<true, false><<<grid, block, 0, st>>>(c);
+    else if (pdl && static_cast<uint64_t>(grid.x) * grid.y <= 4ull * kNumSMs * kMinBlocks)
+    {
+        // (grids of many waves gain nothing from the overlap - 16384^2: 92.9 us without, 94.2 us with - and keep the
+        // plain edge)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, forest_step_kernel<false, true>, c);
+    }
     else
-        forest_step_kernel<false><<<grid, block, 0, st>>>(c);
+        forest_step_kernel<false, false><<<grid, block, 0, st>>>(c);
     return cudaGetLastError();
 }
 

@@ -864,7 +864,9 @@ static int32_t forest_launch_one(Sim& s, uint64_t step, int graph_offset, Forest
     {
         // 2 B per cell-update (1 B read + 1 B written)
         KTimer kt(s, fused ? "forest_step_fused_halo" : "forest_step", 2.0 * slab_w * fm.H);
-        INC_CUDA(launch_forest_step_ex(a, ov_lo, ov_hi, fm.d_ov_owner, s.stream, fused ? &pr : nullptr));
+        // captured runs of steps (one GPU): every step is a programmatic dependent of the one before it
+        const bool pdl = graph_offset >= 0 && !fused && fm.graph_pdl;
+        INC_CUDA(launch_forest_step_ex(a, ov_lo, ov_hi, fm.d_ov_owner, s.stream, fused ? &pr : nullptr, pdl));
     }
     fm.cur = 1 - fm.cur;
     if (args_out) *args_out = a;
@@ -930,29 +932,44 @@ static int32_t forest_graph_ensure(Sim& s)
     if (fm.graph_exec && fm.graph_cur == fm.cur && fm.graph_series_values == sv && fm.graph_series_capacity == sc)
         return INCERTO_OK;
     forest_graph_free(fm);
-    cudaGraph_t graph = nullptr;
     const int cur0 = fm.cur;
-    INC_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
-    int32_t st = INCERTO_OK;
-    ForestArgs last;
-    for (uint32_t i = 0; i < kGraphSteps && st == INCERTO_OK; ++i) st = forest_launch_one(s, 0, static_cast<int>(i), &last);
-    if (st == INCERTO_OK)
+    // first with programmatic dependencies between the steps (INCERTO_B200_NO_PDL=1 or a runtime that cannot capture
+    // them: plain kernel-after-kernel edges)
+    static const bool no_pdl = [] { const char* e = std::getenv("INCERTO_B200_NO_PDL"); return e && e[0] == '1'; }();
+    for (int attempt = no_pdl ? 1 : 0; attempt < 2 && !fm.graph_exec; ++attempt)
     {
-        // the graph's last node puts its last step on record and advances the device StepNumber by the steps held
-        last.step_base = kGraphSteps - 1;
-        if (launch_forest_publish(last, kGraphSteps, s.stream) != cudaSuccess) st = INCERTO_ERR_CUDA;
-    }
-    cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
-    fm.cur = cur0; // nothing ran yet
-    if (st != INCERTO_OK)
-    {
+        fm.graph_pdl = attempt == 0;
+        cudaGraph_t graph = nullptr;
+        const uint64_t launches0 = s.launches;
+        INC_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        int32_t st = INCERTO_OK;
+        ForestArgs last;
+        for (uint32_t i = 0; i < kGraphSteps && st == INCERTO_OK; ++i) st = forest_launch_one(s, 0, static_cast<int>(i), &last);
+        if (st == INCERTO_OK)
+        {
+            // the graph's last node puts its last step on record and advances the device StepNumber by the steps held
+            last.step_base = kGraphSteps - 1;
+            if (launch_forest_publish(last, kGraphSteps, s.stream) != cudaSuccess) st = INCERTO_ERR_CUDA;
+        }
+        cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+        fm.cur = cur0; // nothing ran yet
+        if (st == INCERTO_OK && e == cudaSuccess) e = cudaGraphInstantiate(&fm.graph_exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
-        return st;
+        if (st != INCERTO_OK || e != cudaSuccess)
+        {
+            fm.graph_exec = nullptr;
+            (void)cudaGetLastError();
+            s.launches = launches0;
+            if (attempt == 1 || !fm.graph_pdl)
+            {
+                if (st != INCERTO_OK) return st;
+                INC_CUDA(e);
+            }
+            // the launches counted during the failed capture did not run
+            kstat(s, "forest_step").launches -= kGraphSteps;
+            kstat(s, "forest_step").algorithmic_bytes -= 2.0 * (fm.x_end - fm.x_begin) * fm.H * kGraphSteps;
+        }
     }
-    INC_CUDA(e);
-    e = cudaGraphInstantiate(&fm.graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    INC_CUDA(e);
     fm.graph_steps = kGraphSteps;
     fm.graph_cur = cur0;
     fm.graph_series_values = sv;

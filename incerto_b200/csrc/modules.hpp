@@ -68,6 +68,7 @@ struct ForestModule
     uint32_t* peer_mail_hi = nullptr;
     uint32_t* d_mail = nullptr;      // [0] steps pushed by the lower neighbour, [1] by the upper one
     uint32_t peer_slab_w_lo = 0;     // lower neighbour's slab width (to find its upper halo column)
+    bool graph_pdl = false;          // the captured steps are programmatic dependents of each other
     uint32_t pushes = 0;             // steps whose boundary I pushed so far
     uint32_t rendezvous = 0;         // epochs of forest_cold_rendezvous
     void* ipc_opened[12] = {};

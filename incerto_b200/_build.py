@@ -35,6 +35,7 @@ SOURCES = [
     "kernels_coin.cu",
     "kernels_forest.cu",
     "kernels_grid.cu",
+    "debug_lottery.cu",
 ]
 
 NVCC_FLAGS = [

@@ -1466,6 +1466,8 @@ int32_t incerto_sim_flush_l2(incerto_sim* s)
     if (!S.d_flush)
     {
         S.flush_bytes = 512ull << 20; // 4x the 126 MB L2
+        if (const char* e = std::getenv("INCERTO_B200_FLUSH_MB")) // experiments
+            S.flush_bytes = static_cast<uint64_t>(std::max(1l, std::atol(e))) << 20;
         INC_CUDA(cudaMalloc(&S.d_flush, S.flush_bytes));
     }
     static uint32_t v = 0;

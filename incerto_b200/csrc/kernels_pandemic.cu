@@ -129,19 +129,16 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
                     }
             }
         }
-        uint32_t old[kRows];
-        uint32_t linked = 0;
-#pragma unroll
-        for (int k = 0; k < kRows; ++k)
+        if (a.do_move)
         {
-            const uint32_t fl = static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu;
-            old[k] = 0;
-            if (a.do_move)
+#pragma unroll
+            for (int k = 0; k < kRows; ++k)
             {
                 // :121 stay put (bit 3 clear); :125 x axis (bit 2 clear) else y axis; :128/:147 negative (bit 1 clear)
                 // else positive direction; saturating at 0 and G-1.  Branch-free: the stepped coordinate t = c +- 1 is in
                 // range iff (unsigned) t < G (c - 1 wraps to 2^32 - 1 at the lower wall), and the halves of the packed
                 // word never carry into each other because the move is refused at the walls.
+                const uint32_t fl = static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu;
                 const uint32_t nib = nib8 >> (4 * k);
                 const uint32_t sh = (nib & 4u) << 2;                               // 0: x, 16: y
                 const uint32_t dlt = (nib & 2u) - 1u;                              // +1 / -1
@@ -149,17 +146,6 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
                 const uint32_t go = (t < G ? 1u : 0u) & (nib >> 3) & fl;           // in range, moves, alive (bit 0)
                 r.p[k] += (dlt << sh) & (0u - (go & 1u));
             }
-            if (a.do_infect && (fl & 1u) && (fl & a.bit_infected))
-            {
-                // per-cell list of infected people (order irrelevant: the draws are keyed by the pair)
-                const uint32_t cell = (r.p[k] & 0xffffu) * G + (r.p[k] >> 16);
-                atomicOr(&a.cell_bits[cell >> 5], 1u << (cell & 31));
-                old[k] = atomicExch(&a.cell_head[head_slot(a, cell)], tag | static_cast<uint32_t>(row0 + k));
-                linked |= 1u << k;
-            }
-        }
-        if (a.do_move)
-        {
             if (full)
             {
                 *reinterpret_cast<uint4*>(a.pos + row0) = make_uint4(r.p[0], r.p[1], r.p[2], r.p[3]);
@@ -168,10 +154,45 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
             else
                 for (uint64_t k = 0; row0 + k < a.n; ++k) a.pos[row0 + k] = r.p[k];
         }
+        if (!a.do_infect) continue;
+        // Per-cell lists of infected people (order irrelevant: the draws are keyed by the pair).  The infected are 5-10 %
+        // of the rows: instead of one predicated pass per row position (eight passes, each run by the warp whenever ANY
+        // lane has an infected person at that position - almost always -, half of this kernel's instructions), every
+        // lane walks the set bits of its own 8-bit "alive and infected" mask.  Three unrolled passes keep up to three
+        // returning exchanges per lane in flight before any result is used; the rare fourth and later ones follow one
+        // at a time.
+        const unsigned long long sick8 = r.f & (r.f >> (__ffs(a.bit_infected) - 1)) & 0x0101010101010101ull;
+        uint32_t m8 = static_cast<uint32_t>((sick8 * 0x0102040810204080ull) >> 56); // bit k: row k
+        auto link = [&](uint32_t k, uint32_t& old_head) {
+            const uint32_t p = k & 4u ? (k & 2u ? (k & 1u ? r.p[7] : r.p[6]) : (k & 1u ? r.p[5] : r.p[4]))
+                                      : (k & 2u ? (k & 1u ? r.p[3] : r.p[2]) : (k & 1u ? r.p[1] : r.p[0]));
+            const uint32_t cell = (p & 0xffffu) * G + (p >> 16);
+            atomicOr(&a.cell_bits[cell >> 5], 1u << (cell & 31));
+            old_head = atomicExch(&a.cell_head[head_slot(a, cell)], tag | static_cast<uint32_t>(row0 + k));
+        };
+        auto chain = [&](uint32_t k, uint32_t old_head) {
+            a.next_infected[row0 + k] = ((old_head & 0xff000000u) == tag) ? (old_head & 0x00ffffffu) : 0x00ffffffu;
+        };
+        uint32_t kk[3] = {8u, 8u, 8u}, oo[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int k = 0; k < kRows; ++k)
-            if ((linked >> k) & 1u)
-                a.next_infected[row0 + k] = ((old[k] & 0xff000000u) == tag) ? (old[k] & 0x00ffffffu) : 0x00ffffffu;
+        for (int j = 0; j < 3; ++j)
+            if (m8)
+            {
+                kk[j] = __ffs(m8) - 1;
+                m8 &= m8 - 1;
+                link(kk[j], oo[j]);
+            }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (kk[j] < 8u) chain(kk[j], oo[j]);
+        while (m8)
+        {
+            const uint32_t k = __ffs(m8) - 1;
+            m8 &= m8 - 1;
+            uint32_t o;
+            link(k, o);
+            chain(k, o);
+        }
     }
 }
 

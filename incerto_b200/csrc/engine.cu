@@ -11,6 +11,9 @@
 #include <cstdio>
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "kernels_grid.hpp"
 #include "modules.hpp"
@@ -35,6 +38,99 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line)
     return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? INCERTO_ERR_NO_DEVICE : INCERTO_ERR_CUDA;
 }
 
+// ------------------------------------------------------- device block cache
+namespace
+{
+struct BlockCache
+{
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void*>> free_blocks; // (device, bytes) -> blocks
+    std::map<void*, std::pair<int, size_t>> owner;                    // blocks handed out by dev_alloc_bytes
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCached = 3ull << 30;
+};
+BlockCache& block_cache()
+{
+    static BlockCache* c = new BlockCache; // never destroyed: the CUDA context may be gone at exit
+    return *c;
+}
+} // namespace
+
+cudaError_t dev_alloc_bytes(void** p, size_t bytes)
+{
+    static const bool off = [] { const char* e = std::getenv("INCERTO_B200_NO_BLOCK_CACHE"); return e && e[0] == '1'; }();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    BlockCache& c = block_cache();
+    if (!off)
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.free_blocks.find({dev, bytes});
+        if (it != c.free_blocks.end() && !it->second.empty())
+        {
+            *p = it->second.back();
+            it->second.pop_back();
+            c.cached_bytes -= bytes;
+            c.owner[*p] = {dev, bytes};
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !off)
+    {
+        // out of memory with blocks parked in the cache: give them back and try again
+        std::lock_guard<std::mutex> lk(c.mu);
+        for (auto& kv : c.free_blocks)
+            if (kv.first.first == dev)
+            {
+                for (void* q : kv.second) cudaFree(q);
+                c.cached_bytes -= kv.first.second * kv.second.size();
+                kv.second.clear();
+            }
+        (void)cudaGetLastError();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess && !off)
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        c.owner[*p] = {dev, bytes};
+    }
+    return e;
+}
+
+void dev_release(void* p, bool cache)
+{
+    if (!p) return;
+    BlockCache& c = block_cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.owner.find(p);
+        if (it != c.owner.end())
+        {
+            const std::pair<int, size_t> key = it->second;
+            c.owner.erase(it);
+            if (cache && c.cached_bytes + key.second <= BlockCache::kMaxCached)
+            {
+                c.free_blocks[key].push_back(p);
+                c.cached_bytes += key.second;
+                return;
+            }
+        }
+    }
+    cudaFree(p);
+}
+
+cudaError_t dev_free(void* p)
+{
+    if (!p) return cudaSuccess;
+    {
+        BlockCache& c = block_cache();
+        std::lock_guard<std::mutex> lk(c.mu);
+        c.owner.erase(p);
+    }
+    return cudaFree(p);
+}
+
 // ---------------------------------------------------------------------- Sim
 Sim::Sim() : mods(new Modules) {}
 
@@ -52,31 +148,31 @@ Sim::~Sim()
     {
         for (auto& c : t.cols)
         {
-            cudaFree(c.d);
-            cudaFree(c.d_alt);
+            dev_release(c.d);
+            dev_release(c.d_alt);
         }
-        cudaFree(t.d_flags);
-        cudaFree(t.d_flags_alt);
-        cudaFree(t.d_uid);
+        dev_release(t.d_flags);
+        dev_release(t.d_flags_alt);
+        dev_release(t.d_uid);
     }
     for (auto& se : series)
     {
-        cudaFree(se.d_values);
-        cudaFree(se.d_counts);
+        dev_release(se.d_values);
+        dev_release(se.d_counts);
     }
     for (auto& g : grids)
     {
-        cudaFree(g.d_cell_start);
-        cudaFree(g.d_cursor);
-        cudaFree(g.d_sorted_rows);
-        cudaFree(g.d_snap_pos);
-        cudaFree(g.d_snap_flags);
+        dev_release(g.d_cell_start);
+        dev_release(g.d_cursor);
+        dev_release(g.d_sorted_rows);
+        dev_release(g.d_snap_pos);
+        dev_release(g.d_snap_flags);
     }
-    cudaFree(d_scratch);
-    cudaFree(d_ticket);
-    cudaFree(d_error);
-    cudaFree(d_flush);
-    cudaFree(mods->d_step);
+    dev_release(d_scratch);
+    dev_release(d_ticket);
+    dev_release(d_error);
+    dev_release(d_flush);
+    dev_release(mods->d_step);
     if (h_pinned) cudaFreeHost(h_pinned);
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
@@ -94,11 +190,11 @@ int32_t ensure_scratch(Sim& s, size_t bytes)
     if (s.d_scratch)
     {
         INC_CUDA(cudaStreamSynchronize(s.stream));
-        INC_CUDA(cudaFree(s.d_scratch));
+        INC_CUDA(dev_free(s.d_scratch));
         s.d_scratch = nullptr;
     }
     bytes = (bytes + 0xfffff) & ~static_cast<size_t>(0xfffff);
-    INC_CUDA(cudaMalloc(&s.d_scratch, bytes));
+    INC_CUDA(dev_alloc(&s.d_scratch, bytes));
     s.scratch_bytes = bytes;
     return INCERTO_OK;
 }
@@ -489,9 +585,9 @@ static int32_t run_spawners(Sim& s, bool first_time)
         {
             if (t.d_flags == nullptr && t.n)
             {
-                INC_CUDA(cudaMalloc(&t.d_flags, t.n));
+                INC_CUDA(dev_alloc(&t.d_flags, t.n));
                 for (auto& c : t.cols)
-                    if (c.d == nullptr) INC_CUDA(cudaMalloc(&c.d, t.n * c.row_bytes));
+                    if (c.d == nullptr) INC_CUDA(dev_alloc(&c.d, t.n * c.row_bytes));
             }
         }
         // engine-managed columns start empty (Trader.portfolio: HashMap::new(), traders.rs:123)
@@ -585,7 +681,7 @@ static int32_t run_spawners(Sim& s, bool first_time)
         t.n = t.n_spawned;
         if (t.d_uid)
         {
-            INC_CUDA(cudaFree(t.d_uid));
+            INC_CUDA(dev_free(t.d_uid));
             t.d_uid = nullptr;
         }
     }
@@ -610,13 +706,13 @@ int32_t table_sort_by_cell(Sim& s, int ti, int pos_comp, const GridDesc& g, cons
     if (n_cells == 0 || n_cells >= (1ull << 32)) return INCERTO_OK;
     uint32_t *d_start = nullptr, *d_cursor = nullptr, *d_perm = nullptr, *d_scan = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_start);
-        cudaFree(d_cursor);
-        cudaFree(d_scan);
-        cudaFree(d_perm);
+        dev_free(d_start);
+        dev_free(d_cursor);
+        dev_free(d_scan);
+        dev_free(d_perm);
     };
-    if (cudaMalloc(&d_start, (n_cells + 1) * 4) != cudaSuccess || cudaMalloc(&d_cursor, n_cells * 4) != cudaSuccess ||
-        cudaMalloc(&d_perm, t.n * 4) != cudaSuccess || cudaMalloc(&d_scan, scan_scratch_bytes(n_cells) + 256) != cudaSuccess)
+    if (dev_alloc(&d_start, (n_cells + 1) * 4) != cudaSuccess || dev_alloc(&d_cursor, n_cells * 4) != cudaSuccess ||
+        dev_alloc(&d_perm, t.n * 4) != cudaSuccess || dev_alloc(&d_scan, scan_scratch_bytes(n_cells) + 256) != cudaSuccess)
     {
         cudaGetLastError();
         cleanup();
@@ -637,10 +733,10 @@ int32_t table_sort_by_cell(Sim& s, int ti, int pos_comp, const GridDesc& g, cons
     KTimer kt(s, "table_sort_by_cell", 0.0);
     auto permute = [&](void*& buf, size_t row_bytes) -> int32_t {
         void* nb = nullptr;
-        INC_CUDA(cudaMalloc(&nb, t.n * row_bytes));
+        INC_CUDA(dev_alloc(&nb, t.n * row_bytes));
         launch_gather_rows(buf, nb, static_cast<uint32_t>(row_bytes), d_perm, t.n, s.stream);
         INC_CUDA(cudaStreamSynchronize(s.stream));
-        INC_CUDA(cudaFree(buf));
+        INC_CUDA(dev_free(buf));
         buf = nb;
         return INCERTO_OK;
     };
@@ -1195,11 +1291,11 @@ int32_t incerto_builder_build(incerto_builder* b, incerto_sim** out)
     INC_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     INC_CUDA(cudaEventCreate(&S.ev_begin));
     INC_CUDA(cudaEventCreate(&S.ev_end));
-    INC_CUDA(cudaMalloc(&S.d_ticket, 64));
+    INC_CUDA(dev_alloc(&S.d_ticket, 64));
     INC_CUDA(cudaMemsetAsync(S.d_ticket, 0, 64, S.stream));
-    INC_CUDA(cudaMalloc(&S.d_error, 64));
+    INC_CUDA(dev_alloc(&S.d_error, 64));
     INC_CUDA(cudaMemsetAsync(S.d_error, 0, 64, S.stream));
-    INC_CUDA(cudaMalloc(&S.mods->d_step, 64));
+    INC_CUDA(dev_alloc(&S.mods->d_step, 64));
     const uint32_t one = 1;
     INC_CUDA(cudaMemcpyAsync(S.mods->d_step, &one, sizeof(one), cudaMemcpyHostToDevice, S.stream));
     INC_TRY(ensure_scratch(S, 1u << 20));
@@ -1468,7 +1564,7 @@ int32_t incerto_sim_flush_l2(incerto_sim* s)
         S.flush_bytes = 512ull << 20; // 4x the 126 MB L2
         if (const char* e = std::getenv("INCERTO_B200_FLUSH_MB")) // experiments
             S.flush_bytes = static_cast<uint64_t>(std::max(1l, std::atol(e))) << 20;
-        INC_CUDA(cudaMalloc(&S.d_flush, S.flush_bytes));
+        INC_CUDA(dev_alloc(&S.d_flush, S.flush_bytes));
     }
     static uint32_t v = 0;
     launch_flush(S.d_flush, S.flush_bytes, ++v, S.stream);

@@ -268,6 +268,16 @@ struct Builder
 
 // ---- helpers implemented in engine.cu
 int32_t ensure_scratch(Sim& s, size_t bytes);
+// Device allocations of a handle's life come from a small process-wide cache of freed blocks (exact size match, per
+// device): building simulation after simulation - the end-to-end job of bench.py, replica after replica - then costs no
+// cudaMalloc / cudaFree (each a device synchronisation and a page-table update; their cost also grows with what the
+// process freed before).  dev_release may only be called for memory no stream is using any more (the destroy path,
+// after the handle's stream was synchronised); `cache` = false frees for real (memory exported through CUDA IPC).
+cudaError_t dev_alloc_bytes(void** p, size_t bytes);
+template <typename T>
+inline cudaError_t dev_alloc(T** p, size_t bytes) { return dev_alloc_bytes(reinterpret_cast<void**>(p), bytes); }
+void dev_release(void* p, bool cache = true);
+cudaError_t dev_free(void* p); // cudaFree of a dev_alloc block that may still be in use (synchronises like cudaFree)
 int32_t ensure_pinned(Sim& s, size_t bytes);
 int table_for_components(Sim& s, const std::vector<int>& comps); // first table holding all data comps, -1 if none
 struct RowFilter

@@ -83,7 +83,7 @@ int32_t air_bind(Sim& s)
         }
         g.lazy = true; // the kernels use their own occupancy index; the dense table is only built for host queries
     }
-    INC_CUDA(cudaMalloc(&am.d_acc, 64));
+    INC_CUDA(dev_alloc(&am.d_acc, 64));
     INC_CUDA(cudaMemsetAsync(am.d_acc, 0, 64, s.stream));
     if (am.table < 0) return INCERTO_OK;
     Table& t = s.tables[am.table];
@@ -99,7 +99,7 @@ int32_t air_bind(Sim& s)
         while ((1ull << bits) < want) ++bits;
         am.n_slots = 1u << bits;
         am.slot_bits = bits;
-        INC_CUDA(cudaMalloc(&am.d_slots, static_cast<size_t>(am.n_slots) * 8));
+        INC_CUDA(dev_alloc(&am.d_slots, static_cast<size_t>(am.n_slots) * 8));
         INC_CUDA(cudaMemsetAsync(am.d_slots, 0, static_cast<size_t>(am.n_slots) * 8, s.stream));
         // pre-filter bitmap: >= 32 bits per aircraft (at most ~3 % of the bits set)
         // (one airspace split over the ranks: this rank sets bits for its own share of the aircraft only; twice the
@@ -108,9 +108,9 @@ int32_t air_bind(Sim& s)
         uint32_t fb = 16;
         while ((1ull << fb) < 32 * filter_n && fb < 32) ++fb;
         am.filter_bits = fb;
-        INC_CUDA(cudaMalloc(&am.d_bits, (1ull << fb) / 8));
-        INC_CUDA(cudaMalloc(&am.d_bits_next, (1ull << fb) / 8));
-        INC_CUDA(cudaMalloc(&am.d_cand, std::max<uint64_t>(t.n, 2)));
+        INC_CUDA(dev_alloc(&am.d_bits, (1ull << fb) / 8));
+        INC_CUDA(dev_alloc(&am.d_bits_next, (1ull << fb) / 8));
+        INC_CUDA(dev_alloc(&am.d_cand, std::max<uint64_t>(t.n, 2)));
     }
     INC_TRY(air_sort_rows(s));
     return air_partition_setup(s);
@@ -152,11 +152,11 @@ static int32_t air_partition_setup(Sim& s)
     const uint32_t cap = static_cast<uint32_t>(std::min<uint64_t>(8 * (t.n / static_cast<uint64_t>(ext_x) + 1) + 1024, std::max<uint64_t>(t.n, 1)));
     if (!am.d_mail || cap != am.mail_cap)
     {
-        cudaFree(am.d_mail);
+        dev_free(am.d_mail);
         am.d_mail = nullptr;
         am.mail_cap = cap;
         const size_t one = (AirMailbox::bytes(cap) + 255) & ~size_t(255);
-        INC_CUDA(cudaMalloc(&am.d_mail, 4 * one));
+        INC_CUDA(dev_alloc(&am.d_mail, 4 * one));
     }
     const size_t one = (AirMailbox::bytes(am.mail_cap) + 255) & ~size_t(255);
     INC_CUDA(cudaMemsetAsync(am.d_mail, 0, 4 * one, s.stream));
@@ -165,11 +165,11 @@ static int32_t air_partition_setup(Sim& s)
         const uint32_t hdr[4] = {0u, 0u, am.mail_cap, 0u};
         INC_CUDA(cudaMemcpyAsync(air_mailbox(am, k), hdr, sizeof(hdr), cudaMemcpyHostToDevice, s.stream));
     }
-    cudaFree(am.d_row_of_uid);
+    dev_free(am.d_row_of_uid);
     am.d_row_of_uid = nullptr;
     if (t.d_uid)
     {
-        INC_CUDA(cudaMalloc(&am.d_row_of_uid, std::max<uint64_t>(t.n_spawned, 1) * 4));
+        INC_CUDA(dev_alloc(&am.d_row_of_uid, std::max<uint64_t>(t.n_spawned, 1) * 4));
         launch_invert_permutation(t.d_uid, am.d_row_of_uid, t.n, s.stream);
     }
     am.part = true;
@@ -212,14 +212,14 @@ int32_t air_reset(Sim& s)
 void air_free(Sim& s)
 {
     AirModule& am = s.mods->air;
-    cudaFree(am.d_slots);
-    cudaFree(am.d_acc);
-    cudaFree(am.d_bits);
-    cudaFree(am.d_bits_next);
+    dev_free(am.d_slots);
+    dev_free(am.d_acc);
+    dev_free(am.d_bits);
+    dev_free(am.d_bits_next);
     am.d_bits_next = nullptr;
-    cudaFree(am.d_cand);
-    cudaFree(am.d_mail);
-    cudaFree(am.d_row_of_uid);
+    dev_free(am.d_cand);
+    dev_free(am.d_mail);
+    dev_free(am.d_row_of_uid);
     am.d_mail = nullptr;
     am.d_row_of_uid = nullptr;
     am.d_bits = nullptr;

@@ -45,25 +45,25 @@ static int32_t forest_alloc(Sim& s, ForestModule& fm)
     fm.slab_bytes = bytes;
     for (int i = 0; i < 2; ++i)
     {
-        INC_CUDA(cudaMalloc(&fm.d_alloc[i], bytes + 2 * kLead));
+        INC_CUDA(dev_alloc(&fm.d_alloc[i], bytes + 2 * kLead));
         fm.d_slab[i] = fm.d_alloc[i] + kLead;
     }
-    INC_CUDA(cudaMalloc(&fm.d_stats_run, 16 * sizeof(uint64_t)));
+    INC_CUDA(dev_alloc(&fm.d_stats_run, 16 * sizeof(uint64_t)));
     INC_CUDA(cudaMemsetAsync(fm.d_stats_run, 0, 16 * sizeof(uint64_t), s.stream));
-    INC_CUDA(cudaMalloc(&fm.d_stats, 8 * sizeof(uint64_t)));
+    INC_CUDA(dev_alloc(&fm.d_stats, 8 * sizeof(uint64_t)));
     const size_t nov = std::max<uint32_t>(fm.n_overlay, 1);
-    INC_CUDA(cudaMalloc(&fm.d_ov_pos, nov * 2 * sizeof(int16_t)));
-    for (int i = 0; i < 2; ++i) INC_CUDA(cudaMalloc(&fm.d_ov[i], nov));
+    INC_CUDA(dev_alloc(&fm.d_ov_pos, nov * 2 * sizeof(int16_t)));
+    for (int i = 0; i < 2; ++i) INC_CUDA(dev_alloc(&fm.d_ov[i], nov));
     // inboxes of the neighbours' overlay states: two slots each (the peer-memory transports alternate by step parity,
     // so that a neighbour one step ahead never overwrites what this rank still reads); NCCL only uses slot 0
-    INC_CUDA(cudaMalloc(&fm.d_ov_lo, 2 * kOvSlot));
-    INC_CUDA(cudaMalloc(&fm.d_ov_hi, 2 * kOvSlot));
-    INC_CUDA(cudaMalloc(&fm.d_ov_owner, nov));
+    INC_CUDA(dev_alloc(&fm.d_ov_lo, 2 * kOvSlot));
+    INC_CUDA(dev_alloc(&fm.d_ov_hi, 2 * kOvSlot));
+    INC_CUDA(dev_alloc(&fm.d_ov_owner, nov));
     {
         uint32_t tc, tr;
         forest_tile_shape(&tc, &tr);
         const size_t tiles = static_cast<size_t>(fm.pitch / tr) * ((forest_alloc_cols(static_cast<int32_t>(slab_w)) - 2) / tc);
-        INC_CUDA(cudaMalloc(&fm.d_near_bits, (tiles / 32 + 1) * sizeof(uint32_t)));
+        INC_CUDA(dev_alloc(&fm.d_near_bits, (tiles / 32 + 1) * sizeof(uint32_t)));
     }
     return INCERTO_OK;
 }
@@ -78,7 +78,7 @@ void forest_peer_free(Sim& s)
         if (p) cudaIpcCloseMemHandle(p);
         p = nullptr;
     }
-    cudaFree(fm.d_mail);
+    dev_release(fm.d_mail, false);
     fm.d_mail = nullptr;
     fm.peer = false;
     fm.peer_alloc_lo[0] = fm.peer_alloc_lo[1] = fm.peer_alloc_hi[0] = fm.peer_alloc_hi[1] = nullptr;
@@ -107,7 +107,7 @@ int32_t forest_peer_setup(Sim& s)
     fm.fused = !(env && std::strcmp(env, "peer") == 0);
     Pack mine;
     std::memset(&mine, 0, sizeof(mine));
-    INC_CUDA(cudaMalloc(&fm.d_mail, 64));
+    INC_CUDA(dev_alloc(&fm.d_mail, 64));
     INC_CUDA(cudaMemsetAsync(fm.d_mail, 0, 64, s.stream));
     mine.ok = want && cudaIpcGetMemHandle(&mine.alloc[0], fm.d_alloc[0]) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.alloc[1], fm.d_alloc[1]) == cudaSuccess &&
@@ -186,22 +186,23 @@ int32_t forest_peer_setup(Sim& s)
 void forest_free(Sim& s)
 {
     ForestModule& fm = s.mods->forest;
+    if (s.stream && fm.d_alloc[0]) cudaStreamSynchronize(s.stream); // the blocks go back to the cache: nothing may still use them
     forest_peer_free(s);
     forest_graph_free(fm);
     for (int i = 0; i < 2; ++i)
     {
-        cudaFree(fm.d_alloc[i]);
+        dev_release(fm.d_alloc[i], s.part_world <= 1); // slabs of a row-split grid were exported through CUDA IPC
         fm.d_alloc[i] = fm.d_slab[i] = nullptr;
-        cudaFree(fm.d_ov[i]);
+        dev_release(fm.d_ov[i], s.part_world <= 1);
         fm.d_ov[i] = nullptr;
     }
-    cudaFree(fm.d_stats_run);
-    cudaFree(fm.d_stats);
-    cudaFree(fm.d_ov_pos);
-    cudaFree(fm.d_ov_lo);
-    cudaFree(fm.d_ov_hi);
-    cudaFree(fm.d_ov_owner);
-    cudaFree(fm.d_near_bits);
+    dev_release(fm.d_stats_run, s.part_world <= 1);
+    dev_release(fm.d_stats, s.part_world <= 1);
+    dev_release(fm.d_ov_pos, s.part_world <= 1);
+    dev_release(fm.d_ov_lo, s.part_world <= 1);
+    dev_release(fm.d_ov_hi, s.part_world <= 1);
+    dev_release(fm.d_ov_owner, s.part_world <= 1);
+    dev_release(fm.d_near_bits, s.part_world <= 1);
     fm.d_near_bits = nullptr;
     fm.d_stats_run = nullptr;
     fm.d_stats = nullptr;
@@ -618,10 +619,10 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     // the generic columns are no longer needed
     for (auto& c : t.cols)
     {
-        cudaFree(c.d);
+        dev_free(c.d);
         c.d = nullptr;
     }
-    cudaFree(t.d_flags);
+    dev_free(t.d_flags);
     t.d_flags = nullptr;
     t.dense_w = fm.W;
     t.dense_h = fm.H;

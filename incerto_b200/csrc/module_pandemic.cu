@@ -83,7 +83,7 @@ int32_t pandemic_bind(Sim& s)
     {
         const uint64_t cells = static_cast<uint64_t>(pm.grid_size) * pm.grid_size;
         pm.bits_vec4 = cells / 128 + 1;
-        INC_CUDA(cudaMalloc(&pm.d_cell_bits, 2 * pm.bits_vec4 * 16));
+        INC_CUDA(dev_alloc(&pm.d_cell_bits, 2 * pm.bits_vec4 * 16));
         INC_CUDA(cudaMemsetAsync(pm.d_cell_bits, 0, 2 * pm.bits_vec4 * 16, s.stream));
         // list heads: one slot per cell while that stays small, else ~n/4 hashed slots (a power of two): with the
         // reference's density (0.4 people per cell, ~10 % infected) the exact table would be 10 x the population's own
@@ -104,8 +104,8 @@ int32_t pandemic_bind(Sim& s)
             while ((1ull << lg) < want) ++lg;
             pm.head_shift = 32 - lg;
         }
-        INC_CUDA(cudaMalloc(&pm.d_cell_head, pm.head_slots * 4));
-        INC_CUDA(cudaMalloc(&pm.d_next, std::max<uint64_t>(t.n, 1) * 4));
+        INC_CUDA(dev_alloc(&pm.d_cell_head, pm.head_slots * 4));
+        INC_CUDA(dev_alloc(&pm.d_next, std::max<uint64_t>(t.n, 1) * 4));
         INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, pm.head_slots * 4, s.stream));
     }
     return pandemic_sort_rows(s);
@@ -144,9 +144,9 @@ int32_t pandemic_reset(Sim& s)
 void pandemic_free(Sim& s)
 {
     PandemicModule& pm = s.mods->pandemic;
-    cudaFree(pm.d_cell_bits);
-    cudaFree(pm.d_cell_head);
-    cudaFree(pm.d_next);
+    dev_free(pm.d_cell_bits);
+    dev_free(pm.d_cell_head);
+    dev_free(pm.d_next);
     pm.d_cell_bits = pm.d_cell_head = pm.d_next = nullptr;
 }
 

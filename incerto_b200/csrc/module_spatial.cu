@@ -102,14 +102,14 @@ int32_t spatial_bind(Sim& s)
     }
     const uint64_t cells = static_cast<uint64_t>(p.grid_size) * p.grid_size;
     const uint64_t n = std::max<uint64_t>(t.n, 1);
-    INC_CUDA(cudaMalloc(&sm.d_aux, n));
-    INC_CUDA(cudaMalloc(&sm.d_count, cells * 4));
-    INC_CUDA(cudaMalloc(&sm.d_src_bits, (cells / 32 + 1) * 4));
-    INC_CUDA(cudaMalloc(&sm.d_src_head, cells * 4));
-    INC_CUDA(cudaMalloc(&sm.d_src_next, n * 4));
-    INC_CUDA(cudaMalloc(&sm.d_mark, cells * 8));
-    INC_CUDA(cudaMalloc(&sm.d_marked, (n / 32 + 2) * 4));
-    INC_CUDA(cudaMalloc(&sm.d_stats_acc, 64));
+    INC_CUDA(dev_alloc(&sm.d_aux, n));
+    INC_CUDA(dev_alloc(&sm.d_count, cells * 4));
+    INC_CUDA(dev_alloc(&sm.d_src_bits, (cells / 32 + 1) * 4));
+    INC_CUDA(dev_alloc(&sm.d_src_head, cells * 4));
+    INC_CUDA(dev_alloc(&sm.d_src_next, n * 4));
+    INC_CUDA(dev_alloc(&sm.d_mark, cells * 8));
+    INC_CUDA(dev_alloc(&sm.d_marked, (n / 32 + 2) * 4));
+    INC_CUDA(dev_alloc(&sm.d_stats_acc, 64));
     return spatial_reset(s);
 }
 
@@ -139,14 +139,14 @@ int32_t spatial_reset(Sim& s)
 void spatial_free(Sim& s)
 {
     SpatialModule& sm = s.mods->spatial;
-    cudaFree(sm.d_aux);
-    cudaFree(sm.d_count);
-    cudaFree(sm.d_src_bits);
-    cudaFree(sm.d_src_head);
-    cudaFree(sm.d_src_next);
-    cudaFree(sm.d_mark);
-    cudaFree(sm.d_stats_acc);
-    cudaFree(sm.d_marked);
+    dev_free(sm.d_aux);
+    dev_free(sm.d_count);
+    dev_free(sm.d_src_bits);
+    dev_free(sm.d_src_head);
+    dev_free(sm.d_src_next);
+    dev_free(sm.d_mark);
+    dev_free(sm.d_stats_acc);
+    dev_free(sm.d_marked);
     sm.d_marked = nullptr;
     sm.d_stats_acc = nullptr;
     sm.d_aux = nullptr;

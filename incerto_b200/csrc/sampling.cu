@@ -573,16 +573,16 @@ static int32_t series_reserve(Sim& s, SeriesInst& se, uint64_t slots)
     const uint64_t rec = se.per_entity ? se.record_size * se.n_rows : raw_size(se.agg.kind);
     uint8_t* nv = nullptr;
     uint64_t* nc = nullptr;
-    INC_CUDA(cudaMalloc(&nv, cap * rec));
-    INC_CUDA(cudaMalloc(&nc, cap * sizeof(uint64_t)));
+    INC_CUDA(dev_alloc(&nv, cap * rec));
+    INC_CUDA(dev_alloc(&nc, cap * sizeof(uint64_t)));
     INC_CUDA(cudaMemsetAsync(nc, 0, cap * sizeof(uint64_t), s.stream));
     if (se.d_values)
     {
         INC_CUDA(cudaMemcpyAsync(nv, se.d_values, se.capacity * rec, cudaMemcpyDeviceToDevice, s.stream));
         INC_CUDA(cudaMemcpyAsync(nc, se.d_counts, se.capacity * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s.stream));
         INC_CUDA(cudaStreamSynchronize(s.stream));
-        INC_CUDA(cudaFree(se.d_values));
-        INC_CUDA(cudaFree(se.d_counts));
+        INC_CUDA(dev_free(se.d_values));
+        INC_CUDA(dev_free(se.d_counts));
     }
     se.d_values = nv;
     se.d_counts = nc;
@@ -702,7 +702,7 @@ static int32_t series_materialize(Sim& s, SeriesInst& se)
             // read the series the same number of times between runs (documented at incerto_sim_get_aggregate_time_series)
             uint64_t* d = nullptr;
             const size_t words = raw.size() / 8 + counts.size();
-            INC_CUDA(cudaMalloc(&d, words * 8));
+            INC_CUDA(dev_alloc(&d, words * 8));
             INC_CUDA(cudaMemcpyAsync(d, raw.data(), raw.size(), cudaMemcpyHostToDevice, s.stream));
             INC_CUDA(cudaMemcpyAsync(d + raw.size() / 8, counts.data(), counts.size() * 8, cudaMemcpyHostToDevice, s.stream));
             int32_t st = comm_allreduce(s, d, static_cast<uint32_t>(words), 0, 0);
@@ -714,7 +714,7 @@ static int32_t series_materialize(Sim& s, SeriesInst& se)
                     ce = cudaMemcpyAsync(counts.data(), d + raw.size() / 8, counts.size() * 8, cudaMemcpyDeviceToHost, s.stream);
                 if (ce == cudaSuccess) ce = cudaStreamSynchronize(s.stream);
             }
-            cudaFree(d);
+            dev_free(d);
             INC_TRY(st);
             INC_CUDA(ce);
         }
@@ -738,9 +738,9 @@ static int32_t series_materialize(Sim& s, SeriesInst& se)
 static int32_t grid_alloc_dense(GridInst& g)
 {
     if (g.d_cell_start) return INCERTO_OK;
-    INC_CUDA(cudaMalloc(&g.d_cell_start, (g.n_cells + 1) * 4));
-    INC_CUDA(cudaMalloc(&g.d_cursor, g.n_cells * 4));
-    INC_CUDA(cudaMalloc(&g.d_sorted_rows, std::max<uint64_t>(g.cap_rows, 1) * 4));
+    INC_CUDA(dev_alloc(&g.d_cell_start, (g.n_cells + 1) * 4));
+    INC_CUDA(dev_alloc(&g.d_cursor, g.n_cells * 4));
+    INC_CUDA(dev_alloc(&g.d_sorted_rows, std::max<uint64_t>(g.cap_rows, 1) * 4));
     return INCERTO_OK;
 }
 
@@ -810,8 +810,8 @@ static int32_t grid_rebuild(Sim& s, GridInst& g, uint64_t step, bool last_of_run
         if (!last_of_run) return INCERTO_OK;
         if (!g.d_snap_pos)
         {
-            INC_CUDA(cudaMalloc(&g.d_snap_pos, std::max<uint64_t>(g.cap_rows, 1) * pc->row_bytes));
-            INC_CUDA(cudaMalloc(&g.d_snap_flags, std::max<uint64_t>(g.cap_rows, 1)));
+            INC_CUDA(dev_alloc(&g.d_snap_pos, std::max<uint64_t>(g.cap_rows, 1) * pc->row_bytes));
+            INC_CUDA(dev_alloc(&g.d_snap_flags, std::max<uint64_t>(g.cap_rows, 1)));
         }
         KTimer kt(s, "grid_snapshot", 2.0 * t.n * (pc->row_bytes + 1));
         INC_CUDA(cudaMemcpyAsync(g.d_snap_pos, pc->d, t.n * pc->row_bytes, cudaMemcpyDeviceToDevice, s.stream));
@@ -871,9 +871,9 @@ static int32_t grid_ensure_built(Sim& s, GridInst& g)
         }
         if (cells != g.n_cells || !g.d_cell_start)
         {
-            cudaFree(g.d_cell_start);
-            cudaFree(g.d_cursor);
-            cudaFree(g.d_sorted_rows);
+            dev_free(g.d_cell_start);
+            dev_free(g.d_cursor);
+            dev_free(g.d_sorted_rows);
             g.d_cell_start = g.d_cursor = g.d_sorted_rows = nullptr;
             g.n_cells = cells;
         }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <utility>
 
 namespace incerto
 {
@@ -24,6 +25,12 @@ __device__ __forceinline__ void st_stream_v4(void* p, const uint4& v)
                  "r"(v.w)
                  : "memory");
 }
+
+// Programmatic dependent launch (see launch_pdl): let the next kernel of the stream be scheduled while this one drains,
+// and wait - before the first access to anything the previous kernel wrote - until that kernel has completed.  Both
+// are no-ops for a kernel launched the plain way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v)
@@ -79,6 +86,24 @@ __device__ __forceinline__ bool last_block_arrives(uint32_t* ticket, uint32_t to
     const bool last = s_last != 0;
     if (last) __threadfence();
     return last;
+}
+
+// Launch `kernel` as a programmatic dependent of the previous launch on `st`: its CTAs may start as SM slots free up;
+// the kernel must call pdl_wait() before it touches the previous kernel's results.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 } // namespace incerto

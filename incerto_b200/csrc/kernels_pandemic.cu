@@ -22,6 +22,8 @@
 //           2*(uid&7) (die) / 2*(uid&7)+1 (recover) must be zero; L2 = philox(key[PFAT], (uid,0,step,1)):
 //           die = L2.x < thr(256 p_die), recover = L2.y < thr(256 p_rec).  Otherwise L2 alone with thr(p).
 //   infect  pair (healthy h, infected i) in the same cell: word 0 of philox(key[PINF], (uid_h, uid_i, step, 0)) < thr(p)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels_pandemic.hpp"
 
@@ -102,6 +104,8 @@ __device__ __forceinline__ uint32_t head_slot(const PandemicArgs& a, uint32_t ce
 // issued before any result is consumed: the returning exchanges that link the infected into their cells overlap.
 __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // positions and flags are the previous kernel's (interact of the step before)
     const uint64_t ntiles = (a.n + kRows - 1) / kRows;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const uint32_t G = a.grid_size;
@@ -218,6 +222,8 @@ __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, uint32_t& to
 // with full warps instead of once per row position with two or three lanes active.
 __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads what pandemic_move wrote
     __shared__ uint32_t s_queue[kThreads / 32][2][32 * kRows]; // item = row | flags << 24 (rows < 2^24)
     __shared__ uint32_t s_qpos[kThreads / 32][32 * kRows];     // packed position of the rows in queue 1
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -348,11 +354,19 @@ void launch_pandemic_spawn(const PandemicArgs& a, cudaStream_t st)
 }
 void launch_pandemic_move(const PandemicArgs& a, cudaStream_t st)
 {
-    pandemic_move_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
+    static const bool plain = [] { const char* e = std::getenv("INCERTO_B200_NO_PDL"); return e && e[0] == '1'; }();
+    if (plain)
+        pandemic_move_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
+    else
+        launch_pdl(pandemic_move_kernel, dim3(blocks_for((a.n + kRows - 1) / kRows)), dim3(kThreads), 0, st, a);
 }
 void launch_pandemic_interact(const PandemicArgs& a, cudaStream_t st)
 {
-    pandemic_interact_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
+    static const bool plain = [] { const char* e = std::getenv("INCERTO_B200_NO_PDL"); return e && e[0] == '1'; }();
+    if (plain)
+        pandemic_interact_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
+    else
+        launch_pdl(pandemic_interact_kernel, dim3(blocks_for((a.n + kRows - 1) / kRows)), dim3(kThreads), 0, st, a);
 }
 
 } // namespace incerto

@@ -88,20 +88,6 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v)
-{
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Fused halo transport, stamp side.  "Step k of this rank is complete" is announced by the launch that FOLLOWS step k
 // (the first thread of step k+1's grid, or the publish kernel at the end of a run): the kernel boundary has already made
 // every cell and overlay state of step k visible, so the stamp is one plain store - into this rank's OWN mailbox (slot

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <utility>
 
@@ -86,6 +88,22 @@ __device__ __forceinline__ bool last_block_arrives(uint32_t* ticket, uint32_t to
     const bool last = s_last != 0;
     if (last) __threadfence();
     return last;
+}
+
+// Blocks of `waves` resident waves of `kernel` (occupancy x SMs): the grid of a grid-stride loop whose iterations cost
+// about the same - every warp gets an equal share, where a fixed cap of k blocks per SM leaves a last wave that is partly
+// empty.  How many waves is measured per kernel (one for the streaming kernels; two where a second wave hides the first
+// one's tail).  INCERTO_B200_WAVES=<w> (experiments) overrides it everywhere.
+template <typename K>
+inline int wave_blocks(K kernel, int threads, double waves = 1.0, size_t smem = 0)
+{
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    static const double forced = [] { const char* e = std::getenv("INCERTO_B200_WAVES"); return e ? std::atof(e) : 0.0; }();
+    if (forced > 0) waves = forced;
+    return std::max(1, static_cast<int>(per_sm * sms * waves));
 }
 
 // Launch `kernel` as a programmatic dependent of the previous launch on `st`: its CTAs may start as SM slots free up;

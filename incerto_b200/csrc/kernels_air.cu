@@ -23,6 +23,8 @@
 //          x = mulhi(a.x,SIZE), y = mulhi(a.y,SIZE), z = mulhi(a.z,HEIGHT), type = mulhi(a.w,3), target = mulhi(b.x,HEIGHT)
 //   move   r = philox(key[AMOV], (uid,0,step,0)); horizontal = r.x < thr(0.7); dx = mulhi(r.y,3)-1; dy = mulhi(r.z,3)-1
 #include "../../include/incerto_b200.h"
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels_air.hpp"
 
@@ -454,10 +456,15 @@ void launch_air_spawn(const AirArgs& a, int16_t* target_out, uint8_t* flags_out,
     air_spawn_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a, target_out, flags_out);
 }
 void launch_air_bits(const AirArgs& a, cudaStream_t st) { air_bits_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
-void launch_air_candidates(const AirArgs& a, cudaStream_t st) { air_candidates_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
+void launch_air_candidates(const AirArgs& a, cudaStream_t st)
+{
+    static const int wave = wave_blocks(air_candidates_kernel, kThreads);
+    air_candidates_kernel<<<std::min(blocks_for(a.n), wave), kThreads, 0, st>>>(a);
+}
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
-    air_step_kernel<<<blocks_for((a.n + 1) / 2), kThreads, 0, st>>>(a);
+    static const int wave = wave_blocks(air_step_kernel, kThreads);
+    air_step_kernel<<<std::min(blocks_for((a.n + 1) / 2), wave), kThreads, 0, st>>>(a);
 }
 void launch_air_own_init(const AirArgs& a, AirMailbox* in_lo, AirMailbox* in_hi, cudaStream_t st)
 {

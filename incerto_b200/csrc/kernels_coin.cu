@@ -6,6 +6,8 @@
 // entities a thread updates with one 128-bit load/store per column.
 //
 // Algorithmic bytes per entity-update: 16 (u32 heads + u32 tosses, read+write).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.hpp"
 #include "../../include/incerto_b200.h"
@@ -251,9 +253,19 @@ void launch_coin_odds(const void* heads, const void* tosses, int dtype, const ui
     if (dtype == INCERTO_U32)
     {
         if (flags == nullptr && n >= 128)
-            coin_odds_quad_kernel<<<static_cast<int>(b), 256, 0, st>>>(static_cast<const uint32_t*>(heads),
-                                                                       static_cast<const uint32_t*>(tosses), n, out,
-                                                                       static_cast<double*>(scratch), ticket);
+        {
+            // exactly one resident wave of a grid-stride loop: every warp gets the same share (1184 blocks on the 444
+            // slots its 72 registers leave were 2.67 waves, the last one two thirds empty)
+            static const int per_sm = [] {
+                int o = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, coin_odds_quad_kernel, 256, 0) != cudaSuccess || o < 1) o = 1;
+                return o;
+            }();
+            const uint64_t wave = static_cast<uint64_t>(kNumSMs) * per_sm;
+            coin_odds_quad_kernel<<<static_cast<int>(std::min(b, wave)), 256, 0, st>>>(static_cast<const uint32_t*>(heads),
+                                                                                     static_cast<const uint32_t*>(tosses), n, out,
+                                                                                     static_cast<double*>(scratch), ticket);
+        }
         else
             coin_odds_kernel<uint32_t><<<static_cast<int>(b), 256, 0, st>>>(
             static_cast<const uint32_t*>(heads), static_cast<const uint32_t*>(tosses), flags, need_set, need_clear,

@@ -22,6 +22,7 @@
 //           2*(uid&7) (die) / 2*(uid&7)+1 (recover) must be zero; L2 = philox(key[PFAT], (uid,0,step,1)):
 //           die = L2.x < thr(256 p_die), recover = L2.y < thr(256 p_rec).  Otherwise L2 alone with thr(p).
 //   infect  pair (healthy h, infected i) in the same cell: word 0 of philox(key[PINF], (uid_h, uid_i, step, 0)) < thr(p)
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -358,7 +359,10 @@ void launch_pandemic_move(const PandemicArgs& a, cudaStream_t st)
     if (plain)
         pandemic_move_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
     else
-        launch_pdl(pandemic_move_kernel, dim3(blocks_for((a.n + kRows - 1) / kRows)), dim3(kThreads), 0, st, a);
+    {
+        static const int wave = wave_blocks(pandemic_move_kernel, kThreads, 2.0);
+        launch_pdl(pandemic_move_kernel, dim3(std::min(blocks_for((a.n + kRows - 1) / kRows), wave)), dim3(kThreads), 0, st, a);
+    }
 }
 void launch_pandemic_interact(const PandemicArgs& a, cudaStream_t st)
 {
@@ -366,7 +370,10 @@ void launch_pandemic_interact(const PandemicArgs& a, cudaStream_t st)
     if (plain)
         pandemic_interact_kernel<<<blocks_for((a.n + kRows - 1) / kRows), kThreads, 0, st>>>(a);
     else
-        launch_pdl(pandemic_interact_kernel, dim3(blocks_for((a.n + kRows - 1) / kRows)), dim3(kThreads), 0, st, a);
+    {
+        static const int wave = wave_blocks(pandemic_interact_kernel, kThreads, 2.0);
+        launch_pdl(pandemic_interact_kernel, dim3(std::min(blocks_for((a.n + kRows - 1) / kRows), wave)), dim3(kThreads), 0, st, a);
+    }
 }
 
 } // namespace incerto

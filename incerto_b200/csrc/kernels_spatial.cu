@@ -29,6 +29,8 @@
 //   transmit pair (healthy T, infectious S): philox(key[STRN], (uid_T, uid_S, step, 0)).x < thr(distance)
 //   move     r = philox(key[SMOV], (uid,0,step,0)): attempt = r.x < thr(0.5); choose = mulhi(r.y, #best_moves)
 #include "../../include/incerto_b200.h"
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels_spatial.hpp"
 
@@ -661,8 +663,16 @@ inline int blocks_for(uint64_t items)
 } // namespace
 
 void launch_spatial_spawn(const SpatialArgs& a, cudaStream_t st) { spatial_spawn_kernel<<<blocks_for(a.n), kThreads, 0, st>>>(a); }
-void launch_spatial_prepare(const SpatialArgs& a, cudaStream_t st) { spatial_prepare_kernel<<<blocks_for((a.n + 7) / 8), kThreads, 0, st>>>(a); }
-void launch_spatial_interact(const SpatialArgs& a, cudaStream_t st) { spatial_interact_kernel<<<blocks_for((a.n + 7) / 8), kThreads, 0, st>>>(a); }
+void launch_spatial_prepare(const SpatialArgs& a, cudaStream_t st)
+{
+    static const int wave = wave_blocks(spatial_prepare_kernel, kThreads);
+    spatial_prepare_kernel<<<std::min(blocks_for((a.n + 7) / 8), wave), kThreads, 0, st>>>(a);
+}
+void launch_spatial_interact(const SpatialArgs& a, cudaStream_t st)
+{
+    static const int wave = wave_blocks(spatial_interact_kernel, kThreads);
+    spatial_interact_kernel<<<std::min(blocks_for((a.n + 7) / 8), wave), kThreads, 0, st>>>(a);
+}
 void launch_spatial_stats_finalize(const uint64_t* acc, uint64_t initial_population, uint64_t* out6, cudaStream_t st)
 {
     spatial_stats_finalize_kernel<<<1, 1, 0, st>>>(acc, initial_population, out6);

@@ -22,6 +22,8 @@
 //         L2 against floor(256 p / T1 * 2^32)
 //   sell  same with key[TSEL]; drawn for owned stocks only                          (:218)
 //   price stock s: z = det_normal(philox(key[TPRC], (s, 0, step, 0))) (detmath.cuh); change = mean + sd * z (:148-155)
+#include <algorithm>
+
 #include "common.cuh"
 #include "detmath.cuh"
 #include "kernels_traders.hpp"
@@ -314,7 +316,10 @@ void launch_traders_step(const TradersArgs& a, cudaStream_t st)
     else if (nw <= 8)
         traders_step_kernel<8><<<blocks, kThreads, 0, st>>>(a);
     else if (nw <= 14)
-        traders_step_kernel<14><<<blocks, kThreads, 0, st>>>(a);
+    {
+        static const int wave = wave_blocks(traders_step_kernel<14>, kThreads, 2.0);
+        traders_step_kernel<14><<<std::min(blocks, wave), kThreads, 0, st>>>(a);
+    }
     else
         traders_step_kernel<32><<<blocks, kThreads, 0, st>>>(a);
 }

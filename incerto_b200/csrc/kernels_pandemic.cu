@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
 {
     pdl_launch_dependents();
     pdl_wait(); // everything below reads what pandemic_move wrote
-    __shared__ uint32_t s_queue[kThreads / 32][2][32 * kRows]; // item = row | flags << 24 (rows < 2^24)
+    __shared__ uint16_t s_queue[kThreads / 32][2][32 * kRows]; // item = row - tile base | flags << 8 (half the bytes: the L1 gets them)
     __shared__ uint32_t s_qpos[kThreads / 32][32 * kRows];     // packed position of the rows in queue 1
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
 #pragma unroll
         for (int k = 0; k < kRows; ++k)
         {
-            const uint32_t item = static_cast<uint32_t>(row0 + k) | ((static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu) << 24);
+            const uint16_t item = static_cast<uint16_t>((lane * kRows + k) | ((static_cast<uint32_t>(r.f >> (8 * k)) & 0xffu) << 8));
             if ((sick >> k) & 1u) s_queue[warp][0][o_sick++] = item;
             if ((hit >> k) & 1u)
             {
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
         for (uint32_t j = lane; j < n_sick; j += 32)
         {
             const uint32_t item = s_queue[warp][0][j];
-            const uint32_t row = item & 0x00ffffffu, fl = item >> 24;
+            const uint32_t row = static_cast<uint32_t>(base) + (item & 0xffu), fl = item >> 8;
             const uint32_t uid = a.uid ? a.uid[row] : row;
             bool l1_die = true, l1_rec = true;
             if (a.fate_two_level)
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
         for (uint32_t j = lane; j < n_hit; j += 32)
         {
             const uint32_t item = s_queue[warp][1][j];
-            const uint32_t row = item & 0x00ffffffu, fl = item >> 24;
+            const uint32_t row = static_cast<uint32_t>(base) + (item & 0xffu), fl = item >> 8;
             const uint32_t uid = a.uid ? a.uid[row] : row;
             const uint32_t p = s_qpos[warp][j];
             const uint32_t cell = (p & 0xffffu) * G + (p >> 16);

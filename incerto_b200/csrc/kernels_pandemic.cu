@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
     const uint64_t ntiles = (a.n + kRows - 1) / kRows;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const uint32_t G = a.grid_size;
-    const uint32_t tag = (a.step & 0xffu) << 24;
+    const uint32_t tag = ((a.step & 0xffu) << 24) & ~a.link_mask; // no stamp in the heads of a population of >= 2^24 rows
     for (uint64_t q = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < ntiles; q += gstride)
     {
         const uint64_t row0 = q * kRows;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) pandemic_move_kernel(PandemicArgs a)
             old_head = atomicExch(&a.cell_head[head_slot(a, cell)], tag | static_cast<uint32_t>(row0 + k));
         };
         auto chain = [&](uint32_t k, uint32_t old_head) {
-            a.next_infected[row0 + k] = ((old_head & 0xff000000u) == tag) ? (old_head & 0x00ffffffu) : 0x00ffffffu;
+            a.next_infected[row0 + k] = ((old_head & ~a.link_mask) == tag) ? (old_head & a.link_mask) : a.link_mask;
         };
         uint32_t kk[3] = {8u, 8u, 8u}, oo[3] = {0u, 0u, 0u};
 #pragma unroll
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
     const uint64_t warp0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     const uint32_t G = a.grid_size;
-    const uint32_t tag = (a.step & 0xffu) << 24;
+    const uint32_t tag = ((a.step & 0xffu) << 24) & ~a.link_mask; // no stamp in the heads of a population of >= 2^24 rows
     const bool fate = (a.do_die | a.do_recover) != 0;
     // the other bitmap (the next step's) is cleared on the side: no memset between the steps
     if (a.cell_bits_clear)
@@ -318,10 +318,10 @@ __global__ void __launch_bounds__(kThreads) pandemic_interact_kernel(PandemicArg
             const uint32_t p = s_qpos[warp][j];
             const uint32_t cell = (p & 0xffffu) * G + (p >> 16);
             const uint32_t h = a.cell_head[head_slot(a, cell)];
-            uint32_t cur = ((h & 0xff000000u) == tag) ? (h & 0x00ffffffu) : 0x00ffffffu;
+            uint32_t cur = ((h & ~a.link_mask) == tag) ? (h & a.link_mask) : a.link_mask;
             bool infected = false;
             // (the guard only bounds the walk should the list ever be corrupt: never hang the device)
-            for (uint32_t guard = 0; cur != 0x00ffffffu && guard < 0x01000000u; ++guard)
+            for (uint64_t guard = 0; cur != a.link_mask && guard < a.n; ++guard)
             {
                 const uint32_t nxt = a.next_infected[cur];
                 if (!a.head_shift || a.pos[cur] == p) // a hashed slot also lists the infected of other cells

@@ -27,6 +27,9 @@ struct PandemicArgs
     uint32_t* cell_bits_clear; // the next step's bitmap, zeroed by this step's interact kernel (bits_vec4 x 16 B)
     uint64_t bits_vec4;
     uint32_t* cell_head;     // (step & 0xff) << 24 | row of the list head; slot = cell, or hashed (head_shift)
+    uint32_t link_mask;      // 0x00ffffff: 24-bit row links + the step stamp in the heads (stale heads read as empty, the
+                             // table is cleared every 256 steps); 0xffffffff for >= 2^24 - 1 rows: 32-bit links, no stamp,
+                             // the heads are cleared before every step.  link_mask is also the end-of-list marker.
     uint32_t head_shift;     // 0: one slot per cell; else slot = (cell * 0x9E3779B1) >> head_shift
     uint32_t* next_infected; // per row: next infected row in the same cell, 0xffffff = end
 };

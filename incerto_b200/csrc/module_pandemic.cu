@@ -74,9 +74,9 @@ int32_t pandemic_bind(Sim& s)
     pm.active = true;
     if (pm.table < 0) return INCERTO_OK; // no person was spawned: the systems have nothing to iterate
     Table& t = s.tables[pm.table];
-    if (t.n >= 0x00ffffffu)
+    if (t.n >= 0xffffffffull)
     {
-        set_error("pandemic: at most 2^24-2 people per replica (infected lists use 24-bit row links)");
+        set_error("pandemic: at most 2^32-2 people per replica (32-bit row links)");
         return INCERTO_ERR_UNSUPPORTED;
     }
     if (pm.do_infect)
@@ -179,6 +179,7 @@ static void pandemic_fill(Sim& s, PandemicModule& pm, PandemicArgs& a, Table& t,
     a.bits_vec4 = pm.bits_vec4;
     a.cell_head = pm.d_cell_head;
     a.head_shift = pm.head_shift;
+    a.link_mask = t.n >= 0x00ffffffu ? 0xffffffffu : 0x00ffffffu;
     a.next_infected = pm.d_next;
 }
 
@@ -195,7 +196,9 @@ int32_t pandemic_step(Sim& s, uint64_t first_step, uint32_t nsteps)
         pandemic_fill(s, pm, a, t, step);
         if (pm.do_infect)
         {
-            if ((step & 0xffu) == 0) INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, pm.head_slots * 4, s.stream));
+            // the heads carry the step's stamp (8 bits) next to a 24-bit row: cleared when the stamp wraps; a population
+            // too large for 24-bit rows uses the whole word for the row and clears the heads before every step
+            if ((step & 0xffu) == 0 || t.n >= 0x00ffffffu) INC_CUDA(cudaMemsetAsync(pm.d_cell_head, 0xff, pm.head_slots * 4, s.stream));
         }
         if (pm.do_move || pm.do_infect)
         {

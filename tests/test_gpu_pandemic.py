@@ -102,6 +102,17 @@ def test_host_spawn_crowded_cell_and_walls():
         check_state(sim, o, person, infected, position)
 
 
+def test_more_than_2_pow_24_people():
+    """Populations of 2^24 - 1 rows and more use 32-bit list links (no step stamp in the heads, which are cleared before
+    every step) instead of the 24-bit links of smaller ones: same results as the oracle, person by person."""
+    n, G = (1 << 24) + 12345, 6500
+    sim, person, infected, position = build(n, G)
+    o = PandemicOracle(SEED, 0, n, G, nested_loop=False).spawn()
+    sim.run(3)
+    o.run(3)
+    check_state(sim, o, person, infected, position)
+
+
 def test_step_tag_wraparound():
     """The per-cell list heads are stamped with step & 0xff: run across several wrap-arounds."""
     n, G = 2000, 8

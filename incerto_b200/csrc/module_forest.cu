@@ -11,7 +11,7 @@
 namespace incerto
 {
 
-static constexpr size_t kOvSlot = 256; // bytes per overlay inbox slot (at most 256 overlay entities)
+static constexpr size_t kOvSlot = 4096; // bytes per overlay inbox slot (at most 4096 overlay entities)
 static constexpr size_t kLead = 256; // bytes before column 0 / after the last column (reads of y-1 / y+1 bytes)
 
 static void forest_partition(const Sim& s, ForestModule& fm)
@@ -586,9 +586,9 @@ static int32_t forest_adopt_host_table(Sim& s, ForestModule& fm)
     stage_mark("forest adopt: host checks");
     const uint8_t* dense = dense_states ? dense_states : st.data();
     fm.n_overlay = static_cast<uint32_t>(std::min<uint64_t>(total - dense_rows, 0xffffffffu));
-    if (fm.n_overlay > 256)
+    if (fm.n_overlay > kOvSlot)
     {
-        set_error("forest: at most 256 overlay entities on top of the dense grid");
+        set_error("forest: at most 4096 overlay entities on top of the dense grid");
         return INCERTO_ERR_UNSUPPORTED;
     }
     forest_partition(s, fm);

@@ -128,6 +128,34 @@ def test_parity_host_spawn_with_overlays():
     assert sim.grid_neighbors_of(g, (0, 0), orthogonal=True) == sorted([1, H])
 
 
+def test_many_overlay_entities():
+    """1500 overlay entities (igniters and bystanders) scattered over a 280 x 4096 grid (about 20 near every CTA tile) - more than one block of threads
+    stages per pass, several CTA tiles in both directions: every step against the oracle."""
+    W, H, n_ov = 280, 4096, 1500
+    rng = np.random.default_rng(21)
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H), indexing="ij")
+    xy = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int32)
+    st = np.where(rng.random(W * H) < 0.8, HEALTHY, EMPTY).astype(np.uint8)
+    ov_xy = np.stack([rng.integers(0, W, n_ov), rng.integers(0, H, n_ov)], 1).astype(np.int32)
+    ov_st = rng.choice(np.array([3, 2, 1, HEALTHY, EMPTY, BURNED], np.uint8), n_ov)
+    all_xy, all_st = np.concatenate([xy, ov_xy]), np.concatenate([st, ov_st])
+    b = ib.SimulationBuilder(seed=SEED)
+    pos = b.component("GridPosition2D", F.I16, lanes=2)
+    cell = b.component("ForestCell.state", F.U8)
+    b.add_spatial_grid_2d(pos, cell, bounds=((0, 0), (W - 1, H - 1)))
+    b.add_entity_spawner(lambda s: s.spawn_batch(len(all_st), {pos: all_xy.astype(np.int16), cell: all_st}))
+    b.add_systems(ib.FireSpread(pos, cell, 0.6, 3), ib.BurnProgression(pos, cell), ib.Regrowth(pos, cell, 0.002))
+    b.record_aggregate_time_series(ib.FireStatsOf(cell), 1)
+    sim = b.build()
+    o = ForestOracle(SEED, 0, W, H, p_regrow=0.002, fires=0).spawn_explicit(all_xy, all_st)
+    for _ in range(12):
+        sim.run(1)
+        o.run(1)
+        assert np.array_equal(sim.read_component(cell), o.cells()[0])
+    assert np.array_equal(np.array([stats_tuple(v) for v in sim.get_aggregate_time_series(ib.FireStatsOf(cell)).values()],
+                                   dtype=np.uint64), o.series())
+
+
 def test_reset_and_replicas():
     sim, pos, cell = build_device_forest(64, 64, replica=4)
     sim.run(30)

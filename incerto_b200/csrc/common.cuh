@@ -119,8 +119,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool plain = [] { const char* e = std::getenv("INCERTO_B200_NO_PDL"); return e && e[0] == '1'; }();
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = plain ? 0 : 1; // INCERTO_B200_NO_PDL=1: ordinary stream order (A/B measurements)
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(kThreads) air_bits_kernel(AirArgs a)
 // One thread = 2 consecutive rows (one 128-bit position load, twelve independent bit probes in flight).
 __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads what the previous kernel of the step wrote
     const uint64_t npairs = (a.n + 1) >> 1;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -202,6 +204,8 @@ __global__ void __launch_bounds__(kThreads) air_candidates_kernel(AirArgs a)
 // check_conflicts + move_aircraft; one thread = 2 consecutive rows (one 128-bit position load/store)
 __global__ void __launch_bounds__(kThreads) air_step_kernel(AirArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads what the previous kernel of the step wrote
     const uint64_t npairs = (a.n + 1) >> 1;
     const uint64_t gstride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t conflicts = 0, indexed = 0;
@@ -459,12 +463,12 @@ void launch_air_bits(const AirArgs& a, cudaStream_t st) { air_bits_kernel<<<bloc
 void launch_air_candidates(const AirArgs& a, cudaStream_t st)
 {
     static const int wave = wave_blocks(air_candidates_kernel, kThreads);
-    air_candidates_kernel<<<std::min(blocks_for(a.n), wave), kThreads, 0, st>>>(a);
+    launch_pdl(air_candidates_kernel, dim3(std::min(blocks_for(a.n), wave)), dim3(kThreads), 0, st, a);
 }
 void launch_air_step(const AirArgs& a, cudaStream_t st)
 {
     static const int wave = wave_blocks(air_step_kernel, kThreads);
-    air_step_kernel<<<std::min(blocks_for((a.n + 1) / 2), wave), kThreads, 0, st>>>(a);
+    launch_pdl(air_step_kernel, dim3(std::min(blocks_for((a.n + 1) / 2), wave)), dim3(kThreads), 0, st, a);
 }
 void launch_air_own_init(const AirArgs& a, AirMailbox* in_lo, AirMailbox* in_hi, cudaStream_t st)
 {

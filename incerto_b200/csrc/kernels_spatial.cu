@@ -209,6 +209,8 @@ __device__ __forceinline__ uint32_t enqueue(WorkQueue& wq, uint32_t warp, const 
 // independent predicated loads, so that its latencies overlap.  Results go back by byte stores.
 __global__ void __launch_bounds__(kThreads) spatial_prepare_kernel(SpatialArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads what the previous kernel of the step wrote
     __shared__ WorkQueue wq;
     const uint32_t G = static_cast<uint32_t>(a.G);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -393,6 +395,8 @@ __device__ constexpr int kOff13[13][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 
 
 __global__ void __launch_bounds__(kThreads) spatial_interact_kernel(SpatialArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads what the previous kernel of the step wrote
     __shared__ WorkQueue wq;
     const int G = a.G;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -666,12 +670,12 @@ void launch_spatial_spawn(const SpatialArgs& a, cudaStream_t st) { spatial_spawn
 void launch_spatial_prepare(const SpatialArgs& a, cudaStream_t st)
 {
     static const int wave = wave_blocks(spatial_prepare_kernel, kThreads);
-    spatial_prepare_kernel<<<std::min(blocks_for((a.n + 7) / 8), wave), kThreads, 0, st>>>(a);
+    launch_pdl(spatial_prepare_kernel, dim3(std::min(blocks_for((a.n + 7) / 8), wave)), dim3(kThreads), 0, st, a);
 }
 void launch_spatial_interact(const SpatialArgs& a, cudaStream_t st)
 {
     static const int wave = wave_blocks(spatial_interact_kernel, kThreads);
-    spatial_interact_kernel<<<std::min(blocks_for((a.n + 7) / 8), wave), kThreads, 0, st>>>(a);
+    launch_pdl(spatial_interact_kernel, dim3(std::min(blocks_for((a.n + 7) / 8), wave)), dim3(kThreads), 0, st, a);
 }
 void launch_spatial_stats_finalize(const uint64_t* acc, uint64_t initial_population, uint64_t* out6, cudaStream_t st)
 {

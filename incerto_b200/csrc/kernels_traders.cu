@@ -116,6 +116,8 @@ __device__ __forceinline__ uint32_t mask16(const unsigned long long (&m)[NC], in
 template <int NW>
 __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads what the previous kernel of the step wrote
     constexpr int NB = (NW + 1) / 2;  // 16-stock blocks
     constexpr int NC = (NW + 7) / 8;  // 64-stock mask words
     __shared__ double s_price[kTradersMaxStocks];
@@ -273,6 +275,8 @@ __global__ void __launch_bounds__(kThreads) traders_step_kernel(TradersArgs a)
 
 __global__ void stocks_price_change_kernel(TradersArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait(); // everything below reads what the previous kernel of the step wrote
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.num_stocks) return;
     const uint32_t fl = a.stock_flags[s];
@@ -318,14 +322,14 @@ void launch_traders_step(const TradersArgs& a, cudaStream_t st)
     else if (nw <= 14)
     {
         static const int wave = wave_blocks(traders_step_kernel<14>, kThreads, 2.0);
-        traders_step_kernel<14><<<std::min(blocks, wave), kThreads, 0, st>>>(a);
+        launch_pdl(traders_step_kernel<14>, dim3(std::min(blocks, wave)), dim3(kThreads), 0, st, a);
     }
     else
         traders_step_kernel<32><<<blocks, kThreads, 0, st>>>(a);
 }
 void launch_stocks_price_change(const TradersArgs& a, cudaStream_t st)
 {
-    stocks_price_change_kernel<<<(a.num_stocks + 127) / 128, 128, 0, st>>>(a);
+    launch_pdl(stocks_price_change_kernel, dim3((a.num_stocks + 127) / 128), dim3(128), 0, st, a);
 }
 void launch_fill_f64(double* p, double v, uint64_t n, cudaStream_t st)
 {

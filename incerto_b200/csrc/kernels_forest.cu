@@ -208,19 +208,16 @@ __device__ __forceinline__ bool overlay_marked(const ForestConst& c, const NearO
     return false;
 }
 
-// The vectorised body: each thread owns kColsPerThread (6) adjacent columns x 16 cells (eight 128-bit loads incl. the
-// W/E neighbour columns).  Width and registers have to be tuned together: with the register budget of the 4-column
-// kernel (<= 48) wider threads spill and lose (an early sweep: 8 / 16 / 24 columns 135 / 159 / 198 us against 127 us
-// at 16384^2); given 56-72 registers, 6 / 8 columns run 16384^2 in 120 / 118 us against 131 us for 4 columns (fewer
-// neighbour-column loads, event-queue and vote overhead per cell), while a 4096^2 step (18.5-18.8 us) prefers <= 6:
-// profiles/r01_forest_cols_sweep.txt.
-//  * streaming path, fully unrolled and register resident: 128-bit loads of the chunk and its W/E
-//    neighbours, a warp-uniform "is there any fire around" vote that skips progression/spread work for the
-//    (vast majority of) warps far from the front, the level-1 regrowth draw (one Philox call per 16 cells),
-//    the 128-bit store;
-//  * rare events — healthy cells next to fire, empty cells that passed level 1 — are packed into one
-//    event word per column and handled afterwards by a single rolled loop that patches single bytes of
-//    the freshly written buffer;
+// The vectorised body: each thread owns kColsPerThread (7) adjacent columns x 16 cells (nine 128-bit loads incl. the
+// W/E neighbour columns), a CTA of 4 warps 28 columns x 512 cells, 8 CTAs per SM at 64 registers: a 4096^2 grid is ONE
+// resident wave (1176 CTAs on 1184 slots).  Width and registers have to be tuned together (profiles/r01_forest_cols_sweep.txt,
+// profiles/r02_forest_lottery_sweeps.txt).
+//  * streaming path, fully unrolled and register resident: 128-bit loads of the chunk and its W/E neighbours, one
+//    warp-wide OR that says which of the warp's columns have fire in or next to them (progression / spread work is done
+//    for those only; by far most warps have none and copy), the 128-bit store;
+//  * rare events - healthy cells next to fire (packed into one event word per column), the Empty cells among the
+//    winners of the step's regrowth lottery (queued directly) - are handled afterwards by a single rolled loop that
+//    patches single bytes of the freshly written buffer;
 //  * FireStats are kept incrementally: only state transitions are counted (one warp-aggregated atomic
 //    when a warp saw any) into the step's delta slot; see forest_publish for who puts the step on record.
 // FireStats bookkeeping (forest_fire.rs:104-134, sampled every step by the fused series, time_series.rs:68-87).

@@ -126,7 +126,7 @@ struct ForestArgs
     uint64_t* stats_run;      // 12 u64: totals (healthy, burning, empty), last published step, two delta slots of
                               // this slab + owned overlays (layout: kernels_forest.cu, forest_publish)
     uint32_t* error;          // device error flag
-    uint32_t* ticket;
+    uint32_t* ticket;         // (unused by the step kernel since the stamps left it; kept for layout)
     uint64_t* stats_out;      // 5 u64: healthy, burning, burned, empty, total (state after this step)
     uint8_t* series_values;   // nullptr or ring of incerto_fire_stats
     uint64_t* series_counts;
